@@ -1,0 +1,187 @@
+/*
+ * phertilizer_b200 -- C ABI of the B200-native likelihood hot path of Phertilizer.
+ *
+ * The reference (elkebir-group/phertilizer) has no FFI: its seam is the Python `Data` dataclass
+ * (phertilizer/data.py:8-20) holding four DENSE n x m numpy arrays (var, total, like0, like1_marg) that the
+ * tree operations read through `M[np.ix_(cells, muts)].<reduce>` expressions.  This library owns a
+ * device-resident sparse replacement of that state (one handle per GPU) and exports one entry point per
+ * family of those expressions.  Every function cites the reference lines it replaces.
+ *
+ * Conventions
+ *   - plain C, no torch / C++ types; all sizes are explicit.
+ *   - a "label" array assigns every cell (or SNV) to a cluster: 0 = not in any cluster (excluded from the
+ *     np.ix_ subset), 1..C = cluster index.  This is how `cells`, `cellsA`, `cellsB`, `muts`, ... index arrays of
+ *     the reference are passed.
+ *   - `on_device != 0`: every data pointer of the call is a device pointer on the handle's GPU and the call is
+ *     enqueued on `stream` (a cudaStream_t passed as void*, may be NULL) WITHOUT synchronising.
+ *     `on_device == 0`: pointers are host memory; the call stages them through pinned buffers, runs, copies
+ *     the results back and synchronises before returning.
+ *   - return value: PH_OK or an error code; `ph_last_error()` gives the message of the last failure on the
+ *     calling thread.  There is NO CPU fallback: without a usable GPU every compute call fails with PH_ERR_CUDA.
+ *   - one caller thread per handle (the reference is single threaded).
+ */
+#ifndef PHERTILIZER_B200_H
+#define PHERTILIZER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PH_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define PH_API __attribute__((visibility("default")))
+#else
+#define PH_API
+#endif
+
+enum ph_status {
+  PH_OK = 0,
+  PH_ERR_ARG = 1,         /* bad argument (null pointer, label out of range, ...) */
+  PH_ERR_CUDA = 2,        /* CUDA runtime error, message in ph_last_error() */
+  PH_ERR_UNSUPPORTED = 3  /* shape outside what the kernels support (see message) */
+};
+
+#define PH_MAX_FAST_CLUSTERS 3 /* clusters per pass on the packed-counter fast path */
+#define PH_MAX_TREE_NODES 64   /* tree nodes for ph_tree_loglik / general tables */
+
+typedef struct ph_handle ph_handle;
+
+typedef struct ph_info {
+  int32_t n_cells, n_snvs, n_codes;
+  int64_t nnz;
+  int32_t dense_codes_by_snv;  /* D of the SNV-major (CSC-like) copy  */
+  int32_t dense_codes_by_cell; /* D of the cell-major (CSR-like) copy */
+  int64_t device_bytes;        /* bytes of HBM owned by the handle */
+  int32_t device, sm_count;
+  int32_t group_by_snv, group_by_cell; /* lanes cooperating on one SNV / one cell */
+  int32_t labels_in_smem_by_snv, labels_in_smem_by_cell;
+} ph_info;
+
+PH_API const char* ph_last_error(void);
+PH_API int ph_abi_version(void);
+
+/* Number of CUDA kernels this library has launched in this process (bench.py's gpu_launches). */
+PH_API int64_t ph_kernel_launches(void);
+
+/*
+ * Build the device-resident observation store.  Replaces `sparse_matrix()` + the four dense matrices of `Data`
+ * (phertilizer/phertilizer.py:153-161, 295-306; data.py:8-20).
+ *   cell/snv [nnz]  : COO coordinates, 0 <= cell < n_cells, 0 <= snv < n_snvs, no duplicates
+ *   code [nnz]      : index of the observation's (var,total) pair in the likelihood table, 0 <= code < n_codes,
+ *                     codes ordered by DESCENDING frequency (code 0 = most frequent pair)
+ *   L0/L1 [n_codes] : log-likelihoods of the pair under y=0 / y=1 (phertilizer.py:121-151)
+ *   var_pos[n_codes]: 1 iff var > 0 for the pair (np.count_nonzero(var...) call sites)
+ *   coo_on_device   : cell/snv/code are device pointers (they are only read)
+ */
+PH_API int ph_create(int32_t n_cells, int32_t n_snvs, int64_t nnz, const int32_t* cell, const int32_t* snv,
+              const uint16_t* code, int coo_on_device, int32_t n_codes, const double* L0, const double* L1,
+              const uint8_t* var_pos, int device, ph_handle** out);
+PH_API void ph_destroy(ph_handle* h);
+PH_API int ph_get_info(const ph_handle* h, ph_info* out);
+
+/* Tuning knob for experiments: lanes per SNV / per cell (4, 8, 16, 32) ; 0 = automatic. */
+PH_API int ph_set_group(ph_handle* h, int group_by_snv, int group_by_cell);
+
+/*
+ * K1 -- per-SNV table over cell clusters.
+ *   for every listed SNV j and cluster c in 1..C:
+ *     S0[j,c] = sum_{i in cluster c} like0[i,j]      S1[j,c] = sum like1[i,j]
+ *     Nobs[j,c] = #{i in c : total[i,j] > 0}         Nvar[j,c] = #{i in c : var[i,j] > 0}
+ * Replaces: linear_split.py:186-188 (Nvar,Nobs), 224 (Nobs), 229-230 (S0,S1);
+ *           branching_split.py:316-317, 332-337; check_reads axis=0 (linear_split.py:393-396,
+ *           branching_split.py:428-431); clonal_tree.py:581-591 (find_bad_snvs), 1136 (Seed.strip: sum(var)==0 <=> Nvar==0).
+ *   cell_label [n_cells] ; snv_list [n_list] optional subset of SNVs (NULL = all, then n_list = n_snvs)
+ *   outputs [n_list * C], row k = k-th listed SNV, column c-1.  Any output pointer may be NULL.
+ */
+PH_API int ph_snv_table(ph_handle* h, const uint8_t* cell_label, int32_t C, const int32_t* snv_list, int32_t n_list,
+                 double* S0, double* S1, int32_t* Nobs, int32_t* Nvar, int on_device, void* stream);
+
+/*
+ * K1 + K1a -- fused SNV reassignment of the linear split (linear_split.py:203-237).
+ *   cluster 1 of cell_label = cellsA.  For every listed SNV:
+ *     nobs_out[k]  = Nobs[j,A]                                   (input of the q75 gate, line 224-227)
+ *     label_out[k] = 2 (mutsB) if S0[j,A]/lenA >= S1[j,A]/lenA else 1 (mutsA)     (lines 229-234; ties -> mutsB)
+ *   The quantile gate itself stays with the caller (it needs all nobs).
+ */
+PH_API int ph_assign_linear(ph_handle* h, const uint8_t* cell_label, double lenA, const int32_t* snv_list, int32_t n_list,
+                     uint8_t* label_out, int32_t* nobs_out, int on_device, void* stream);
+
+/*
+ * K1 + K1a -- fused 3-way SNV reassignment of the branching split (branching_split.py:293-348).
+ *   clusters 1, 2 of cell_label = cellsA, cellsB.
+ *     candA = S1[j,A] + S0[j,B]; candB = S0[j,A] + S1[j,B]; candC = S1[j,A] + S1[j,B]
+ *     label_out[k] = 1 (mutsA) if candA == max, else 2 (mutsB) if candB == max, else 3 (mutsC)   (lines 340-346)
+ *     nobs_out[2k], nobs_out[2k+1] = Nobs[j,A], Nobs[j,B]                                         (lines 316-319)
+ */
+PH_API int ph_assign_branching(ph_handle* h, const uint8_t* cell_label, const int32_t* snv_list, int32_t n_list,
+                        uint8_t* label_out, int32_t* nobs_out, int on_device, void* stream);
+
+/*
+ * K2 -- per-cell table over SNV clusters (transpose of K1).
+ *   A0[i,q] = sum_{j in cluster q} like0[i,j], A1 likewise, Nobs[i,q], Nvar[i,q].
+ * Replaces: linear_split.py:301-304 (tmb features), 400-410 (check_metrics), check_reads axis=1;
+ *           branching_split.py:166-171 (calc_tmb), 395-411; clonal_tree.py:539-548, 1140 (Seed.strip).
+ */
+PH_API int ph_cell_table(ph_handle* h, const uint8_t* snv_label, int32_t Q, const int32_t* cell_list, int32_t n_list,
+                  double* A0, double* A1, int32_t* Nobs, int32_t* Nvar, int on_device, void* stream);
+
+/*
+ * K3 -- block sums over the rectangular blocks (cell cluster c) x (SNV cluster q), c in 1..C, q in 1..Q:
+ *   sum0[q-1][c-1] = sum like0, sum1 = sum like1, nobs = #observed, nvar = #(var > 0).
+ * Replaces: utils.py:218-220 (check_obs), clonal_tree.py:1144-1146 (Seed.count_obs), phertilizer.py:405,
+ *           linear_split.py:549-554 and branching_split.py:460-466 (compute_norm_likelihood).
+ * Outputs [Q * C] row-major (SNV cluster major).
+ */
+PH_API int ph_block_sums(ph_handle* h, const uint8_t* cell_label, int32_t C, const uint8_t* snv_label, int32_t Q,
+                  double* sum0, double* sum1, int64_t* nobs, int64_t* nvar, int on_device, void* stream);
+
+/*
+ * a-9 -- variant read-count log-likelihood of a clonal tree, per node
+ * (clonal_tree.py:932-944 with presence_by_node 343-358 and get_ancestral_muts 979-992):
+ *   per_node[k] = sum_{i : cell_node[i]==k} sum_j ( present(k, snv_node[j]) ? like1[i,j] : like0[i,j] )
+ *   cell_node [n_cells] : tree node of each cell, 255 = cell not in the tree
+ *   snv_node  [n_snvs]  : node whose incoming edge carries the SNV, 255 = SNV not in the tree (always absent)
+ *   present [K*K]       : present[k*K + q] != 0 iff SNVs of node q are present in cells of node k
+ *                         (q on the root->k path, minus losses)
+ *   per_node [K] ; per_cell [n_cells] optional (NULL to skip): the cell's own log-likelihood under its node
+ */
+PH_API int ph_tree_loglik(ph_handle* h, const uint8_t* cell_node, const uint8_t* snv_node, const uint8_t* present,
+                   int32_t K, double* per_node, double* per_cell, int on_device, void* stream);
+
+/*
+ * a-11 -- general tables for post_process (clonal_tree.py:612-666): for every listed SNV j and every candidate
+ * node k in 0..K-1:  T[j,k] = sum_i ( member[k*K + cell_node[i]] ? like1[i,j] : like0[i,j] )  over ALL cells
+ * (cells with cell_node == 255 count as like0), i.e. `np.dot(y,like1)+np.dot(1-y,like0)` of reassign_snv with
+ * y = c_dict[k].  ph_cell_node_table is the transpose for reassign_cell (y = y_dict[k] over SNVs).
+ */
+PH_API int ph_snv_node_table(ph_handle* h, const uint8_t* cell_node, const uint8_t* member, int32_t K,
+                      const int32_t* snv_list, int32_t n_list, double* T, int on_device, void* stream);
+PH_API int ph_cell_node_table(ph_handle* h, const uint8_t* snv_node, const uint8_t* member, int32_t K,
+                       const int32_t* cell_list, int32_t n_list, double* T, int on_device, void* stream);
+
+/*
+ * K4 -- Gaussian read-depth log-likelihood of the embedding per tree node (clonal_tree.py:395-407):
+ * per node mean and population variance per dimension, then the diagonal `multivariate_normal(mean, diag(var),
+ * allow_singular=True).logpdf(x).sum()` with scipy's singular-covariance rules (eps = 1e6*DBL_EPSILON*max|var|,
+ * dims with var <= eps dropped, rank-dependent normaliser, -inf for rows off the support).
+ *   X [n_cells * D] row-major float64 ; cell_node [n_cells], 255 = skip ; per_node [K] (0 for empty nodes)
+ */
+PH_API int ph_gauss_node_ll(ph_handle* h, const double* X, int32_t D, const uint8_t* cell_node, int32_t K,
+                     double* per_node, double* per_cell, int on_device, void* stream);
+
+/*
+ * K5 -- pairwise Euclidean distance of the embedding, `squareform(pdist(X))` (phertilizer.py:286):
+ *   out[i*n + j] = sqrt(sum_d (X[i,d]-X[j,d])^2) computed by direct differences in float64, rows
+ *   [row_begin, row_end) only (row-block sharding);  out has (row_end-row_begin) * n entries.
+ * Does not need a handle (no sparse data involved).
+ */
+PH_API int ph_pairwise_dist(const double* X, int32_t n, int32_t D, int32_t row_begin, int32_t row_end, double* out,
+                     int device, int on_device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHERTILIZER_B200_H */

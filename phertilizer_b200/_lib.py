@@ -1,0 +1,88 @@
+"""ctypes binding of the C-ABI library ``libphertilizer_b200.so`` (declared in include/phertilizer_b200.h).
+
+There is no CPU fallback: if the shared library has not been built (``python -c "import __graft_entry__ as g;
+g.build()"`` or ``make -C phertilizer_b200/csrc``) importing the product path raises immediately.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libphertilizer_b200.so")
+
+PH_OK = 0
+
+
+class PhError(RuntimeError):
+    pass
+
+
+class PhInfo(C.Structure):
+    _fields_ = [
+        ("n_cells", C.c_int32), ("n_snvs", C.c_int32), ("n_codes", C.c_int32),
+        ("nnz", C.c_int64),
+        ("dense_codes_by_snv", C.c_int32), ("dense_codes_by_cell", C.c_int32),
+        ("device_bytes", C.c_int64),
+        ("device", C.c_int32), ("sm_count", C.c_int32),
+        ("group_by_snv", C.c_int32), ("group_by_cell", C.c_int32),
+        ("labels_in_smem_by_snv", C.c_int32), ("labels_in_smem_by_cell", C.c_int32),
+    ]
+
+
+# every symbol include/phertilizer_b200.h declares (tests check the .so exports all of them)
+EXPORTS = [
+    "ph_last_error", "ph_abi_version", "ph_kernel_launches", "ph_create", "ph_destroy", "ph_get_info", "ph_set_group",
+    "ph_snv_table", "ph_assign_linear", "ph_assign_branching", "ph_cell_table", "ph_block_sums", "ph_tree_loglik",
+    "ph_snv_node_table", "ph_cell_node_table", "ph_gauss_node_ll", "ph_pairwise_dist",
+]
+
+_lib = None
+_vp = C.c_void_p
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PhError(
+            f"{LIB_PATH} is missing: the sm_100a CUDA library has not been built and phertilizer_b200 has no CPU "
+            "fallback. Run `make -C phertilizer_b200/csrc` (or __graft_entry__.build()).")
+    L = C.CDLL(LIB_PATH)
+    L.ph_last_error.restype = C.c_char_p
+    L.ph_abi_version.restype = C.c_int
+    L.ph_kernel_launches.restype = C.c_int64
+    L.ph_create.argtypes = [C.c_int32, C.c_int32, C.c_int64, _vp, _vp, _vp, C.c_int, C.c_int32, _vp, _vp, _vp, C.c_int,
+                            C.POINTER(_vp)]
+    L.ph_destroy.argtypes = [_vp]
+    L.ph_destroy.restype = None
+    L.ph_get_info.argtypes = [_vp, C.POINTER(PhInfo)]
+    L.ph_set_group.argtypes = [_vp, C.c_int, C.c_int]
+    L.ph_snv_table.argtypes = [_vp, _vp, C.c_int32, _vp, C.c_int32, _vp, _vp, _vp, _vp, C.c_int, _vp]
+    L.ph_cell_table.argtypes = L.ph_snv_table.argtypes
+    L.ph_assign_linear.argtypes = [_vp, _vp, C.c_double, _vp, C.c_int32, _vp, _vp, C.c_int, _vp]
+    L.ph_assign_branching.argtypes = [_vp, _vp, _vp, C.c_int32, _vp, _vp, C.c_int, _vp]
+    L.ph_block_sums.argtypes = [_vp, _vp, C.c_int32, _vp, C.c_int32, _vp, _vp, _vp, _vp, C.c_int, _vp]
+    L.ph_tree_loglik.argtypes = [_vp, _vp, _vp, _vp, C.c_int32, _vp, _vp, C.c_int, _vp]
+    L.ph_snv_node_table.argtypes = [_vp, _vp, _vp, C.c_int32, _vp, C.c_int32, _vp, C.c_int, _vp]
+    L.ph_cell_node_table.argtypes = L.ph_snv_node_table.argtypes
+    L.ph_gauss_node_ll.argtypes = [_vp, _vp, C.c_int32, _vp, C.c_int32, _vp, _vp, C.c_int, _vp]
+    L.ph_pairwise_dist.argtypes = [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, C.c_int, C.c_int, _vp]
+    for name in EXPORTS:
+        fn = getattr(L, name)
+        if name not in ("ph_last_error", "ph_kernel_launches", "ph_destroy"):
+            fn.restype = C.c_int
+    if L.ph_abi_version() != 1:
+        raise PhError(f"ABI version mismatch: library {L.ph_abi_version()} != binding 1")
+    _lib = L
+    return L
+
+
+def check(rc: int):
+    if rc != PH_OK:
+        raise PhError(f"phertilizer_b200 error {rc}: {lib().ph_last_error().decode()}")
+
+
+def kernel_launches() -> int:
+    return int(lib().ph_kernel_launches())

@@ -1,0 +1,337 @@
+// Device-resident observation store: COO -> two code-segmented sparse copies (by SNV, by cell).
+// Replaces the dense `sparse_matrix()` unstack of the reference (phertilizer/phertilizer.py:153-161, 295-306).
+#include <cub/device/device_radix_sort.cuh>
+
+#include <new>
+
+#include "ph_common.cuh"
+
+thread_local char ph_err_msg[512] = "";
+static int64_t g_launches = 0;
+void ph_count_launch(int n) { g_launches += n; }
+
+extern "C" const char* ph_last_error(void) { return ph_err_msg; }
+extern "C" int ph_abi_version(void) { return PH_ABI_VERSION; }
+extern "C" int64_t ph_kernel_launches(void) { return g_launches; }
+
+namespace {
+
+__global__ void k_code_hist(const uint16_t* __restrict__ code, int64_t nnz, unsigned long long* hist, int n_codes,
+                            int* bad) {
+  __shared__ unsigned int sh[64];  // the hot codes are counted per block first
+  if (threadIdx.x < 64) sh[threadIdx.x] = 0;
+  __syncthreads();
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < nnz; i += stride) {
+    int c = code[i];
+    if (c >= n_codes) {
+      *bad = 1;
+    } else if (c >= 64) {
+      atomicAdd(&hist[c], 1ull);
+    } else {
+      atomicAdd(&sh[c], 1u);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 64 && threadIdx.x < n_codes && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
+}
+
+__global__ void k_make_keys(const int32_t* __restrict__ major, const int32_t* __restrict__ minor,
+                            const uint16_t* __restrict__ code, int64_t nnz, int D, int minor_bits, int n_major,
+                            int n_minor, uint64_t* __restrict__ keys, int* bad) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < nnz; i += stride) {
+    uint32_t mj = (uint32_t)major[i], mn = (uint32_t)minor[i], c = code[i];
+    if (mj >= (uint32_t)n_major || mn >= (uint32_t)n_minor) *bad = 2;
+    uint32_t seg = c < (uint32_t)D ? c : (uint32_t)D;
+    uint32_t word = c < (uint32_t)D ? mn : (mn | (c << minor_bits));
+    keys[i] = ((uint64_t)(mj * (uint32_t)(D + 1) + seg) << 32) | word;
+  }
+}
+
+__global__ void k_extract(const uint64_t* __restrict__ keys, int64_t nnz, uint32_t* __restrict__ words, int* dup) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < nnz; i += stride) {
+    uint64_t k = keys[i];
+    words[i] = (uint32_t)k;
+    if (i > 0 && keys[i - 1] == k) *dup = 1;
+  }
+}
+
+// seg_off[s] = first position whose segment id >= s  (s in 0..nseg)
+__global__ void k_seg_offsets(const uint64_t* __restrict__ keys, int64_t nnz, int64_t nseg, int64_t* __restrict__ off) {
+  int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (s > nseg) return;
+  int64_t lo = 0, hi = nnz;
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if ((int64_t)(keys[mid] >> 32) < s) lo = mid + 1; else hi = mid;
+  }
+  off[s] = lo;
+}
+
+int choose_group(double avg) {
+  // lanes cooperating on one line; each lane moves 16 B per step
+  if (avg >= 1536) return 16;
+  if (avg >= 192) return 8;
+  return 4;
+}
+
+int build_orient(ph_handle* h, PhOrient* o, const int32_t* d_major, const int32_t* d_minor, const uint16_t* d_code,
+                 int n_major, int n_minor, const unsigned long long* code_count, uint64_t* kbuf0, uint64_t* kbuf1,
+                 void* d_temp, size_t temp_bytes, int* d_flag) {
+  const int64_t nnz = h->nnz;
+  o->n_major = n_major;
+  o->n_minor = n_minor;
+  o->minor_bits = ph_ceil_log2((uint64_t)n_minor > 1 ? (uint64_t)n_minor : 2);
+  int D = 0;
+  while (D < PH_DMAX && D < h->n_codes && (double)code_count[D] >= 4.0 * (double)n_major) ++D;
+  o->D = D;
+  if (h->n_codes > D) {
+    if (o->minor_bits >= 32 || (uint64_t)(h->n_codes - 1) >= (1ull << (32 - o->minor_bits)))
+      PH_FAIL(PH_ERR_UNSUPPORTED, "%d (var,total) codes do not fit next to a %d-bit index in a 32-bit word",
+              h->n_codes, o->minor_bits);
+  }
+  const int64_t nseg = (int64_t)n_major * (D + 1);
+  if (nseg >= (1ll << 31)) PH_FAIL(PH_ERR_UNSUPPORTED, "too many segments (%lld)", (long long)nseg);
+  o->group = choose_group(n_major > 0 ? (double)nnz / n_major : 0.0);
+  o->labels_in_smem = 1;
+
+  PH_CUDA(cudaMalloc(&o->words, (size_t)(nnz + 8) * sizeof(uint32_t)));
+  PH_CUDA(cudaMalloc(&o->seg_off, (size_t)(nseg + 1) * sizeof(int64_t)));
+  PH_CUDA(cudaMemset(o->words + nnz, 0, 8 * sizeof(uint32_t)));
+  h->device_bytes += (nnz + 8) * (int64_t)sizeof(uint32_t) + (nseg + 1) * (int64_t)sizeof(int64_t);
+
+  const int threads = 256;
+  const int blocks = h->sm_count * 8;
+  if (nnz > 0) {
+    k_make_keys<<<blocks, threads>>>(d_major, d_minor, d_code, nnz, D, o->minor_bits, n_major, n_minor, kbuf0, d_flag);
+    ph_count_launch();
+    cub::DoubleBuffer<uint64_t> db(kbuf0, kbuf1);
+    int end_bit = 32 + ph_ceil_log2((uint64_t)nseg + 1);
+    if (end_bit > 64) end_bit = 64;
+    PH_CUDA(cub::DeviceRadixSort::SortKeys(d_temp, temp_bytes, db, nnz, 0, end_bit));
+    ph_count_launch(4);
+    k_extract<<<blocks, threads>>>(db.Current(), nnz, o->words, d_flag + 1);
+    ph_count_launch();
+    k_seg_offsets<<<(unsigned)((nseg + 1 + threads - 1) / threads), threads>>>(db.Current(), nnz, nseg, o->seg_off);
+    ph_count_launch();
+  } else {
+    PH_CUDA(cudaMemset(o->seg_off, 0, (size_t)(nseg + 1) * sizeof(int64_t)));
+  }
+  PH_CUDA(cudaGetLastError());
+  return PH_OK;
+}
+
+}  // namespace
+
+extern "C" void ph_destroy(ph_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaFree(h->by_snv.words);
+  cudaFree(h->by_snv.seg_off);
+  cudaFree(h->by_cell.words);
+  cudaFree(h->by_cell.seg_off);
+  cudaFree(h->d_L0);
+  cudaFree(h->d_L1);
+  cudaFree(h->d_varpos);
+  cudaFree(h->d_lab_minor);
+  cudaFree(h->d_lab_major);
+  cudaFree(h->d_list);
+  cudaFree(h->d_f64);
+  cudaFree(h->d_i32);
+  cudaFree(h->d_u8);
+  cudaFree(h->d_small);
+  cudaFree(h->d_map);
+  if (h->h_stage) cudaFreeHost(h->h_stage);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+extern "C" int ph_create(int32_t n_cells, int32_t n_snvs, int64_t nnz, const int32_t* cell, const int32_t* snv,
+                         const uint16_t* code, int coo_on_device, int32_t n_codes, const double* L0, const double* L1,
+                         const uint8_t* var_pos, int device, ph_handle** out) {
+  if (!out) PH_FAIL(PH_ERR_ARG, "out is NULL");
+  *out = nullptr;
+  if (n_cells <= 0 || n_snvs <= 0 || nnz < 0 || n_codes <= 0 || n_codes > 65535)
+    PH_FAIL(PH_ERR_ARG, "bad sizes n_cells=%d n_snvs=%d nnz=%lld n_codes=%d", n_cells, n_snvs, (long long)nnz, n_codes);
+  if (nnz > 0 && (!cell || !snv || !code)) PH_FAIL(PH_ERR_ARG, "COO pointer is NULL");
+  if (!L0 || !L1 || !var_pos) PH_FAIL(PH_ERR_ARG, "likelihood table pointer is NULL");
+  int ndev = 0;
+  PH_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) PH_FAIL(PH_ERR_CUDA, "device %d not available (%d CUDA devices)", device, ndev);
+  PH_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  PH_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) PH_FAIL(PH_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+
+  ph_handle* h = new (std::nothrow) ph_handle();
+  if (!h) PH_FAIL(PH_ERR_ARG, "out of host memory");
+  memset(h, 0, sizeof(*h));
+  h->device = device;
+  h->sm_count = prop.multiProcessorCount;
+  h->max_smem = (int)prop.sharedMemPerBlockOptin;
+  h->n_cells = n_cells;
+  h->n_snvs = n_snvs;
+  h->n_codes = n_codes;
+  h->nnz = nnz;
+
+  int rc = PH_OK;
+  int32_t *d_cell = nullptr, *d_snv = nullptr;
+  uint16_t* d_code = nullptr;
+  uint64_t *kbuf0 = nullptr, *kbuf1 = nullptr;
+  void* d_temp = nullptr;
+  unsigned long long* d_hist = nullptr;
+  int* d_flag = nullptr;
+  unsigned long long* h_hist = nullptr;
+  size_t temp_bytes = 0;
+  const int32_t nmax = n_cells > n_snvs ? n_cells : n_snvs;
+
+#define PH_TRY(expr)                 \
+  do {                               \
+    rc = [&]() -> int {              \
+      PH_CUDA(expr);                 \
+      return PH_OK;                  \
+    }();                             \
+    if (rc != PH_OK) goto done;      \
+  } while (0)
+
+  PH_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  PH_TRY(cudaMalloc(&h->d_L0, n_codes * sizeof(double)));
+  PH_TRY(cudaMalloc(&h->d_L1, n_codes * sizeof(double)));
+  PH_TRY(cudaMalloc(&h->d_varpos, n_codes));
+  PH_TRY(cudaMemcpy(h->d_L0, L0, n_codes * sizeof(double), cudaMemcpyHostToDevice));
+  PH_TRY(cudaMemcpy(h->d_L1, L1, n_codes * sizeof(double), cudaMemcpyHostToDevice));
+  PH_TRY(cudaMemcpy(h->d_varpos, var_pos, n_codes, cudaMemcpyHostToDevice));
+
+  if (coo_on_device) {
+    d_cell = const_cast<int32_t*>(cell);
+    d_snv = const_cast<int32_t*>(snv);
+    d_code = const_cast<uint16_t*>(code);
+  } else if (nnz > 0) {
+    PH_TRY(cudaMalloc(&d_cell, nnz * sizeof(int32_t)));
+    PH_TRY(cudaMalloc(&d_snv, nnz * sizeof(int32_t)));
+    PH_TRY(cudaMalloc(&d_code, nnz * sizeof(uint16_t)));
+    PH_TRY(cudaMemcpy(d_cell, cell, nnz * sizeof(int32_t), cudaMemcpyHostToDevice));
+    PH_TRY(cudaMemcpy(d_snv, snv, nnz * sizeof(int32_t), cudaMemcpyHostToDevice));
+    PH_TRY(cudaMemcpy(d_code, code, nnz * sizeof(uint16_t), cudaMemcpyHostToDevice));
+  }
+  PH_TRY(cudaMalloc(&d_hist, n_codes * sizeof(unsigned long long)));
+  PH_TRY(cudaMemset(d_hist, 0, n_codes * sizeof(unsigned long long)));
+  PH_TRY(cudaMalloc(&d_flag, 4 * sizeof(int)));
+  PH_TRY(cudaMemset(d_flag, 0, 4 * sizeof(int)));
+  h_hist = new unsigned long long[n_codes];
+  if (nnz > 0) {
+    k_code_hist<<<h->sm_count * 8, 256>>>(d_code, nnz, d_hist, n_codes, d_flag);
+    ph_count_launch();
+  }
+  PH_TRY(cudaMemcpy(h_hist, d_hist, n_codes * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  {
+    int flags[4];
+    PH_TRY(cudaMemcpy(flags, d_flag, sizeof(flags), cudaMemcpyDeviceToHost));
+    if (flags[0]) {
+      snprintf(ph_err_msg, sizeof(ph_err_msg), "code out of range (>= n_codes=%d)", n_codes);
+      rc = PH_ERR_ARG;
+      goto done;
+    }
+  }
+  for (int c = 1; c < n_codes && c <= PH_DMAX; ++c) {
+    if (h_hist[c] > h_hist[c - 1]) {
+      snprintf(ph_err_msg, sizeof(ph_err_msg), "codes must be ordered by descending frequency (code %d > code %d)", c, c - 1);
+      rc = PH_ERR_ARG;
+      goto done;
+    }
+  }
+
+  if (nnz > 0) {
+    PH_TRY(cudaMalloc(&kbuf0, nnz * sizeof(uint64_t)));
+    PH_TRY(cudaMalloc(&kbuf1, nnz * sizeof(uint64_t)));
+    {
+      cub::DoubleBuffer<uint64_t> db(kbuf0, kbuf1);
+      PH_TRY(cub::DeviceRadixSort::SortKeys(nullptr, temp_bytes, db, nnz, 0, 64));
+    }
+    PH_TRY(cudaMalloc(&d_temp, temp_bytes ? temp_bytes : 16));
+  }
+  rc = build_orient(h, &h->by_snv, d_snv, d_cell, d_code, n_snvs, n_cells, h_hist, kbuf0, kbuf1, d_temp, temp_bytes, d_flag);
+  if (rc != PH_OK) goto done;
+  rc = build_orient(h, &h->by_cell, d_cell, d_snv, d_code, n_cells, n_snvs, h_hist, kbuf0, kbuf1, d_temp, temp_bytes, d_flag);
+  if (rc != PH_OK) goto done;
+  PH_TRY(cudaDeviceSynchronize());
+  {
+    int flags[4];
+    PH_TRY(cudaMemcpy(flags, d_flag, sizeof(flags), cudaMemcpyDeviceToHost));
+    if (flags[0] == 2) {
+      snprintf(ph_err_msg, sizeof(ph_err_msg), "COO index out of range");
+      rc = PH_ERR_ARG;
+      goto done;
+    }
+    if (flags[1]) {
+      snprintf(ph_err_msg, sizeof(ph_err_msg), "duplicate (cell, snv) observation in COO input");
+      rc = PH_ERR_ARG;
+      goto done;
+    }
+  }
+
+  // scratch
+  PH_TRY(cudaMalloc(&h->d_lab_minor, (size_t)nmax + 16));
+  PH_TRY(cudaMalloc(&h->d_lab_major, (size_t)nmax + 16));
+  PH_TRY(cudaMalloc(&h->d_list, (size_t)nmax * sizeof(int32_t)));
+  PH_TRY(cudaMalloc(&h->d_f64, (size_t)nmax * 2 * PH_MAX_FAST_CLUSTERS * sizeof(double)));
+  PH_TRY(cudaMalloc(&h->d_i32, (size_t)nmax * 2 * PH_MAX_FAST_CLUSTERS * sizeof(int32_t)));
+  PH_TRY(cudaMalloc(&h->d_u8, (size_t)nmax + 16));
+  PH_TRY(cudaMalloc(&h->d_small, 4096 * sizeof(double)));
+  PH_TRY(cudaMalloc(&h->d_map, 65 * 65 + 64));
+  h->device_bytes += (int64_t)nmax * (3 + 4 + 2 * PH_MAX_FAST_CLUSTERS * 12) + 4096 * 8;
+  h->h_stage_bytes = (size_t)nmax * (2 * PH_MAX_FAST_CLUSTERS * 12 + 8) + (1 << 16);
+  PH_TRY(cudaMallocHost(&h->h_stage, h->h_stage_bytes));
+
+done:
+  if (!coo_on_device) {
+    cudaFree(d_cell);
+    cudaFree(d_snv);
+    cudaFree(d_code);
+  }
+  cudaFree(kbuf0);
+  cudaFree(kbuf1);
+  cudaFree(d_temp);
+  cudaFree(d_hist);
+  cudaFree(d_flag);
+  delete[] h_hist;
+  if (rc != PH_OK) {
+    ph_destroy(h);
+    return rc;
+  }
+  *out = h;
+  return PH_OK;
+#undef PH_TRY
+}
+
+extern "C" int ph_get_info(const ph_handle* h, ph_info* out) {
+  if (!h || !out) PH_FAIL(PH_ERR_ARG, "null argument");
+  out->n_cells = h->n_cells;
+  out->n_snvs = h->n_snvs;
+  out->n_codes = h->n_codes;
+  out->nnz = h->nnz;
+  out->dense_codes_by_snv = h->by_snv.D;
+  out->dense_codes_by_cell = h->by_cell.D;
+  out->device_bytes = h->device_bytes;
+  out->device = h->device;
+  out->sm_count = h->sm_count;
+  out->group_by_snv = h->by_snv.group;
+  out->group_by_cell = h->by_cell.group;
+  out->labels_in_smem_by_snv = h->by_snv.labels_in_smem;
+  out->labels_in_smem_by_cell = h->by_cell.labels_in_smem;
+  return PH_OK;
+}
+
+extern "C" int ph_set_group(ph_handle* h, int group_by_snv, int group_by_cell) {
+  if (!h) PH_FAIL(PH_ERR_ARG, "null handle");
+  auto ok = [](int g) { return g == 0 || g == 4 || g == 8 || g == 16 || g == 32; };
+  if (!ok(group_by_snv) || !ok(group_by_cell)) PH_FAIL(PH_ERR_ARG, "group must be 0, 4, 8, 16 or 32");
+  if (group_by_snv) h->by_snv.group = group_by_snv;
+  if (group_by_cell) h->by_cell.group = group_by_cell;
+  return PH_OK;
+}

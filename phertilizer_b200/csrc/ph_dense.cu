@@ -1,0 +1,322 @@
+// Dense embedding kernels: K4 (Gaussian read-depth log-likelihood per tree node, clonal_tree.py:395-407) and
+// K5 (pairwise Euclidean distance, phertilizer.py:286).  Both are fp64 (the reference's scipy arithmetic is fp64 and
+// parity is 1e-9 relative), so they run on the CUDA-core fp64 pipe; tcgen05 has no fp64 MMA.
+#include <float.h>
+#include <math.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "ph_common.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------- K4
+// rows[] lists the cells of every node consecutively (stable order), node_off[k]..node_off[k+1].
+// stat pass: column sums of f(x) over the rows of node k, f = x (pass 0) or (x-mean)^2 (pass 1).
+// block = 32 dims x 8 row lanes, grid = (ceil(D/32), K).  Fixed summation order -> deterministic.
+__global__ void k_gauss_stat(const double* __restrict__ X, int D, const int32_t* __restrict__ rows,
+                             const int32_t* __restrict__ node_off, const double* __restrict__ mean, int pass,
+                             double* __restrict__ out) {
+  const int k = blockIdx.y;
+  const int d = blockIdx.x * 32 + threadIdx.x;
+  const int beg = node_off[k], end = node_off[k + 1];
+  const int cnt = end - beg;
+  double acc = 0.0;
+  if (d < D && cnt > 0) {
+    const double mu = pass ? mean[(size_t)k * D + d] : 0.0;
+    for (int r = beg + threadIdx.y; r < end; r += 8) {
+      const double x = X[(size_t)rows[r] * D + d];
+      if (pass) {
+        const double t = x - mu;
+        acc += t * t;
+      } else {
+        acc += x;
+      }
+    }
+  }
+  __shared__ double sh[8][33];
+  sh[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && d < D) {
+    double t = sh[0][threadIdx.x];
+#pragma unroll
+    for (int y = 1; y < 8; ++y) t += sh[y][threadIdx.x];
+    out[(size_t)k * D + d] = cnt > 0 ? t / (double)cnt : 0.0;
+  }
+}
+
+// per node: eps = 1e6*DBL_EPSILON*max|var|, rank, log_pdet; inv[d] = 1/var (kept) or 0 (dropped)
+// cst[k*4 + {0,1,2,3}] = {eps, rank, log_pdet, min var}
+__global__ void k_gauss_consts(const double* __restrict__ var, int D, double* __restrict__ inv, double* __restrict__ cst) {
+  const int k = blockIdx.x;
+  const double* v = var + (size_t)k * D;
+  __shared__ double r[1024];
+  __shared__ double r2[1024];
+  double mx = 0.0, mn = INFINITY;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    mx = fmax(mx, fabs(v[d]));
+    mn = fmin(mn, v[d]);
+  }
+  r[threadIdx.x] = mx;
+  r2[threadIdx.x] = mn;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) {
+      r[threadIdx.x] = fmax(r[threadIdx.x], r[threadIdx.x + s]);
+      r2[threadIdx.x] = fmin(r2[threadIdx.x], r2[threadIdx.x + s]);
+    }
+    __syncthreads();
+  }
+  const double eps = 1e6 * DBL_EPSILON * r[0];
+  const double vmin = r2[0];
+  __syncthreads();
+  double lp = 0.0, rk = 0.0;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    const double s = v[d];
+    const bool keep = s > eps;
+    inv[(size_t)k * D + d] = keep ? 1.0 / s : 0.0;
+    if (keep) {
+      lp += log(s);
+      rk += 1.0;
+    }
+  }
+  r[threadIdx.x] = lp;
+  r2[threadIdx.x] = rk;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) {
+      r[threadIdx.x] += r[threadIdx.x + s];
+      r2[threadIdx.x] += r2[threadIdx.x + s];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    cst[k * 4 + 0] = eps;
+    cst[k * 4 + 1] = r2[0];
+    cst[k * 4 + 2] = r[0];
+    cst[k * 4 + 3] = vmin;
+  }
+}
+
+// one warp per cell: maha over kept dims, squared residual over dropped dims
+__global__ void k_gauss_logpdf(const double* __restrict__ X, int n, int D, const uint8_t* __restrict__ cell_node, int K,
+                               const double* __restrict__ mean, const double* __restrict__ inv,
+                               const double* __restrict__ cst, double* __restrict__ per_cell) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= n) return;
+  const int k = cell_node[warp];
+  if (k >= K) {
+    if (lane == 0) per_cell[warp] = 0.0;
+    return;
+  }
+  const double* x = X + (size_t)warp * D;
+  const double* mu = mean + (size_t)k * D;
+  const double* iv = inv + (size_t)k * D;
+  double maha = 0.0, res = 0.0;
+  for (int d = lane; d < D; d += 32) {
+    const double t = x[d] - mu[d];
+    const double w = iv[d];
+    const double t2 = t * t;
+    maha += t2 * w;
+    res += (w == 0.0) ? t2 : 0.0;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    maha += __shfl_xor_sync(0xffffffffu, maha, o);
+    res += __shfl_xor_sync(0xffffffffu, res, o);
+  }
+  if (lane == 0) {
+    const double eps = cst[k * 4 + 0], rank = cst[k * 4 + 1], lpd = cst[k * 4 + 2];
+    const double LOG_2PI = 1.8378770664093453;  // scipy.stats._multivariate._LOG_2PI
+    double out = -0.5 * (rank * LOG_2PI + lpd + maha);
+    if (rank < (double)D && !(sqrt(res) < 1e3 * eps)) out = -INFINITY;
+    per_cell[warp] = out;
+  }
+}
+
+__global__ void k_node_reduce_d(const double* __restrict__ v, const int32_t* __restrict__ rows,
+                                const int32_t* __restrict__ node_off, double* out) {
+  const int k = blockIdx.x;
+  double acc = 0.0;
+  for (int r = node_off[k] + threadIdx.x; r < node_off[k + 1]; r += blockDim.x) acc += v[rows[r]];
+  __shared__ double sh[1024];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[k] = sh[0];
+}
+
+// ---------------------------------------------------------------- K5
+// 64x64 output tile per block, 4x4 outputs per thread, embedding staged through shared memory in slabs of 16 dims.
+// Each output accumulates d = 0..D-1 in order with separately rounded multiply and add (scipy's C loop).
+constexpr int PT = 64, PK = 16;
+__global__ void __launch_bounds__(256) k_pdist(const double* __restrict__ X, int n, int D, int row_begin, int row_end,
+                                               double* __restrict__ out) {
+  __shared__ double sa[PK][PT + 1];
+  __shared__ double sb[PK][PT + 1];
+  const int i0 = row_begin + blockIdx.y * PT;
+  const int j0 = blockIdx.x * PT;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  double acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+  for (int d0 = 0; d0 < D; d0 += PK) {
+    for (int t = threadIdx.x; t < PT * PK; t += 256) {
+      const int r = t / PK, c = t % PK;
+      const int d = d0 + c;
+      const int gi = i0 + r, gj = j0 + r;
+      sa[c][r] = (gi < row_end && d < D) ? X[(size_t)gi * D + d] : 0.0;
+      sb[c][r] = (gj < n && d < D) ? X[(size_t)gj * D + d] : 0.0;
+    }
+    __syncthreads();
+    const int kmax = min(PK, D - d0);
+    for (int c = 0; c < kmax; ++c) {
+      double xa[4], xb[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) xa[a] = sa[c][ty * 4 + a];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) xb[b] = sb[c][tx * 4 + b];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const double t = __dsub_rn(xa[a], xb[b]);
+          acc[a][b] = __dadd_rn(acc[a][b], __dmul_rn(t, t));
+        }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int gi = i0 + ty * 4 + a;
+    if (gi >= row_end) continue;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int gj = j0 + tx * 4 + b;
+      if (gj < n) out[(size_t)(gi - row_begin) * n + gj] = sqrt(acc[a][b]);
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int ph_gauss_node_ll(ph_handle* h, const double* X, int32_t D, const uint8_t* cell_node, int32_t K,
+                                double* per_node, double* per_cell, int on_device, void* stream) {
+  if (!h) PH_FAIL(PH_ERR_ARG, "null handle");
+  if (!X || !cell_node || !per_node) PH_FAIL(PH_ERR_ARG, "null pointer");
+  if (D < 1 || K < 1 || K > PH_MAX_TREE_NODES) PH_FAIL(PH_ERR_ARG, "D=%d K=%d out of range", D, K);
+  PH_CUDA(cudaSetDevice(h->device));
+  const int n = h->n_cells;
+  cudaStream_t st = on_device ? (cudaStream_t)stream : h->stream;
+  // host copy of the node labels -> stable per-node row lists
+  std::vector<uint8_t> lab(n);
+  if (on_device) {
+    PH_CUDA(cudaMemcpyAsync(lab.data(), cell_node, n, cudaMemcpyDeviceToHost, st));
+    PH_CUDA(cudaStreamSynchronize(st));
+  } else {
+    memcpy(lab.data(), cell_node, n);
+  }
+  std::vector<int32_t> off(K + 1, 0), rows(n > 0 ? n : 1);
+  for (int i = 0; i < n; ++i)
+    if (lab[i] < K) off[lab[i] + 1]++;
+  for (int k = 0; k < K; ++k) off[k + 1] += off[k];
+  {
+    std::vector<int32_t> pos(off.begin(), off.end() - 1);
+    for (int i = 0; i < n; ++i)
+      if (lab[i] < K) rows[pos[lab[i]]++] = i;
+  }
+  double *dX = nullptr, *d_mean = nullptr, *d_var = nullptr, *d_inv = nullptr, *d_cst = nullptr, *d_pc = nullptr, *d_pn = nullptr;
+  int32_t *d_rows = nullptr, *d_off = nullptr;
+  uint8_t* d_lab = nullptr;
+  int rc = PH_OK;
+  auto body = [&]() -> int {
+    const size_t kd = (size_t)K * D;
+    PH_CUDA(cudaMalloc(&d_mean, kd * 8));
+    PH_CUDA(cudaMalloc(&d_var, kd * 8));
+    PH_CUDA(cudaMalloc(&d_inv, kd * 8));
+    PH_CUDA(cudaMalloc(&d_cst, (size_t)K * 4 * 8));
+    PH_CUDA(cudaMalloc(&d_rows, (size_t)(n > 0 ? n : 1) * 4));
+    PH_CUDA(cudaMalloc(&d_off, (size_t)(K + 1) * 4));
+    PH_CUDA(cudaMemcpyAsync(d_rows, rows.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    PH_CUDA(cudaMemcpyAsync(d_off, off.data(), (size_t)(K + 1) * 4, cudaMemcpyHostToDevice, st));
+    const double* Xd = X;
+    const uint8_t* labd = cell_node;
+    if (!on_device) {
+      PH_CUDA(cudaMalloc(&dX, (size_t)n * D * 8));
+      PH_CUDA(cudaMemcpyAsync(dX, X, (size_t)n * D * 8, cudaMemcpyHostToDevice, st));
+      PH_CUDA(cudaMalloc(&d_lab, (size_t)n + 16));
+      PH_CUDA(cudaMemcpyAsync(d_lab, lab.data(), n, cudaMemcpyHostToDevice, st));
+      Xd = dX;
+      labd = d_lab;
+      PH_CUDA(cudaMalloc(&d_pn, (size_t)K * 8));
+    }
+    if (!on_device || !per_cell) PH_CUDA(cudaMalloc(&d_pc, (size_t)n * 8));
+    double* pc = (on_device && per_cell) ? per_cell : d_pc;
+    double* pn = on_device ? per_node : d_pn;
+    dim3 gs((D + 31) / 32, K), bs(32, 8);
+    k_gauss_stat<<<gs, bs, 0, st>>>(Xd, D, d_rows, d_off, nullptr, 0, d_mean);
+    k_gauss_stat<<<gs, bs, 0, st>>>(Xd, D, d_rows, d_off, d_mean, 1, d_var);
+    k_gauss_consts<<<K, 1024, 0, st>>>(d_var, D, d_inv, d_cst);
+    k_gauss_logpdf<<<(n * 32 + 255) / 256, 256, 0, st>>>(Xd, n, D, labd, K, d_mean, d_inv, d_cst, pc);
+    k_node_reduce_d<<<K, 1024, 0, st>>>(pc, d_rows, d_off, pn);
+    ph_count_launch(5);
+    PH_CUDA(cudaGetLastError());
+    if (!on_device) {
+      PH_CUDA(cudaMemcpyAsync(per_node, pn, (size_t)K * 8, cudaMemcpyDeviceToHost, st));
+      if (per_cell) PH_CUDA(cudaMemcpyAsync(per_cell, pc, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    }
+    PH_CUDA(cudaStreamSynchronize(st));  // temporaries are freed below
+    return PH_OK;
+  };
+  rc = body();
+  cudaFree(dX); cudaFree(d_mean); cudaFree(d_var); cudaFree(d_inv); cudaFree(d_cst); cudaFree(d_pc); cudaFree(d_pn);
+  cudaFree(d_rows); cudaFree(d_off); cudaFree(d_lab);
+  return rc;
+}
+
+extern "C" int ph_pairwise_dist(const double* X, int32_t n, int32_t D, int32_t row_begin, int32_t row_end, double* out,
+                                int device, int on_device, void* stream) {
+  if (!X || !out) PH_FAIL(PH_ERR_ARG, "null pointer");
+  if (n < 1 || D < 1 || row_begin < 0 || row_end > n || row_begin > row_end)
+    PH_FAIL(PH_ERR_ARG, "bad shape n=%d D=%d rows=[%d,%d)", n, D, row_begin, row_end);
+  int ndev = 0;
+  PH_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) PH_FAIL(PH_ERR_CUDA, "device %d not available (%d CUDA devices)", device, ndev);
+  PH_CUDA(cudaSetDevice(device));
+  const int nr = row_end - row_begin;
+  if (nr == 0) return PH_OK;
+  cudaStream_t st = on_device ? (cudaStream_t)stream : (cudaStream_t)0;
+  double *dX = nullptr, *dO = nullptr;
+  const double* Xd = X;
+  double* Od = out;
+  int rc = PH_OK;
+  auto body = [&]() -> int {
+    if (!on_device) {
+      PH_CUDA(cudaMalloc(&dX, (size_t)n * D * 8));
+      PH_CUDA(cudaMalloc(&dO, (size_t)nr * n * 8));
+      PH_CUDA(cudaMemcpyAsync(dX, X, (size_t)n * D * 8, cudaMemcpyHostToDevice, st));
+      Xd = dX;
+      Od = dO;
+    }
+    dim3 grid((n + PT - 1) / PT, (nr + PT - 1) / PT);
+    k_pdist<<<grid, 256, 0, st>>>(Xd, n, D, row_begin, row_end, Od);
+    ph_count_launch();
+    PH_CUDA(cudaGetLastError());
+    if (!on_device) {
+      PH_CUDA(cudaMemcpyAsync(out, dO, (size_t)nr * n * 8, cudaMemcpyDeviceToHost, st));
+      PH_CUDA(cudaStreamSynchronize(st));
+    }
+    return PH_OK;
+  };
+  rc = body();
+  cudaFree(dX);
+  cudaFree(dO);
+  return rc;
+}

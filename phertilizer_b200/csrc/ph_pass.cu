@@ -1,0 +1,820 @@
+// The sparse likelihood passes (K1/K1a/K2/K3/a-9/a-11) -- hand-written for sm_100a.
+//
+// One kernel template walks either orientation of the store.  G lanes cooperate on one line (an SNV for the
+// CSC-like copy, a cell for the CSR-like copy).  The cluster label of every minor index lives in shared memory,
+// pre-scaled to a bit shift, so one observation costs: 1/4 LDG.128 + LDS.U8 + SHF + IADD.  Because a line's
+// entries are segmented by (var,total) code, the lanes only COUNT observations per (code, cluster) in packed
+// 10-bit integer fields; the fp64 log-likelihood sums are  sum_code count * L[code]  evaluated once per line in a
+// fixed order -> exact integer tables, deterministic fp64 results, no atomics anywhere.
+//
+// HBM traffic: 4 B per observation (+ segment offsets), the roofline of these kernels.
+#include "ph_common.cuh"
+
+namespace {
+
+enum { MODE_TABLE = 0, MODE_LINEAR = 1, MODE_BRANCHING = 2, MODE_MAPPED = 3 };
+
+constexpr int kBlock = 512;  // threads per CTA, 1 CTA / SM, <= 128 registers per thread
+constexpr int kUnroll = 4;   // independent 16-byte loads in flight per lane
+
+struct PassArgs {
+  const uint32_t* __restrict__ words;
+  const int64_t* __restrict__ seg_off;
+  int D, minor_bits, n_minor;
+  const uint8_t* __restrict__ minor_label;  // raw labels [n_minor]; SMEM_LAB=false: pre-scaled shifts
+  const int32_t* __restrict__ list;         // optional list of lines
+  int n_work;
+  const double* __restrict__ L0;
+  const double* __restrict__ L1;
+  const uint8_t* __restrict__ varpos;
+  int n_codes;
+  int lut_in_smem;
+  int C;
+  double* S0; double* S1; int32_t* Nobs; int32_t* Nvar;  // TABLE
+  uint8_t* label_out; int32_t* nobs_out; double lenA;    // LINEAR / BRANCHING
+  const uint8_t* __restrict__ major_label;               // MAPPED: label of each line (255 = skip)
+  const uint8_t* __restrict__ map;                       // MAPPED: [K+1][K+1] bytes, != 0 -> "present"
+  int K;
+  double* per_line;                                      // MAPPED
+};
+
+__device__ __forceinline__ uint4 ld_stream(const uint32_t* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
+
+// raw label byte (0 excluded, 1..3) -> shift of its 10-bit counter field (excluded -> 30: spills off the top)
+__device__ __forceinline__ uint32_t scale_labels4(uint32_t w) {
+  uint32_t sel = (w & 0x3u) | ((w >> 4) & 0x30u) | ((w >> 8) & 0x300u) | ((w >> 12) & 0x3000u);
+  return __byte_perm(0x140A001Eu, 0u, sel);
+}
+
+template <int G, int MODE, bool SMEM_LAB>
+__global__ void __launch_bounds__(kBlock, 1) k_pass(const PassArgs a) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  // ---- shared memory carve-up: [labels][map][L0][L1][varpos]
+  uint8_t* s_lab = smem;
+  size_t off = 0;
+  if (SMEM_LAB) off = ((size_t)a.n_minor + 15) & ~(size_t)15;
+  uint8_t* s_map = smem + off;
+  if (MODE == MODE_MAPPED) off += (((size_t)(a.K + 1) * (a.K + 1)) + 15) & ~(size_t)15;
+  double* s_L0 = reinterpret_cast<double*>(smem + off);
+  double* s_L1 = s_L0 + (a.lut_in_smem ? a.n_codes : 0);
+  uint8_t* s_vp = reinterpret_cast<uint8_t*>(s_L1 + (a.lut_in_smem ? a.n_codes : 0));
+
+  if (SMEM_LAB) {
+    const int nw = (a.n_minor + 3) >> 2;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(a.minor_label);  // buffers are padded to 16 B
+    uint32_t* dst = reinterpret_cast<uint32_t*>(s_lab);
+    for (int i = threadIdx.x; i < nw; i += kBlock) {
+      uint32_t w = src[i];
+      if (MODE == MODE_MAPPED) {
+        // raw node ids; anything >= K (255 = not in tree) -> K
+        uint32_t r = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          uint32_t v = (w >> (8 * b)) & 0xFFu;
+          v = v < (uint32_t)a.K ? v : (uint32_t)a.K;
+          r |= v << (8 * b);
+        }
+        dst[i] = r;
+      } else {
+        dst[i] = scale_labels4(w);
+      }
+    }
+  }
+  if (MODE == MODE_MAPPED) {
+    const int nm = (a.K + 1) * (a.K + 1);
+    for (int i = threadIdx.x; i < nm; i += kBlock) s_map[i] = a.map[i] ? PH_FIELD_BITS : 0;
+  }
+  if (a.lut_in_smem) {
+    for (int i = threadIdx.x; i < a.n_codes; i += kBlock) {
+      s_L0[i] = a.L0[i];
+      s_L1[i] = a.L1[i];
+      s_vp[i] = a.varpos[i];
+    }
+  }
+  __syncthreads();
+  const double* L0 = a.lut_in_smem ? s_L0 : a.L0;
+  const double* L1 = a.lut_in_smem ? s_L1 : a.L1;
+  const uint8_t* VP = a.lut_in_smem ? s_vp : a.varpos;
+  const uint8_t* lab = SMEM_LAB ? s_lab : a.minor_label;
+
+  const int lane = threadIdx.x & 31;
+  const int g = lane & (G - 1);
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
+  constexpr int groups_per_block = kBlock / G;
+  const int total_groups = gridDim.x * groups_per_block;
+  const int D = a.D;
+  const uint32_t mmask = (a.minor_bits >= 32) ? 0xffffffffu : ((1u << a.minor_bits) - 1u);
+  constexpr int STEP = 4 * G;
+
+  for (int wi = blockIdx.x * groups_per_block + (threadIdx.x / G); wi < a.n_work; wi += total_groups) {
+    const int line = a.list ? a.list[wi] : wi;
+    const uint8_t* maprow = nullptr;
+    if (MODE == MODE_MAPPED) {
+      const uint32_t ml = a.major_label[line];
+      if (ml >= (uint32_t)a.K) {  // cell not in the tree: contributes nothing
+        if (g == 0) a.per_line[wi] = 0.0;
+        continue;
+      }
+      maprow = s_map + ml * (a.K + 1);
+    }
+    auto shift_of = [&](uint32_t minor) -> uint32_t {
+      uint32_t l = SMEM_LAB ? (uint32_t)lab[minor] : (uint32_t)__ldg(lab + minor);
+      if (MODE == MODE_MAPPED) l = maprow[l];
+      return l;
+    };
+
+    const int64_t* so = a.seg_off + (int64_t)line * (D + 1);
+    const int64_t b0 = so[0];
+    const int64_t base = b0 & ~(int64_t)3;
+    int rb[PH_DMAX + 1];
+    rb[0] = (int)(b0 - base);
+#pragma unroll
+    for (int d = 1; d <= PH_DMAX; ++d) rb[d] = (int)(so[d < D ? d : D] - base);
+    const int rD = rb[PH_DMAX];
+    const int rend = (int)(so[D + 1] - base);
+    const uint32_t* wp = a.words + base;
+
+    unsigned cnt[PH_DMAX][3];
+#pragma unroll
+    for (int d = 0; d < PH_DMAX; ++d) cnt[d][0] = cnt[d][1] = cnt[d][2] = 0;
+
+    // ---------------- dense segments: count labels per code ----------------
+    int rp = g * 4;
+    while (rp < rD) {
+      unsigned acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
+      for (int blk = 0; blk < PH_CHUNK_ITERS / kUnroll && rp < rD; ++blk, rp += kUnroll * STEP) {
+        uint4 w[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+          if (rp + u * STEP < rD) w[u] = ld_stream(wp + rp + u * STEP);
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          const int r = rp + u * STEP;
+          if (r < rD) {
+            if (r >= rb[0] && r + 4 <= rb[1]) {
+              acc0 += (1u << shift_of(w[u].x)) + (1u << shift_of(w[u].y)) + (1u << shift_of(w[u].z)) + (1u << shift_of(w[u].w));
+            } else if (r >= rb[1] && r + 4 <= rb[2]) {
+              acc1 += (1u << shift_of(w[u].x)) + (1u << shift_of(w[u].y)) + (1u << shift_of(w[u].z)) + (1u << shift_of(w[u].w));
+            } else if (r >= rb[2] && r + 4 <= rb[3]) {
+              acc2 += (1u << shift_of(w[u].x)) + (1u << shift_of(w[u].y)) + (1u << shift_of(w[u].z)) + (1u << shift_of(w[u].w));
+            } else if (r >= rb[3] && r + 4 <= rb[4]) {
+              acc3 += (1u << shift_of(w[u].x)) + (1u << shift_of(w[u].y)) + (1u << shift_of(w[u].z)) + (1u << shift_of(w[u].w));
+            } else {
+              const uint32_t ww[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const int q = r + t;
+                if (q >= rb[0] && q < rD) {
+                  const unsigned inc = 1u << shift_of(ww[t]);
+                  const int d = (q >= rb[1]) + (q >= rb[2]) + (q >= rb[3]);
+                  if (d == 0) acc0 += inc; else if (d == 1) acc1 += inc; else if (d == 2) acc2 += inc; else acc3 += inc;
+                }
+              }
+            }
+          }
+        }
+      }
+      const unsigned fm = (1u << PH_FIELD_BITS) - 1u;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        cnt[0][c] += (acc0 >> (PH_FIELD_BITS * c)) & fm;
+        cnt[1][c] += (acc1 >> (PH_FIELD_BITS * c)) & fm;
+        cnt[2][c] += (acc2 >> (PH_FIELD_BITS * c)) & fm;
+        cnt[3][c] += (acc3 >> (PH_FIELD_BITS * c)) & fm;
+      }
+    }
+
+    // ---------------- combine: integer counts -> fp64 sums (fixed order) ----------------
+    double s0[3] = {0.0, 0.0, 0.0}, s1[3] = {0.0, 0.0, 0.0};
+    unsigned nob[3] = {0, 0, 0}, nva[3] = {0, 0, 0};
+#pragma unroll
+    for (int d = 0; d < PH_DMAX; ++d) {
+      if (d < D) {
+        const double l0 = L0[d], l1 = L1[d];
+        const bool vp = VP[d] != 0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const unsigned t = __reduce_add_sync(gmask, cnt[d][c]);
+          s0[c] = fma((double)t, l0, s0[c]);
+          s1[c] = fma((double)t, l1, s1[c]);
+          nob[c] += t;
+          nva[c] += vp ? t : 0u;
+        }
+      }
+    }
+
+    // ---------------- tail: rare codes, word = minor | code << minor_bits ----------------
+    if (rend > rD) {
+      double t0[3] = {0.0, 0.0, 0.0}, t1[3] = {0.0, 0.0, 0.0};
+      unsigned tn = 0, tv = 0;  // packed 10-bit fields (a lane sees < 1024 tail entries per chunk)
+      int iter = 0;
+      for (int r0 = rD; r0 < rend; r0 += G, ++iter) {  // trip count is uniform across the group
+        const int r = r0 + g;
+        if (r < rend) {
+          const uint32_t w = wp[r];
+          const uint32_t code = w >> a.minor_bits;
+          const uint32_t sh = shift_of(w & mmask);
+          const double l0 = L0[code], l1 = L1[code];
+          const unsigned inc = 1u << sh;
+          tn += inc;
+          tv += VP[code] ? inc : 0u;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            if (sh == (uint32_t)(PH_FIELD_BITS * c)) {
+              t0[c] += l0;
+              t1[c] += l1;
+            }
+          }
+        }
+        if ((iter % 1000) == 999) {  // flush packed tail counters before a field can overflow
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            nob[c] += __reduce_add_sync(gmask, (tn >> (PH_FIELD_BITS * c)) & 1023u);
+            nva[c] += __reduce_add_sync(gmask, (tv >> (PH_FIELD_BITS * c)) & 1023u);
+          }
+          tn = tv = 0;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        nob[c] += __reduce_add_sync(gmask, (tn >> (PH_FIELD_BITS * c)) & 1023u);
+        nva[c] += __reduce_add_sync(gmask, (tv >> (PH_FIELD_BITS * c)) & 1023u);
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) {
+          t0[c] += __shfl_xor_sync(gmask, t0[c], o);
+          t1[c] += __shfl_xor_sync(gmask, t1[c], o);
+        }
+        s0[c] += t0[c];
+        s1[c] += t1[c];
+      }
+    }
+
+    // ---------------- epilogue ----------------
+    if (g == 0) {
+      if (MODE == MODE_TABLE) {
+        for (int c = 0; c < a.C; ++c) {
+          const size_t o = (size_t)wi * a.C + c;
+          if (a.S0) a.S0[o] = s0[c];
+          if (a.S1) a.S1[o] = s1[c];
+          if (a.Nobs) a.Nobs[o] = (int32_t)nob[c];
+          if (a.Nvar) a.Nvar[o] = (int32_t)nva[c];
+        }
+      } else if (MODE == MODE_LINEAR) {
+        // linear_split.py:229-234  like0.mean(axis=0) >= like1.mean(axis=0) -> mutsB (ties -> mutsB)
+        const double m0 = s0[0] / a.lenA, m1 = s1[0] / a.lenA;
+        a.label_out[wi] = (m0 >= m1) ? 2 : 1;
+        a.nobs_out[wi] = (int32_t)nob[0];
+      } else if (MODE == MODE_BRANCHING) {
+        // branching_split.py:332-346
+        const double cA = s1[0] + s0[1];
+        const double cB = s0[0] + s1[1];
+        const double cC = s1[0] + s1[1];
+        const double mx = fmax(cA, fmax(cB, cC));
+        a.label_out[wi] = (cA == mx) ? 1 : ((cB == mx) ? 2 : 3);
+        a.nobs_out[2 * (size_t)wi] = (int32_t)nob[0];
+        a.nobs_out[2 * (size_t)wi + 1] = (int32_t)nob[1];
+      } else {  // MODE_MAPPED: absent -> field 0 uses like0, present -> field 1 uses like1
+        a.per_line[wi] = s0[0] + s1[1];
+      }
+    }
+  }
+}
+
+// pre-scale labels for the global-memory label path
+__global__ void k_scale_labels(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < ((n + 3) >> 2)) reinterpret_cast<uint32_t*>(out)[i] = scale_labels4(reinterpret_cast<const uint32_t*>(in)[i]);
+}
+
+// deterministic block sums of a per-line table by the line's own label: out[(q-1)*C + c]
+__global__ void k_block_reduce(const double* __restrict__ S0, const double* __restrict__ S1,
+                               const int32_t* __restrict__ Nobs, const int32_t* __restrict__ Nvar,
+                               const uint8_t* __restrict__ line_label, int n_lines, int C, double* out0, double* out1,
+                               long long* outn, long long* outv) {
+  const int q = blockIdx.x / C + 1, c = blockIdx.x % C;
+  double a0 = 0.0, a1 = 0.0;
+  long long an = 0, av = 0;
+  for (int j = threadIdx.x; j < n_lines; j += blockDim.x) {
+    if (line_label[j] == q) {
+      const size_t o = (size_t)j * C + c;
+      a0 += S0[o];
+      a1 += S1[o];
+      an += Nobs[o];
+      av += Nvar[o];
+    }
+  }
+  __shared__ double r0[1024], r1[1024];
+  __shared__ long long rn[1024], rv[1024];
+  r0[threadIdx.x] = a0; r1[threadIdx.x] = a1; rn[threadIdx.x] = an; rv[threadIdx.x] = av;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) {
+      r0[threadIdx.x] += r0[threadIdx.x + s];
+      r1[threadIdx.x] += r1[threadIdx.x + s];
+      rn[threadIdx.x] += rn[threadIdx.x + s];
+      rv[threadIdx.x] += rv[threadIdx.x + s];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    out0[blockIdx.x] = r0[0]; out1[blockIdx.x] = r1[0]; outn[blockIdx.x] = rn[0]; outv[blockIdx.x] = rv[0];
+  }
+}
+
+// deterministic per-node sum of per-line values
+__global__ void k_node_reduce(const double* __restrict__ v, const uint8_t* __restrict__ label, int n, double* out) {
+  const int k = blockIdx.x;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    if (label[i] == k) acc += v[i];
+  __shared__ double r[1024];
+  r[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) r[threadIdx.x] += r[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[k] = r[0];
+}
+
+// ---- general node tables (a-11): per line, sums per minor node r in 0..K (K = "not in tree"), then
+//      T[line,k] = sum_r ( member[k][r] ? S1[r] : S0[r] ).  G lanes per line, counters in shared memory.
+template <int G, bool SMEM_LAB>
+__global__ void __launch_bounds__(kBlock, 1) k_node_table(const PassArgs a, const uint8_t* __restrict__ member, double* T) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int K = a.K, K1 = K + 1;
+  constexpr int groups_per_block = kBlock / G;
+  size_t off = 0;
+  uint8_t* s_lab = smem;
+  if (SMEM_LAB) off = ((size_t)a.n_minor + 15) & ~(size_t)15;
+  double* s_acc0 = reinterpret_cast<double*>(smem + off);
+  double* s_acc1 = s_acc0 + groups_per_block * K1;
+  unsigned* s_cnt = reinterpret_cast<unsigned*>(s_acc1 + groups_per_block * K1);
+  uint8_t* s_mem = reinterpret_cast<uint8_t*>(s_cnt + groups_per_block * K1);
+  if (SMEM_LAB) {
+    for (int i = threadIdx.x; i < a.n_minor; i += kBlock) {
+      uint32_t v = a.minor_label[i];
+      s_lab[i] = (uint8_t)(v < (uint32_t)K ? v : (uint32_t)K);
+    }
+  }
+  for (int i = threadIdx.x; i < K * K1; i += kBlock) s_mem[i] = (i % K1) < K ? member[(i / K1) * K + (i % K1)] : 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, g = lane & (G - 1);
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
+  const int grp = threadIdx.x / G;
+  double* acc0 = s_acc0 + grp * K1;
+  double* acc1 = s_acc1 + grp * K1;
+  unsigned* cnt = s_cnt + grp * K1;
+  const int total_groups = gridDim.x * groups_per_block;
+  const int D = a.D;
+  const uint32_t mmask = (a.minor_bits >= 32) ? 0xffffffffu : ((1u << a.minor_bits) - 1u);
+  auto node_of = [&](uint32_t minor) -> uint32_t {
+    if (SMEM_LAB) return s_lab[minor];
+    uint32_t v = __ldg(a.minor_label + minor);
+    return v < (uint32_t)K ? v : (uint32_t)K;
+  };
+  for (int wi = blockIdx.x * groups_per_block + grp; wi < a.n_work; wi += total_groups) {
+    const int line = a.list ? a.list[wi] : wi;
+    const int64_t* so = a.seg_off + (int64_t)line * (D + 1);
+    for (int r = g; r < K1; r += G) { acc0[r] = 0.0; acc1[r] = 0.0; cnt[r] = 0; }
+    __syncwarp(gmask);
+    for (int d = 0; d < D; ++d) {
+      const int64_t b = so[d], e = so[d + 1];
+      for (int64_t p = b + g; p < e; p += G) atomicAdd(&cnt[node_of(a.words[p])], 1u);
+      __syncwarp(gmask);
+      const double l0 = a.L0[d], l1 = a.L1[d];
+      for (int r = g; r < K1; r += G) {
+        const double c = (double)cnt[r];
+        acc0[r] = fma(c, l0, acc0[r]);
+        acc1[r] = fma(c, l1, acc1[r]);
+        cnt[r] = 0;
+      }
+      __syncwarp(gmask);
+    }
+    if (g == 0) {  // rare codes: serial, in storage order (deterministic)
+      for (int64_t p = so[D]; p < so[D + 1]; ++p) {
+        const uint32_t w = a.words[p];
+        const uint32_t code = w >> a.minor_bits;
+        const uint32_t r = node_of(w & mmask);
+        acc0[r] += a.L0[code];
+        acc1[r] += a.L1[code];
+      }
+    }
+    __syncwarp(gmask);
+    for (int k = g; k < K; k += G) {
+      double t = 0.0;
+      const uint8_t* mrow = s_mem + k * K1;
+      for (int r = 0; r < K1; ++r) t += mrow[r] ? acc1[r] : acc0[r];
+      T[(size_t)wi * K + k] = t;
+    }
+    __syncwarp(gmask);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+
+struct Staged {
+  cudaStream_t st;
+  bool host;
+};
+
+size_t pass_smem_bytes(const ph_handle* h, const PhOrient* o, int mode, int K, bool smem_lab, int* lut_in_smem) {
+  size_t b = 0;
+  if (smem_lab) b += ((size_t)o->n_minor + 15) & ~(size_t)15;
+  if (mode == MODE_MAPPED) b += (((size_t)(K + 1) * (K + 1)) + 15) & ~(size_t)15;
+  size_t lut = (size_t)h->n_codes * 17 + 16;
+  *lut_in_smem = (b + lut <= (size_t)h->max_smem && h->n_codes <= 4096) ? 1 : 0;
+  if (*lut_in_smem) b += lut;
+  return b;
+}
+
+template <int MODE>
+int launch_pass(ph_handle* h, const PhOrient* o, PassArgs& a, cudaStream_t st) {
+  if (a.n_work <= 0) return PH_OK;
+  int lut = 0;
+  bool smem_lab = true;
+  size_t smem = pass_smem_bytes(h, o, MODE, a.K, true, &lut);
+  if (smem > (size_t)h->max_smem) {
+    smem_lab = false;
+    smem = pass_smem_bytes(h, o, MODE, a.K, false, &lut);
+  }
+  a.lut_in_smem = lut;
+  const uint8_t* raw = a.minor_label;
+  if (!smem_lab) {
+    if (MODE == MODE_MAPPED) PH_FAIL(PH_ERR_UNSUPPORTED, "tree pass needs the %d minor labels in shared memory", o->n_minor);
+    // pre-scale into scratch; d_lab_major is free in every non-MAPPED mode
+    k_scale_labels<<<((o->n_minor + 3) / 4 + 255) / 256, 256, 0, st>>>(raw, h->d_lab_major, o->n_minor);
+    ph_count_launch();
+    a.minor_label = h->d_lab_major;
+  }
+  const int grid = h->sm_count;
+#define PH_LAUNCH(GG, SL)                                                                                        \
+  do {                                                                                                           \
+    auto kern = k_pass<GG, MODE, SL>;                                                                            \
+    PH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->max_smem));          \
+    kern<<<grid, kBlock, smem, st>>>(a);                                                                         \
+  } while (0)
+  switch (o->group) {
+    case 4: if (smem_lab) PH_LAUNCH(4, true); else PH_LAUNCH(4, false); break;
+    case 8: if (smem_lab) PH_LAUNCH(8, true); else PH_LAUNCH(8, false); break;
+    case 16: if (smem_lab) PH_LAUNCH(16, true); else PH_LAUNCH(16, false); break;
+    default: if (smem_lab) PH_LAUNCH(32, true); else PH_LAUNCH(32, false); break;
+  }
+#undef PH_LAUNCH
+  ph_count_launch();
+  PH_CUDA(cudaGetLastError());
+  const_cast<PhOrient*>(o)->labels_in_smem = smem_lab ? 1 : 0;
+  return PH_OK;
+}
+
+void fill_common(const ph_handle* h, const PhOrient* o, PassArgs& a) {
+  memset(&a, 0, sizeof(a));
+  a.words = o->words;
+  a.seg_off = o->seg_off;
+  a.D = o->D;
+  a.minor_bits = o->minor_bits;
+  a.n_minor = o->n_minor;
+  a.L0 = h->d_L0;
+  a.L1 = h->d_L1;
+  a.varpos = h->d_varpos;
+  a.n_codes = h->n_codes;
+}
+
+// host-pointer helpers: carve the pinned staging buffer
+struct Pin {
+  uint8_t* p;
+  size_t left;
+  void* take(size_t bytes) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (bytes > left) return nullptr;
+    void* r = p;
+    p += bytes;
+    left -= bytes;
+    return r;
+  }
+};
+
+int check_labels(const uint8_t* lab, int n, int maxv, const char* what) {
+  for (int i = 0; i < n; ++i)
+    if (lab[i] > maxv) PH_FAIL(PH_ERR_ARG, "%s[%d] = %d exceeds %d", what, i, lab[i], maxv);
+  return PH_OK;
+}
+
+// common driver for the per-line "fast" passes (TABLE / LINEAR / BRANCHING)
+int run_fast(ph_handle* h, PhOrient* o, int mode, const uint8_t* minor_label, int C, double lenA, const int32_t* list,
+             int32_t n_list, double* S0, double* S1, int32_t* Nobs, int32_t* Nvar, uint8_t* label_out,
+             int32_t* nobs_out, int on_device, void* stream) {
+  if (!h) PH_FAIL(PH_ERR_ARG, "null handle");
+  if (!minor_label) PH_FAIL(PH_ERR_ARG, "label array is NULL");
+  if (C < 1 || C > PH_MAX_FAST_CLUSTERS) PH_FAIL(PH_ERR_ARG, "C=%d outside 1..%d", C, PH_MAX_FAST_CLUSTERS);
+  if (!list) n_list = o->n_major;
+  if (n_list < 0 || n_list > o->n_major) PH_FAIL(PH_ERR_ARG, "n_list=%d outside 0..%d", n_list, o->n_major);
+  PH_CUDA(cudaSetDevice(h->device));
+  PassArgs a;
+  fill_common(h, o, a);
+  a.C = C;
+  a.lenA = lenA;
+  a.n_work = n_list;
+  const int nobs_per = mode == MODE_BRANCHING ? 2 : 1;
+  if (on_device) {
+    cudaStream_t st = (cudaStream_t)stream;
+    a.minor_label = minor_label;
+    a.list = list;
+    a.S0 = S0; a.S1 = S1; a.Nobs = Nobs; a.Nvar = Nvar; a.label_out = label_out; a.nobs_out = nobs_out;
+    if (mode == MODE_TABLE) return launch_pass<MODE_TABLE>(h, o, a, st);
+    if (!label_out || !nobs_out) PH_FAIL(PH_ERR_ARG, "output pointer is NULL");
+    if (mode == MODE_LINEAR) return launch_pass<MODE_LINEAR>(h, o, a, st);
+    return launch_pass<MODE_BRANCHING>(h, o, a, st);
+  }
+  // host pointers: validate, stage through pinned memory, run on the private stream, copy back, sync
+  int rc = check_labels(minor_label, o->n_minor, C, "label");
+  if (rc != PH_OK) return rc;
+  if (list)
+    for (int i = 0; i < n_list; ++i)
+      if (list[i] < 0 || list[i] >= o->n_major) PH_FAIL(PH_ERR_ARG, "list[%d]=%d out of range", i, list[i]);
+  cudaStream_t st = h->stream;
+  Pin pin{h->h_stage, h->h_stage_bytes};
+  uint8_t* p_lab = (uint8_t*)pin.take(o->n_minor);
+  memcpy(p_lab, minor_label, o->n_minor);
+  PH_CUDA(cudaMemcpyAsync(h->d_lab_minor, p_lab, o->n_minor, cudaMemcpyHostToDevice, st));
+  a.minor_label = h->d_lab_minor;
+  if (list) {
+    int32_t* p_list = (int32_t*)pin.take((size_t)n_list * 4);
+    memcpy(p_list, list, (size_t)n_list * 4);
+    PH_CUDA(cudaMemcpyAsync(h->d_list, p_list, (size_t)n_list * 4, cudaMemcpyHostToDevice, st));
+    a.list = h->d_list;
+  }
+  const size_t nt = (size_t)n_list * C;
+  double* dS0 = h->d_f64;
+  double* dS1 = h->d_f64 + (size_t)o->n_major * PH_MAX_FAST_CLUSTERS;
+  int32_t* dNo = h->d_i32;
+  int32_t* dNv = h->d_i32 + (size_t)o->n_major * PH_MAX_FAST_CLUSTERS;
+  if (mode == MODE_TABLE) {
+    a.S0 = S0 ? dS0 : nullptr; a.S1 = S1 ? dS1 : nullptr; a.Nobs = Nobs ? dNo : nullptr; a.Nvar = Nvar ? dNv : nullptr;
+    rc = launch_pass<MODE_TABLE>(h, o, a, st);
+    if (rc != PH_OK) return rc;
+    double* pS0 = S0 ? (double*)pin.take(nt * 8) : nullptr;
+    double* pS1 = S1 ? (double*)pin.take(nt * 8) : nullptr;
+    int32_t* pNo = Nobs ? (int32_t*)pin.take(nt * 4) : nullptr;
+    int32_t* pNv = Nvar ? (int32_t*)pin.take(nt * 4) : nullptr;
+    if (pS0) PH_CUDA(cudaMemcpyAsync(pS0, dS0, nt * 8, cudaMemcpyDeviceToHost, st));
+    if (pS1) PH_CUDA(cudaMemcpyAsync(pS1, dS1, nt * 8, cudaMemcpyDeviceToHost, st));
+    if (pNo) PH_CUDA(cudaMemcpyAsync(pNo, dNo, nt * 4, cudaMemcpyDeviceToHost, st));
+    if (pNv) PH_CUDA(cudaMemcpyAsync(pNv, dNv, nt * 4, cudaMemcpyDeviceToHost, st));
+    PH_CUDA(cudaStreamSynchronize(st));
+    if (pS0) memcpy(S0, pS0, nt * 8);
+    if (pS1) memcpy(S1, pS1, nt * 8);
+    if (pNo) memcpy(Nobs, pNo, nt * 4);
+    if (pNv) memcpy(Nvar, pNv, nt * 4);
+    return PH_OK;
+  }
+  if (!label_out || !nobs_out) PH_FAIL(PH_ERR_ARG, "output pointer is NULL");
+  a.label_out = h->d_u8;
+  a.nobs_out = dNo;
+  rc = mode == MODE_LINEAR ? launch_pass<MODE_LINEAR>(h, o, a, st) : launch_pass<MODE_BRANCHING>(h, o, a, st);
+  if (rc != PH_OK) return rc;
+  uint8_t* pL = (uint8_t*)pin.take(n_list);
+  int32_t* pN = (int32_t*)pin.take((size_t)n_list * 4 * nobs_per);
+  PH_CUDA(cudaMemcpyAsync(pL, h->d_u8, n_list, cudaMemcpyDeviceToHost, st));
+  PH_CUDA(cudaMemcpyAsync(pN, dNo, (size_t)n_list * 4 * nobs_per, cudaMemcpyDeviceToHost, st));
+  PH_CUDA(cudaStreamSynchronize(st));
+  memcpy(label_out, pL, n_list);
+  memcpy(nobs_out, pN, (size_t)n_list * 4 * nobs_per);
+  return PH_OK;
+}
+
+}  // namespace
+
+extern "C" int ph_snv_table(ph_handle* h, const uint8_t* cell_label, int32_t C, const int32_t* snv_list, int32_t n_list,
+                            double* S0, double* S1, int32_t* Nobs, int32_t* Nvar, int on_device, void* stream) {
+  if (!h) PH_FAIL(PH_ERR_ARG, "null handle");
+  return run_fast(h, &h->by_snv, MODE_TABLE, cell_label, C, 1.0, snv_list, n_list, S0, S1, Nobs, Nvar, nullptr, nullptr,
+                  on_device, stream);
+}
+
+extern "C" int ph_cell_table(ph_handle* h, const uint8_t* snv_label, int32_t Q, const int32_t* cell_list, int32_t n_list,
+                             double* A0, double* A1, int32_t* Nobs, int32_t* Nvar, int on_device, void* stream) {
+  if (!h) PH_FAIL(PH_ERR_ARG, "null handle");
+  return run_fast(h, &h->by_cell, MODE_TABLE, snv_label, Q, 1.0, cell_list, n_list, A0, A1, Nobs, Nvar, nullptr, nullptr,
+                  on_device, stream);
+}
+
+extern "C" int ph_assign_linear(ph_handle* h, const uint8_t* cell_label, double lenA, const int32_t* snv_list,
+                                int32_t n_list, uint8_t* label_out, int32_t* nobs_out, int on_device, void* stream) {
+  if (!h) PH_FAIL(PH_ERR_ARG, "null handle");
+  return run_fast(h, &h->by_snv, MODE_LINEAR, cell_label, 1, lenA, snv_list, n_list, nullptr, nullptr, nullptr, nullptr,
+                  label_out, nobs_out, on_device, stream);
+}
+
+extern "C" int ph_assign_branching(ph_handle* h, const uint8_t* cell_label, const int32_t* snv_list, int32_t n_list,
+                                   uint8_t* label_out, int32_t* nobs_out, int on_device, void* stream) {
+  if (!h) PH_FAIL(PH_ERR_ARG, "null handle");
+  return run_fast(h, &h->by_snv, MODE_BRANCHING, cell_label, 2, 1.0, snv_list, n_list, nullptr, nullptr, nullptr, nullptr,
+                  label_out, nobs_out, on_device, stream);
+}
+
+extern "C" int ph_block_sums(ph_handle* h, const uint8_t* cell_label, int32_t C, const uint8_t* snv_label, int32_t Q,
+                             double* sum0, double* sum1, int64_t* nobs, int64_t* nvar, int on_device, void* stream) {
+  if (!h) PH_FAIL(PH_ERR_ARG, "null handle");
+  if (!cell_label || !snv_label || !sum0 || !sum1 || !nobs || !nvar) PH_FAIL(PH_ERR_ARG, "null pointer");
+  if (C < 1 || C > PH_MAX_FAST_CLUSTERS || Q < 1 || Q > 16) PH_FAIL(PH_ERR_ARG, "C=%d / Q=%d out of range", C, Q);
+  PH_CUDA(cudaSetDevice(h->device));
+  PhOrient* o = &h->by_snv;
+  cudaStream_t st = on_device ? (cudaStream_t)stream : h->stream;
+  const uint8_t* d_cl = cell_label;
+  const uint8_t* d_sl = snv_label;
+  Pin pin{h->h_stage, h->h_stage_bytes};
+  if (!on_device) {
+    int rc = check_labels(cell_label, h->n_cells, C, "cell_label");
+    if (rc != PH_OK) return rc;
+    uint8_t* p1 = (uint8_t*)pin.take(h->n_cells);
+    uint8_t* p2 = (uint8_t*)pin.take(h->n_snvs);
+    memcpy(p1, cell_label, h->n_cells);
+    memcpy(p2, snv_label, h->n_snvs);
+    PH_CUDA(cudaMemcpyAsync(h->d_lab_minor, p1, h->n_cells, cudaMemcpyHostToDevice, st));
+    PH_CUDA(cudaMemcpyAsync(h->d_u8, p2, h->n_snvs, cudaMemcpyHostToDevice, st));
+    d_cl = h->d_lab_minor;
+    d_sl = h->d_u8;
+  }
+  PassArgs a;
+  fill_common(h, o, a);
+  a.C = C;
+  a.n_work = o->n_major;
+  a.minor_label = d_cl;
+  double* dS0 = h->d_f64;
+  double* dS1 = h->d_f64 + (size_t)o->n_major * PH_MAX_FAST_CLUSTERS;
+  int32_t* dNo = h->d_i32;
+  int32_t* dNv = h->d_i32 + (size_t)o->n_major * PH_MAX_FAST_CLUSTERS;
+  a.S0 = dS0; a.S1 = dS1; a.Nobs = dNo; a.Nvar = dNv;
+  int rc = launch_pass<MODE_TABLE>(h, o, a, st);
+  if (rc != PH_OK) return rc;
+  const int nb = Q * C;
+  double* d0 = on_device ? sum0 : h->d_small;
+  double* d1 = on_device ? sum1 : h->d_small + 64;
+  long long* dn = on_device ? (long long*)nobs : (long long*)(h->d_small + 128);
+  long long* dv = on_device ? (long long*)nvar : (long long*)(h->d_small + 192);
+  k_block_reduce<<<nb, 1024, 0, st>>>(dS0, dS1, dNo, dNv, d_sl, o->n_major, C, d0, d1, dn, dv);
+  ph_count_launch();
+  PH_CUDA(cudaGetLastError());
+  if (!on_device) {
+    double* p = (double*)pin.take(256 * 8);
+    PH_CUDA(cudaMemcpyAsync(p, h->d_small, 256 * 8, cudaMemcpyDeviceToHost, st));
+    PH_CUDA(cudaStreamSynchronize(st));
+    memcpy(sum0, p, nb * 8);
+    memcpy(sum1, p + 64, nb * 8);
+    memcpy(nobs, p + 128, nb * 8);
+    memcpy(nvar, p + 192, nb * 8);
+  }
+  return PH_OK;
+}
+
+extern "C" int ph_tree_loglik(ph_handle* h, const uint8_t* cell_node, const uint8_t* snv_node, const uint8_t* present,
+                              int32_t K, double* per_node, double* per_cell, int on_device, void* stream) {
+  if (!h) PH_FAIL(PH_ERR_ARG, "null handle");
+  if (!cell_node || !snv_node || !present || !per_node) PH_FAIL(PH_ERR_ARG, "null pointer");
+  if (K < 1 || K > PH_MAX_TREE_NODES) PH_FAIL(PH_ERR_ARG, "K=%d outside 1..%d", K, PH_MAX_TREE_NODES);
+  PH_CUDA(cudaSetDevice(h->device));
+  PhOrient* o = &h->by_cell;
+  cudaStream_t st = on_device ? (cudaStream_t)stream : h->stream;
+  Pin pin{h->h_stage, h->h_stage_bytes};
+  const int K1 = K + 1;
+  const uint8_t *d_cn = cell_node, *d_sn = snv_node;
+  // (K+1)x(K+1) class map: row = node of the cell, column = node of the SNV (K = not in tree -> absent)
+  uint8_t* p_map = (uint8_t*)pin.take((size_t)K1 * K1);
+  if (on_device) {
+    uint8_t tmp[65 * 65];
+    PH_CUDA(cudaMemcpyAsync(tmp, present, (size_t)K * K, cudaMemcpyDeviceToHost, st));
+    PH_CUDA(cudaStreamSynchronize(st));
+    for (int k = 0; k < K1; ++k)
+      for (int q = 0; q < K1; ++q) p_map[k * K1 + q] = (k < K && q < K) ? tmp[k * K + q] : 0;
+  } else {
+    for (int k = 0; k < K1; ++k)
+      for (int q = 0; q < K1; ++q) p_map[k * K1 + q] = (k < K && q < K) ? present[k * K + q] : 0;
+    uint8_t* p1 = (uint8_t*)pin.take(h->n_cells);
+    uint8_t* p2 = (uint8_t*)pin.take(h->n_snvs);
+    memcpy(p1, cell_node, h->n_cells);
+    memcpy(p2, snv_node, h->n_snvs);
+    PH_CUDA(cudaMemcpyAsync(h->d_lab_major, p1, h->n_cells, cudaMemcpyHostToDevice, st));
+    PH_CUDA(cudaMemcpyAsync(h->d_lab_minor, p2, h->n_snvs, cudaMemcpyHostToDevice, st));
+    d_cn = h->d_lab_major;
+    d_sn = h->d_lab_minor;
+  }
+  PH_CUDA(cudaMemcpyAsync(h->d_map, p_map, (size_t)K1 * K1, cudaMemcpyHostToDevice, st));
+  PassArgs a;
+  fill_common(h, o, a);
+  a.C = 2;
+  a.K = K;
+  a.n_work = o->n_major;
+  a.minor_label = d_sn;
+  a.major_label = d_cn;
+  a.map = h->d_map;
+  double* d_pc = (on_device && per_cell) ? per_cell : h->d_f64;
+  a.per_line = d_pc;
+  int rc = launch_pass<MODE_MAPPED>(h, o, a, st);
+  if (rc != PH_OK) return rc;
+  double* d_pn = on_device ? per_node : h->d_small;
+  k_node_reduce<<<K, 1024, 0, st>>>(d_pc, d_cn, h->n_cells, d_pn);
+  ph_count_launch();
+  PH_CUDA(cudaGetLastError());
+  if (!on_device) {
+    double* p = (double*)pin.take((size_t)K * 8);
+    double* pc = per_cell ? (double*)pin.take((size_t)h->n_cells * 8) : nullptr;
+    PH_CUDA(cudaMemcpyAsync(p, d_pn, (size_t)K * 8, cudaMemcpyDeviceToHost, st));
+    if (pc) PH_CUDA(cudaMemcpyAsync(pc, d_pc, (size_t)h->n_cells * 8, cudaMemcpyDeviceToHost, st));
+    PH_CUDA(cudaStreamSynchronize(st));
+    memcpy(per_node, p, (size_t)K * 8);
+    if (pc) memcpy(per_cell, pc, (size_t)h->n_cells * 8);
+  }
+  return PH_OK;
+}
+
+namespace {
+int run_node_table(ph_handle* h, PhOrient* o, const uint8_t* minor_node, const uint8_t* member, int32_t K,
+                   const int32_t* list, int32_t n_list, double* T, int on_device, void* stream) {
+  if (!minor_node || !member || !T) PH_FAIL(PH_ERR_ARG, "null pointer");
+  if (K < 1 || K > PH_MAX_TREE_NODES) PH_FAIL(PH_ERR_ARG, "K=%d outside 1..%d", K, PH_MAX_TREE_NODES);
+  if (!list) n_list = o->n_major;
+  if (n_list < 0 || n_list > o->n_major) PH_FAIL(PH_ERR_ARG, "n_list=%d out of range", n_list);
+  if (n_list == 0) return PH_OK;
+  PH_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = on_device ? (cudaStream_t)stream : h->stream;
+  Pin pin{h->h_stage, h->h_stage_bytes};
+  PassArgs a;
+  fill_common(h, o, a);
+  a.K = K;
+  a.n_work = n_list;
+  const uint8_t* d_member = member;
+  double* dT = T;
+  if (on_device) {
+    a.minor_label = minor_node;
+    a.list = list;
+  } else {
+    uint8_t* p1 = (uint8_t*)pin.take(o->n_minor);
+    memcpy(p1, minor_node, o->n_minor);
+    PH_CUDA(cudaMemcpyAsync(h->d_lab_minor, p1, o->n_minor, cudaMemcpyHostToDevice, st));
+    a.minor_label = h->d_lab_minor;
+    uint8_t* pm = (uint8_t*)pin.take((size_t)K * K);
+    memcpy(pm, member, (size_t)K * K);
+    PH_CUDA(cudaMemcpyAsync(h->d_map, pm, (size_t)K * K, cudaMemcpyHostToDevice, st));
+    d_member = h->d_map;
+    if (list) {
+      for (int i = 0; i < n_list; ++i)
+        if (list[i] < 0 || list[i] >= o->n_major) PH_FAIL(PH_ERR_ARG, "list[%d]=%d out of range", i, list[i]);
+      int32_t* pl = (int32_t*)pin.take((size_t)n_list * 4);
+      memcpy(pl, list, (size_t)n_list * 4);
+      PH_CUDA(cudaMemcpyAsync(h->d_list, pl, (size_t)n_list * 4, cudaMemcpyHostToDevice, st));
+      a.list = h->d_list;
+    }
+    if ((size_t)n_list * K > (size_t)(o->n_major > o->n_minor ? o->n_major : o->n_minor) * 2 * PH_MAX_FAST_CLUSTERS)
+      PH_FAIL(PH_ERR_UNSUPPORTED, "node table of %d x %d exceeds the staging scratch; pass fewer lines per call", n_list, K);
+    dT = h->d_f64;
+  }
+  const int G = 8;
+  const int gpb = kBlock / G;
+  const int K1 = K + 1;
+  size_t extra = (size_t)gpb * K1 * (8 + 8 + 4) + (size_t)K * K1 + 16;
+  size_t lab = ((size_t)o->n_minor + 15) & ~(size_t)15;
+  bool smem_lab = lab + extra <= (size_t)h->max_smem;
+  size_t smem = (smem_lab ? lab : 0) + extra;
+  if (smem_lab) {
+    auto kern = k_node_table<8, true>;
+    PH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->max_smem));
+    kern<<<h->sm_count, kBlock, smem, st>>>(a, d_member, dT);
+  } else {
+    auto kern = k_node_table<8, false>;
+    PH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->max_smem));
+    kern<<<h->sm_count, kBlock, smem, st>>>(a, d_member, dT);
+  }
+  ph_count_launch();
+  PH_CUDA(cudaGetLastError());
+  if (!on_device) {
+    const size_t nb = (size_t)n_list * K * 8;
+    double* p = (double*)pin.take(nb);
+    if (!p) PH_FAIL(PH_ERR_UNSUPPORTED, "node table too large for the pinned staging buffer");
+    PH_CUDA(cudaMemcpyAsync(p, dT, nb, cudaMemcpyDeviceToHost, st));
+    PH_CUDA(cudaStreamSynchronize(st));
+    memcpy(T, p, nb);
+  }
+  return PH_OK;
+}
+}  // namespace
+
+extern "C" int ph_snv_node_table(ph_handle* h, const uint8_t* cell_node, const uint8_t* member, int32_t K,
+                                 const int32_t* snv_list, int32_t n_list, double* T, int on_device, void* stream) {
+  if (!h) PH_FAIL(PH_ERR_ARG, "null handle");
+  return run_node_table(h, &h->by_snv, cell_node, member, K, snv_list, n_list, T, on_device, stream);
+}
+
+extern "C" int ph_cell_node_table(ph_handle* h, const uint8_t* snv_node, const uint8_t* member, int32_t K,
+                                  const int32_t* cell_list, int32_t n_list, double* T, int on_device, void* stream) {
+  if (!h) PH_FAIL(PH_ERR_ARG, "null handle");
+  return run_node_table(h, &h->by_cell, snv_node, member, K, cell_list, n_list, T, on_device, stream);
+}

@@ -1,0 +1,24 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+
+
+@pytest.fixture(scope="session")
+def example_golden():
+    from tests.golden_util import load_golden
+    return load_golden("example")
+
+
+@pytest.fixture(scope="session")
+def synth_golden():
+    from tests.golden_util import load_golden
+    return load_golden("synth_t0")

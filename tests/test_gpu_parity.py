@@ -1,0 +1,343 @@
+"""GPU parity: the CUDA path (through the C-ABI, host buffers) vs the reference's recorded outputs (tests/golden) and vs
+the CPU oracle on seeded inputs.  Integers / index arrays / assignments: exact.  Log-likelihoods: 1e-9 relative."""
+import numpy as np
+import pytest
+
+from oracle import oracle_np as O
+from tests.golden_util import load_golden, rel_close, tree_from_record
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+@pytest.fixture(scope="module", params=["example", "synth_t0"])
+def env(request):
+    from phertilizer_b200.store import ObservationStore
+
+    g = load_golden(request.param)
+    i = g.inputs
+    st = ObservationStore.from_coo(g.n, g.m, i["cell"], i["snv"], i["var"], i["total"])
+    D = O.DenseData(g.n, g.m, i["cell"], i["snv"], i["var"], i["total"])
+    yield g, st, D
+    st.close()
+
+
+def test_store_tables_match_reference_values(env):
+    g, st, D = env
+    i = g.inputs
+    # the device LUT reproduces the reference's per-observation values bit for bit
+    from phertilizer_b200.like_lut import encode_pairs
+
+    _, _, _, code = encode_pairs(i["var"], i["total"])
+    assert np.array_equal(st.L0[code], i["like0"]) and np.array_equal(st.L1[code], i["like1"])
+    info = st.info()
+    assert info["nnz"] == len(i["cell"]) and info["n_cells"] == g.n and info["n_snvs"] == g.m
+
+
+def test_linear_mut_assignment_golden(env):
+    g, st, D = env
+    for r in g.of("linear_mut_assignment"):
+        lab, nobs = st.assign_linear(st.cell_labels(r.cellsA), len(r.cellsA), r.muts)
+        gate = np.quantile(nobs, 0.75) < r.nobs_per_cluster
+        assert gate == (r.mutsB is None)
+        if not gate:
+            muts = r.muts.astype(np.int64)
+            mutsB = muts[lab == 2]
+            mutsA = np.setdiff1d(muts, mutsB)
+            assert np.array_equal(mutsA, r.mutsA) and np.array_equal(mutsB, r.mutsB)
+
+
+def test_branching_mut_assignment_golden(env):
+    g, st, D = env
+    for r in g.of("branching_mut_assignment"):
+        lab, nobs = st.assign_branching(st.cell_labels(r.cellsA, r.cellsB), r.muts)
+        gate = np.quantile(nobs[:, 0], 0.75) < r.nobs_per_cluster or np.quantile(nobs[:, 1], 0.75) < r.nobs_per_cluster
+        muts = r.muts.astype(np.int64)
+        if gate:
+            assert len(r.mutsA) == 0 and len(r.mutsB) == 0 and np.array_equal(r.mutsC, muts)
+        else:
+            assert np.array_equal(muts[lab == 1], r.mutsA)
+            assert np.array_equal(muts[lab == 2], r.mutsB)
+            assert np.array_equal(muts[lab == 3], r.mutsC)
+
+
+def test_snv_table_vs_oracle_and_golden(env):
+    g, st, D = env
+    for r in g.of("weighted_init_vaf"):
+        t = st.snv_table(st.cell_labels(r.cells), 1, r.muts, want=("Nobs", "Nvar"))
+        vaf = t["Nvar"][:, 0] / t["Nobs"][:, 0]
+        assert np.array_equal(vaf, r.vaf, equal_nan=True)
+    for r in g.of("branching_mut_assignment")[:4]:
+        t = st.snv_table(st.cell_labels(r.cellsA, r.cellsB), 2, r.muts)
+        S0, S1, No, Nv = O.snv_table(D, [r.cellsA, r.cellsB], r.muts)
+        assert np.array_equal(t["Nobs"], No) and np.array_equal(t["Nvar"], Nv)
+        assert rel_close(t["S0"], S0, TOL) and rel_close(t["S1"], S1, TOL)
+
+
+def test_cell_table_golden(env):
+    g, st, D = env
+    for r in g.of("calc_tmb"):
+        t = st.cell_table(st.snv_labels(r.muts), 1, r.cells, want=("Nobs", "Nvar"))
+        tmb = (t["Nvar"][:, 0] / t["Nobs"][:, 0]).reshape(-1, 1)
+        assert np.array_equal(tmb, r.tmb, equal_nan=True)
+    for r in g.of("linear_affinity_features"):
+        t = st.cell_table(st.snv_labels(r.mutsB), 1, r.cells, want=("Nobs", "Nvar"))
+        assert np.array_equal(t["Nobs"][:, 0], r.nobs) and np.array_equal(t["Nvar"][:, 0], r.nvar)
+    for r in g.of("linear_check_metrics")[:3]:
+        t = st.cell_table(st.snv_labels(r.ma, r.mb), 2, r.ca)
+        A0, A1, No, Nv = O.cell_table(D, r.ca, [r.ma, r.mb])
+        assert np.array_equal(t["Nobs"], No) and np.array_equal(t["Nvar"], Nv)
+        assert rel_close(t["S0"], A0, TOL) and rel_close(t["S1"], A1, TOL)
+
+
+def test_block_sums_golden(env):
+    g, st, D = env
+    for r in g.of("check_obs") + g.of("count_obs"):
+        _, _, no, _ = st.block_sums(st.cell_labels(r.cells), 1, st.snv_labels(r.muts), 1)
+        assert int(no[0, 0]) == r.value
+    for r in g.of("linear_norm_likelihood"):
+        # cells: A = cellsA, B = rest of the seed; SNVs: 1 = mutsA, 2 = mutsB   (linear_split.py:549-554)
+        rest = np.setdiff1d(r.all_cells, r.cellsA)
+        s0, s1, no, _ = st.block_sums(st.cell_labels(r.cellsA, rest), 2, st.snv_labels(r.mutsA, r.mutsB), 2)
+        total_like = s0[1, 0] + (s1[0, 0] + s1[0, 1])
+        total = no[1, 0] + no[0, 0] + no[0, 1]
+        assert rel_close(total_like / total, r.value, TOL)
+    for r in g.of("branching_norm_likelihood"):
+        rest = np.setdiff1d(r.all_cells, np.concatenate([r.cellsA, r.cellsB]))
+        s0, s1, no, _ = st.block_sums(st.cell_labels(r.cellsA, r.cellsB, rest), 3, st.snv_labels(r.mutsA, r.mutsB, r.mutsC), 3)
+        total_like = s1[2].sum() + s0[1, 0] + s0[0, 1]
+        total = no[2].sum() + no[1, 0] + no[0, 1]
+        assert rel_close(total_like / total, r.value, TOL)
+
+
+def test_seed_strip_golden(env):
+    g, st, D = env
+    for r in g.of("seed_strip"):
+        cells, muts = r.cells.astype(np.int64), r.muts.astype(np.int64)
+        nv = st.snv_table(st.cell_labels(cells), 1, muts, want=("Nvar",))["Nvar"][:, 0]
+        muts2 = np.setdiff1d(muts, muts[nv == 0])
+        nc = st.cell_table(st.snv_labels(muts2), 1, cells, want=("Nvar",))["Nvar"][:, 0]
+        cells2 = np.setdiff1d(cells, cells[nc == 0])
+        assert np.array_equal(cells2, r.cells_out) and np.array_equal(muts2, r.muts_out)
+
+
+def _tree_arrays(g, r):
+    import networkx as nx
+
+    nodes, edges, cells, muts = tree_from_record(r)
+    K = max(nodes) + 1
+    T = nx.DiGraph()
+    T.add_nodes_from(nodes)
+    T.add_edges_from(edges)
+    cell_node = np.full(g.n + 16, 255, np.uint8)[: g.n]
+    snv_node = np.full(g.m + 16, 255, np.uint8)[: g.m]
+    for k in nodes:
+        cell_node[cells[k]] = k
+        snv_node[muts[k]] = k
+    present = np.zeros((K, K), np.uint8)
+    root = [k for k in nodes if T.in_degree(k) == 0][0]
+    for k in nodes:
+        for q in nx.shortest_path(T, root, k):
+            present[k, q] = 1
+    return nodes, cell_node, snv_node, present, T
+
+
+def test_tree_likelihood_golden(env):
+    g, st, D = env
+    X = g.inputs["read_depth"].astype(np.float64)
+    recs = g.of("tree_likelihood")
+    assert recs
+    for r in recs:
+        nodes, cell_node, snv_node, present, _ = _tree_arrays(g, r)
+        per_node = st.tree_loglik(cell_node, snv_node, present)
+        variant = sum(per_node[k] for k in nodes if len(getattr(r, f"cells_{k}")) > 0)
+        assert rel_close(variant, r.variant, TOL)
+        gn = st.gauss_node_ll(X, cell_node, present.shape[0])
+        binll = sum(gn[k] for k in nodes if len(getattr(r, f"cells_{k}")) > 0)
+        assert rel_close(binll, r.bin, TOL)
+        assert rel_close(variant + binll, r.loglikelihood, TOL)
+
+
+def test_variant_likelihood_by_node_golden(env):
+    g, st, D = env
+    for r in g.of("variant_likelihood_by_node"):
+        cell_node = np.full(g.n + 16, 255, np.uint8)[: g.n]
+        snv_node = np.full(g.m + 16, 255, np.uint8)[: g.m]
+        cell_node[r.cells] = 0
+        snv_node[r.present_muts] = 0
+        v = st.tree_loglik(cell_node, snv_node, np.ones((1, 1), np.uint8))
+        assert rel_close(v[0], r.value, TOL)
+
+
+def test_gauss_node_ll_golden(env):
+    g, st, D = env
+    X = g.inputs["read_depth"].astype(np.float64)
+    for r in g.of("read_depth_likelihood_by_node"):
+        cell_node = np.full(g.n + 16, 255, np.uint8)[: g.n]
+        cell_node[r.cells] = 0
+        tot, pc = st.gauss_node_ll(X, cell_node, 1, per_cell=True)
+        assert rel_close(pc[r.cells], r.per_cell, TOL)
+        assert rel_close(tot[0], r.value, TOL)
+
+
+def test_reassign_snv_scores_golden(env):
+    g, st, D = env
+    recs = g.of("reassign_snv")
+    assert recs
+    # group consecutive records that share the same c_dict into one batched call
+    i = 0
+    while i < len(recs):
+        j = i
+        while j < len(recs) and recs[j].cdict.shape == recs[i].cdict.shape and np.array_equal(recs[j].cdict, recs[i].cdict):
+            j += 1
+        batch = recs[i:j]
+        cd = batch[0].cdict  # [n_nodes, n_cells]: 1 iff the cell is in the clade of node k
+        K = cd.shape[0]
+        # cell "node" = index of the distinct column pattern; member[k][pattern] = cd[k, representative]
+        pats, inv = np.unique(cd.T, axis=0, return_inverse=True)
+        P = len(pats)
+        assert P <= 64
+        KK = max(K, P)
+        member = np.zeros((KK, KK), np.uint8)
+        member[:K, :P] = pats.T
+        cell_node = np.full(g.n + 16, 255, np.uint8)[: g.n]
+        cell_node[:] = inv.reshape(-1).astype(np.uint8)
+        T = st.snv_node_table(cell_node, member, np.array([r.s for r in batch]))
+        for row, r in zip(T, batch):
+            assert rel_close(row[:K], r.scores, TOL)
+            # strict > scan in dict order (clonal_tree.py:656-661)
+            best, bl = None, -np.inf
+            for k in range(K):
+                if row[k] > bl:
+                    bl, best = row[k], int(r.nodes[k])
+            assert best == r.after
+        i = j
+
+
+def test_find_bad_snvs_golden(env):
+    g, st, D = env
+    for r in g.of("find_bad_snvs"):
+        muts = r.muts.astype(np.int64)
+        t = st.snv_table(st.cell_labels(r.clade_cells), 1, muts, want=("Nobs", "Nvar"))
+        tot, mc = t["Nobs"][:, 0], t["Nvar"][:, 0]
+        na = muts[tot == 0]
+        keep = tot > 0
+        vaf = mc[keep] / tot[keep]
+        m2 = muts[keep]
+        order = np.argsort(m2)
+        m2, vaf = m2[order], vaf[order]
+        bad = m2[vaf <= np.quantile(vaf, r.q)] if len(vaf) else np.empty(0, int)
+        assert np.array_equal(np.union1d(bad, na), r.bad)
+
+
+def test_pairwise_dist(env):
+    g, st, D = env
+    from phertilizer_b200.store import pairwise_dist
+
+    X = g.inputs["read_depth"].astype(np.float64)[:333]
+    got = pairwise_dist(X)
+    ref = O.pairwise_dist(X)
+    assert got.shape == ref.shape and np.all(np.diag(got) == 0) and np.array_equal(got, got.T)
+    assert rel_close(got, ref, TOL)
+    part = pairwise_dist(X, 100, 171)
+    assert np.array_equal(part, got[100:171])
+
+
+# ------------------------------------------------------------------------------------------- seeded random inputs
+@pytest.fixture(scope="module")
+def synth_env():
+    from phertilizer_b200.store import ObservationStore
+    from phertilizer_b200.synth import make_config
+
+    s = make_config("T1", with_embedding=False)
+    cell, snv, var, total = (x.numpy() for x in (s.cell, s.snv, s.var, s.total))
+    # add a few deep-coverage observations so the rare-code ("tail") path and large codes are exercised
+    rng = np.random.default_rng(5)
+    extra = rng.choice(len(cell), 300, replace=False)
+    total = total.copy(); var = var.copy()
+    total[extra] = rng.integers(2, 40, 300)
+    var[extra] = rng.integers(0, total[extra] + 1)
+    st = ObservationStore.from_coo(s.n, s.m, cell, snv, var, total)
+    D = O.DenseData(s.n, s.m, cell, snv, var, total)
+    yield s, st, D
+    st.close()
+
+
+@pytest.mark.parametrize("group", [4, 8, 16, 32])
+def test_random_labels_all_group_sizes(synth_env, group):
+    s, st, D = synth_env
+    st.set_group(group, group)
+    rng = np.random.default_rng(100 + group)
+    for trial in range(3):
+        C = int(rng.integers(1, 4))
+        lab = np.zeros(s.n + 16, np.uint8)[: s.n]
+        lab[:] = rng.integers(0, C + 1, s.n)
+        if trial == 2:
+            lab[:] = 0
+            lab[rng.choice(s.n, 5, replace=False)] = 1  # nearly empty cluster: exact-zero ties
+        groups = [np.nonzero(lab == c)[0] for c in range(1, C + 1)]
+        muts = np.sort(rng.choice(s.m, int(rng.integers(1, s.m)), replace=False))
+        t = st.snv_table(lab, C, muts)
+        S0, S1, No, Nv = O.snv_table(D, groups, muts)
+        assert np.array_equal(t["Nobs"], No) and np.array_equal(t["Nvar"], Nv)
+        assert rel_close(t["S0"], S0, TOL) and rel_close(t["S1"], S1, TOL)
+        # fused assignments == oracle assignments
+        if len(groups[0]):
+            labA, nobs = st.assign_linear(st.cell_labels(groups[0]), len(groups[0]), muts)
+            a, b = O.linear_mut_assignment(D, groups[0], muts, nobs_per_cluster=-1)
+            assert np.array_equal(muts[labA == 2], b) and np.array_equal(np.setdiff1d(muts, muts[labA == 2]), a)
+            assert np.array_equal(nobs, No[:, 0])
+        if C >= 2 and len(groups[0]) and len(groups[1]):
+            lab3, nobs2 = st.assign_branching(st.cell_labels(groups[0], groups[1]), muts)
+            a, b, c = O.branching_mut_assignment(D, groups[0], groups[1], muts, nobs_per_cluster=-1)
+            assert np.array_equal(muts[lab3 == 1], a) and np.array_equal(muts[lab3 == 2], b) and np.array_equal(muts[lab3 == 3], c)
+        # transpose
+        Q = int(rng.integers(1, 4))
+        sl = np.zeros(s.m + 16, np.uint8)[: s.m]
+        sl[:] = rng.integers(0, Q + 1, s.m)
+        mg = [np.nonzero(sl == q)[0] for q in range(1, Q + 1)]
+        cells = np.sort(rng.choice(s.n, int(rng.integers(1, s.n)), replace=False))
+        t2 = st.cell_table(sl, Q, cells)
+        A0, A1, No2, Nv2 = O.cell_table(D, cells, mg)
+        assert np.array_equal(t2["Nobs"], No2) and np.array_equal(t2["Nvar"], Nv2)
+        assert rel_close(t2["S0"], A0, TOL) and rel_close(t2["S1"], A1, TOL)
+        bs = st.block_sums(lab, C, sl, Q)
+        ob = O.block_sums(D, groups, mg)
+        assert np.array_equal(bs[2], ob[2]) and np.array_equal(bs[3], ob[3])
+        assert rel_close(bs[0], ob[0], TOL) and rel_close(bs[1], ob[1], TOL)
+    st.set_group(0, 0)
+
+
+def test_empty_and_degenerate_inputs(synth_env):
+    s, st, D = synth_env
+    empty = np.zeros(s.n + 16, np.uint8)[: s.n]
+    t = st.snv_table(empty, 1)
+    assert not t["Nobs"].any() and not t["S0"].any() and not t["S1"].any()
+    lab, nobs = st.assign_linear(empty, 1.0)
+    assert np.all(lab == 2) and not nobs.any()            # 0 >= 0 -> mutsB  (linear_split.py:232)
+    lab3, _ = st.assign_branching(empty)
+    assert np.all(lab3 == 1)                              # all candidates 0 -> mutsA (branching_split.py:341)
+    t = st.snv_table(empty, 1, np.empty(0, np.int32))
+    assert t["Nobs"].shape == (0, 1)
+    from phertilizer_b200._lib import PhError
+
+    bad = empty.copy(); bad[3] = 9
+    with pytest.raises(PhError):
+        st.snv_table(bad, 2)
+    with pytest.raises(PhError):
+        st.snv_table(empty, 1, np.array([s.m + 5], np.int32))
+
+
+def test_determinism(synth_env):
+    s, st, D = synth_env
+    rng = np.random.default_rng(3)
+    lab = np.zeros(s.n + 16, np.uint8)[: s.n]
+    lab[:] = rng.integers(0, 3, s.n)
+    a = st.snv_table(lab, 2)
+    b = st.snv_table(lab, 2)
+    for k in a:
+        assert np.array_equal(a[k], b[k])
+    st.set_group(32, 32)
+    c = st.snv_table(lab, 2)
+    st.set_group(0, 0)
+    assert np.array_equal(a["Nobs"], c["Nobs"]) and rel_close(a["S0"], c["S0"], 1e-13)

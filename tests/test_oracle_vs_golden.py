@@ -1,0 +1,124 @@
+"""Pins oracle/oracle_np.py (the CPU restatement) against outputs of the UNMODIFIED reference recorded in
+tests/golden/ (per-call capture while the reference ran config 1 and a small synthetic).  Integers and index arrays
+must match exactly; floats to 1e-9 relative (the north-star tolerance)."""
+import numpy as np
+import pytest
+
+from oracle import oracle_np as O
+from tests.golden_util import rel_close, tree_from_record
+
+STEMS = ["example", "synth_t0"]
+
+
+@pytest.fixture(scope="module", params=STEMS)
+def gd(request):
+    from tests.golden_util import load_golden
+
+    g = load_golden(request.param)
+    i = g.inputs
+    D = O.DenseData(g.n, g.m, i["cell"], i["snv"], i["var"], i["total"])
+    return g, D
+
+
+def test_per_observation_likelihoods_bit_exact(gd):
+    g, D = gd
+    i = g.inputs
+    assert np.array_equal(D.like0[i["cell"], i["snv"]], i["like0"])
+    assert np.array_equal(D.like1[i["cell"], i["snv"]], i["like1"])
+
+
+def test_kat_bit_exact():
+    import os
+    from tests.golden_util import GOLDEN_DIR
+
+    k = np.load(os.path.join(GOLDEN_DIR, "kat_like.npz"))
+    for s, (alpha, mc) in enumerate(k["settings"]):
+        l0, l1 = O.like0_like1(k["var"], k["total"], float(alpha), int(mc))
+        assert np.array_equal(l0, k[f"like0_{s}"])
+        assert np.array_equal(l1, k[f"like1_{s}"])
+
+
+def test_linear_mut_assignment(gd):
+    g, D = gd
+    recs = g.of("linear_mut_assignment")
+    assert recs
+    for r in recs:
+        a, b = O.linear_mut_assignment(D, r.cellsA, r.muts, r.nobs_per_cluster)
+        assert np.array_equal(a, r.mutsA)
+        assert (b is None and r.mutsB is None) or np.array_equal(b, r.mutsB)
+
+
+def test_branching_mut_assignment(gd):
+    g, D = gd
+    for r in g.of("branching_mut_assignment"):
+        a, b, c = O.branching_mut_assignment(D, r.cellsA, r.cellsB, r.muts, r.nobs_per_cluster)
+        assert np.array_equal(a, r.mutsA) and np.array_equal(b, r.mutsB) and np.array_equal(c, r.mutsC)
+
+
+def test_weighted_init_vaf(gd):
+    g, D = gd
+    for r in g.of("weighted_init_vaf"):
+        vaf, prob = O.weighted_init_vaf(D, r.cells, r.muts)
+        assert np.array_equal(vaf, r.vaf, equal_nan=True)
+        assert np.array_equal(prob, r.vaf_prob, equal_nan=True)
+
+
+def test_tmb_and_affinity_features(gd):
+    g, D = gd
+    for r in g.of("calc_tmb"):
+        assert np.array_equal(O.calc_tmb(D, r.cells, r.muts), r.tmb, equal_nan=True)
+    for r in g.of("linear_affinity_features"):
+        _, _, no, nv = O.cell_table(D, r.cells, [r.mutsB])
+        assert np.array_equal(no[:, 0], r.nobs) and np.array_equal(nv[:, 0], r.nvar)
+
+
+def test_check_metrics(gd):
+    g, D = gd
+    for r in g.of("linear_check_metrics"):
+        f1, f2, f3 = O.linear_check_metrics(D, r.all_cells, r.ca, r.cb, r.ma, r.mb, r.nobs_per_cluster)
+        assert rel_close(f1, r.f1, 0) and rel_close(f2, r.f2, 0) and bool(f3) == r.f3
+    for r in g.of("branching_check_metrics"):
+        f1, f2, f3, feats = O.branching_check_metrics(D, r.ca, r.cb, r.ma, r.mb, r.nobs_per_cluster)
+        assert rel_close(f1, r.f1, 0) and bool(f3) == r.f3 and np.array_equal(np.array(feats, bool), r.feats.astype(bool))
+
+
+def test_norm_likelihoods_and_counts(gd):
+    g, D = gd
+    for r in g.of("linear_norm_likelihood"):
+        assert rel_close(O.linear_norm_likelihood(D, r.all_cells, r.cellsA, r.mutsA, r.mutsB), r.value)
+    for r in g.of("branching_norm_likelihood"):
+        assert rel_close(O.branching_norm_likelihood(D, r.all_cells, r.cellsA, r.cellsB, r.mutsA, r.mutsB, r.mutsC), r.value)
+    for r in g.of("check_obs") + g.of("count_obs"):
+        assert O.check_obs(D, r.cells, r.muts) == r.value
+    for r in g.of("seed_strip"):
+        c, m = O.seed_strip(D, r.cells, r.muts)
+        assert np.array_equal(c, r.cells_out) and np.array_equal(m, r.muts_out)
+
+
+def test_tree_level(gd):
+    g, D = gd
+    for r in g.of("variant_likelihood_by_node"):
+        assert rel_close(O.variant_likelihood_by_node(D, r.cells, r.present_muts), r.value)
+    for r in g.of("reassign_snv"):
+        sc = O.snv_node_scores(D, r.s, {int(k): r.cdict[i].astype(int) for i, k in enumerate(r.nodes)})
+        assert rel_close([sc[int(k)] for k in r.nodes], r.scores)
+    for r in g.of("find_bad_snvs"):
+        assert np.array_equal(O.find_bad_snvs(D, r.clade_cells, r.muts, r.q), r.bad)
+
+
+def test_gaussian_node_likelihood(gd):
+    g, D = gd
+    X = g.inputs["read_depth"].astype(float)
+    recs = g.of("read_depth_likelihood_by_node")
+    assert recs
+    for r in recs:
+        tot, per = O.gauss_node_loglik(X, r.cells)
+        assert rel_close(per, r.per_cell), (tot, r.value)
+        assert rel_close(tot, r.value)
+
+
+def test_pairwise_dist_matches_scipy(gd):
+    g, D = gd
+    X = g.inputs["read_depth"].astype(float)[:200]
+    d = O.pairwise_dist(X)
+    assert d.shape == (200, 200) and np.allclose(d, d.T) and np.all(np.diag(d) == 0)
