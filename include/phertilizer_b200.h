@@ -82,7 +82,7 @@ PH_API int ph_create(int32_t n_cells, int32_t n_snvs, int64_t nnz, const int32_t
 PH_API void ph_destroy(ph_handle* h);
 PH_API int ph_get_info(const ph_handle* h, ph_info* out);
 
-/* Tuning knob for experiments: lanes per SNV / per cell (4, 8, 16, 32) ; 0 = automatic. */
+/* Tuning knob for experiments: lanes per SNV / per cell (8, 16, 32) ; 0 = automatic. */
 PH_API int ph_set_group(ph_handle* h, int group_by_snv, int group_by_cell);
 
 /*

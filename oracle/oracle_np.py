@@ -128,6 +128,14 @@ def branching_mut_assignment(D: DenseData, cellsA, cellsB, muts, nobs_per_cluste
     return muts[isA], muts[isB], muts[~isA & ~isB]
 
 
+def branching_candidates(D: DenseData, cellsA, cellsB, muts):
+    """branching_split.py:332-337: the three candidate log-likelihoods per SNV."""
+    candA = _ix(D.like1, cellsA, muts).sum(axis=0) + _ix(D.like0, cellsB, muts).sum(axis=0)
+    candB = _ix(D.like0, cellsA, muts).sum(axis=0) + _ix(D.like1, cellsB, muts).sum(axis=0)
+    candC = _ix(D.like1, cellsA, muts).sum(axis=0) + _ix(D.like1, cellsB, muts).sum(axis=0)
+    return candA, candB, candC
+
+
 def weighted_init_vaf(D: DenseData, cells, muts):
     """linear_split.py:186-191: binary VAF per SNV and its normalisation."""
     bc = np.count_nonzero(_ix(D.var, cells, muts), axis=0)

@@ -75,9 +75,9 @@ __global__ void k_seg_offsets(const uint64_t* __restrict__ keys, int64_t nnz, in
 
 int choose_group(double avg) {
   // lanes cooperating on one line; each lane moves 16 B per step
-  if (avg >= 1536) return 16;
-  if (avg >= 192) return 8;
-  return 4;
+  if (avg >= 768) return 32;
+  if (avg >= 256) return 16;
+  return 8;
 }
 
 int build_orient(ph_handle* h, PhOrient* o, const int32_t* d_major, const int32_t* d_minor, const uint16_t* d_code,
@@ -146,6 +146,7 @@ extern "C" void ph_destroy(ph_handle* h) {
   cudaFree(h->d_u8);
   cudaFree(h->d_small);
   cudaFree(h->d_map);
+  cudaFree(h->d_counter);
   if (h->h_stage) cudaFreeHost(h->h_stage);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -174,6 +175,7 @@ extern "C" int ph_create(int32_t n_cells, int32_t n_snvs, int64_t nnz, const int
   h->device = device;
   h->sm_count = prop.multiProcessorCount;
   h->max_smem = (int)prop.sharedMemPerBlockOptin;
+  h->smem_per_sm = (int)prop.sharedMemPerMultiprocessor;
   h->n_cells = n_cells;
   h->n_snvs = n_snvs;
   h->n_codes = n_codes;
@@ -284,6 +286,7 @@ extern "C" int ph_create(int32_t n_cells, int32_t n_snvs, int64_t nnz, const int
   PH_TRY(cudaMalloc(&h->d_u8, (size_t)nmax + 16));
   PH_TRY(cudaMalloc(&h->d_small, 4096 * sizeof(double)));
   PH_TRY(cudaMalloc(&h->d_map, 65 * 65 + 64));
+  PH_TRY(cudaMalloc(&h->d_counter, 64));
   h->device_bytes += (int64_t)nmax * (3 + 4 + 2 * PH_MAX_FAST_CLUSTERS * 12) + 4096 * 8;
   h->h_stage_bytes = (size_t)nmax * (2 * PH_MAX_FAST_CLUSTERS * 12 + 8) + (1 << 16);
   PH_TRY(cudaMallocHost(&h->h_stage, h->h_stage_bytes));
@@ -329,8 +332,8 @@ extern "C" int ph_get_info(const ph_handle* h, ph_info* out) {
 
 extern "C" int ph_set_group(ph_handle* h, int group_by_snv, int group_by_cell) {
   if (!h) PH_FAIL(PH_ERR_ARG, "null handle");
-  auto ok = [](int g) { return g == 0 || g == 4 || g == 8 || g == 16 || g == 32; };
-  if (!ok(group_by_snv) || !ok(group_by_cell)) PH_FAIL(PH_ERR_ARG, "group must be 0, 4, 8, 16 or 32");
+  auto ok = [](int g) { return g == 0 || g == 8 || g == 16 || g == 32; };
+  if (!ok(group_by_snv) || !ok(group_by_cell)) PH_FAIL(PH_ERR_ARG, "group must be 0, 8, 16 or 32");
   if (group_by_snv) h->by_snv.group = group_by_snv;
   if (group_by_cell) h->by_cell.group = group_by_cell;
   return PH_OK;

@@ -48,6 +48,7 @@ struct ph_handle {
   int device;
   int sm_count;
   int max_smem;  // opt-in dynamic shared memory per block
+  int smem_per_sm;
   int32_t n_cells, n_snvs, n_codes;
   int64_t nnz;
   PhOrient by_snv, by_cell;
@@ -64,6 +65,7 @@ struct ph_handle {
   uint8_t* d_u8;         // [max(n,m)] label outputs
   double* d_small;       // [4096] small outputs (block sums, per-node)
   uint8_t* d_map;        // [65*65] class / member maps
+  unsigned* d_counter;   // batch dispenser of the pass kernels
   // pinned host staging
   uint8_t* h_stage;
   size_t h_stage_bytes;

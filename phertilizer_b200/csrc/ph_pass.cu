@@ -15,7 +15,6 @@ namespace {
 enum { MODE_TABLE = 0, MODE_LINEAR = 1, MODE_BRANCHING = 2, MODE_MAPPED = 3 };
 
 constexpr int kBlock = 512;  // threads per CTA, 1 CTA / SM, <= 128 registers per thread
-constexpr int kUnroll = 4;   // independent 16-byte loads in flight per lane
 
 struct PassArgs {
   const uint32_t* __restrict__ words;
@@ -36,24 +35,36 @@ struct PassArgs {
   const uint8_t* __restrict__ map;                       // MAPPED: [K+1][K+1] bytes, != 0 -> "present"
   int K;
   double* per_line;                                      // MAPPED
+  unsigned* counter;                                     // batch dispenser, zeroed before every launch
 };
 
 __device__ __forceinline__ uint4 ld_stream(const uint32_t* p) {
   uint4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-               : "l"(p));
+  asm("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+      : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+      : "l"(p));
   return v;
 }
 
-// raw label byte (0 excluded, 1..3) -> shift of its 10-bit counter field (excluded -> 30: spills off the top)
+// raw label byte (0 = excluded, 1..NC = cluster) -> bit position of its 10-bit counter field.  Excluded (and any
+// label > NC) lands in the field just above the counted ones; for NC = 3 that is bit 30 and simply spills off the top.
+template <int NC>
 __device__ __forceinline__ uint32_t scale_labels4(uint32_t w) {
+  constexpr uint32_t ex = PH_FIELD_BITS * NC;
+  constexpr uint32_t t2 = NC >= 2 ? PH_FIELD_BITS : ex, t3 = NC >= 3 ? 2 * PH_FIELD_BITS : ex;
+  constexpr uint32_t table = ex | (0u << 8) | (t2 << 16) | (t3 << 24);
   uint32_t sel = (w & 0x3u) | ((w >> 4) & 0x30u) | ((w >> 8) & 0x300u) | ((w >> 12) & 0x3000u);
-  return __byte_perm(0x140A001Eu, 0u, sel);
+  return __byte_perm(table, 0u, sel);
 }
 
-template <int G, int MODE, bool SMEM_LAB>
-__global__ void __launch_bounds__(kBlock, 1) k_pass(const PassArgs a) {
+// One warp walks a BATCH of B = 8 * (32 / G) lines handed out by an atomic counter.  G lanes cooperate on one line
+// (32 / G lines at a time): the dense part is counted cooperatively with coalesced 16-byte loads; the per-line totals
+// are then parked in "holder" lane (line % B).  After the batch every holder finishes ITS line alone -- rare-code tail,
+// fp64 sums, epilogue, store -- so the per-line scalar work is spread over the lanes instead of being replicated 32x.
+// NC = counted classes; MINB = resident CTAs per SM (2 when two copies of the label table fit in shared memory).
+template <int G, int MODE, int NC, bool SMEM_LAB>
+__global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
+  const int kBlock = blockDim.x;  // 512 (two CTAs per SM) or 1024 (one CTA per SM): 32 warps per SM either way
   extern __shared__ __align__(16) uint8_t smem[];
   // ---- shared memory carve-up: [labels][map][L0][L1][varpos]
   uint8_t* s_lab = smem;
@@ -67,7 +78,7 @@ __global__ void __launch_bounds__(kBlock, 1) k_pass(const PassArgs a) {
 
   if (SMEM_LAB) {
     const int nw = (a.n_minor + 3) >> 2;
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(a.minor_label);  // buffers are padded to 16 B
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(a.minor_label);  // buffers are padded to 4 B
     uint32_t* dst = reinterpret_cast<uint32_t*>(s_lab);
     for (int i = threadIdx.x; i < nw; i += kBlock) {
       uint32_t w = src[i];
@@ -82,7 +93,7 @@ __global__ void __launch_bounds__(kBlock, 1) k_pass(const PassArgs a) {
         }
         dst[i] = r;
       } else {
-        dst[i] = scale_labels4(w);
+        dst[i] = scale_labels4<NC>(w);
       }
     }
   }
@@ -103,163 +114,230 @@ __global__ void __launch_bounds__(kBlock, 1) k_pass(const PassArgs a) {
   const uint8_t* VP = a.lut_in_smem ? s_vp : a.varpos;
   const uint8_t* lab = SMEM_LAB ? s_lab : a.minor_label;
 
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr int NG = 32 / G;      // lines in flight per warp
+  constexpr int B = 8 * NG;       // lines per batch (holder lanes 0..B-1)
+  constexpr int PARTS = 32 / B;   // lanes sharing the tail of one line
+  constexpr int STEP = 4 * G;     // words per cooperative step
+  constexpr unsigned FM = (1u << PH_FIELD_BITS) - 1u;
   const int lane = threadIdx.x & 31;
   const int g = lane & (G - 1);
-  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
-  constexpr int groups_per_block = kBlock / G;
-  const int total_groups = gridDim.x * groups_per_block;
+  const int q = lane / G;
+  const unsigned gmask = (G == 32) ? FULL : (((1u << G) - 1u) << (lane & ~(G - 1)));
   const int D = a.D;
   const uint32_t mmask = (a.minor_bits >= 32) ? 0xffffffffu : ((1u << a.minor_bits) - 1u);
-  constexpr int STEP = 4 * G;
+  const int n_batches = (a.n_work + B - 1) / B;
 
-  for (int wi = blockIdx.x * groups_per_block + (threadIdx.x / G); wi < a.n_work; wi += total_groups) {
-    const int line = a.list ? a.list[wi] : wi;
-    const uint8_t* maprow = nullptr;
-    if (MODE == MODE_MAPPED) {
-      const uint32_t ml = a.major_label[line];
-      if (ml >= (uint32_t)a.K) {  // cell not in the tree: contributes nothing
-        if (g == 0) a.per_line[wi] = 0.0;
-        continue;
+  auto shift_of = [&](uint32_t minor, const uint8_t* maprow) -> uint32_t {
+    uint32_t l = SMEM_LAB ? (uint32_t)lab[minor] : (uint32_t)__ldg(lab + minor);
+    if (MODE == MODE_MAPPED) l = maprow[l];
+    return l;
+  };
+
+  for (;;) {
+    unsigned bidx = 0;
+    if (lane == 0) bidx = atomicAdd(a.counter, 1u);
+    bidx = __shfl_sync(FULL, bidx, 0);
+    if (bidx >= (unsigned)n_batches) break;
+
+    // ---- every lane loads the offsets of "its" line of the batch (lane % B); lanes >= B duplicate for the tail split
+    const int myw = (int)bidx * B + (lane % B);
+    const bool have = myw < a.n_work;
+    int64_t h_base = 0;
+    int h_rb[PH_DMAX + 1], h_rend = 0;
+#pragma unroll
+    for (int d = 0; d <= PH_DMAX; ++d) h_rb[d] = 0;
+    uint32_t h_ml = 0;
+    bool h_skip = !have;
+    if (have) {
+      const int line = a.list ? __ldg(a.list + myw) : myw;
+      const int64_t* p = a.seg_off + (int64_t)line * (D + 1);
+      const int64_t b0 = __ldg(p);
+      h_base = b0 & ~(int64_t)3;
+      h_rb[0] = (int)(b0 - h_base);
+#pragma unroll
+      for (int d = 1; d <= PH_DMAX; ++d) h_rb[d] = (int)(__ldg(p + (d < D ? d : D)) - h_base);
+      h_rend = (int)(__ldg(p + D + 1) - h_base);
+      if (MODE == MODE_MAPPED) {
+        h_ml = a.major_label[line];
+        if (h_ml >= (uint32_t)a.K) {  // cell not in the tree: contributes nothing
+          h_skip = true;
+          h_ml = 0;
+          h_rend = h_rb[0];
+#pragma unroll
+          for (int d = 1; d <= PH_DMAX; ++d) h_rb[d] = h_rb[0];
+        }
       }
-      maprow = s_map + ml * (a.K + 1);
     }
-    auto shift_of = [&](uint32_t minor) -> uint32_t {
-      uint32_t l = SMEM_LAB ? (uint32_t)lab[minor] : (uint32_t)__ldg(lab + minor);
-      if (MODE == MODE_MAPPED) l = maprow[l];
-      return l;
-    };
+    unsigned hcnt[PH_DMAX][NC];
+#pragma unroll
+    for (int d = 0; d < PH_DMAX; ++d)
+#pragma unroll
+      for (int c = 0; c < NC; ++c) hcnt[d][c] = 0;
 
-    const int64_t* so = a.seg_off + (int64_t)line * (D + 1);
-    const int64_t b0 = so[0];
-    const int64_t base = b0 & ~(int64_t)3;
-    int rb[PH_DMAX + 1];
-    rb[0] = (int)(b0 - base);
+    // ---- dense part: the warp's NG groups walk the batch, 8 rounds
+#pragma unroll 1
+    for (int it = 0; it < 8; ++it) {
+      const int src = it * NG + q;  // holder lane of my group's current line
+      const int64_t base = __shfl_sync(FULL, h_base, src);
+      int rb[PH_DMAX + 1];
 #pragma unroll
-    for (int d = 1; d <= PH_DMAX; ++d) rb[d] = (int)(so[d < D ? d : D] - base);
-    const int rD = rb[PH_DMAX];
-    const int rend = (int)(so[D + 1] - base);
-    const uint32_t* wp = a.words + base;
+      for (int d = 0; d <= PH_DMAX; ++d) rb[d] = __shfl_sync(FULL, h_rb[d], src);
+      const int rD = rb[PH_DMAX];
+      const uint8_t* maprow = nullptr;
+      if (MODE == MODE_MAPPED) maprow = s_map + __shfl_sync(FULL, h_ml, src) * (a.K + 1);
+      const uint32_t* wp = a.words + base;
 
-    unsigned cnt[PH_DMAX][3];
+      unsigned cnt[PH_DMAX][NC];
+      unsigned accd[PH_DMAX];
 #pragma unroll
-    for (int d = 0; d < PH_DMAX; ++d) cnt[d][0] = cnt[d][1] = cnt[d][2] = 0;
+      for (int d = 0; d < PH_DMAX; ++d) {
+        accd[d] = 0;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) cnt[d][c] = 0;
+      }
 
-    // ---------------- dense segments: count labels per code ----------------
-    int rp = g * 4;
-    while (rp < rD) {
-      unsigned acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
-      for (int blk = 0; blk < PH_CHUNK_ITERS / kUnroll && rp < rD; ++blk, rp += kUnroll * STEP) {
-        uint4 w[kUnroll];
+      // straddling 4-word groups: one per unaligned segment boundary, one word per lane
+      for (int k = g; k < 4 * (D + 1); k += G) {
+        const int e = k >> 2, t = k & 3;
+        const int be = e == 0 ? rb[0] : e == 1 ? rb[1] : e == 2 ? rb[2] : e == 3 ? rb[3] : rb[4];
+        const int bp = e <= 1 ? rb[0] : e == 2 ? rb[1] : e == 3 ? rb[2] : rb[3];
+        const bool mine = ((be & 3) != 0) && !(e > 0 && (bp & 3) != 0 && (bp >> 2) == (be >> 2));
+        const int qq = (be & ~3) + t;
+        if (mine && qq >= rb[0] && qq < rD) {
+          const unsigned inc = 1u << shift_of(__ldg(wp + qq), maprow);
+          const int dsel = (qq >= rb[1]) + (qq >= rb[2]) + (qq >= rb[3]);
+          if (dsel == 0) accd[0] += inc; else if (dsel == 1) accd[1] += inc; else if (dsel == 2) accd[2] += inc; else accd[3] += inc;
+        }
+      }
+
+      // aligned interior of every dense segment: double-buffered 16-byte loads through one running pointer
 #pragma unroll
-        for (int u = 0; u < kUnroll; ++u)
-          if (rp + u * STEP < rD) w[u] = ld_stream(wp + rp + u * STEP);
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-          const int r = rp + u * STEP;
-          if (r < rD) {
-            if (r >= rb[0] && r + 4 <= rb[1]) {
-              acc0 += (1u << shift_of(w[u].x)) + (1u << shift_of(w[u].y)) + (1u << shift_of(w[u].z)) + (1u << shift_of(w[u].w));
-            } else if (r >= rb[1] && r + 4 <= rb[2]) {
-              acc1 += (1u << shift_of(w[u].x)) + (1u << shift_of(w[u].y)) + (1u << shift_of(w[u].z)) + (1u << shift_of(w[u].w));
-            } else if (r >= rb[2] && r + 4 <= rb[3]) {
-              acc2 += (1u << shift_of(w[u].x)) + (1u << shift_of(w[u].y)) + (1u << shift_of(w[u].z)) + (1u << shift_of(w[u].w));
-            } else if (r >= rb[3] && r + 4 <= rb[4]) {
-              acc3 += (1u << shift_of(w[u].x)) + (1u << shift_of(w[u].y)) + (1u << shift_of(w[u].z)) + (1u << shift_of(w[u].w));
-            } else {
-              const uint32_t ww[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                const int q = r + t;
-                if (q >= rb[0] && q < rD) {
-                  const unsigned inc = 1u << shift_of(ww[t]);
-                  const int d = (q >= rb[1]) + (q >= rb[2]) + (q >= rb[3]);
-                  if (d == 0) acc0 += inc; else if (d == 1) acc1 += inc; else if (d == 2) acc2 += inc; else acc3 += inc;
-                }
-              }
+      for (int d = 0; d < PH_DMAX; ++d) {
+        if (d < D) {
+          const int A = (rb[d] + 3) & ~3;
+          const int E = rb[d + 1] & ~3;
+          constexpr int CH = 248 * STEP;  // a 10-bit field gains <= 4 per step: at most 248 steps between spills
+          unsigned acc = accd[d];
+          for (int c0 = A; c0 < E; c0 += CH) {
+            const int ce = (E - c0 > CH) ? c0 + CH : E;
+            const uint32_t* p = wp + c0 + 4 * g;
+            int left = ce - (c0 + 4 * g);
+            auto inc4 = [&](const uint4& w) -> unsigned {
+              return ((1u << shift_of(w.x, maprow)) + (1u << shift_of(w.y, maprow))) +
+                     ((1u << shift_of(w.z, maprow)) + (1u << shift_of(w.w, maprow)));
+            };
+            uint4 wa0, wa1, wb0, wb1;
+            if (left > 0) wa0 = ld_stream(p);
+            if (left > STEP) wa1 = ld_stream(p + STEP);
+            while (left > 0) {
+              if (left > 2 * STEP) wb0 = ld_stream(p + 2 * STEP);
+              if (left > 3 * STEP) wb1 = ld_stream(p + 3 * STEP);
+              acc += inc4(wa0);
+              if (left > STEP) acc += inc4(wa1);
+              if (left <= 2 * STEP) break;
+              if (left > 4 * STEP) wa0 = ld_stream(p + 4 * STEP);
+              if (left > 5 * STEP) wa1 = ld_stream(p + 5 * STEP);
+              acc += inc4(wb0);
+              if (left > 3 * STEP) acc += inc4(wb1);
+              p += 4 * STEP;
+              left -= 4 * STEP;
             }
+#pragma unroll
+            for (int c = 0; c < NC; ++c) cnt[d][c] += (acc >> (PH_FIELD_BITS * c)) & FM;
+            acc = 0;
           }
+          // segments without an aligned interior still carry their straddling-group counts
+#pragma unroll
+          for (int c = 0; c < NC; ++c) cnt[d][c] += (acc >> (PH_FIELD_BITS * c)) & FM;
         }
       }
-      const unsigned fm = (1u << PH_FIELD_BITS) - 1u;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        cnt[0][c] += (acc0 >> (PH_FIELD_BITS * c)) & fm;
-        cnt[1][c] += (acc1 >> (PH_FIELD_BITS * c)) & fm;
-        cnt[2][c] += (acc2 >> (PH_FIELD_BITS * c)) & fm;
-        cnt[3][c] += (acc3 >> (PH_FIELD_BITS * c)) & fm;
-      }
-    }
 
-    // ---------------- combine: integer counts -> fp64 sums (fixed order) ----------------
-    double s0[3] = {0.0, 0.0, 0.0}, s1[3] = {0.0, 0.0, 0.0};
-    unsigned nob[3] = {0, 0, 0}, nva[3] = {0, 0, 0};
+      // group totals -> holder lane
 #pragma unroll
-    for (int d = 0; d < PH_DMAX; ++d) {
-      if (d < D) {
-        const double l0 = L0[d], l1 = L1[d];
-        const bool vp = VP[d] != 0;
+      for (int d = 0; d < PH_DMAX; ++d) {
+        if (d < D) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const unsigned t = __reduce_add_sync(gmask, cnt[d][c]);
-          s0[c] = fma((double)t, l0, s0[c]);
-          s1[c] = fma((double)t, l1, s1[c]);
-          nob[c] += t;
-          nva[c] += vp ? t : 0u;
+          for (int c = 0; c < NC; ++c) {
+            unsigned t = __reduce_add_sync(gmask, cnt[d][c]);
+            if (NG > 1) t = __shfl_sync(FULL, t, (((lane % B) - it * NG) & (NG - 1)) * G);
+            if ((lane % B) / NG == it) hcnt[d][c] = t;
+          }
         }
       }
     }
 
-    // ---------------- tail: rare codes, word = minor | code << minor_bits ----------------
-    if (rend > rD) {
-      double t0[3] = {0.0, 0.0, 0.0}, t1[3] = {0.0, 0.0, 0.0};
-      unsigned tn = 0, tv = 0;  // packed 10-bit fields (a lane sees < 1024 tail entries per chunk)
-      int iter = 0;
-      for (int r0 = rD; r0 < rend; r0 += G, ++iter) {  // trip count is uniform across the group
-        const int r = r0 + g;
-        if (r < rend) {
-          const uint32_t w = wp[r];
-          const uint32_t code = w >> a.minor_bits;
-          const uint32_t sh = shift_of(w & mmask);
-          const double l0 = L0[code], l1 = L1[code];
-          const unsigned inc = 1u << sh;
-          tn += inc;
-          tv += VP[code] ? inc : 0u;
+    // ---- holders: tail (rare codes, word = minor | code << minor_bits), shared by PARTS lanes per line
+    const uint8_t* h_maprow = (MODE == MODE_MAPPED) ? s_map + h_ml * (a.K + 1) : nullptr;
+    double t0[NC], t1[NC];
+    unsigned tn[NC], tv[NC];
 #pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            if (sh == (uint32_t)(PH_FIELD_BITS * c)) {
-              t0[c] += l0;
-              t1[c] += l1;
-            }
+    for (int c = 0; c < NC; ++c) { t0[c] = 0.0; t1[c] = 0.0; tn[c] = 0; tv[c] = 0; }
+    {
+      const uint32_t* wp = a.words + h_base;
+      for (int r = h_rb[PH_DMAX] + lane / B; r < h_rend; r += PARTS) {
+        const uint32_t w = __ldg(wp + r);
+        const uint32_t code = w >> a.minor_bits;
+        const uint32_t sh = shift_of(w & mmask, h_maprow);
+        const double l0 = L0[code], l1 = L1[code];
+        const unsigned vp = VP[code] ? 1u : 0u;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          if (sh == (uint32_t)(PH_FIELD_BITS * c)) {
+            t0[c] += l0;
+            t1[c] += l1;
+            tn[c] += 1u;
+            tv[c] += vp;
           }
         }
-        if ((iter % 1000) == 999) {  // flush packed tail counters before a field can overflow
+      }
+    }
+    if (PARTS > 1) {
 #pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            nob[c] += __reduce_add_sync(gmask, (tn >> (PH_FIELD_BITS * c)) & 1023u);
-            nva[c] += __reduce_add_sync(gmask, (tv >> (PH_FIELD_BITS * c)) & 1023u);
+      for (int o = B; o < 32; o <<= 1) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          t0[c] += __shfl_xor_sync(FULL, t0[c], o);
+          t1[c] += __shfl_xor_sync(FULL, t1[c], o);
+          tn[c] += __shfl_xor_sync(FULL, tn[c], o);
+          tv[c] += __shfl_xor_sync(FULL, tv[c], o);
+        }
+      }
+    }
+
+    // ---- holders: integer counts -> fp64 sums in a fixed order, epilogue, store
+    if (lane < B && have) {
+      double s0[NC], s1[NC];
+      unsigned nob[NC], nva[NC];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) { s0[c] = 0.0; s1[c] = 0.0; nob[c] = 0; nva[c] = 0; }
+#pragma unroll
+      for (int d = 0; d < PH_DMAX; ++d) {
+        if (d < D) {
+          const double l0 = L0[d], l1 = L1[d];
+          const bool vp = VP[d] != 0;
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            const unsigned t = hcnt[d][c];
+            s0[c] = fma((double)t, l0, s0[c]);
+            s1[c] = fma((double)t, l1, s1[c]);
+            nob[c] += t;
+            nva[c] += vp ? t : 0u;
           }
-          tn = tv = 0;
         }
       }
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        nob[c] += __reduce_add_sync(gmask, (tn >> (PH_FIELD_BITS * c)) & 1023u);
-        nva[c] += __reduce_add_sync(gmask, (tv >> (PH_FIELD_BITS * c)) & 1023u);
-#pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) {
-          t0[c] += __shfl_xor_sync(gmask, t0[c], o);
-          t1[c] += __shfl_xor_sync(gmask, t1[c], o);
-        }
+      for (int c = 0; c < NC; ++c) {
         s0[c] += t0[c];
         s1[c] += t1[c];
+        nob[c] += tn[c];
+        nva[c] += tv[c];
       }
-    }
-
-    // ---------------- epilogue ----------------
-    if (g == 0) {
+      const int wi = myw;
       if (MODE == MODE_TABLE) {
-        for (int c = 0; c < a.C; ++c) {
-          const size_t o = (size_t)wi * a.C + c;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const size_t o = (size_t)wi * NC + c;
           if (a.S0) a.S0[o] = s0[c];
           if (a.S1) a.S1[o] = s1[c];
           if (a.Nobs) a.Nobs[o] = (int32_t)nob[c];
@@ -272,24 +350,25 @@ __global__ void __launch_bounds__(kBlock, 1) k_pass(const PassArgs a) {
         a.nobs_out[wi] = (int32_t)nob[0];
       } else if (MODE == MODE_BRANCHING) {
         // branching_split.py:332-346
-        const double cA = s1[0] + s0[1];
-        const double cB = s0[0] + s1[1];
-        const double cC = s1[0] + s1[1];
+        const double cA = s1[0] + s0[NC > 1 ? 1 : 0];
+        const double cB = s0[0] + s1[NC > 1 ? 1 : 0];
+        const double cC = s1[0] + s1[NC > 1 ? 1 : 0];
         const double mx = fmax(cA, fmax(cB, cC));
         a.label_out[wi] = (cA == mx) ? 1 : ((cB == mx) ? 2 : 3);
         a.nobs_out[2 * (size_t)wi] = (int32_t)nob[0];
-        a.nobs_out[2 * (size_t)wi + 1] = (int32_t)nob[1];
+        a.nobs_out[2 * (size_t)wi + 1] = (int32_t)nob[NC > 1 ? 1 : 0];
       } else {  // MODE_MAPPED: absent -> field 0 uses like0, present -> field 1 uses like1
-        a.per_line[wi] = s0[0] + s1[1];
+        a.per_line[wi] = h_skip ? 0.0 : s0[0] + s1[NC > 1 ? 1 : 0];
       }
     }
   }
 }
 
 // pre-scale labels for the global-memory label path
+template <int NC>
 __global__ void k_scale_labels(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < ((n + 3) >> 2)) reinterpret_cast<uint32_t*>(out)[i] = scale_labels4(reinterpret_cast<const uint32_t*>(in)[i]);
+  if (i < ((n + 3) >> 2)) reinterpret_cast<uint32_t*>(out)[i] = scale_labels4<NC>(reinterpret_cast<const uint32_t*>(in)[i]);
 }
 
 // deterministic block sums of a per-line table by the line's own label: out[(q-1)*C + c]
@@ -436,7 +515,7 @@ size_t pass_smem_bytes(const ph_handle* h, const PhOrient* o, int mode, int K, b
   return b;
 }
 
-template <int MODE>
+template <int MODE, int NC>
 int launch_pass(ph_handle* h, const PhOrient* o, PassArgs& a, cudaStream_t st) {
   if (a.n_work <= 0) return PH_OK;
   int lut = 0;
@@ -451,28 +530,45 @@ int launch_pass(ph_handle* h, const PhOrient* o, PassArgs& a, cudaStream_t st) {
   if (!smem_lab) {
     if (MODE == MODE_MAPPED) PH_FAIL(PH_ERR_UNSUPPORTED, "tree pass needs the %d minor labels in shared memory", o->n_minor);
     // pre-scale into scratch; d_lab_major is free in every non-MAPPED mode
-    k_scale_labels<<<((o->n_minor + 3) / 4 + 255) / 256, 256, 0, st>>>(raw, h->d_lab_major, o->n_minor);
+    k_scale_labels<NC><<<((o->n_minor + 3) / 4 + 255) / 256, 256, 0, st>>>(raw, h->d_lab_major, o->n_minor);
     ph_count_launch();
     a.minor_label = h->d_lab_major;
   }
-  const int grid = h->sm_count;
+  // two CTAs per SM when two copies of the shared-memory image fit (each CTA also pays 1 KB of reserved smem)
+  const bool two = !smem_lab || 2 * (smem + 1024) <= (size_t)h->smem_per_sm;
+  const int grid = h->sm_count * (two ? 2 : 1);
+  a.counter = h->d_counter;
+  PH_CUDA(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned), st));
+  const int threads = two ? 512 : 1024;
 #define PH_LAUNCH(GG, SL)                                                                                        \
   do {                                                                                                           \
-    auto kern = k_pass<GG, MODE, SL>;                                                                            \
+    auto kern = k_pass<GG, MODE, NC, SL>;                                                                        \
     PH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->max_smem));          \
-    kern<<<grid, kBlock, smem, st>>>(a);                                                                         \
+    kern<<<grid, threads, smem, st>>>(a);                                                                        \
+  } while (0)
+#define PH_LAUNCH_G(GG)                                                        \
+  do {                                                                         \
+    if (!smem_lab) PH_LAUNCH(GG, false);                                       \
+    else PH_LAUNCH(GG, true);                                                  \
   } while (0)
   switch (o->group) {
-    case 4: if (smem_lab) PH_LAUNCH(4, true); else PH_LAUNCH(4, false); break;
-    case 8: if (smem_lab) PH_LAUNCH(8, true); else PH_LAUNCH(8, false); break;
-    case 16: if (smem_lab) PH_LAUNCH(16, true); else PH_LAUNCH(16, false); break;
-    default: if (smem_lab) PH_LAUNCH(32, true); else PH_LAUNCH(32, false); break;
+    case 8: PH_LAUNCH_G(8); break;
+    case 16: PH_LAUNCH_G(16); break;
+    default: PH_LAUNCH_G(32); break;
   }
+#undef PH_LAUNCH_G
 #undef PH_LAUNCH
   ph_count_launch();
   PH_CUDA(cudaGetLastError());
   const_cast<PhOrient*>(o)->labels_in_smem = smem_lab ? 1 : 0;
   return PH_OK;
+}
+
+template <int MODE>
+int launch_table(ph_handle* h, const PhOrient* o, PassArgs& a, cudaStream_t st) {
+  if (a.C == 1) return launch_pass<MODE, 1>(h, o, a, st);
+  if (a.C == 2) return launch_pass<MODE, 2>(h, o, a, st);
+  return launch_pass<MODE, 3>(h, o, a, st);
 }
 
 void fill_common(const ph_handle* h, const PhOrient* o, PassArgs& a) {
@@ -529,10 +625,10 @@ int run_fast(ph_handle* h, PhOrient* o, int mode, const uint8_t* minor_label, in
     a.minor_label = minor_label;
     a.list = list;
     a.S0 = S0; a.S1 = S1; a.Nobs = Nobs; a.Nvar = Nvar; a.label_out = label_out; a.nobs_out = nobs_out;
-    if (mode == MODE_TABLE) return launch_pass<MODE_TABLE>(h, o, a, st);
+    if (mode == MODE_TABLE) return launch_table<MODE_TABLE>(h, o, a, st);
     if (!label_out || !nobs_out) PH_FAIL(PH_ERR_ARG, "output pointer is NULL");
-    if (mode == MODE_LINEAR) return launch_pass<MODE_LINEAR>(h, o, a, st);
-    return launch_pass<MODE_BRANCHING>(h, o, a, st);
+    if (mode == MODE_LINEAR) return launch_pass<MODE_LINEAR, 1>(h, o, a, st);
+    return launch_pass<MODE_BRANCHING, 2>(h, o, a, st);
   }
   // host pointers: validate, stage through pinned memory, run on the private stream, copy back, sync
   int rc = check_labels(minor_label, o->n_minor, C, "label");
@@ -559,7 +655,7 @@ int run_fast(ph_handle* h, PhOrient* o, int mode, const uint8_t* minor_label, in
   int32_t* dNv = h->d_i32 + (size_t)o->n_major * PH_MAX_FAST_CLUSTERS;
   if (mode == MODE_TABLE) {
     a.S0 = S0 ? dS0 : nullptr; a.S1 = S1 ? dS1 : nullptr; a.Nobs = Nobs ? dNo : nullptr; a.Nvar = Nvar ? dNv : nullptr;
-    rc = launch_pass<MODE_TABLE>(h, o, a, st);
+    rc = launch_table<MODE_TABLE>(h, o, a, st);
     if (rc != PH_OK) return rc;
     double* pS0 = S0 ? (double*)pin.take(nt * 8) : nullptr;
     double* pS1 = S1 ? (double*)pin.take(nt * 8) : nullptr;
@@ -579,7 +675,7 @@ int run_fast(ph_handle* h, PhOrient* o, int mode, const uint8_t* minor_label, in
   if (!label_out || !nobs_out) PH_FAIL(PH_ERR_ARG, "output pointer is NULL");
   a.label_out = h->d_u8;
   a.nobs_out = dNo;
-  rc = mode == MODE_LINEAR ? launch_pass<MODE_LINEAR>(h, o, a, st) : launch_pass<MODE_BRANCHING>(h, o, a, st);
+  rc = mode == MODE_LINEAR ? launch_pass<MODE_LINEAR, 1>(h, o, a, st) : launch_pass<MODE_BRANCHING, 2>(h, o, a, st);
   if (rc != PH_OK) return rc;
   uint8_t* pL = (uint8_t*)pin.take(n_list);
   int32_t* pN = (int32_t*)pin.take((size_t)n_list * 4 * nobs_per);
@@ -654,7 +750,7 @@ extern "C" int ph_block_sums(ph_handle* h, const uint8_t* cell_label, int32_t C,
   int32_t* dNo = h->d_i32;
   int32_t* dNv = h->d_i32 + (size_t)o->n_major * PH_MAX_FAST_CLUSTERS;
   a.S0 = dS0; a.S1 = dS1; a.Nobs = dNo; a.Nvar = dNv;
-  int rc = launch_pass<MODE_TABLE>(h, o, a, st);
+  int rc = launch_table<MODE_TABLE>(h, o, a, st);
   if (rc != PH_OK) return rc;
   const int nb = Q * C;
   double* d0 = on_device ? sum0 : h->d_small;
@@ -718,7 +814,7 @@ extern "C" int ph_tree_loglik(ph_handle* h, const uint8_t* cell_node, const uint
   a.map = h->d_map;
   double* d_pc = (on_device && per_cell) ? per_cell : h->d_f64;
   a.per_line = d_pc;
-  int rc = launch_pass<MODE_MAPPED>(h, o, a, st);
+  int rc = launch_pass<MODE_MAPPED, 2>(h, o, a, st);
   if (rc != PH_OK) return rc;
   double* d_pn = on_device ? per_node : h->d_small;
   k_node_reduce<<<K, 1024, 0, st>>>(d_pc, d_cn, h->n_cells, d_pn);

@@ -6,6 +6,8 @@ from phertilizer_b200.synth import make_config
 from phertilizer_b200.store import ObservationStore
 
 name = sys.argv[1] if len(sys.argv) > 1 else "C3"
+GS = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [8, 16, 32]
+REPS = int(sys.argv[3]) if len(sys.argv) > 3 else 10
 dev = torch.device("cuda:0")
 t = time.time()
 s = make_config(name, device=dev, with_embedding=False)
@@ -25,7 +27,7 @@ S0 = torch.empty(max(s.n, s.m) * 3, dtype=torch.float64, device=dev); S1 = torch
 No = torch.empty(max(s.n, s.m) * 3, dtype=torch.int32, device=dev); Nv = torch.empty_like(No)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-def timeit(fn, reps=10):
+def timeit(fn, reps=REPS):
     for _ in range(3): fn()
     torch.cuda.synchronize()
     ts = []
@@ -38,7 +40,7 @@ def timeit(fn, reps=10):
     return ts[len(ts) // 2]
 
 stream = None
-for G in (4, 8, 16, 32):
+for G in GS:
     st.set_group(G, G)
     r = {}
     r["lin"] = timeit(lambda: st.assign_linear_dev(cl, s.n / 2, lab_out, nobs_out))
