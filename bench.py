@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py -- likelihood hot path of Phertilizer on B200: nnz/s of one SNV-reassignment pass.
+
+A "step" is one pass of the hot path over all observations: the SNV reassignment of the linear split
+(reference linear_split.py:203-237, `Linear_split.mut_assignment`) = K1 (per-SNV like0/like1 sums + observation
+counts over cellsA) fused with K1a (mean-likelihood decision), for a balanced random cellsA and all SNVs active.
+Workload (BASELINE.json configs[2], the one the north-star target is quoted on; it fits one GPU): synthetic
+100k cells x 200k SNVs at 0.02x coverage, 12 clones, ~396 M observations.  With --gpus N the cells are sharded
+across ranks (strong scaling: the total work is fixed) and the per-SNV partial tables are combined with one NCCL
+all-reduce per step.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C3]
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "likelihood_nnz_per_sec"
+UNIT = "nnz/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons of one GPU while a timed region runs (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows if len(r) > 3 + i)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------------------ data
+def make_workload(name, device, lo_frac=0.0, hi_frac=1.0):
+    """Synthetic COO of the named config; keeps only the cells of this rank's block."""
+    import torch
+
+    from phertilizer_b200.synth import CONFIGS, make_config
+
+    s = make_config(name, device=device, with_embedding=False)
+    n = s.n
+    lo, hi = int(round(lo_frac * n)), int(round(hi_frac * n))
+    nnz_total = s.nnz
+    if lo > 0 or hi < n:
+        keep = (s.cell >= lo) & (s.cell < hi)
+        cell, snv, var, total = (s.cell[keep] - lo).contiguous(), s.snv[keep].contiguous(), s.var[keep].contiguous(), s.total[keep].contiguous()
+    else:
+        cell, snv, var, total = s.cell, s.snv, s.var, s.total
+    cfg = dict(CONFIGS[name])
+    return dict(n=n, m=s.m, lo=lo, hi=hi, n_local=hi - lo, cell=cell, snv=snv, var=var, total=total, nnz_total=nnz_total,
+                nnz_local=int(cell.numel()), cfg=cfg)
+
+
+def alg_bytes(nnz, n, m, C=1):
+    """nnz*(4 B index + 2 B (var,total) code) + (m+1)*8 offsets + n labels + m*C*24 outputs."""
+    return nnz * 6 + (m + 1) * 8 + n + m * C * 24
+
+
+def host_csc(w, code_t):
+    """Device COO -> host CSC (colptr, row, code) for the CPU oracle; the sort runs on the GPU (plumbing)."""
+    import torch
+
+    key = w["snv"].to(torch.int64) * w["n_local"] + w["cell"].to(torch.int64)
+    order = torch.argsort(key)
+    del key
+    row = w["cell"][order].cpu().numpy()
+    code = code_t[order].cpu().numpy().astype(np.uint16)
+    cnt = torch.bincount(w["snv"].to(torch.int64), minlength=w["m"]).cpu().numpy()
+    colptr = np.zeros(w["m"] + 1, np.int64)
+    np.cumsum(cnt, out=colptr[1:])
+    del order
+    return colptr, row, code
+
+
+def cpu_linear_passes(orc, labels, lenA, budget_s, max_passes):
+    t_tot, passes, out = 0.0, 0, None
+    while passes < max_passes and (t_tot < budget_s or passes < 2):
+        t0 = time.perf_counter()
+        out = orc.assign_linear(labels[passes % len(labels)], lenA[passes % len(labels)])
+        t_tot += time.perf_counter() - t0
+        passes += 1
+    return t_tot, passes, out
+
+
+# ------------------------------------------------------------------------------------------------ arms
+def run_reference(args):
+    """CPU arm: the sparse oracle port of the reference path (OpenMP, all host cores) on the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+
+    from oracle.oracle_sparse import SparseOracle, threads
+    from phertilizer_b200.like_lut import like_tables
+    from phertilizer_b200.store import encode_pairs_device
+
+    dev = "cuda:0" if torch.cuda.is_available() else "cpu"
+    t0 = time.time()
+    w = make_workload(args.workload, dev)
+    pv, pt, code_t = encode_pairs_device(w["var"], w["total"])
+    L0, L1 = like_tables(pv, pt)
+    colptr, row, code = host_csc(w, code_t)
+    orc = SparseOracle.from_csc(w["n"], w["m"], colptr, row, code, L0, L1, pv > 0)
+    log(f"[reference] data ready in {time.time() - t0:.1f}s, nnz={w['nnz_total']}, threads={threads()}")
+    rng = np.random.default_rng(7)
+    labels = [(rng.random(w["n"]) < 0.5).astype(np.uint8) for _ in range(4)]
+    lenA = [float(l.sum()) for l in labels]
+    for i in range(args.warmup):
+        orc.assign_linear(labels[i % 4], lenA[i % 4])
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        orc.assign_linear(labels[i % 4], lenA[i % 4])
+    dt = time.perf_counter() - t0
+    value = args.steps * w["nnz_total"] / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, w, 1, "host memory (no GPU on this arm)"),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads(), "kind": "port",
+                         "sample": f"all {w['nnz_total']} observations, {args.steps} timed passes; the dense reference "
+                                   "cannot allocate this shape (4 x 160 GB), oracle/oracle_sparse.c restates its sums over CSC"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, w, world, residency):
+    c = w["cfg"]
+    return {"workload": f"{args.workload}: synthetic {c['n']} cells x {c['m']} SNVs, coverage {c['cov']}, {c['K']} clones "
+                        f"(BASELINE.json configs[2]); step = linear-split SNV reassignment pass (K1+K1a) over all observations",
+            "nnz": w["nnz_total"], "cells": c["n"], "snvs": c["m"], "coverage": c["cov"], "clones": c["K"],
+            "sharding": f"cells sharded over {world} rank(s), all-reduce of the [S0|S1|Nobs] table" if world > 1 else "single GPU",
+            "l2_policy": "inputs larger than L2 (1.6 GB of observations per pass vs 126 MB L2); label vectors rotate every step",
+            "residency": residency}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from phertilizer_b200 import _lib
+    from phertilizer_b200.store import ObservationStore, encode_pairs_device
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl=ours) needs a CUDA device: phertilizer_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    t0 = time.time()
+    w = make_workload(args.workload, dev, rank / world, (rank + 1) / world)
+    n_loc, m, nnz_loc, nnz_tot = w["n_local"], w["m"], w["nnz_local"], w["nnz_total"]
+    pv, pt, code_t = encode_pairs_device(w["var"], w["total"]) if (rank == 0 and world == 1 and not args.no_cpu) else (None, None, None)
+    st = ObservationStore.from_coo(n_loc, m, w["cell"], w["snv"], w["var"], w["total"], device=local)
+    torch.cuda.synchronize()
+    info = st.info()
+    log(f"[rank {rank}] store ready in {time.time() - t0:.1f}s: {info}")
+
+    # label sets: balanced random cellsA (global draw, local slice), rotating so no step repeats its predecessor
+    P = 4
+    g = torch.Generator(device="cpu")
+    g.manual_seed(7)
+    labs_h, labs_d, lenA = [], [], []
+    for _ in range(P):
+        full = (torch.rand(w["n"], generator=g) < 0.5).to(torch.uint8)
+        lenA.append(float(full.sum()))
+        loc = torch.zeros(n_loc + 16, dtype=torch.uint8)
+        loc[:n_loc] = full[w["lo"]:w["hi"]]
+        labs_h.append(loc.pin_memory())
+        labs_d.append(loc.to(dev))
+    lab_out = torch.empty(m + 16, dtype=torch.uint8, device=dev)
+    nobs_out = torch.empty(m, dtype=torch.int32, device=dev)
+    packed = torch.empty(3 * m, dtype=torch.float64, device=dev) if world > 1 else None
+    lab_out_h = torch.empty(m + 16, dtype=torch.uint8).pin_memory()
+    nobs_out_h = torch.empty(m, dtype=torch.int32).pin_memory()
+    stream = torch.cuda.current_stream().cuda_stream
+
+    kern_ev = []
+
+    def step_device(i, record=False):
+        if world == 1:
+            st.assign_linear_dev(labs_d[i % P], lenA[i % P], lab_out, nobs_out, stream=stream)
+        else:
+            if record:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            st.snv_partial_dev(labs_d[i % P], 1, packed, stream=stream)
+            if record:
+                e1.record()
+                kern_ev.append((e0, e1))
+            dist.all_reduce(packed)
+            ObservationStore.finish_linear_dev(packed, m, lenA[i % P], lab_out, nobs_out, stream=stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput (value) ----------------
+    for i in range(args.warmup):
+        step_device(i)
+    barrier()
+    launches0 = _lib.kernel_launches()
+    with ClockSampler(local) as clk:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for i in range(args.steps):
+            step_device(args.warmup + i, record=True)
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.kernel_launches() - launches0
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        launches += args.steps  # the NCCL all-reduce kernel of every step
+    value = args.steps * nnz_tot / (ms * 1e-3)
+    kernel_ms = (sum(a.elapsed_time(b) for a, b in kern_ev) / len(kern_ev)) if kern_ev else ms / args.steps
+
+    # ---------------- end to end through the C-ABI with HOST buffers ----------------
+    def step_e2e(i):
+        if world == 1:
+            # ph_assign_linear(on_device=0): pinned staging, H2D labels, kernel, D2H labels + counts, sync
+            return st.assign_linear(labs_h[i % P].numpy()[:n_loc], lenA[i % P])
+        labs_d[i % P].copy_(labs_h[i % P], non_blocking=True)
+        st.snv_partial_dev(labs_d[i % P], 1, packed, stream=stream)
+        dist.all_reduce(packed)
+        ObservationStore.finish_linear_dev(packed, m, lenA[i % P], lab_out, nobs_out, stream=stream)
+        lab_out_h.copy_(lab_out, non_blocking=True)
+        nobs_out_h.copy_(nobs_out, non_blocking=True)
+        torch.cuda.synchronize()
+        return lab_out_h, nobs_out_h
+
+    for i in range(min(args.warmup, 3)):
+        step_e2e(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step_e2e(i)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = args.steps * nnz_tot / e2e_s
+
+    # ---------------- CPU baseline (rank 0, N = 1): the oracle port on the host cores, and a parity spot check ----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle.oracle_sparse import SparseOracle, threads
+        from phertilizer_b200.like_lut import like_tables
+
+        t0 = time.time()
+        L0, L1 = like_tables(pv, pt)
+        colptr, row, code = host_csc(w, code_t)
+        orc = SparseOracle.from_csc(w["n"], m, colptr, row, code, L0, L1, pv > 0)
+        log(f"[cpu] host CSC ready in {time.time() - t0:.1f}s")
+        hl = [l.numpy()[:n_loc] for l in labs_h]
+        t_tot, passes, (o_lab, o_nobs) = cpu_linear_passes(orc, hl, lenA, args.cpu_seconds, 40)
+        g_lab, g_nobs = st.assign_linear(hl[(passes - 1) % P], lenA[(passes - 1) % P])
+        same = bool(np.array_equal(g_lab, o_lab) and np.array_equal(g_nobs, o_nobs))
+        log(f"[cpu] {passes} passes in {t_tot:.2f}s on {threads()} threads; GPU labels == oracle labels: {same}")
+        if not same:
+            raise SystemExit("bench: GPU assignment differs from the CPU oracle on the benchmark workload")
+        cpu = {"value": passes * nnz_tot / t_tot, "unit": UNIT, "cores": threads(), "kind": "port",
+               "sample": f"all {nnz_tot} observations x {passes} passes of oracle/oracle_sparse.c orc_assign_linear (OpenMP); "
+                         "the dense numpy reference cannot allocate this shape (4 x 160 GB)",
+               "gpu_matches_oracle": same}
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (burst copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        ab = alg_bytes(nnz_loc, n_loc, m, 1)
+        achieved = ab / (kernel_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{args.workload}_assign_linear_dram_bytes")
+        except Exception:
+            pass
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, w, world, "observations resident in HBM; `value` also has labels resident, `e2e` copies them every step"),
+            "clocks": clk.summary(),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n_loc) * world, "d2h_bytes_per_step": 5 * m * world,
+                    "ms_per_step": 1e3 * e2e_s / args.steps,
+                    "path": "ph_assign_linear(on_device=0): host labels -> pinned -> H2D, kernel, D2H SNV labels + Nobs, sync"
+                            if world == 1 else "pinned H2D labels, ph_snv_partial, NCCL all-reduce, ph_finish_linear, D2H labels + Nobs"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "k_pass<MODE_LINEAR>" if world == 1 else "k_pass<MODE_TABLE>",
+                         "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": ab, "physical_bytes_per_nnz": 4,
+                         "physical_gbs": (4 * nnz_loc + (m * (info['dense_codes_by_snv'] + 1) + 1) * 8) / (kernel_ms * 1e-3) / 1e9,
+                         "peak_source": peak_src + ", of measured"},
+            "cpu_baseline": cpu,
+            "store": {k: info[k] for k in ("dense_codes_by_snv", "group_by_snv", "labels_in_smem_by_snv", "device_bytes")},
+        }
+        print(json.dumps(line), flush=True)
+    st.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C3")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU baseline budget (N=1 only)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

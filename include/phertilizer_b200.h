@@ -120,6 +120,19 @@ PH_API int ph_assign_branching(ph_handle* h, const uint8_t* cell_label, const in
                         uint8_t* label_out, int32_t* nobs_out, int on_device, void* stream);
 
 /*
+ * Cell-sharded K1 (multi-GPU): every rank holds a contiguous block of cells and all SNVs.
+ * ph_snv_partial writes THIS rank's partial table packed as  [S0 | S1 | Nobs]  (3 * n_list * C doubles, counts are
+ * exact in a double) so that one sum all-reduce (NCCL over NVLink) combines the ranks; ph_finish_linear /
+ * ph_finish_branching then apply the K1a decision rules of ph_assign_linear / ph_assign_branching to the summed
+ * table (C = 1 resp. 2).  Device pointers only; enqueued on `stream` of the current device.
+ */
+PH_API int ph_snv_partial(ph_handle* h, const uint8_t* cell_label, int32_t C, const int32_t* snv_list, int32_t n_list,
+                   double* packed, int on_device, void* stream);
+PH_API int ph_finish_linear(const double* packed, int32_t n_list, double lenA, uint8_t* label_out, int32_t* nobs_out,
+                     void* stream);
+PH_API int ph_finish_branching(const double* packed, int32_t n_list, uint8_t* label_out, int32_t* nobs_out, void* stream);
+
+/*
  * K2 -- per-cell table over SNV clusters (transpose of K1).
  *   A0[i,q] = sum_{j in cluster q} like0[i,j], A1 likewise, Nobs[i,q], Nvar[i,q].
  * Replaces: linear_split.py:301-304 (tmb features), 400-410 (check_metrics), check_reads axis=1;

@@ -35,6 +35,7 @@ EXPORTS = [
     "ph_last_error", "ph_abi_version", "ph_kernel_launches", "ph_create", "ph_destroy", "ph_get_info", "ph_set_group",
     "ph_snv_table", "ph_assign_linear", "ph_assign_branching", "ph_cell_table", "ph_block_sums", "ph_tree_loglik",
     "ph_snv_node_table", "ph_cell_node_table", "ph_gauss_node_ll", "ph_pairwise_dist",
+    "ph_snv_partial", "ph_finish_linear", "ph_finish_branching",
 ]
 
 _lib = None
@@ -67,6 +68,9 @@ def lib():
     L.ph_tree_loglik.argtypes = [_vp, _vp, _vp, _vp, C.c_int32, _vp, _vp, C.c_int, _vp]
     L.ph_snv_node_table.argtypes = [_vp, _vp, _vp, C.c_int32, _vp, C.c_int32, _vp, C.c_int, _vp]
     L.ph_cell_node_table.argtypes = L.ph_snv_node_table.argtypes
+    L.ph_snv_partial.argtypes = [_vp, _vp, C.c_int32, _vp, C.c_int32, _vp, C.c_int, _vp]
+    L.ph_finish_linear.argtypes = [_vp, C.c_int32, C.c_double, _vp, _vp, _vp]
+    L.ph_finish_branching.argtypes = [_vp, C.c_int32, _vp, _vp, _vp]
     L.ph_gauss_node_ll.argtypes = [_vp, _vp, C.c_int32, _vp, C.c_int32, _vp, _vp, C.c_int, _vp]
     L.ph_pairwise_dist.argtypes = [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, C.c_int, C.c_int, _vp]
     for name in EXPORTS:

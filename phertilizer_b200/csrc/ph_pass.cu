@@ -30,6 +30,7 @@ struct PassArgs {
   int lut_in_smem;
   int C;
   double* S0; double* S1; int32_t* Nobs; int32_t* Nvar;  // TABLE
+  double* NobsF;                                         // TABLE: Nobs as double (packed all-reduce buffer)
   uint8_t* label_out; int32_t* nobs_out; double lenA;    // LINEAR / BRANCHING
   const uint8_t* __restrict__ major_label;               // MAPPED: label of each line (255 = skip)
   const uint8_t* __restrict__ map;                       // MAPPED: [K+1][K+1] bytes, != 0 -> "present"
@@ -342,6 +343,7 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
           if (a.S1) a.S1[o] = s1[c];
           if (a.Nobs) a.Nobs[o] = (int32_t)nob[c];
           if (a.Nvar) a.Nvar[o] = (int32_t)nva[c];
+          if (a.NobsF) a.NobsF[o] = (double)nob[c];
         }
       } else if (MODE == MODE_LINEAR) {
         // linear_split.py:229-234  like0.mean(axis=0) >= like1.mean(axis=0) -> mutsB (ties -> mutsB)
@@ -913,4 +915,73 @@ extern "C" int ph_cell_node_table(ph_handle* h, const uint8_t* snv_node, const u
                                   const int32_t* cell_list, int32_t n_list, double* T, int on_device, void* stream) {
   if (!h) PH_FAIL(PH_ERR_ARG, "null handle");
   return run_node_table(h, &h->by_cell, snv_node, member, K, cell_list, n_list, T, on_device, stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// cell-sharded (multi-GPU) K1: per-rank partial tables packed for ONE all-reduce, then the K1a epilogue on the sum
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void k_finish_linear(const double* __restrict__ t, int k, double lenA, uint8_t* __restrict__ label,
+                                int32_t* __restrict__ nobs) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= k) return;
+  const double m0 = t[j] / lenA, m1 = t[(size_t)k + j] / lenA;  // linear_split.py:229-232
+  label[j] = (m0 >= m1) ? 2 : 1;
+  nobs[j] = (int32_t)t[2 * (size_t)k + j];
+}
+__global__ void k_finish_branching(const double* __restrict__ t, int k, uint8_t* __restrict__ label,
+                                   int32_t* __restrict__ nobs) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= k) return;
+  const size_t kc = 2 * (size_t)k;  // packed [3][k][2]
+  const double s0a = t[2 * (size_t)j], s0b = t[2 * (size_t)j + 1];
+  const double s1a = t[kc + 2 * (size_t)j], s1b = t[kc + 2 * (size_t)j + 1];
+  const double cA = s1a + s0b, cB = s0a + s1b, cC = s1a + s1b;  // branching_split.py:332-346
+  const double mx = fmax(cA, fmax(cB, cC));
+  label[j] = (cA == mx) ? 1 : ((cB == mx) ? 2 : 3);
+  nobs[2 * (size_t)j] = (int32_t)t[2 * kc + 2 * (size_t)j];
+  nobs[2 * (size_t)j + 1] = (int32_t)t[2 * kc + 2 * (size_t)j + 1];
+}
+}  // namespace
+
+extern "C" int ph_snv_partial(ph_handle* h, const uint8_t* cell_label, int32_t C, const int32_t* snv_list, int32_t n_list,
+                              double* packed, int on_device, void* stream) {
+  if (!h) PH_FAIL(PH_ERR_ARG, "null handle");
+  if (!on_device) PH_FAIL(PH_ERR_UNSUPPORTED, "ph_snv_partial works on device buffers only (it feeds an all-reduce)");
+  if (!cell_label || !packed) PH_FAIL(PH_ERR_ARG, "null pointer");
+  if (C < 1 || C > PH_MAX_FAST_CLUSTERS) PH_FAIL(PH_ERR_ARG, "C=%d outside 1..%d", C, PH_MAX_FAST_CLUSTERS);
+  PhOrient* o = &h->by_snv;
+  if (!snv_list) n_list = o->n_major;
+  if (n_list < 0 || n_list > o->n_major) PH_FAIL(PH_ERR_ARG, "n_list=%d out of range", n_list);
+  PH_CUDA(cudaSetDevice(h->device));
+  PassArgs a;
+  fill_common(h, o, a);
+  a.C = C;
+  a.n_work = n_list;
+  a.minor_label = cell_label;
+  a.list = snv_list;
+  const size_t kc = (size_t)n_list * C;
+  a.S0 = packed;
+  a.S1 = packed + kc;
+  a.NobsF = packed + 2 * kc;
+  return launch_table<MODE_TABLE>(h, o, a, (cudaStream_t)stream);
+}
+
+extern "C" int ph_finish_linear(const double* packed, int32_t n_list, double lenA, uint8_t* label_out, int32_t* nobs_out,
+                                void* stream) {
+  if (!packed || !label_out || !nobs_out) PH_FAIL(PH_ERR_ARG, "null pointer");
+  if (n_list <= 0) return PH_OK;
+  k_finish_linear<<<(n_list + 255) / 256, 256, 0, (cudaStream_t)stream>>>(packed, n_list, lenA, label_out, nobs_out);
+  ph_count_launch();
+  PH_CUDA(cudaGetLastError());
+  return PH_OK;
+}
+
+extern "C" int ph_finish_branching(const double* packed, int32_t n_list, uint8_t* label_out, int32_t* nobs_out, void* stream) {
+  if (!packed || !label_out || !nobs_out) PH_FAIL(PH_ERR_ARG, "null pointer");
+  if (n_list <= 0) return PH_OK;
+  k_finish_branching<<<(n_list + 255) / 256, 256, 0, (cudaStream_t)stream>>>(packed, n_list, label_out, nobs_out);
+  ph_count_launch();
+  PH_CUDA(cudaGetLastError());
+  return PH_OK;
 }

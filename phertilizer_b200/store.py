@@ -37,6 +37,30 @@ def _padded_u8(n: int, fill: int = 0) -> np.ndarray:
     return buf[:n]
 
 
+def torch_int32():
+    import torch
+
+    return torch.int32
+
+
+def encode_pairs_device(var, total):
+    """Device twin of like_lut.encode_pairs: distinct (var,total) pairs by descending frequency, int16 codes."""
+    import torch
+
+    width = int(var.max().item()) + 1 if var.numel() else 1
+    key = total.to(torch.int64) * width + var.to(torch.int64)
+    uniq, inv, cnt = torch.unique(key, return_inverse=True, return_counts=True)
+    uniq_c, cnt_c = uniq.cpu().numpy(), cnt.cpu().numpy()
+    if len(uniq_c) > 32767:
+        raise _lib.PhError(f"{len(uniq_c)} distinct (var,total) pairs exceed the device code space")
+    order = np.lexsort((uniq_c, -cnt_c))
+    rank = np.empty_like(order)
+    rank[order] = np.arange(len(order))
+    code = torch.from_numpy(rank.astype(np.int16)).to(key.device)[inv].contiguous()
+    u = uniq_c[order]
+    return (u % width).astype(np.int64), (u // width).astype(np.int64), code
+
+
 class ObservationStore:
     def __init__(self, handle, n_cells, n_snvs, pair_var, pair_total, L0, L1, device):
         self._h = handle
@@ -55,21 +79,9 @@ class ObservationStore:
         L = _lib.lib()
         on_dev = not isinstance(cell, np.ndarray)
         if on_dev:
-            import torch
-
-            width = int(var.max().item()) + 1 if var.numel() else 1
-            key = total.to(torch.int64) * width + var.to(torch.int64)
-            uniq, inv, cnt = torch.unique(key, return_inverse=True, return_counts=True)
-            uniq_c, cnt_c = uniq.cpu().numpy(), cnt.cpu().numpy()
-            order = np.lexsort((uniq_c, -cnt_c))
-            rank = np.empty_like(order)
-            rank[order] = np.arange(len(order))
-            code = torch.from_numpy(rank.astype(np.int16)).to(key.device)[inv].contiguous()
-            del key, inv
-            u = uniq_c[order]
-            pv, pt = (u % width).astype(np.int64), (u // width).astype(np.int64)
-            cell = cell.to(torch.int32).contiguous()
-            snv = snv.to(torch.int32).contiguous()
+            pv, pt, code = encode_pairs_device(var, total)
+            cell = cell.to(torch_int32()).contiguous()
+            snv = snv.to(torch_int32()).contiguous()
             nnz = int(cell.numel())
         else:
             pv, pt, _, code32 = encode_pairs(var, total)
@@ -225,6 +237,19 @@ class ObservationStore:
         k = self.n_snvs if snv_list_t is None else int(snv_list_t.numel())
         _lib.check(_lib.lib().ph_assign_branching(self._h, _ptr(cell_label_t), _ptr(snv_list_t), k, _ptr(label_out_t),
                                                   _ptr(nobs_out_t), 1, stream))
+
+    def snv_partial_dev(self, cell_label_t, C_, packed_t, snv_list_t=None, stream=None):
+        """This rank's partial [S0|S1|Nobs] table (float64, 3*k*C) for one NCCL all-reduce (cell-sharded K1)."""
+        k = self.n_snvs if snv_list_t is None else int(snv_list_t.numel())
+        _lib.check(_lib.lib().ph_snv_partial(self._h, _ptr(cell_label_t), C_, _ptr(snv_list_t), k, _ptr(packed_t), 1, stream))
+
+    @staticmethod
+    def finish_linear_dev(packed_t, k, lenA, label_out_t, nobs_out_t, stream=None):
+        _lib.check(_lib.lib().ph_finish_linear(_ptr(packed_t), k, float(lenA), _ptr(label_out_t), _ptr(nobs_out_t), stream))
+
+    @staticmethod
+    def finish_branching_dev(packed_t, k, label_out_t, nobs_out_t, stream=None):
+        _lib.check(_lib.lib().ph_finish_branching(_ptr(packed_t), k, _ptr(label_out_t), _ptr(nobs_out_t), stream))
 
     def block_sums_dev(self, cell_label_t, C_, snv_label_t, Q, s0, s1, no, nv, stream=None):
         _lib.check(_lib.lib().ph_block_sums(self._h, _ptr(cell_label_t), C_, _ptr(snv_label_t), Q, _ptr(s0), _ptr(s1),

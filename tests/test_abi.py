@@ -19,7 +19,7 @@ def test_library_exports_every_declared_symbol():
     from phertilizer_b200 import _lib
 
     syms = _header_symbols()
-    assert len(syms) >= 17 and set(syms) == set(_lib.EXPORTS)
+    assert len(syms) >= 20 and set(syms) == set(_lib.EXPORTS)
     L = ctypes.CDLL(_lib.LIB_PATH)
     for s in syms:
         assert hasattr(L, s), s
