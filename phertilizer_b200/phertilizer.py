@@ -1,0 +1,215 @@
+"""`Phertilizer`: grows a clonal tree from ultra-low-coverage single-cell DNA sequencing data.
+
+Drop-in for the reference's `phertilizer.phertilizer.Phertilizer` (phertilizer/phertilizer.py:163-745): same constructor
+and `phertilize` arguments, same return values, same RNG streams and the same planting / growing control flow on the
+host.  What changes is the data layer: instead of densifying four n x m matrices (lines 295-306) the observations are
+handed to the CUDA library once (`ObservationStore.from_coo`) and every reduction over them runs on the B200.
+"""
+from __future__ import annotations
+
+from collections import deque
+from copy import deepcopy
+
+import numpy as np
+import pandas as pd
+
+from . import branching_split as bs
+from . import linear_split as ls
+from .clonal_tree import IdentityTree, Seed
+from .clonal_tree_list import ClonalTreeList
+from .data import Data
+from .params import Params
+from .store import ObservationStore, pairwise_dist
+from .utils import check_obs, power_calc
+
+
+def _embed(bin_counts: np.ndarray, dim_reduce: bool) -> np.ndarray:
+    """Row-normalise + UMAP (phertilizer.py:267-279) or the raw bins (284-285).  UMAP is third-party and stays so."""
+    if not dim_reduce:
+        return bin_counts
+    try:
+        import umap
+    except ImportError as e:
+        raise ImportError("umap-learn is not installed: pass dim_reduce=False (--no-umap) or a precomputed embedding") from e
+    norm = bin_counts / (bin_counts.sum(axis=1).reshape(-1, 1))
+    reducer = umap.UMAP(n_neighbors=40, min_dist=0, n_components=2, spread=1, metric="manhattan", random_state=55)
+    return reducer.fit_transform(norm)
+
+
+class Phertilizer:
+    def __init__(self, variant_count_data, bin_count_data, alpha=0.001, max_copies=5, mode="var", dim_reduce=True,
+                 device=None):
+        use_read_depth = mode != "var"
+        self.mapping_list = None
+        self.explored_seeds = None
+        device = int(__import__("os").environ.get("PHERTILIZER_DEVICE", "0")) if device is None else device
+
+        # labels -> dense indices: sorted unique cell ids and "chr_mutation" strings (phertilizer.py:235-253)
+        vc = variant_count_data
+        chr_mut = vc["chr"].astype("str") + "_" + vc["mutation_id"].astype(str)
+        cell_labels = np.sort(vc["cell_id"].unique())
+        mut_labels = np.sort(chr_mut.unique())
+        self.cells = np.arange(cell_labels.shape[0], dtype="int")
+        self.muts = np.arange(mut_labels.shape[0], dtype="int")
+        cell_series = pd.Series(data=self.cells, index=cell_labels)
+        mut_series = pd.Series(data=self.muts, index=mut_labels)
+        cell_lookup = pd.Series(data=cell_labels, index=self.cells)
+        mut_lookup = pd.Series(data=mut_labels, index=self.muts)
+        cell_idx = cell_series[vc["cell_id"]].to_numpy()
+        mut_idx = mut_series[chr_mut].to_numpy()
+
+        # binned read counts in cell-index order (259-263), embedding, pairwise copy distance on the GPU (286)
+        bc = bin_count_data.copy()
+        bc["cell_index"] = cell_series[bc["cell"]].values
+        bc = bc.sort_values(by=["cell_index"]).drop(["cell", "cell_index"], axis=1).to_numpy()
+        embedding = _embed(bc, dim_reduce)
+        copy_distance = pairwise_dist(np.asarray(embedding, dtype=np.float64), device=device)
+
+        # per-observation likelihoods become a (var,total) -> (like0, like1) table inside the store (295-306)
+        store = ObservationStore.from_coo(len(self.cells), len(self.muts), cell_idx, mut_idx, vc["var"].to_numpy(),
+                                          vc["total"].to_numpy(), alpha=alpha, max_copies=max_copies, device=device)
+        self.data = Data(cell_lookup, mut_lookup, store, embedding, copy_distance, use_read_depth)
+
+    # ------------------------------------------------------------------ small accessors
+    def save_embedding(self, fname):
+        cells = self.data.cell_lookup.sort_index().values.reshape(-1, 1)
+        pd.DataFrame(np.hstack([cells, self.data.read_depth]), columns=["cell", "V1", "V2"]).to_csv(fname, index=False)
+
+    def get_id_mappings(self):
+        return self.data.cell_lookup, self.data.mut_lookup
+
+    # ------------------------------------------------------------------ main entry
+    def phertilize(self, max_iterations=10, starts=3, seed=1026, radius=0.8, low_cmb=0.05, high_cmb=0.15,
+                   nobs_per_cluster=3.0, gamma=0.95, d=7, use_copy_kernel=False, post_process=False):
+        """Enumerate clonal trees and return (best tree, ClonalTreeList of all trees, Series of normalised
+        log-likelihoods) -- phertilizer.py:350-460."""
+        Nmax = check_obs(self.cells, self.muts, self.data.store)
+        minobs = power_calc(d, gamma, 6, Nmax)
+        self.rng = np.random.default_rng(seed)
+        self.params = Params(starts, max_iterations, radius, minobs, seed, post_process, use_copy_kernel, low_cmb,
+                             high_cmb, nobs_per_cluster)
+        self.init_seed = Seed(self.cells, self.muts, key=0)
+        seed_list = deque([self.init_seed])
+        self.mapping_list = {}
+        self.explored_seeds = {}
+        print(f"\nPhertilizing a tree with n: {len(self.cells)} cells and m: {len(self.muts)} SNVs")
+        print("\nStarting planting phase....")
+        self.planting(seed_list)
+        print("\nPlanting phase complete!")
+        print("\nStarting grow phase....")
+        pre_proc_trees = self.grow()
+        print("\nGrowing phase complete!")
+        print("\nIdentifying the maximum likelihood clonal tree....")
+        optimal_tree, loglikelihoods = pre_proc_trees.find_best_tree(self.data)
+        if optimal_tree is None:
+            optimal_tree = IdentityTree(self.cells, self.muts)
+        if post_process:
+            print("Post-processing...")
+            optimal_tree.post_process(self.data)
+        return optimal_tree, pre_proc_trees, loglikelihoods
+
+    # ------------------------------------------------------------------ planting: elementary operations on every seed
+    def planting(self, seed_list):
+        """LIFO over seeds; keys advance only for seeds with enough observations (phertilizer.py:463-535)."""
+        key = 0
+        while len(seed_list) > 0:
+            curr = seed_list.pop()
+            curr.set_key(key)
+            print(curr)
+            self.mapping_list[key] = []
+            self.explored_seeds[key] = deepcopy(curr)
+            if curr.has_linear():
+                operations = [self.sprout_branching]
+                self.mapping_list[key].append(curr.linear_tree)
+            elif curr.has_branching():
+                operations = [self.sprout_linear]
+                self.mapping_list[key].append(curr.branching_tree)
+            else:
+                operations = [self.sprout_linear, self.sprout_branching]
+            curr.strip(self.data.store)          # mutates the seed AFTER it was memoised (reference quirk 8)
+            if curr.count_obs(self.data.store) < self.params.minobs:
+                print("Insufficient number of observations, seed is terminal")
+                continue
+            for op in operations:
+                tree, new_seeds = op(curr)
+                if tree is not None:
+                    print("\n")
+                    print(tree)
+                    self.mapping_list[key].append(tree)
+                    seed_list += new_seeds
+                else:
+                    print("No inferred elementary tree.")
+            print(f"Number of subproblems remaining: {len(seed_list)}")
+            key += 1
+
+    def lookup_seed_key(self, seed):
+        for s in self.explored_seeds:
+            if self.explored_seeds[s] == seed:
+                return s
+
+    # ------------------------------------------------------------------ growing: enumerate trees from the memo
+    def grow(self, max_trees=np.inf):
+        """phertilizer.py:558-614."""
+        all_trees = ClonalTreeList()
+        frontier = ClonalTreeList()
+        for t in self.mapping_list[0]:
+            all_trees.insert(t)
+            if type(t) is not IdentityTree:
+                frontier.insert(t)
+            while frontier.has_trees():
+                if all_trees.size() > max_trees:
+                    break
+                curr = frontier.pop_tree()
+                for leaf in curr.get_leaves():
+                    seed = curr.get_seed_by_node(leaf)
+                    if seed is None:
+                        continue
+                    seed_key = self.lookup_seed_key(seed)
+                    if seed_key is None:
+                        continue
+                    for sub in self.mapping_list[seed_key]:
+                        if type(sub) is IdentityTree:
+                            continue
+                        merged = deepcopy(curr)
+                        merged.merge(sub, leaf)
+                        if not all_trees.contains(merged):
+                            all_trees.insert(merged)
+                        if not frontier.contains(merged):
+                            frontier.insert(merged)
+        return all_trees
+
+    # ------------------------------------------------------------------ elementary operations
+    def sprout_branching(self, seed):
+        print("\nSprouting a branching tree from seed:")
+        print(seed)
+        tree = bs.Branching_split(self.data, seed, self.rng, self.params).sprout()
+        return tree, (tree.get_seeds() if tree is not None else [])
+
+    def sprout_linear(self, seed):
+        """Linear operation; a chain of recursive splits is unrolled into nested seeds (phertilizer.py:655-724)."""
+        print("\nSprouting a linear tree from seed:")
+        print(seed)
+        tree_list, best = ls.Linear_split(self.data, seed, self.rng, self.params).sprout()
+        if best is None:
+            return None, []
+        seed_list = best.get_seeds()
+        seed.set_linear(best)
+        idx = tree_list.size() - 2
+        if idx >= 0:
+            ca_cells, ma_muts = best.get_tip_cells(0), best.get_tip_muts(0)
+            curr_seed = seed_list[0]
+            while idx >= 0:
+                nxt = tree_list.index_tree(idx)
+                cA, mA = nxt.get_tip_cells(0), nxt.get_tip_muts(0)
+                nxt.cell_mapping[0] = {0: np.setdiff1d(cA, ca_cells)}
+                nxt.mut_mapping[0] = np.setdiff1d(mA, ma_muts)
+                curr_seed.set_linear(nxt)
+                ca_cells, ma_muts = cA, mA
+                next_seeds = nxt.get_seeds()
+                seed_list += next_seeds
+                curr_seed = next_seeds[0]
+                idx -= 1
+        return best, seed_list
+
+    def sprout_identity(self, seed):
+        return IdentityTree(seed.cells, seed.muts, None)

@@ -1,0 +1,137 @@
+"""Host helpers of the tree operations.  Semantics follow phertilizer/utils.py of the reference (cited per function);
+the observation counts come from the device store instead of dense matrices."""
+from __future__ import annotations
+
+import pickle
+
+import numpy as np
+from pandas import DataFrame, Series, concat
+from scipy.special import comb
+
+
+def snv_kernel_width(dmat):
+    """utils.py:75-78."""
+    return 0.2 * (np.max(dmat) - np.min(dmat))
+
+
+def cnv_kernel_width(dmat):
+    """utils.py:80-84."""
+    return 0.2 * (np.max(dmat) - np.min(dmat))
+
+
+def impute_mut_features(c_mat, mut_features, cells):
+    """Fill NaN feature rows with the features of the closest (copy distance) cell of `cells` that has features
+    (utils.py:87-129).  The reference argsorts a masked n x n matrix to read its first column; the nearest valid
+    neighbour is found here with one masked arg-min per cell to impute, which is the same element.
+    """
+    cells = np.asarray(cells)
+    na = np.isnan(mut_features.sum(axis=1).reshape(-1))
+    if na.sum() > 0.5 * len(cells):
+        return mut_features  # not enough cells to impute from (utils.py:96-98)
+    donors = cells[~na]
+    donor_rows = np.nonzero(~na)[0]
+    for row in np.nonzero(na)[0]:
+        c = cells[row]
+        d = c_mat[c, donors]
+        mut_features[row, :] = mut_features[donor_rows[int(np.argmin(d))], :]
+    assert not np.any(np.isnan(mut_features))
+    return mut_features
+
+
+def normalizedMinCut(W, index, random_state=None):
+    """Two-way normalized min cut by sklearn spectral clustering (utils.py:131-150)."""
+    from sklearn.cluster import spectral_clustering
+
+    stats = {}
+    if W.shape[0] == 1 or np.any(np.isnan(W)):
+        return (index, np.empty(shape=0)), None, None, stats
+    labels = spectral_clustering(W, n_clusters=2, random_state=random_state, assign_labels="cluster_qr",
+                                 eigen_solver="lobpcg")
+    stats.update(jump_perc=0.08, first_gap=0.03, largest_gap=0.5, spectral_num_k=2)
+    return (index[labels == 0], index[labels == 1]), None, labels, stats
+
+
+def success_prob(N, parts, d):
+    """utils.py:195-199."""
+    denom = comb(N + parts - 1, N)
+    free = N - parts * d
+    return comb(free + parts - 1, free) / denom
+
+
+def power_calc(d, gamma, parts, Nmax):
+    """Smallest number of observations with success probability >= gamma (utils.py:203-216)."""
+    n = 0
+    for n in range(1, Nmax + 1):
+        if success_prob(n, parts, d) >= gamma:
+            break
+    return n
+
+
+def check_obs(cells, muts, store):
+    """Number of observed entries in the block cells x muts (utils.py:218-220), from the device store (K3)."""
+    if len(cells) == 0 or len(muts) == 0:
+        return 0
+    _, _, nobs, _ = store.block_sums(store.cell_labels(cells), 1, store.snv_labels(muts), 1)
+    return int(nobs[0, 0])
+
+
+def get_next_label(T):
+    """utils.py:222-228."""
+    return np.max(np.array(list(T.nodes()))) + 1
+
+
+def pickle_save(obj, fname):
+    with open(fname, "wb") as handle:
+        pickle.dump(obj, handle, protocol=pickle.HIGHEST_PROTOCOL)
+
+
+def pickle_load(fname):
+    with open(fname, "rb") as handle:
+        return pickle.load(handle)
+
+
+def mapping_to_dataframe(mapping, id_name, cell=False):
+    """cluster mapping -> long dataframe sorted by id (utils.py:24-45)."""
+    if len(mapping) == 0:
+        return DataFrame(columns=[id_name, "cluster"])
+    parts = []
+    for k in mapping:
+        if cell:
+            for s in mapping[k]:
+                part = DataFrame(mapping[k][s], columns=[id_name])
+                part["cluster"] = k
+                part["subcluster"] = s
+                parts.append(part)
+        else:
+            part = DataFrame(mapping[k], columns=[id_name])
+            part["cluster"] = k
+            parts.append(part)
+    return concat(parts).sort_values(by=[id_name])
+
+
+def generate_cell_dataframe(cell_mapping, cell_lookup):
+    """utils.py:309-316."""
+    df = mapping_to_dataframe(cell_mapping, "cell_id", cell=True)
+    df["cell"] = cell_lookup[df["cell_id"]].values
+    return df.drop(["cell_id"], axis=1)
+
+
+def generate_mut_dataframe(mut_mapping, mut_lookup):
+    """utils.py:318-327."""
+    df = mapping_to_dataframe(mut_mapping, "mutation_id")
+    df["mutation"] = mut_lookup[df["mutation_id"]].values
+    return df.drop(["mutation_id"], axis=1)
+
+
+def dict_to_series(event_mapping):
+    series = [Series(np.full(shape=len(event_mapping[s]), fill_value=s), index=event_mapping[s]) for s in event_mapping]
+    return concat(series).sort_index()
+
+
+def dict_to_dataframe(event_mapping):
+    if event_mapping is None or len(event_mapping) == 0:
+        return DataFrame()
+    df = concat([dict_to_series(event_mapping[n]) for n in event_mapping], axis=1)
+    df.columns = [f"node_{n}" for n in list(event_mapping.keys())]
+    df.index.rename("bin", inplace=True)
+    return df

@@ -1,0 +1,85 @@
+"""End-to-end drop-in check: `phertilizer_b200.Phertilizer` (GPU store, host control flow) reproduces the reference's
+recorded run -- same seed, `--no-umap`, `-s 3 -j 10 --post_process` on the bundled example (config 1) and `-s 2 -j 6`
+on the small synthetic.  Assignments and tree must be identical, log-likelihoods within 1e-9 relative."""
+import io
+from contextlib import redirect_stdout
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from tests.golden_util import load_golden, rel_close, tree_from_record
+
+pytestmark = pytest.mark.gpu
+
+
+def frames_from_golden(g):
+    i = g.inputs
+    mut_labels = i["mut_labels"]
+    cell_ids = i["cell_labels"].astype(np.int64)
+    chrom = np.array([s.rsplit("_", 1)[0] for s in mut_labels])
+    mid = np.array([s.rsplit("_", 1)[1] for s in mut_labels])
+    vc = pd.DataFrame({"chr": chrom[i["snv"]], "mutation_id": mid[i["snv"]], "cell_id": cell_ids[i["cell"]], "base": "A",
+                       "var": i["var"].astype(np.int64), "total": i["total"].astype(np.int64)})
+    rd = i["read_depth"]
+    bc = pd.DataFrame(rd, columns=[f"b{k}" for k in range(rd.shape[1])])
+    bc.insert(0, "cell", cell_ids)
+    # shuffle the rows: the constructor must restore cell-index order (phertilizer.py:259-263)
+    return vc.sample(frac=1.0, random_state=3).reset_index(drop=True), bc.sample(frac=1.0, random_state=4).reset_index(drop=True)
+
+
+@pytest.mark.parametrize("stem,starts,iters,seed", [("synth_t0", 2, 6, 4242), ("example", 3, 10, 100 * 99059)])
+def test_phertilize_matches_reference_run(stem, starts, iters, seed):
+    from phertilizer_b200.phertilizer import Phertilizer
+
+    g = load_golden(stem)
+    vc, bc = frames_from_golden(g)
+    ph = Phertilizer(vc, bc, alpha=0.001, max_copies=5, mode="rd", dim_reduce=False)
+    assert list(ph.data.mut_lookup.to_numpy().astype(str)) == list(g.inputs["mut_labels"])
+    buf = io.StringIO()
+    with redirect_stdout(buf):
+        tree, tree_list, loglikes = ph.phertilize(max_iterations=iters, starts=starts, seed=seed, radius=1, gamma=0.95, d=10,
+                                                  use_copy_kernel=True, post_process=True, low_cmb=0.05, high_cmb=0.15,
+                                                  nobs_per_cluster=3)
+    fin = g.of("final")[0]
+    assert ph.params.minobs == fin.minobs
+    assert tree_list.size() == fin.n_trees
+    assert rel_close(loglikes.to_numpy(), fin.loglikes, 1e-9), (loglikes.to_numpy(), fin.loglikes)
+    assert list(loglikes.index) == list(fin.loglike_keys)
+    # candidate trees: identical topology, cells and SNVs per node
+    for rec, t in zip(g.of("candidate_tree"), tree_list.get_all_trees()):
+        nodes, edges, cells, muts = tree_from_record(rec)
+        assert sorted(t.tree.edges()) == sorted(edges)
+        for k in nodes:
+            assert np.array_equal(t.get_tip_cells(k), cells[k]), (rec.index, k)
+            assert np.array_equal(np.asarray(t.get_tip_muts(k)).astype(np.int64), muts[k]), (rec.index, k)
+    # final (post-processed) tree
+    nodes, edges, cells, muts = tree_from_record(fin)
+    assert sorted(tree.tree.edges()) == sorted(edges)
+    for k in nodes:
+        assert np.array_equal(tree.get_tip_cells(k), cells[k])
+        assert np.array_equal(np.asarray(tree.get_tip_muts(k)).astype(np.int64), muts[k])
+    assert rel_close(tree.norm_loglikelihood, fin.norm, 1e-9)
+    pe = g.of("post_process_end")[0]
+    assert rel_close(tree.variant_likelihood, pe.variant, 1e-9) and rel_close(tree.loglikelihood, pe.loglikelihood, 1e-9)
+    # output frames (generate_results)
+    ff = g.of("final_frames")[0]
+    pcell, pmut, _, _ = tree.generate_results(*ph.get_id_mappings())
+    assert np.array_equal(pcell["cluster"].to_numpy(), ff.cell_cluster) and list(pcell["cell"].astype(str)) == list(ff.cell_id)
+    assert np.array_equal(pmut["cluster"].to_numpy(), ff.mut_cluster) and list(pmut["mutation"].astype(str)) == list(ff.mut_id)
+
+
+def test_pairwise_distance_bitwise_vs_scipy():
+    """copy_distance feeds quantiles and exp() kernels of the cell clustering; report exactness vs scipy."""
+    from scipy.spatial.distance import pdist, squareform
+
+    from phertilizer_b200.store import pairwise_dist
+
+    g = load_golden("example")
+    X = g.inputs["read_depth"].astype(np.float64)
+    got = pairwise_dist(X)
+    ref = squareform(pdist(X, metric="euclidean"))
+    assert rel_close(got, ref, 1e-12)
+    frac_exact = float(np.mean(got == ref))
+    print("pairwise distance bit-exact fraction:", frac_exact)
+    assert frac_exact > 0.5
