@@ -21,19 +21,26 @@ def cnv_kernel_width(dmat):
 
 def impute_mut_features(c_mat, mut_features, cells):
     """Fill NaN feature rows with the features of the closest (copy distance) cell of `cells` that has features
-    (utils.py:87-129).  The reference argsorts a masked n x n matrix to read its first column; the nearest valid
-    neighbour is found here with one masked arg-min per cell to impute, which is the same element.
+    (utils.py:87-129).  The reference argsorts a masked copy of the whole n x n matrix and reads column 0 of the
+    rows it needs; only those rows are sorted here.  The row content (NaN on the diagonal, on cells outside `cells` and
+    on cells that themselves need imputation) and the sort call are the reference's, so exact distance ties -- which do
+    occur with integer bin counts -- resolve to the same neighbour.
     """
     cells = np.asarray(cells)
     na = np.isnan(mut_features.sum(axis=1).reshape(-1))
     if na.sum() > 0.5 * len(cells):
         return mut_features  # not enough cells to impute from (utils.py:96-98)
-    donors = cells[~na]
-    donor_rows = np.nonzero(~na)[0]
+    if not na.any():
+        return mut_features
+    donor_mask = np.zeros(c_mat.shape[0], dtype=bool)
+    donor_mask[cells[~na]] = True
+    row_of = {int(c): i for i, c in enumerate(cells)}
     for row in np.nonzero(na)[0]:
         c = cells[row]
-        d = c_mat[c, donors]
-        mut_features[row, :] = mut_features[donor_rows[int(np.argmin(d))], :]
+        d = np.where(donor_mask, c_mat[c, :].astype(float), np.nan)
+        d[c] = np.nan
+        nearest = int(np.argsort(d)[0])
+        mut_features[row, :] = mut_features[row_of[nearest], :]
     assert not np.any(np.isnan(mut_features))
     return mut_features
 
