@@ -191,6 +191,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     from phertilizer_b200 import _lib
+    from phertilizer_b200.sharded import CudaBackend, ShardedStore
     from phertilizer_b200.store import ObservationStore, encode_pairs_device
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -207,6 +208,7 @@ def run_ours(args):
     n_loc, m, nnz_loc, nnz_tot = w["n_local"], w["m"], w["nnz_local"], w["nnz_total"]
     pv, pt, code_t = encode_pairs_device(w["var"], w["total"]) if (rank == 0 and world == 1 and not args.no_cpu) else (None, None, None)
     st = ObservationStore.from_coo(n_loc, m, w["cell"], w["snv"], w["var"], w["total"], device=local)
+    sharded = ShardedStore(CudaBackend(st, dev), w["n"], m, w["lo"], w["hi"]) if world > 1 else None
     torch.cuda.synchronize()
     info = st.info()
     log(f"[rank {rank}] store ready in {time.time() - t0:.1f}s: {info}")
@@ -239,12 +241,13 @@ def run_ours(args):
             if record:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-            st.snv_partial_dev(labs_d[i % P], 1, packed, stream=stream)
+            # == ShardedStore.assign_linear_dev, unrolled here only to bracket the partial-table kernel with events
+            sharded.b.snv_partial(labs_d[i % P], 1, packed)
             if record:
                 e1.record()
                 kern_ev.append((e0, e1))
             dist.all_reduce(packed)
-            ObservationStore.finish_linear_dev(packed, m, lenA[i % P], lab_out, nobs_out, stream=stream)
+            sharded.b.finish_linear(packed, m, lenA[i % P], lab_out, nobs_out)
 
     def barrier():
         if world > 1:
@@ -280,9 +283,7 @@ def run_ours(args):
             # ph_assign_linear(on_device=0): pinned staging, H2D labels, kernel, D2H labels + counts, sync
             return st.assign_linear(labs_h[i % P].numpy()[:n_loc], lenA[i % P])
         labs_d[i % P].copy_(labs_h[i % P], non_blocking=True)
-        st.snv_partial_dev(labs_d[i % P], 1, packed, stream=stream)
-        dist.all_reduce(packed)
-        ObservationStore.finish_linear_dev(packed, m, lenA[i % P], lab_out, nobs_out, stream=stream)
+        sharded.assign_linear_dev(labs_d[i % P], lenA[i % P], packed, lab_out, nobs_out)
         lab_out_h.copy_(lab_out, non_blocking=True)
         nobs_out_h.copy_(nobs_out, non_blocking=True)
         torch.cuda.synchronize()
