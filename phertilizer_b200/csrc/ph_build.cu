@@ -2,6 +2,8 @@
 // Replaces the dense `sparse_matrix()` unstack of the reference (phertilizer/phertilizer.py:153-161, 295-306).
 #include <cub/device/device_radix_sort.cuh>
 
+#include <stdlib.h>
+
 #include <new>
 
 #include "ph_common.cuh"
@@ -88,7 +90,7 @@ int build_orient(ph_handle* h, PhOrient* o, const int32_t* d_major, const int32_
   o->n_minor = n_minor;
   o->minor_bits = ph_ceil_log2((uint64_t)n_minor > 1 ? (uint64_t)n_minor : 2);
   int D = 0;
-  while (D < PH_DMAX && D < h->n_codes && (double)code_count[D] >= 4.0 * (double)n_major) ++D;
+  while (D < PH_DMAX && D < h->n_codes && (double)code_count[D] >= h->dense_min_avg * (double)n_major) ++D;
   o->D = D;
   if (h->n_codes > D) {
     if (o->minor_bits >= 32 || (uint64_t)(h->n_codes - 1) >= (1ull << (32 - o->minor_bits)))
@@ -180,6 +182,10 @@ extern "C" int ph_create(int32_t n_cells, int32_t n_snvs, int64_t nnz, const int
   h->n_snvs = n_snvs;
   h->n_codes = n_codes;
   h->nnz = nnz;
+  {
+    const char* e = getenv("PH_DENSE_MIN_AVG");  // tuning knob: minimum average entries per line of a dense code
+    h->dense_min_avg = e ? atof(e) : 32.0;
+  }
 
   int rc = PH_OK;
   int32_t *d_cell = nullptr, *d_snv = nullptr;

@@ -56,6 +56,7 @@ struct ph_handle {
   double* d_L1;      // [n_codes]
   uint8_t* d_varpos; // [n_codes]
   int64_t device_bytes;
+  double dense_min_avg;  // a (var,total) code gets its own segment when it has >= this many entries per line on average
   // scratch (device)
   uint8_t* d_lab_minor;  // [max(n,m)] staged labels of the minor axis
   uint8_t* d_lab_major;  // [max(n,m)]

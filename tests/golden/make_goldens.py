@@ -8,8 +8,8 @@ What is recorded (SURVEY.md section 4 "per-call golden capture"):
               like0/like1 values for every distinct (var,total) pair;
   * kat     : like0/like1 from the reference's numba functions for all (k,n), n<=60, three (alpha, max_copies) settings;
   * calls   : (arguments, result) of every hot-path method while the reference runs
-              `-s 3 -j 10 --post_process --no-umap` on the example (config 1) and `-s 2 -j 6 --post_process` on a small
-              synthetic data set (T0);
+              `-s 3 -j 10 --post_process --no-umap` on the example (config 1), `-s 2 -j 6 --post_process` on a small
+              synthetic data set (T0) and `-s 2 -j 5 --post_process` on a 2000 x 3000 synthetic (T1);
   * e2e     : candidate-tree likelihoods, final tree, cell/SNV clusters.
 The GPU box has no /root/reference: tests only read the files written here.
 """
@@ -313,6 +313,12 @@ def main():
     s = make_config("T0")
     vdf, bdf = to_dataframes(s)
     run_reference(vdf, bdf, "synth_t0", starts=2, iterations=6, seed=4242,
+                  inputs_extra=dict(cell_clone=s.cell_clone.numpy(), snv_node=s.snv_node.numpy(), parent=s.parent))
+
+    # ---- mid-size synthetic (T1, 2000 x 3000, 4 clones): an 8-node tree, exercises reassign_cell and deeper recursion
+    s = make_config("T1")
+    vdf, bdf = to_dataframes(s)
+    run_reference(vdf, bdf, "synth_t1", starts=2, iterations=5, seed=777,
                   inputs_extra=dict(cell_clone=s.cell_clone.numpy(), snv_node=s.snv_node.numpy(), parent=s.parent))
 
 

@@ -28,7 +28,7 @@ def frames_from_golden(g):
     return vc.sample(frac=1.0, random_state=3).reset_index(drop=True), bc.sample(frac=1.0, random_state=4).reset_index(drop=True)
 
 
-@pytest.mark.parametrize("stem,starts,iters,seed", [("synth_t0", 2, 6, 4242), ("example", 3, 10, 100 * 99059)])
+@pytest.mark.parametrize("stem,starts,iters,seed", [("synth_t0", 2, 6, 4242), ("example", 3, 10, 100 * 99059), ("synth_t1", 2, 5, 777)])
 def test_phertilize_matches_reference_run(stem, starts, iters, seed):
     from phertilizer_b200.phertilizer import Phertilizer
 

@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-9
 
 
-@pytest.fixture(scope="module", params=["example", "synth_t0"])
+@pytest.fixture(scope="module", params=["example", "synth_t0", "synth_t1"])
 def env(request):
     from phertilizer_b200.store import ObservationStore
 
@@ -209,6 +209,36 @@ def test_reassign_snv_scores_golden(env):
             best, bl = None, -np.inf
             for k in range(K):
                 if row[k] > bl:
+                    bl, best = row[k], int(r.nodes[k])
+            assert best == r.after
+        i = j
+
+
+def test_reassign_cell_scores_golden(env):
+    g, st, D = env
+    recs = g.of("reassign_cell")
+    i = 0
+    while i < len(recs):
+        j = i
+        while j < len(recs) and recs[j].ydict.shape == recs[i].ydict.shape and np.array_equal(recs[j].ydict, recs[i].ydict):
+            j += 1
+        batch = recs[i:j]
+        yd = batch[0].ydict  # [n_nodes, n_snvs]
+        K = yd.shape[0]
+        pats, inv = np.unique(yd.T, axis=0, return_inverse=True)
+        P = len(pats)
+        KK = max(K, P)
+        member = np.zeros((KK, KK), np.uint8)
+        member[:K, :P] = pats.T
+        snv_node = np.zeros(g.m + 16, np.uint8)[: g.m]
+        snv_node[:] = inv.reshape(-1)
+        T = st.cell_node_table(snv_node, member, np.array([r.c for r in batch]))
+        for row, r in zip(T, batch):
+            assert rel_close(row[:K], r.scores, TOL)
+            # clonal_tree.py:616-636: start from the current node (if any), strict > over nodes with <= 1 child
+            best, bl = (None, -np.inf) if r.before < 0 else (r.before, row[list(r.nodes).index(r.before)])
+            for k in range(K):
+                if r.succ[k] <= 1 and row[k] > bl:
                     bl, best = row[k], int(r.nodes[k])
             assert best == r.after
         i = j

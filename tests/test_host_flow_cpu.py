@@ -12,7 +12,7 @@ from tests.oracle_store import patch_phertilizer
 from tests.test_gpu_end_to_end import frames_from_golden
 
 
-@pytest.mark.parametrize("stem,starts,iters,seed", [("synth_t0", 2, 6, 4242), ("example", 3, 10, 100 * 99059)])
+@pytest.mark.parametrize("stem,starts,iters,seed", [("synth_t0", 2, 6, 4242), ("example", 3, 10, 100 * 99059), ("synth_t1", 2, 5, 777)])
 def test_host_flow_matches_reference(monkeypatch, stem, starts, iters, seed):
     patch_phertilizer(monkeypatch)
     from phertilizer_b200.phertilizer import Phertilizer

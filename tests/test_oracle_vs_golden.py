@@ -7,7 +7,7 @@ import pytest
 from oracle import oracle_np as O
 from tests.golden_util import rel_close, tree_from_record
 
-STEMS = ["example", "synth_t0"]
+STEMS = ["example", "synth_t0", "synth_t1"]
 
 
 @pytest.fixture(scope="module", params=STEMS)
@@ -104,6 +104,9 @@ def test_tree_level(gd):
         assert rel_close([sc[int(k)] for k in r.nodes], r.scores)
     for r in g.of("find_bad_snvs"):
         assert np.array_equal(O.find_bad_snvs(D, r.clade_cells, r.muts, r.q), r.bad)
+    for r in g.of("reassign_cell"):
+        sc = O.cell_node_scores(D, r.c, {int(k): r.ydict[i].astype(int) for i, k in enumerate(r.nodes)})
+        assert rel_close([sc[int(k)] for k in r.nodes], r.scores)
 
 
 def test_gaussian_node_likelihood(gd):
