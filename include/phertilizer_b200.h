@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PH_ABI_VERSION 1
+#define PH_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define PH_API __attribute__((visibility("default")))
@@ -56,8 +56,10 @@ typedef struct ph_info {
   int32_t dense_codes_by_cell; /* D of the cell-major (CSR-like) copy */
   int64_t device_bytes;        /* bytes of HBM owned by the handle */
   int32_t device, sm_count;
-  int32_t group_by_snv, group_by_cell; /* lanes cooperating on one SNV / one cell */
+  int32_t group_by_snv, group_by_cell; /* lines (SNVs / cells) per warp batch */
   int32_t labels_in_smem_by_snv, labels_in_smem_by_cell;
+  int32_t chunks_by_snv, chunks_by_cell; /* 65520-index chunks of the minor axis (16-bit entries) */
+  int64_t stream_bytes_by_snv, stream_bytes_by_cell; /* bytes one full pass reads from HBM (entries incl. padding + tail) */
 } ph_info;
 
 PH_API const char* ph_last_error(void);
@@ -82,7 +84,7 @@ PH_API int ph_create(int32_t n_cells, int32_t n_snvs, int64_t nnz, const int32_t
 PH_API void ph_destroy(ph_handle* h);
 PH_API int ph_get_info(const ph_handle* h, ph_info* out);
 
-/* Tuning knob for experiments: lanes per SNV / per cell (8, 16, 32) ; 0 = automatic. */
+/* Tuning knob for experiments: SNVs / cells per warp batch (8 or 32; 16 means 8) ; 0 = keep. */
 PH_API int ph_set_group(ph_handle* h, int group_by_snv, int group_by_cell);
 
 /*

@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libphertilizer_b200.so")
 
 PH_OK = 0
+ABI_VERSION = 2
 
 
 class PhError(RuntimeError):
@@ -27,6 +28,8 @@ class PhInfo(C.Structure):
         ("device", C.c_int32), ("sm_count", C.c_int32),
         ("group_by_snv", C.c_int32), ("group_by_cell", C.c_int32),
         ("labels_in_smem_by_snv", C.c_int32), ("labels_in_smem_by_cell", C.c_int32),
+        ("chunks_by_snv", C.c_int32), ("chunks_by_cell", C.c_int32),
+        ("stream_bytes_by_snv", C.c_int64), ("stream_bytes_by_cell", C.c_int64),
     ]
 
 
@@ -77,8 +80,8 @@ def lib():
         fn = getattr(L, name)
         if name not in ("ph_last_error", "ph_kernel_launches", "ph_destroy"):
             fn.restype = C.c_int
-    if L.ph_abi_version() != 1:
-        raise PhError(f"ABI version mismatch: library {L.ph_abi_version()} != binding 1")
+    if L.ph_abi_version() != ABI_VERSION:
+        raise PhError(f"ABI version mismatch: library {L.ph_abi_version()} != binding {ABI_VERSION}")
     _lib = L
     return L
 

@@ -1,6 +1,7 @@
 // Device-resident observation store: COO -> two code-segmented sparse copies (by SNV, by cell).
 // Replaces the dense `sparse_matrix()` unstack of the reference (phertilizer/phertilizer.py:153-161, 295-306).
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include <stdlib.h>
 
@@ -39,27 +40,33 @@ __global__ void k_code_hist(const uint16_t* __restrict__ code, int64_t nnz, unsi
   if (threadIdx.x < 64 && threadIdx.x < n_codes && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
 }
 
+// key = segment id << 32 | payload.  Segment id = line * (NSUB + 1) + s; s = d * NCH + chunk for a dense code d,
+// s = NSUB for the tail.  Payload: idx16 (dense; optionally with the shared-memory bank of its label above it so that
+// the sort groups a sub-segment's entries by bank) or  minor | code << minor_bits  (tail).
 __global__ void k_make_keys(const int32_t* __restrict__ major, const int32_t* __restrict__ minor,
-                            const uint16_t* __restrict__ code, int64_t nnz, int D, int minor_bits, int n_major,
-                            int n_minor, uint64_t* __restrict__ keys, int* bad) {
+                            const uint16_t* __restrict__ code, int64_t nnz, int D, int NCH, int CH, int minor_bits,
+                            int n_major, int n_minor, int bank_order, uint64_t* __restrict__ keys, int* bad) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const uint32_t NSUB = (uint32_t)(D * NCH);
   for (; i < nnz; i += stride) {
     uint32_t mj = (uint32_t)major[i], mn = (uint32_t)minor[i], c = code[i];
-    if (mj >= (uint32_t)n_major || mn >= (uint32_t)n_minor) *bad = 2;
-    uint32_t seg = c < (uint32_t)D ? c : (uint32_t)D;
-    uint32_t word = c < (uint32_t)D ? mn : (mn | (c << minor_bits));
-    keys[i] = ((uint64_t)(mj * (uint32_t)(D + 1) + seg) << 32) | word;
-  }
-}
-
-__global__ void k_extract(const uint64_t* __restrict__ keys, int64_t nnz, uint32_t* __restrict__ words, int* dup) {
-  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (; i < nnz; i += stride) {
-    uint64_t k = keys[i];
-    words[i] = (uint32_t)k;
-    if (i > 0 && keys[i - 1] == k) *dup = 1;
+    if (mj >= (uint32_t)n_major || mn >= (uint32_t)n_minor) {
+      *bad = 2;
+      mj = 0;
+      mn = 0;
+    }
+    uint32_t s, payload;
+    if (c < (uint32_t)D) {
+      const uint32_t ch = mn / (uint32_t)CH;
+      const uint32_t idx = 16u + (mn - ch * (uint32_t)CH);
+      s = c * (uint32_t)NCH + ch;
+      payload = idx | (bank_order ? (((idx >> 2) & 31u) << 16) : 0u);
+    } else {
+      s = NSUB;
+      payload = mn | (c << minor_bits);
+    }
+    keys[i] = ((uint64_t)(mj * (NSUB + 1u) + s) << 32) | payload;
   }
 }
 
@@ -75,11 +82,65 @@ __global__ void k_seg_offsets(const uint64_t* __restrict__ keys, int64_t nnz, in
   off[s] = lo;
 }
 
-int choose_group(double avg) {
-  // lanes cooperating on one line; each lane moves 16 B per step
-  if (avg >= 768) return 32;
-  if (avg >= 256) return 16;
-  return 8;
+// per sub-segment: groups of 8 entries (rounded up); per line: tail entries
+__global__ void k_seg_sizes(const int64_t* __restrict__ off, int64_t n_major, int NSUB, int64_t* __restrict__ groups,
+                            int64_t* __restrict__ tails) {
+  int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t nseg = n_major * (NSUB + 1);
+  if (k >= nseg) return;
+  const int64_t line = k / (NSUB + 1);
+  const int s = (int)(k - line * (NSUB + 1));
+  const int64_t cnt = off[k + 1] - off[k];
+  if (s < NSUB) groups[line * NSUB + s] = (cnt + 7) >> 3;
+  else tails[line] = cnt;
+}
+
+__global__ void k_narrow(const int64_t* __restrict__ in, int64_t n, uint32_t* __restrict__ out) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (uint32_t)in[i];
+}
+
+// Position of the r-th (in sorted order) of `cnt` entries inside its padded sub-segment of ng = ceil(cnt/8) groups.
+// bank_order = 0: identity.  bank_order = 1: the sorted (by bank) sequence is cut into 32 runs; run q feeds the groups
+// g with g % 32 == q, so that any 32 consecutive groups -- the 32 lanes of one LDS -- read labels from (nearly) 32
+// different shared-memory banks.
+__device__ __forceinline__ int64_t place(int64_t r, int64_t cnt, int bank_order) {
+  if (!bank_order) return r;
+  const int64_t ng = (cnt + 7) >> 3;
+  if (ng < 32) return r;  // short sub-segments: a single LDS row, nothing to spread
+  const int64_t nb = ng >> 5, rem = ng & 31;
+  const int64_t big = 8 * (nb + 1);  // slots of the first `rem` runs
+  int64_t q, col;
+  if (r < big * rem) {
+    q = r / big;
+    col = r - q * big;
+  } else {
+    const int64_t r2 = r - big * rem;
+    q = rem + r2 / (8 * nb);
+    col = r2 - (q - rem) * (8 * nb);
+  }
+  return (((col >> 3) << 5) + q) * 8 + (col & 7);
+}
+
+__global__ void k_scatter(const uint64_t* __restrict__ keys, int64_t nnz, const int64_t* __restrict__ off, int NSUB,
+                          const uint32_t* __restrict__ sub_off, const int64_t* __restrict__ tail_off, int bank_order,
+                          uint16_t* __restrict__ half, uint32_t* __restrict__ tail_words, int* dup) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < nnz; i += stride) {
+    const uint64_t k = keys[i];
+    if (i > 0 && keys[i - 1] == k) *dup = 1;
+    const int64_t seg = (int64_t)(k >> 32);
+    const int64_t line = seg / (NSUB + 1);
+    const int s = (int)(seg - line * (NSUB + 1));
+    const int64_t r = i - off[seg];
+    if (s < NSUB) {
+      const int64_t cnt = off[seg + 1] - off[seg];
+      half[(int64_t)sub_off[line * NSUB + s] * 8 + place(r, cnt, bank_order)] = (uint16_t)k;
+    } else {
+      tail_words[tail_off[line] + r] = (uint32_t)k;
+    }
+  }
 }
 
 int build_orient(ph_handle* h, PhOrient* o, const int32_t* d_major, const int32_t* d_minor, const uint16_t* d_code,
@@ -89,43 +150,99 @@ int build_orient(ph_handle* h, PhOrient* o, const int32_t* d_major, const int32_
   o->n_major = n_major;
   o->n_minor = n_minor;
   o->minor_bits = ph_ceil_log2((uint64_t)n_minor > 1 ? (uint64_t)n_minor : 2);
+  o->chunk_bits = h->chunk_bits;
+  const int CH = (1 << o->chunk_bits) - 16;
+  o->NCH = (n_minor + CH - 1) / CH;
   int D = 0;
   while (D < PH_DMAX && D < h->n_codes && (double)code_count[D] >= h->dense_min_avg * (double)n_major) ++D;
+  while (D > 0 && D * o->NCH > PH_MAX_SUB) --D;
   o->D = D;
+  o->NSUB = D * o->NCH;
   if (h->n_codes > D) {
     if (o->minor_bits >= 32 || (uint64_t)(h->n_codes - 1) >= (1ull << (32 - o->minor_bits)))
       PH_FAIL(PH_ERR_UNSUPPORTED, "%d (var,total) codes do not fit next to a %d-bit index in a 32-bit word",
               h->n_codes, o->minor_bits);
   }
-  const int64_t nseg = (int64_t)n_major * (D + 1);
+  const int NSUB = o->NSUB;
+  const int64_t nseg = (int64_t)n_major * (NSUB + 1);
   if (nseg >= (1ll << 31)) PH_FAIL(PH_ERR_UNSUPPORTED, "too many segments (%lld)", (long long)nseg);
-  o->group = choose_group(n_major > 0 ? (double)nnz / n_major : 0.0);
+  {
+    const int last = n_minor - (o->NCH - 1) * CH;
+    o->lab_bytes = (((o->NCH - 1) << o->chunk_bits) + 16 + last + 15) & ~15;
+  }
+  o->batch = (n_major > 0 && (double)nnz / n_major >= 512.0) ? 8 : 32;
   o->labels_in_smem = 1;
-
-  PH_CUDA(cudaMalloc(&o->words, (size_t)(nnz + 8) * sizeof(uint32_t)));
-  PH_CUDA(cudaMalloc(&o->seg_off, (size_t)(nseg + 1) * sizeof(int64_t)));
-  PH_CUDA(cudaMemset(o->words + nnz, 0, 8 * sizeof(uint32_t)));
-  h->device_bytes += (nnz + 8) * (int64_t)sizeof(uint32_t) + (nseg + 1) * (int64_t)sizeof(int64_t);
 
   const int threads = 256;
   const int blocks = h->sm_count * 8;
-  if (nnz > 0) {
-    k_make_keys<<<blocks, threads>>>(d_major, d_minor, d_code, nnz, D, o->minor_bits, n_major, n_minor, kbuf0, d_flag);
+  int64_t* d_off = nullptr;      // [nseg + 1] positions in the sorted order
+  int64_t* d_sizes = nullptr;    // [n_major * NSUB + 1 | n_major + 1] sizes, then their exclusive sums
+  int rc = PH_OK;
+  auto body = [&]() -> int {
+    const int64_t n_sub = (int64_t)n_major * NSUB;
+    PH_CUDA(cudaMalloc(&d_off, (size_t)(nseg + 1) * sizeof(int64_t)));
+    PH_CUDA(cudaMalloc(&d_sizes, (size_t)(n_sub + 1 + n_major + 1) * sizeof(int64_t)));
+    PH_CUDA(cudaMemset(d_sizes, 0, (size_t)(n_sub + 1 + n_major + 1) * sizeof(int64_t)));
+    int64_t* d_groups = d_sizes;
+    int64_t* d_tails = d_sizes + n_sub + 1;
+    PH_CUDA(cudaMalloc(&o->sub_off, (size_t)(n_sub + 1) * sizeof(uint32_t)));
+    PH_CUDA(cudaMalloc(&o->tail_off, (size_t)(n_major + 1) * sizeof(int64_t)));
+    h->device_bytes += (n_sub + 1) * (int64_t)sizeof(uint32_t) + (n_major + 1) * (int64_t)sizeof(int64_t);
+    const uint64_t* sorted = kbuf0;
+    if (nnz > 0) {
+      k_make_keys<<<blocks, threads>>>(d_major, d_minor, d_code, nnz, D, o->NCH, CH, o->minor_bits, n_major, n_minor,
+                                       h->bank_order, kbuf0, d_flag);
+      ph_count_launch();
+      cub::DoubleBuffer<uint64_t> db(kbuf0, kbuf1);
+      int end_bit = 32 + ph_ceil_log2((uint64_t)nseg + 1);
+      if (end_bit > 64) end_bit = 64;
+      PH_CUDA(cub::DeviceRadixSort::SortKeys(d_temp, temp_bytes, db, nnz, 0, end_bit));
+      ph_count_launch(4);
+      sorted = db.Current();
+    }
+    k_seg_offsets<<<(unsigned)((nseg + 1 + threads - 1) / threads), threads>>>(sorted, nnz, nseg, d_off);
     ph_count_launch();
-    cub::DoubleBuffer<uint64_t> db(kbuf0, kbuf1);
-    int end_bit = 32 + ph_ceil_log2((uint64_t)nseg + 1);
-    if (end_bit > 64) end_bit = 64;
-    PH_CUDA(cub::DeviceRadixSort::SortKeys(d_temp, temp_bytes, db, nnz, 0, end_bit));
-    ph_count_launch(4);
-    k_extract<<<blocks, threads>>>(db.Current(), nnz, o->words, d_flag + 1);
+    if (nseg > 0) {
+      k_seg_sizes<<<(unsigned)((nseg + threads - 1) / threads), threads>>>(d_off, n_major, NSUB, d_groups, d_tails);
+      ph_count_launch();
+    }
+    // exclusive sums in place (the extra trailing zero element receives the total)
+    size_t need = 0, need2 = 0;
+    PH_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, need, d_groups, d_groups, (int)(n_sub + 1)));
+    PH_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, need2, d_tails, d_tails, (int)(n_major + 1)));
+    if (need > temp_bytes || need2 > temp_bytes) PH_FAIL(PH_ERR_CUDA, "scan scratch too small");
+    PH_CUDA(cub::DeviceScan::ExclusiveSum(d_temp, need, d_groups, d_groups, (int)(n_sub + 1)));
+    PH_CUDA(cub::DeviceScan::ExclusiveSum(d_temp, need2, d_tails, d_tails, (int)(n_major + 1)));
+    ph_count_launch(2);
+    int64_t totals[2];
+    PH_CUDA(cudaMemcpy(&totals[0], d_groups + n_sub, sizeof(int64_t), cudaMemcpyDeviceToHost));
+    PH_CUDA(cudaMemcpy(&totals[1], d_tails + n_major, sizeof(int64_t), cudaMemcpyDeviceToHost));
+    o->n_groups = totals[0];
+    o->n_tail = totals[1];
+    if (o->n_groups >= (1ll << 32) - 4096) PH_FAIL(PH_ERR_UNSUPPORTED, "%lld groups exceed 32-bit group offsets", (long long)o->n_groups);
+    k_narrow<<<(unsigned)((n_sub + 1 + threads - 1) / threads), threads>>>(d_groups, n_sub + 1, o->sub_off);
     ph_count_launch();
-    k_seg_offsets<<<(unsigned)((nseg + 1 + threads - 1) / threads), threads>>>(db.Current(), nnz, nseg, o->seg_off);
-    ph_count_launch();
-  } else {
-    PH_CUDA(cudaMemset(o->seg_off, 0, (size_t)(nseg + 1) * sizeof(int64_t)));
-  }
-  PH_CUDA(cudaGetLastError());
-  return PH_OK;
+    PH_CUDA(cudaMemcpy(o->tail_off, d_tails, (size_t)(n_major + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice));
+    // the stream is over-read by up to 3 prefetched steps of 32 groups past a batch: keep 160 zero groups of slack
+    const size_t half_bytes = (size_t)(o->n_groups + 160) * 16;
+    PH_CUDA(cudaMalloc(&o->half, half_bytes));
+    PH_CUDA(cudaMemset(o->half, 0, half_bytes));
+    PH_CUDA(cudaMalloc(&o->tail_words, (size_t)(o->n_tail + 8) * sizeof(uint32_t)));
+    PH_CUDA(cudaMemset(o->tail_words, 0, (size_t)(o->n_tail + 8) * sizeof(uint32_t)));
+    h->device_bytes += (int64_t)half_bytes + (o->n_tail + 8) * (int64_t)sizeof(uint32_t);
+    if (nnz > 0) {
+      k_scatter<<<blocks, threads>>>(sorted, nnz, d_off, NSUB, o->sub_off, o->tail_off, h->bank_order, o->half,
+                                     o->tail_words, d_flag + 1);
+      ph_count_launch();
+    }
+    PH_CUDA(cudaGetLastError());
+    PH_CUDA(cudaDeviceSynchronize());
+    return PH_OK;
+  };
+  rc = body();
+  cudaFree(d_off);
+  cudaFree(d_sizes);
+  return rc;
 }
 
 }  // namespace
@@ -133,10 +250,13 @@ int build_orient(ph_handle* h, PhOrient* o, const int32_t* d_major, const int32_
 extern "C" void ph_destroy(ph_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
-  cudaFree(h->by_snv.words);
-  cudaFree(h->by_snv.seg_off);
-  cudaFree(h->by_cell.words);
-  cudaFree(h->by_cell.seg_off);
+  for (PhOrient* o : {&h->by_snv, &h->by_cell}) {
+    cudaFree(o->half);
+    cudaFree(o->sub_off);
+    cudaFree(o->tail_words);
+    cudaFree(o->tail_off);
+  }
+  cudaFree(h->d_lab_img);
   cudaFree(h->d_L0);
   cudaFree(h->d_L1);
   cudaFree(h->d_varpos);
@@ -185,6 +305,13 @@ extern "C" int ph_create(int32_t n_cells, int32_t n_snvs, int64_t nnz, const int
   {
     const char* e = getenv("PH_DENSE_MIN_AVG");  // tuning knob: minimum average entries per line of a dense code
     h->dense_min_avg = e ? atof(e) : 32.0;
+    e = getenv("PH_CHUNK_BITS");  // test knob: log2 of the label-image stride of one chunk of the minor axis
+    h->chunk_bits = e ? atoi(e) : 16;
+    if (h->chunk_bits < 6 || h->chunk_bits > 16) h->chunk_bits = 16;
+    e = getenv("PH_BANK_ORDER");  // order a sub-segment's entries by shared-memory bank (default on)
+    h->bank_order = e ? atoi(e) : 1;
+    e = getenv("PH_CTAS");  // pass kernels: CTAs per SM (1 x 1024 threads, or 2 x 512 when two label images fit)
+    h->ctas_per_sm = e ? atoi(e) : 1;
   }
 
   int rc = PH_OK;
@@ -261,8 +388,9 @@ extern "C" int ph_create(int32_t n_cells, int32_t n_snvs, int64_t nnz, const int
       cub::DoubleBuffer<uint64_t> db(kbuf0, kbuf1);
       PH_TRY(cub::DeviceRadixSort::SortKeys(nullptr, temp_bytes, db, nnz, 0, 64));
     }
-    PH_TRY(cudaMalloc(&d_temp, temp_bytes ? temp_bytes : 16));
   }
+  if (temp_bytes < (1u << 20)) temp_bytes = 1u << 20;  // also serves the offset scans
+  PH_TRY(cudaMalloc(&d_temp, temp_bytes));
   rc = build_orient(h, &h->by_snv, d_snv, d_cell, d_code, n_snvs, n_cells, h_hist, kbuf0, kbuf1, d_temp, temp_bytes, d_flag);
   if (rc != PH_OK) goto done;
   rc = build_orient(h, &h->by_cell, d_cell, d_snv, d_code, n_cells, n_snvs, h_hist, kbuf0, kbuf1, d_temp, temp_bytes, d_flag);
@@ -286,6 +414,8 @@ extern "C" int ph_create(int32_t n_cells, int32_t n_snvs, int64_t nnz, const int
   // scratch
   PH_TRY(cudaMalloc(&h->d_lab_minor, (size_t)nmax + 16));
   PH_TRY(cudaMalloc(&h->d_lab_major, (size_t)nmax + 16));
+  h->lab_img_bytes = (size_t)(h->by_snv.lab_bytes > h->by_cell.lab_bytes ? h->by_snv.lab_bytes : h->by_cell.lab_bytes) + 64;
+  PH_TRY(cudaMalloc(&h->d_lab_img, h->lab_img_bytes));
   PH_TRY(cudaMalloc(&h->d_list, (size_t)nmax * sizeof(int32_t)));
   PH_TRY(cudaMalloc(&h->d_f64, (size_t)nmax * 2 * PH_MAX_FAST_CLUSTERS * sizeof(double)));
   PH_TRY(cudaMalloc(&h->d_i32, (size_t)nmax * 2 * PH_MAX_FAST_CLUSTERS * sizeof(int32_t)));
@@ -329,8 +459,12 @@ extern "C" int ph_get_info(const ph_handle* h, ph_info* out) {
   out->device_bytes = h->device_bytes;
   out->device = h->device;
   out->sm_count = h->sm_count;
-  out->group_by_snv = h->by_snv.group;
-  out->group_by_cell = h->by_cell.group;
+  out->group_by_snv = h->by_snv.batch;
+  out->group_by_cell = h->by_cell.batch;
+  out->chunks_by_snv = h->by_snv.NCH;
+  out->chunks_by_cell = h->by_cell.NCH;
+  out->stream_bytes_by_snv = h->by_snv.n_groups * 16 + h->by_snv.n_tail * 4;
+  out->stream_bytes_by_cell = h->by_cell.n_groups * 16 + h->by_cell.n_tail * 4;
   out->labels_in_smem_by_snv = h->by_snv.labels_in_smem;
   out->labels_in_smem_by_cell = h->by_cell.labels_in_smem;
   return PH_OK;
@@ -340,7 +474,8 @@ extern "C" int ph_set_group(ph_handle* h, int group_by_snv, int group_by_cell) {
   if (!h) PH_FAIL(PH_ERR_ARG, "null handle");
   auto ok = [](int g) { return g == 0 || g == 8 || g == 16 || g == 32; };
   if (!ok(group_by_snv) || !ok(group_by_cell)) PH_FAIL(PH_ERR_ARG, "group must be 0, 8, 16 or 32");
-  if (group_by_snv) h->by_snv.group = group_by_snv;
-  if (group_by_cell) h->by_cell.group = group_by_cell;
+  // lines per warp batch: 32 for short lines, 8 otherwise (16 is accepted for ABI compatibility and means 8)
+  if (group_by_snv) h->by_snv.batch = group_by_snv == 32 ? 32 : 8;
+  if (group_by_cell) h->by_cell.batch = group_by_cell == 32 ? 32 : 8;
   return PH_OK;
 }

@@ -7,10 +7,10 @@
 
 #include "phertilizer_b200.h"
 
+#define PH_MAX_SUB 32      // max sub-segments (dense codes x chunks) per line
 #define PH_DMAX 4           // max "dense" (var,total) codes that get their own segment per line
-#define PH_BLOCK 1024       // threads per CTA of the pass kernels (one CTA per SM)
 #define PH_FIELD_BITS 10    // packed per-lane counter field width (3 labels x 10 bits, excluded label -> bit 30)
-#define PH_CHUNK_ITERS 255  // 4 increments/iteration -> a field gains <= 1020 < 1024 per chunk
+#define PH_FLUSH_GROUPS 127 // 8 increments per group -> a field gains <= 1016 < 1024 between flushes
 
 extern thread_local char ph_err_msg[512];
 void ph_count_launch(int n = 1);
@@ -32,15 +32,30 @@ void ph_count_launch(int n = 1);
   } while (0)
 
 // One orientation of the observation store: "lines" are SNVs (by_snv, CSC-like) or cells (by_cell, CSR-like).
-// Entries of a line are sorted by (segment, word): segments 0..D-1 hold the D most frequent (var,total) codes
-// (word = minor index only), segment D ("tail") holds everything else with word = minor | code << minor_bits.
+//
+// The minor axis is cut into chunks of CH = 2^chunk_bits - 16 indices, so that an entry is ONE 16-bit half-word
+//   idx16 = 16 + (minor - chunk * CH)            (values 0..15 never occur; 0 is the padding entry)
+// A line's entries with one of the D most frequent ("dense") (var,total) codes are stored as D * NCH sub-segments
+// ordered by (code, chunk); every sub-segment is padded with idx16 = 0 to a whole number of 16-byte GROUPS (8 entries),
+// so a line -- and any run of consecutive lines -- is one contiguous, 16-byte aligned stream of groups.
+//   half    [n_groups * 8]            the stream
+//   sub_off [n_major * NSUB + 1]      first group of every sub-segment (NSUB = D * NCH)
+// Entries with rarer codes go to the "tail": tail_words = minor | code << minor_bits, tail_off per line.
+// The kernels keep a label image of the minor axis in shared memory with the matching layout: chunk c at byte
+// c << chunk_bits, 16 "excluded" bytes (what the padding entries hit) followed by the labels of its indices.
 struct PhOrient {
-  uint32_t* words;    // [nnz + 8]   (padded so 16-byte loads may run past the end)
-  int64_t* seg_off;   // [n_major * (D+1) + 1]
+  uint16_t* half;
+  uint32_t* sub_off;
+  uint32_t* tail_words;  // [n_tail + 8]
+  int64_t* tail_off;     // [n_major + 1]
+  int64_t n_groups, n_tail;
   int32_t n_major, n_minor;
-  int32_t D;          // dense codes, 0..PH_DMAX
-  int32_t minor_bits; // bits of the minor index inside a tail word
-  int32_t group;      // lanes cooperating on one line (4, 8, 16, 32)
+  int32_t D;           // dense codes, 0..PH_DMAX
+  int32_t NCH, NSUB;   // chunks of the minor axis, sub-segments per line
+  int32_t chunk_bits;  // 16 in production (PH_CHUNK_BITS overrides it for tests)
+  int32_t minor_bits;  // bits of the minor index inside a tail word
+  int32_t lab_bytes;   // size of the label image
+  int32_t batch;       // lines per warp batch (8 or 32)
   int32_t labels_in_smem;
 };
 
@@ -56,10 +71,13 @@ struct ph_handle {
   double* d_L1;      // [n_codes]
   uint8_t* d_varpos; // [n_codes]
   int64_t device_bytes;
+  int chunk_bits, bank_order, ctas_per_sm;
   double dense_min_avg;  // a (var,total) code gets its own segment when it has >= this many entries per line on average
   // scratch (device)
   uint8_t* d_lab_minor;  // [max(n,m)] staged labels of the minor axis
   uint8_t* d_lab_major;  // [max(n,m)]
+  uint8_t* d_lab_img;    // label image in global memory (only when it does not fit in shared memory)
+  size_t lab_img_bytes;
   int32_t* d_list;       // [max(n,m)] staged line list
   double* d_f64;         // [max(n,m) * 2 * 3 ... ] table scratch, see PH_SCRATCH_F64
   int32_t* d_i32;        // table scratch

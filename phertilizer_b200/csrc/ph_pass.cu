@@ -1,26 +1,31 @@
 // The sparse likelihood passes (K1/K1a/K2/K3/a-9/a-11) -- hand-written for sm_100a.
 //
-// One kernel template walks either orientation of the store.  G lanes cooperate on one line (an SNV for the
-// CSC-like copy, a cell for the CSR-like copy).  The cluster label of every minor index lives in shared memory,
-// pre-scaled to a bit shift, so one observation costs: 1/4 LDG.128 + LDS.U8 + SHF + IADD.  Because a line's
-// entries are segmented by (var,total) code, the lanes only COUNT observations per (code, cluster) in packed
-// 10-bit integer fields; the fp64 log-likelihood sums are  sum_code count * L[code]  evaluated once per line in a
-// fixed order -> exact integer tables, deterministic fp64 results, no atomics anywhere.
+// One kernel template walks either orientation of the store (ph_common.cuh, PhOrient).  A warp takes a BATCH of
+// consecutive lines (SNVs of the CSC-like copy, cells of the CSR-like copy) and streams their 16-bit entries as one
+// contiguous run of 16-byte groups: lane L reads groups L, L+32, ... through a 4-deep register ring of 16-byte
+// `ld.global.nc` loads, independent of where lines and sub-segments begin.  The cluster label of every minor index
+// lives in shared memory, pre-scaled to a bit shift, so one observation costs  1/8 LDG.128 + PRMT + LDS.U8 + SHF + IADD:
+// the lanes only COUNT observations per (code, cluster) in packed 10-bit fields and flush them with shared-memory
+// integer atomics when their group leaves a (line, code) run.  The fp64 log-likelihood sums are
+// sum_code count * L[code]  evaluated once per line in a fixed order -> exact integer tables, deterministic fp64
+// results, no floating-point atomics anywhere.
 //
-// HBM traffic: 4 B per observation (+ segment offsets), the roofline of these kernels.
+// HBM traffic: 2 B per observation (+ padding to 16 B per sub-segment, + offsets), the roofline of these kernels.
 #include "ph_common.cuh"
 
 namespace {
 
 enum { MODE_TABLE = 0, MODE_LINEAR = 1, MODE_BRANCHING = 2, MODE_MAPPED = 3 };
 
-constexpr int kBlock = 512;  // threads per CTA, 1 CTA / SM, <= 128 registers per thread
+constexpr int kBlock = 512;  // threads per CTA of the node-table kernel
 
 struct PassArgs {
-  const uint32_t* __restrict__ words;
-  const int64_t* __restrict__ seg_off;
-  int D, minor_bits, n_minor;
-  const uint8_t* __restrict__ minor_label;  // raw labels [n_minor]; SMEM_LAB=false: pre-scaled shifts
+  const uint16_t* __restrict__ half;
+  const uint32_t* __restrict__ sub_off;
+  const uint32_t* __restrict__ tail_words;
+  const int64_t* __restrict__ tail_off;
+  int D, NCH, NSUB, chunk_bits, minor_bits, n_minor, lab_bytes;
+  const uint8_t* __restrict__ minor_label;  // raw labels [n_minor] (SMEM_LAB) or the prepared label image (global)
   const int32_t* __restrict__ list;         // optional list of lines
   int n_work;
   const double* __restrict__ L0;
@@ -39,11 +44,11 @@ struct PassArgs {
   unsigned* counter;                                     // batch dispenser, zeroed before every launch
 };
 
-__device__ __forceinline__ uint4 ld_stream(const uint32_t* p) {
+__device__ __forceinline__ uint4 ld_stream(const uint4* p) {
   uint4 v;
-  asm("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-      : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-      : "l"(p));
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
   return v;
 }
 
@@ -58,52 +63,79 @@ __device__ __forceinline__ uint32_t scale_labels4(uint32_t w) {
   return __byte_perm(table, 0u, sel);
 }
 
-// One warp walks a BATCH of B = 8 * (32 / G) lines handed out by an atomic counter.  G lanes cooperate on one line
-// (32 / G lines at a time): the dense part is counted cooperatively with coalesced 16-byte loads; the per-line totals
-// are then parked in "holder" lane (line % B).  After the batch every holder finishes ITS line alone -- rare-code tail,
-// fp64 sums, epilogue, store -- so the per-line scalar work is spread over the lanes instead of being replicated 32x.
-// NC = counted classes; MINB = resident CTAs per SM (2 when two copies of the label table fit in shared memory).
-template <int G, int MODE, int NC, bool SMEM_LAB>
+// node ids: anything >= K (255 = not in the tree) -> K
+__device__ __forceinline__ uint32_t clamp_nodes4(uint32_t w, uint32_t K) {
+  uint32_t r = 0;
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    uint32_t v = (w >> (8 * b)) & 0xFFu;
+    v = v < K ? v : K;
+    r |= v << (8 * b);
+  }
+  return r;
+}
+
+// Label image of the minor axis (ph_common.cuh): chunk c at byte c << cb = 16 "excluded" bytes + the chunk's labels.
+// NODES = false: labels 0..NC -> counter shifts.  NODES = true: node ids clamped to K, padding slots hold K + 1.
+template <bool NODES, int NC>
+__device__ __forceinline__ void fill_label_image(uint8_t* img, const uint8_t* __restrict__ raw, int n_minor, int NCH, int cb,
+                                                 int K, int tid, int nthreads) {
+  const int CH = (1 << cb) - 16;
+  const uint32_t excl = NODES ? (uint32_t)(K + 1) : (uint32_t)(PH_FIELD_BITS * NC);
+  for (int c = 0; c < NCH; ++c) {
+    const int cnt = min(CH, n_minor - c * CH);
+    const int nw = (cnt + 3) >> 2;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(raw + (size_t)c * CH);  // buffers are padded to 4 B
+    uint32_t* dst = reinterpret_cast<uint32_t*>(img + ((size_t)c << cb));
+    if (tid < 4) dst[tid] = excl * 0x01010101u;
+    for (int i = tid; i < nw; i += nthreads) {
+      const uint32_t w = src[i];
+      dst[4 + i] = NODES ? clamp_nodes4(w, (uint32_t)K) : scale_labels4<NC>(w);
+    }
+  }
+}
+
+// per-warp shared-memory words: sub-segment bounds [B][NSUB+1], counters [B][D][NC], line ids [B], line labels [B]
+__host__ __device__ inline int warp_words(int B, int NSUB, int D, int NC) { return B * (NSUB + 1) + B * D * NC + 2 * B; }
+
+// One warp walks a batch of B lines handed out by an atomic counter.  After the streaming phase lane (l % B) finishes
+// line l alone ("holder"): rare-code tail, fp64 sums, epilogue, store.
+// NC = counted classes; S16 = production layout (chunk stride 2^16: the label address is one PRMT).
+template <int B, int MODE, int NC, bool SMEM_LAB, bool S16>
 __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
-  const int kBlock = blockDim.x;  // 512 (two CTAs per SM) or 1024 (one CTA per SM): 32 warps per SM either way
   extern __shared__ __align__(16) uint8_t smem[];
-  // ---- shared memory carve-up: [labels][map][L0][L1][varpos]
+  const int nthreads = blockDim.x;
+  const int D = a.D, NCH = a.NCH, NSUB = a.NSUB, NS1 = NSUB + 1, cb = a.chunk_bits;
+  const int K2 = a.K + 2;
+  // ---- shared memory carve-up: [label image][map][L0][L1][varpos][per-warp tables]
   uint8_t* s_lab = smem;
-  size_t off = 0;
-  if (SMEM_LAB) off = ((size_t)a.n_minor + 15) & ~(size_t)15;
+  size_t off = SMEM_LAB ? (size_t)a.lab_bytes : 0;
   uint8_t* s_map = smem + off;
-  if (MODE == MODE_MAPPED) off += (((size_t)(a.K + 1) * (a.K + 1)) + 15) & ~(size_t)15;
+  if (MODE == MODE_MAPPED) off += ((size_t)K2 * K2 + 15) & ~(size_t)15;
   double* s_L0 = reinterpret_cast<double*>(smem + off);
   double* s_L1 = s_L0 + (a.lut_in_smem ? a.n_codes : 0);
   uint8_t* s_vp = reinterpret_cast<uint8_t*>(s_L1 + (a.lut_in_smem ? a.n_codes : 0));
+  if (a.lut_in_smem) off += ((size_t)a.n_codes * 17 + 15) & ~(size_t)15;
+  const int wsz = warp_words(B, NSUB, D, NC);
+  uint32_t* s_b = reinterpret_cast<uint32_t*>(smem + off) + (threadIdx.x >> 5) * wsz;
+  uint32_t* s_cnt = s_b + B * NS1;
+  int32_t* s_ln = reinterpret_cast<int32_t*>(s_cnt + B * D * NC);
+  uint32_t* s_ml = reinterpret_cast<uint32_t*>(s_ln + B);
 
-  if (SMEM_LAB) {
-    const int nw = (a.n_minor + 3) >> 2;
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(a.minor_label);  // buffers are padded to 4 B
-    uint32_t* dst = reinterpret_cast<uint32_t*>(s_lab);
-    for (int i = threadIdx.x; i < nw; i += kBlock) {
-      uint32_t w = src[i];
-      if (MODE == MODE_MAPPED) {
-        // raw node ids; anything >= K (255 = not in tree) -> K
-        uint32_t r = 0;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          uint32_t v = (w >> (8 * b)) & 0xFFu;
-          v = v < (uint32_t)a.K ? v : (uint32_t)a.K;
-          r |= v << (8 * b);
-        }
-        dst[i] = r;
-      } else {
-        dst[i] = scale_labels4<NC>(w);
-      }
+  if (SMEM_LAB) fill_label_image<MODE == MODE_MAPPED, NC>(s_lab, a.minor_label, a.n_minor, NCH, cb, a.K, threadIdx.x, nthreads);
+  if (MODE == MODE_MAPPED) {
+    // rows: node of the line (K, K+1: not in the tree -> nothing counts); columns: node of the minor index
+    // (K: not in the tree -> absent, K+1: padding -> not counted)
+    constexpr uint32_t EX = PH_FIELD_BITS * NC;
+    for (int i = threadIdx.x; i < K2 * K2; i += nthreads) {
+      const int r = i / K2, q = i - r * K2;
+      uint32_t v = EX;
+      if (r < a.K && q <= a.K) v = (q < a.K && a.map[r * (a.K + 1) + q]) ? PH_FIELD_BITS : 0;
+      s_map[i] = (uint8_t)v;
     }
   }
-  if (MODE == MODE_MAPPED) {
-    const int nm = (a.K + 1) * (a.K + 1);
-    for (int i = threadIdx.x; i < nm; i += kBlock) s_map[i] = a.map[i] ? PH_FIELD_BITS : 0;
-  }
   if (a.lut_in_smem) {
-    for (int i = threadIdx.x; i < a.n_codes; i += kBlock) {
+    for (int i = threadIdx.x; i < a.n_codes; i += nthreads) {
       s_L0[i] = a.L0[i];
       s_L1[i] = a.L1[i];
       s_vp[i] = a.varpos[i];
@@ -116,23 +148,15 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
   const uint8_t* lab = SMEM_LAB ? s_lab : a.minor_label;
 
   constexpr unsigned FULL = 0xffffffffu;
-  constexpr int NG = 32 / G;      // lines in flight per warp
-  constexpr int B = 8 * NG;       // lines per batch (holder lanes 0..B-1)
-  constexpr int PARTS = 32 / B;   // lanes sharing the tail of one line
-  constexpr int STEP = 4 * G;     // words per cooperative step
+  constexpr int PARTS = 32 / B;  // lanes sharing the tail of one line
   constexpr unsigned FM = (1u << PH_FIELD_BITS) - 1u;
   const int lane = threadIdx.x & 31;
-  const int g = lane & (G - 1);
-  const int q = lane / G;
-  const unsigned gmask = (G == 32) ? FULL : (((1u << G) - 1u) << (lane & ~(G - 1)));
-  const int D = a.D;
   const uint32_t mmask = (a.minor_bits >= 32) ? 0xffffffffu : ((1u << a.minor_bits) - 1u);
   const int n_batches = (a.n_work + B - 1) / B;
+  const uint32_t CH = (1u << cb) - 16u;
 
-  auto shift_of = [&](uint32_t minor, const uint8_t* maprow) -> uint32_t {
-    uint32_t l = SMEM_LAB ? (uint32_t)lab[minor] : (uint32_t)__ldg(lab + minor);
-    if (MODE == MODE_MAPPED) l = maprow[l];
-    return l;
+  auto label_at = [&](uint32_t addr) -> uint32_t {
+    return SMEM_LAB ? (uint32_t)lab[addr] : (uint32_t)__ldg(lab + addr);
   };
 
   for (;;) {
@@ -140,146 +164,145 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
     if (lane == 0) bidx = atomicAdd(a.counter, 1u);
     bidx = __shfl_sync(FULL, bidx, 0);
     if (bidx >= (unsigned)n_batches) break;
+    const int first = (int)bidx * B;
+    const int nl = min(B, a.n_work - first);
 
-    // ---- every lane loads the offsets of "its" line of the batch (lane % B); lanes >= B duplicate for the tail split
-    const int myw = (int)bidx * B + (lane % B);
-    const bool have = myw < a.n_work;
-    int64_t h_base = 0;
-    int h_rb[PH_DMAX + 1], h_rend = 0;
-#pragma unroll
-    for (int d = 0; d <= PH_DMAX; ++d) h_rb[d] = 0;
+    // ---- my line (lane % B): holder duties after the streaming phase
+    const int myl = lane % B;
+    const int myw = first + myl;
+    const bool have = myl < nl;
+    const int line = have ? (a.list ? __ldg(a.list + myw) : myw) : -1;
     uint32_t h_ml = 0;
     bool h_skip = !have;
-    if (have) {
-      const int line = a.list ? __ldg(a.list + myw) : myw;
-      const int64_t* p = a.seg_off + (int64_t)line * (D + 1);
-      const int64_t b0 = __ldg(p);
-      h_base = b0 & ~(int64_t)3;
-      h_rb[0] = (int)(b0 - h_base);
-#pragma unroll
-      for (int d = 1; d <= PH_DMAX; ++d) h_rb[d] = (int)(__ldg(p + (d < D ? d : D)) - h_base);
-      h_rend = (int)(__ldg(p + D + 1) - h_base);
-      if (MODE == MODE_MAPPED) {
+    if (MODE == MODE_MAPPED) {
+      h_ml = (uint32_t)a.K;
+      if (have) {
         h_ml = a.major_label[line];
         if (h_ml >= (uint32_t)a.K) {  // cell not in the tree: contributes nothing
           h_skip = true;
-          h_ml = 0;
-          h_rend = h_rb[0];
-#pragma unroll
-          for (int d = 1; d <= PH_DMAX; ++d) h_rb[d] = h_rb[0];
+          h_ml = (uint32_t)a.K;
         }
       }
     }
-    unsigned hcnt[PH_DMAX][NC];
-#pragma unroll
-    for (int d = 0; d < PH_DMAX; ++d)
-#pragma unroll
-      for (int c = 0; c < NC; ++c) hcnt[d][c] = 0;
+    if (lane < B) {
+      s_ln[lane] = line;
+      s_ml[lane] = h_ml;
+    }
+    for (int k = lane; k < B * D * NC; k += 32) s_cnt[k] = 0;
+    __syncwarp();
+    for (int k = lane; k < B * NS1; k += 32) {
+      const int l = k / NS1, s = k - l * NS1;
+      const int ln = s_ln[l];
+      s_b[k] = ln >= 0 ? __ldg(a.sub_off + (size_t)ln * NSUB + s) : 0u;
+    }
+    __syncwarp();
 
-    // ---- dense part: the warp's NG groups walk the batch, 8 rounds
-#pragma unroll 1
-    for (int it = 0; it < 8; ++it) {
-      const int src = it * NG + q;  // holder lane of my group's current line
-      const int64_t base = __shfl_sync(FULL, h_base, src);
-      int rb[PH_DMAX + 1];
-#pragma unroll
-      for (int d = 0; d <= PH_DMAX; ++d) rb[d] = __shfl_sync(FULL, h_rb[d], src);
-      const int rD = rb[PH_DMAX];
-      const uint8_t* maprow = nullptr;
-      if (MODE == MODE_MAPPED) maprow = s_map + __shfl_sync(FULL, h_ml, src) * (a.K + 1);
-      const uint32_t* wp = a.words + base;
+    // ---- dense part: maximal runs of lines that are contiguous in memory are streamed as one range of groups
+    if (NSUB > 0) {
+      int l0 = 0;
+      while (l0 < nl) {
+        int l1 = l0 + 1;
+        while (l1 < nl && s_b[l1 * NS1] == s_b[(l1 - 1) * NS1 + NSUB]) ++l1;
+        const uint32_t gbeg = s_b[l0 * NS1], gend = s_b[(l1 - 1) * NS1 + NSUB];
+        uint32_t g = gbeg + lane;
+        const uint4* gp = reinterpret_cast<const uint4*>(a.half) + g;
+        // cursor over the sub-segments: (l, s = d * NCH + ch), *bp = end of the current sub-segment
+        int l = l0, s = 0, d = 0, ch = 0;
+        const uint32_t* bp = s_b + l0 * NS1 + 1;
+        uint32_t nb = *bp;
+        uint32_t cur_key = 0xffffffffu, acc = 0;
+        int nacc = 0;
+        const uint8_t* maprow = s_map;
 
-      unsigned cnt[PH_DMAX][NC];
-      unsigned accd[PH_DMAX];
-#pragma unroll
-      for (int d = 0; d < PH_DMAX; ++d) {
-        accd[d] = 0;
-#pragma unroll
-        for (int c = 0; c < NC; ++c) cnt[d][c] = 0;
-      }
-
-      // straddling 4-word groups: one per unaligned segment boundary, one word per lane
-      for (int k = g; k < 4 * (D + 1); k += G) {
-        const int e = k >> 2, t = k & 3;
-        const int be = e == 0 ? rb[0] : e == 1 ? rb[1] : e == 2 ? rb[2] : e == 3 ? rb[3] : rb[4];
-        const int bp = e <= 1 ? rb[0] : e == 2 ? rb[1] : e == 3 ? rb[2] : rb[3];
-        const bool mine = ((be & 3) != 0) && !(e > 0 && (bp & 3) != 0 && (bp >> 2) == (be >> 2));
-        const int qq = (be & ~3) + t;
-        if (mine && qq >= rb[0] && qq < rD) {
-          const unsigned inc = 1u << shift_of(__ldg(wp + qq), maprow);
-          const int dsel = (qq >= rb[1]) + (qq >= rb[2]) + (qq >= rb[3]);
-          if (dsel == 0) accd[0] += inc; else if (dsel == 1) accd[1] += inc; else if (dsel == 2) accd[2] += inc; else accd[3] += inc;
-        }
-      }
-
-      // aligned interior of every dense segment: double-buffered 16-byte loads through one running pointer
-#pragma unroll
-      for (int d = 0; d < PH_DMAX; ++d) {
-        if (d < D) {
-          const int A = (rb[d] + 3) & ~3;
-          const int E = rb[d + 1] & ~3;
-          constexpr int CH = 248 * STEP;  // a 10-bit field gains <= 4 per step: at most 248 steps between spills
-          unsigned acc = accd[d];
-          for (int c0 = A; c0 < E; c0 += CH) {
-            const int ce = (E - c0 > CH) ? c0 + CH : E;
-            const uint32_t* p = wp + c0 + 4 * g;
-            int left = ce - (c0 + 4 * g);
-            auto inc4 = [&](const uint4& w) -> unsigned {
-              return ((1u << shift_of(w.x, maprow)) + (1u << shift_of(w.y, maprow))) +
-                     ((1u << shift_of(w.z, maprow)) + (1u << shift_of(w.w, maprow)));
-            };
-            uint4 wa0, wa1, wb0, wb1;
-            if (left > 0) wa0 = ld_stream(p);
-            if (left > STEP) wa1 = ld_stream(p + STEP);
-            while (left > 0) {
-              if (left > 2 * STEP) wb0 = ld_stream(p + 2 * STEP);
-              if (left > 3 * STEP) wb1 = ld_stream(p + 3 * STEP);
-              acc += inc4(wa0);
-              if (left > STEP) acc += inc4(wa1);
-              if (left <= 2 * STEP) break;
-              if (left > 4 * STEP) wa0 = ld_stream(p + 4 * STEP);
-              if (left > 5 * STEP) wa1 = ld_stream(p + 5 * STEP);
-              acc += inc4(wb0);
-              if (left > 3 * STEP) acc += inc4(wb1);
-              p += 4 * STEP;
-              left -= 4 * STEP;
-            }
-#pragma unroll
-            for (int c = 0; c < NC; ++c) cnt[d][c] += (acc >> (PH_FIELD_BITS * c)) & FM;
-            acc = 0;
-          }
-          // segments without an aligned interior still carry their straddling-group counts
-#pragma unroll
-          for (int c = 0; c < NC; ++c) cnt[d][c] += (acc >> (PH_FIELD_BITS * c)) & FM;
-        }
-      }
-
-      // group totals -> holder lane
-#pragma unroll
-      for (int d = 0; d < PH_DMAX; ++d) {
-        if (d < D) {
+        auto flush = [&]() {
+          const uint32_t base = ((cur_key >> 3) * D + (cur_key & 7u)) * NC;
 #pragma unroll
           for (int c = 0; c < NC; ++c) {
-            unsigned t = __reduce_add_sync(gmask, cnt[d][c]);
-            if (NG > 1) t = __shfl_sync(FULL, t, (((lane % B) - it * NG) & (NG - 1)) * G);
-            if ((lane % B) / NG == it) hcnt[d][c] = t;
+            const uint32_t f = (acc >> (PH_FIELD_BITS * c)) & FM;
+            if (f) atomicAdd(&s_cnt[base + c], f);
           }
+        };
+        auto one = [&](uint32_t addr) -> uint32_t {
+          uint32_t sh = label_at(addr);
+          if (MODE == MODE_MAPPED) sh = maprow[sh];
+          return 1u << sh;
+        };
+        auto consume = [&](const uint4& w, uint32_t gg) {
+          while (gg >= nb) {
+            ++s; ++ch; ++bp;
+            if (ch == NCH) { ch = 0; ++d; }
+            if (s == NSUB) { s = 0; d = 0; ++l; ++bp; }
+            nb = *bp;
+          }
+          const uint32_t key = ((uint32_t)l << 3) | (uint32_t)d;
+          if (key != cur_key || nacc == PH_FLUSH_GROUPS) {
+            if (acc) flush();
+            acc = 0;
+            nacc = 0;
+            cur_key = key;
+            if (MODE == MODE_MAPPED) maprow = s_map + s_ml[l] * K2;
+          }
+          ++nacc;
+          const uint32_t cbase = (uint32_t)ch << cb;
+          uint32_t a0, a1, a2, a3, a4, a5, a6, a7;
+          if (S16) {
+            a0 = __byte_perm(w.x, cbase, 0x7610); a1 = __byte_perm(w.x, cbase, 0x7632);
+            a2 = __byte_perm(w.y, cbase, 0x7610); a3 = __byte_perm(w.y, cbase, 0x7632);
+            a4 = __byte_perm(w.z, cbase, 0x7610); a5 = __byte_perm(w.z, cbase, 0x7632);
+            a6 = __byte_perm(w.w, cbase, 0x7610); a7 = __byte_perm(w.w, cbase, 0x7632);
+          } else {
+            a0 = (w.x & 0xFFFFu) | cbase; a1 = (w.x >> 16) | cbase;
+            a2 = (w.y & 0xFFFFu) | cbase; a3 = (w.y >> 16) | cbase;
+            a4 = (w.z & 0xFFFFu) | cbase; a5 = (w.z >> 16) | cbase;
+            a6 = (w.w & 0xFFFFu) | cbase; a7 = (w.w >> 16) | cbase;
+          }
+          acc += ((one(a0) + one(a1)) + (one(a2) + one(a3))) + ((one(a4) + one(a5)) + (one(a6) + one(a7)));
+        };
+
+        uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0, r2 = r0, r3 = r0;
+        if (g < gend) r0 = ld_stream(gp);
+        if (g + 32 < gend) r1 = ld_stream(gp + 32);
+        if (g + 64 < gend) r2 = ld_stream(gp + 64);
+        if (g + 96 < gend) r3 = ld_stream(gp + 96);
+        while (g < gend) {
+          consume(r0, g);
+          if (g + 128 < gend) r0 = ld_stream(gp + 128);
+          if (g + 32 < gend) {
+            consume(r1, g + 32);
+            if (g + 160 < gend) r1 = ld_stream(gp + 160);
+          }
+          if (g + 64 < gend) {
+            consume(r2, g + 64);
+            if (g + 192 < gend) r2 = ld_stream(gp + 192);
+          }
+          if (g + 96 < gend) {
+            consume(r3, g + 96);
+            if (g + 224 < gend) r3 = ld_stream(gp + 224);
+          }
+          g += 128;
+          gp += 128;
         }
+        if (acc) flush();
+        l0 = l1;
       }
     }
+    __syncwarp();
 
     // ---- holders: tail (rare codes, word = minor | code << minor_bits), shared by PARTS lanes per line
-    const uint8_t* h_maprow = (MODE == MODE_MAPPED) ? s_map + h_ml * (a.K + 1) : nullptr;
+    const uint8_t* h_maprow = (MODE == MODE_MAPPED) ? s_map + h_ml * K2 : nullptr;
     double t0[NC], t1[NC];
     unsigned tn[NC], tv[NC];
 #pragma unroll
     for (int c = 0; c < NC; ++c) { t0[c] = 0.0; t1[c] = 0.0; tn[c] = 0; tv[c] = 0; }
-    {
-      const uint32_t* wp = a.words + h_base;
-      for (int r = h_rb[PH_DMAX] + lane / B; r < h_rend; r += PARTS) {
-        const uint32_t w = __ldg(wp + r);
+    if (have) {
+      const int64_t tb = __ldg(a.tail_off + line), te = __ldg(a.tail_off + line + 1);
+      for (int64_t r = tb + lane / B; r < te; r += PARTS) {
+        const uint32_t w = __ldg(a.tail_words + r);
         const uint32_t code = w >> a.minor_bits;
-        const uint32_t sh = shift_of(w & mmask, h_maprow);
+        const uint32_t minor = w & mmask;
+        const uint32_t chq = minor / CH;
+        uint32_t sh = label_at((chq << cb) | (16u + minor - chq * CH));
+        if (MODE == MODE_MAPPED) sh = h_maprow[sh];
         const double l0 = L0[code], l1 = L1[code];
         const unsigned vp = VP[code] ? 1u : 0u;
 #pragma unroll
@@ -312,19 +335,16 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
       unsigned nob[NC], nva[NC];
 #pragma unroll
       for (int c = 0; c < NC; ++c) { s0[c] = 0.0; s1[c] = 0.0; nob[c] = 0; nva[c] = 0; }
+      for (int d = 0; d < D; ++d) {
+        const double l0 = L0[d], l1 = L1[d];
+        const bool vp = VP[d] != 0;
 #pragma unroll
-      for (int d = 0; d < PH_DMAX; ++d) {
-        if (d < D) {
-          const double l0 = L0[d], l1 = L1[d];
-          const bool vp = VP[d] != 0;
-#pragma unroll
-          for (int c = 0; c < NC; ++c) {
-            const unsigned t = hcnt[d][c];
-            s0[c] = fma((double)t, l0, s0[c]);
-            s1[c] = fma((double)t, l1, s1[c]);
-            nob[c] += t;
-            nva[c] += vp ? t : 0u;
-          }
+        for (int c = 0; c < NC; ++c) {
+          const unsigned t = s_cnt[(myl * D + d) * NC + c];
+          s0[c] = fma((double)t, l0, s0[c]);
+          s1[c] = fma((double)t, l1, s1[c]);
+          nob[c] += t;
+          nva[c] += vp ? t : 0u;
         }
       }
 #pragma unroll
@@ -363,14 +383,14 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
         a.per_line[wi] = h_skip ? 0.0 : s0[0] + s1[NC > 1 ? 1 : 0];
       }
     }
+    __syncwarp();
   }
 }
 
-// pre-scale labels for the global-memory label path
-template <int NC>
-__global__ void k_scale_labels(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int n) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < ((n + 3) >> 2)) reinterpret_cast<uint32_t*>(out)[i] = scale_labels4<NC>(reinterpret_cast<const uint32_t*>(in)[i]);
+// label image in global memory, for minor axes whose image does not fit in shared memory
+template <bool NODES, int NC>
+__global__ void k_label_image(uint8_t* img, const uint8_t* __restrict__ raw, int n_minor, int NCH, int cb, int K) {
+  fill_label_image<NODES, NC>(img, raw, n_minor, NCH, cb, K, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
 }
 
 // deterministic block sums of a per-line table by the line's own label: out[(q-1)*C + c]
@@ -433,19 +453,15 @@ __global__ void __launch_bounds__(kBlock, 1) k_node_table(const PassArgs a, cons
   constexpr int groups_per_block = kBlock / G;
   size_t off = 0;
   uint8_t* s_lab = smem;
-  if (SMEM_LAB) off = ((size_t)a.n_minor + 15) & ~(size_t)15;
+  if (SMEM_LAB) off = (size_t)a.lab_bytes;
   double* s_acc0 = reinterpret_cast<double*>(smem + off);
   double* s_acc1 = s_acc0 + groups_per_block * K1;
   unsigned* s_cnt = reinterpret_cast<unsigned*>(s_acc1 + groups_per_block * K1);
   uint8_t* s_mem = reinterpret_cast<uint8_t*>(s_cnt + groups_per_block * K1);
-  if (SMEM_LAB) {
-    for (int i = threadIdx.x; i < a.n_minor; i += kBlock) {
-      uint32_t v = a.minor_label[i];
-      s_lab[i] = (uint8_t)(v < (uint32_t)K ? v : (uint32_t)K);
-    }
-  }
+  if (SMEM_LAB) fill_label_image<true, 1>(s_lab, a.minor_label, a.n_minor, a.NCH, a.chunk_bits, K, threadIdx.x, kBlock);
   for (int i = threadIdx.x; i < K * K1; i += kBlock) s_mem[i] = (i % K1) < K ? member[(i / K1) * K + (i % K1)] : 0;
   __syncthreads();
+  const uint8_t* lab = SMEM_LAB ? s_lab : a.minor_label;
   const int lane = threadIdx.x & 31, g = lane & (G - 1);
   const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
   const int grp = threadIdx.x / G;
@@ -453,21 +469,23 @@ __global__ void __launch_bounds__(kBlock, 1) k_node_table(const PassArgs a, cons
   double* acc1 = s_acc1 + grp * K1;
   unsigned* cnt = s_cnt + grp * K1;
   const int total_groups = gridDim.x * groups_per_block;
-  const int D = a.D;
+  const int D = a.D, NCH = a.NCH, NSUB = a.NSUB, cb = a.chunk_bits;
+  const uint32_t CH = (1u << cb) - 16u;
   const uint32_t mmask = (a.minor_bits >= 32) ? 0xffffffffu : ((1u << a.minor_bits) - 1u);
-  auto node_of = [&](uint32_t minor) -> uint32_t {
-    if (SMEM_LAB) return s_lab[minor];
-    uint32_t v = __ldg(a.minor_label + minor);
-    return v < (uint32_t)K ? v : (uint32_t)K;
-  };
+  auto node_at = [&](uint32_t addr) -> uint32_t { return SMEM_LAB ? (uint32_t)lab[addr] : (uint32_t)__ldg(lab + addr); };
   for (int wi = blockIdx.x * groups_per_block + grp; wi < a.n_work; wi += total_groups) {
     const int line = a.list ? a.list[wi] : wi;
-    const int64_t* so = a.seg_off + (int64_t)line * (D + 1);
+    const uint32_t* so = a.sub_off + (size_t)line * NSUB;
     for (int r = g; r < K1; r += G) { acc0[r] = 0.0; acc1[r] = 0.0; cnt[r] = 0; }
     __syncwarp(gmask);
     for (int d = 0; d < D; ++d) {
-      const int64_t b = so[d], e = so[d + 1];
-      for (int64_t p = b + g; p < e; p += G) atomicAdd(&cnt[node_of(a.words[p])], 1u);
+      for (int ch = 0; ch < NCH; ++ch) {
+        const int64_t pb = (int64_t)so[d * NCH + ch] * 8, pe = (int64_t)so[d * NCH + ch + 1] * 8;
+        for (int64_t p = pb + g; p < pe; p += G) {
+          const uint32_t idx = a.half[p];
+          if (idx) atomicAdd(&cnt[node_at(((uint32_t)ch << cb) | idx)], 1u);  // idx 0 = padding
+        }
+      }
       __syncwarp(gmask);
       const double l0 = a.L0[d], l1 = a.L1[d];
       for (int r = g; r < K1; r += G) {
@@ -479,10 +497,12 @@ __global__ void __launch_bounds__(kBlock, 1) k_node_table(const PassArgs a, cons
       __syncwarp(gmask);
     }
     if (g == 0) {  // rare codes: serial, in storage order (deterministic)
-      for (int64_t p = so[D]; p < so[D + 1]; ++p) {
-        const uint32_t w = a.words[p];
+      for (int64_t p = a.tail_off[line]; p < a.tail_off[line + 1]; ++p) {
+        const uint32_t w = a.tail_words[p];
         const uint32_t code = w >> a.minor_bits;
-        const uint32_t r = node_of(w & mmask);
+        const uint32_t minor = w & mmask;
+        const uint32_t chq = minor / CH;
+        const uint32_t r = node_at((chq << cb) | (16u + minor - chq * CH));
         acc0[r] += a.L0[code];
         acc1[r] += a.L1[code];
       }
@@ -502,63 +522,71 @@ __global__ void __launch_bounds__(kBlock, 1) k_node_table(const PassArgs a, cons
 // host side
 // ------------------------------------------------------------------------------------------------
 
-struct Staged {
-  cudaStream_t st;
-  bool host;
-};
-
-size_t pass_smem_bytes(const ph_handle* h, const PhOrient* o, int mode, int K, bool smem_lab, int* lut_in_smem) {
+// shared memory of one k_pass CTA with `threads` threads; 0 = does not fit
+size_t pass_smem_bytes(const ph_handle* h, const PhOrient* o, int mode, int NC, int K, bool smem_lab, int threads, int B,
+                       int* lut_in_smem) {
   size_t b = 0;
-  if (smem_lab) b += ((size_t)o->n_minor + 15) & ~(size_t)15;
-  if (mode == MODE_MAPPED) b += (((size_t)(K + 1) * (K + 1)) + 15) & ~(size_t)15;
-  size_t lut = (size_t)h->n_codes * 17 + 16;
-  *lut_in_smem = (b + lut <= (size_t)h->max_smem && h->n_codes <= 4096) ? 1 : 0;
+  if (smem_lab) b += (size_t)o->lab_bytes;
+  if (mode == MODE_MAPPED) b += (((size_t)(K + 2) * (K + 2)) + 15) & ~(size_t)15;
+  const size_t warps = (size_t)(threads / 32) * warp_words(B, o->NSUB, o->D, NC) * 4 + 16;
+  const size_t lut = ((size_t)h->n_codes * 17 + 15) & ~(size_t)15;
+  *lut_in_smem = (b + warps + lut <= (size_t)h->max_smem && h->n_codes <= 4096) ? 1 : 0;
   if (*lut_in_smem) b += lut;
-  return b;
+  b += warps;
+  return b <= (size_t)h->max_smem ? b : 0;
 }
 
 template <int MODE, int NC>
 int launch_pass(ph_handle* h, const PhOrient* o, PassArgs& a, cudaStream_t st) {
   if (a.n_work <= 0) return PH_OK;
-  int lut = 0;
+  const int B = o->batch == 32 ? 32 : 8;
+  int lut = 0, threads = 0;
   bool smem_lab = true;
-  size_t smem = pass_smem_bytes(h, o, MODE, a.K, true, &lut);
-  if (smem > (size_t)h->max_smem) {
-    smem_lab = false;
-    smem = pass_smem_bytes(h, o, MODE, a.K, false, &lut);
+  size_t smem = 0;
+  for (int pass = 0; pass < 2 && !smem; ++pass) {
+    smem_lab = pass == 0;
+    for (threads = 1024; threads >= 256 && !smem; threads >>= 1) smem = pass_smem_bytes(h, o, MODE, NC, a.K, smem_lab, threads, B, &lut);
+    if (smem) threads <<= 1;
   }
+  if (!smem) PH_FAIL(PH_ERR_UNSUPPORTED, "pass kernel tables do not fit in shared memory (K=%d, %d sub-segments)", a.K, o->NSUB);
   a.lut_in_smem = lut;
-  const uint8_t* raw = a.minor_label;
   if (!smem_lab) {
-    if (MODE == MODE_MAPPED) PH_FAIL(PH_ERR_UNSUPPORTED, "tree pass needs the %d minor labels in shared memory", o->n_minor);
-    // pre-scale into scratch; d_lab_major is free in every non-MAPPED mode
-    k_scale_labels<NC><<<((o->n_minor + 3) / 4 + 255) / 256, 256, 0, st>>>(raw, h->d_lab_major, o->n_minor);
+    // the label image goes to global memory (gathered through L1/L2)
+    if ((size_t)o->lab_bytes > h->lab_img_bytes) PH_FAIL(PH_ERR_UNSUPPORTED, "label image scratch too small");
+    k_label_image<MODE == MODE_MAPPED, NC><<<h->sm_count, 256, 0, st>>>(h->d_lab_img, a.minor_label, o->n_minor, o->NCH,
+                                                                        o->chunk_bits, a.K);
     ph_count_launch();
-    a.minor_label = h->d_lab_major;
+    a.minor_label = h->d_lab_img;
   }
-  // two CTAs per SM when two copies of the shared-memory image fit (each CTA also pays 1 KB of reserved smem)
-  const bool two = !smem_lab || 2 * (smem + 1024) <= (size_t)h->smem_per_sm;
-  const int grid = h->sm_count * (two ? 2 : 1);
+  // one CTA of up to 32 warps per SM; PH_CTAS=2 halves the CTA instead when two copies of the image fit
+  int ctas = 1;
+  if (h->ctas_per_sm == 2 && threads == 1024) {
+    int lut2 = 0;
+    const size_t smem2 = pass_smem_bytes(h, o, MODE, NC, a.K, smem_lab, 512, B, &lut2);
+    if (smem2 && lut2 == lut && 2 * (smem2 + 1024) <= (size_t)h->smem_per_sm) {
+      ctas = 2;
+      threads = 512;
+      smem = smem2;
+    }
+  }
+  const int grid = h->sm_count * ctas;
   a.counter = h->d_counter;
   PH_CUDA(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned), st));
-  const int threads = two ? 512 : 1024;
-#define PH_LAUNCH(GG, SL)                                                                                        \
+#define PH_LAUNCH(BB, SL, SS)                                                                                    \
   do {                                                                                                           \
-    auto kern = k_pass<GG, MODE, NC, SL>;                                                                        \
+    auto kern = k_pass<BB, MODE, NC, SL, SS>;                                                                    \
     PH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->max_smem));          \
     kern<<<grid, threads, smem, st>>>(a);                                                                        \
   } while (0)
-#define PH_LAUNCH_G(GG)                                                        \
+#define PH_LAUNCH_B(BB)                                                        \
   do {                                                                         \
-    if (!smem_lab) PH_LAUNCH(GG, false);                                       \
-    else PH_LAUNCH(GG, true);                                                  \
+    if (!smem_lab) PH_LAUNCH(BB, false, false);                                \
+    else if (o->chunk_bits == 16) PH_LAUNCH(BB, true, true);                   \
+    else PH_LAUNCH(BB, true, false);                                           \
   } while (0)
-  switch (o->group) {
-    case 8: PH_LAUNCH_G(8); break;
-    case 16: PH_LAUNCH_G(16); break;
-    default: PH_LAUNCH_G(32); break;
-  }
-#undef PH_LAUNCH_G
+  if (B == 32) PH_LAUNCH_B(32);
+  else PH_LAUNCH_B(8);
+#undef PH_LAUNCH_B
 #undef PH_LAUNCH
   ph_count_launch();
   PH_CUDA(cudaGetLastError());
@@ -575,11 +603,17 @@ int launch_table(ph_handle* h, const PhOrient* o, PassArgs& a, cudaStream_t st) 
 
 void fill_common(const ph_handle* h, const PhOrient* o, PassArgs& a) {
   memset(&a, 0, sizeof(a));
-  a.words = o->words;
-  a.seg_off = o->seg_off;
+  a.half = o->half;
+  a.sub_off = o->sub_off;
+  a.tail_words = o->tail_words;
+  a.tail_off = o->tail_off;
   a.D = o->D;
+  a.NCH = o->NCH;
+  a.NSUB = o->NSUB;
+  a.chunk_bits = o->chunk_bits;
   a.minor_bits = o->minor_bits;
   a.n_minor = o->n_minor;
+  a.lab_bytes = o->lab_bytes;
   a.L0 = h->d_L0;
   a.L1 = h->d_L1;
   a.varpos = h->d_varpos;
@@ -879,9 +913,15 @@ int run_node_table(ph_handle* h, PhOrient* o, const uint8_t* minor_node, const u
   const int gpb = kBlock / G;
   const int K1 = K + 1;
   size_t extra = (size_t)gpb * K1 * (8 + 8 + 4) + (size_t)K * K1 + 16;
-  size_t lab = ((size_t)o->n_minor + 15) & ~(size_t)15;
+  size_t lab = (size_t)o->lab_bytes;
   bool smem_lab = lab + extra <= (size_t)h->max_smem;
   size_t smem = (smem_lab ? lab : 0) + extra;
+  if (!smem_lab) {
+    if (lab > h->lab_img_bytes) PH_FAIL(PH_ERR_UNSUPPORTED, "label image scratch too small");
+    k_label_image<true, 1><<<h->sm_count, 256, 0, st>>>(h->d_lab_img, a.minor_label, o->n_minor, o->NCH, o->chunk_bits, K);
+    ph_count_launch();
+    a.minor_label = h->d_lab_img;
+  }
   if (smem_lab) {
     auto kern = k_node_table<8, true>;
     PH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->max_smem));

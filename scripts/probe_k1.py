@@ -6,7 +6,7 @@ from phertilizer_b200.synth import make_config
 from phertilizer_b200.store import ObservationStore
 
 name = sys.argv[1] if len(sys.argv) > 1 else "C3"
-GS = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [8, 16, 32]
+GS = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [8, 32]
 REPS = int(sys.argv[3]) if len(sys.argv) > 3 else 10
 dev = torch.device("cuda:0")
 t = time.time()
@@ -48,4 +48,6 @@ for G in GS:
     r["tab2"] = timeit(lambda: st.snv_table_dev(cl2, 2, S0, S1, No, Nv))
     r["cell2"] = timeit(lambda: st.cell_table_dev(sl, 2, S0, S1, No, Nv))
     out = {k: (round(v, 4), round(s.nnz / v / 1e6, 1)) for k, v in r.items()}
-    print("G", G, "ms, Gnnz/s:", out, " GB/s@4B:", round(4 * s.nnz / r["lin"] / 1e6, 1), flush=True)
+    inf = st.info()
+    print("batch", G, "ms, Gnnz/s:", out, " GB/s physical (lin):", round(inf["stream_bytes_by_snv"] / r["lin"] / 1e6, 1),
+          " (cell2):", round(inf["stream_bytes_by_cell"] / r["cell2"] / 1e6, 1), flush=True)

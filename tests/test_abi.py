@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     L = ctypes.CDLL(_lib.LIB_PATH)
     for s in syms:
         assert hasattr(L, s), s
-    assert _lib.lib().ph_abi_version() == 1
+    assert _lib.lib().ph_abi_version() == _lib.ABI_VERSION
 
 
 def test_no_cpu_fallback_without_gpu():

@@ -274,10 +274,19 @@ def test_pairwise_dist(env):
 
 
 # ------------------------------------------------------------------------------------------- seeded random inputs
-@pytest.fixture(scope="module")
-def synth_env():
+@pytest.fixture(scope="module", params=["default", "chunks512", "chunks64_nobank"])
+def synth_env(request):
+    """T1 (2000 x 3000).  The store is also built with tiny chunks of the minor axis (PH_CHUNK_BITS, a test knob of
+    ph_create) so that the multi-chunk sub-segment logic runs on data the dense oracle can hold."""
+    import os
+
     from phertilizer_b200.store import ObservationStore
     from phertilizer_b200.synth import make_config
+
+    knobs = {"default": {}, "chunks512": {"PH_CHUNK_BITS": "9", "PH_DENSE_MIN_AVG": "4"},
+             "chunks64_nobank": {"PH_CHUNK_BITS": "8", "PH_BANK_ORDER": "0", "PH_DENSE_MIN_AVG": "2"}}[request.param]
+    saved = {k: os.environ.get(k) for k in knobs}
+    os.environ.update(knobs)
 
     s = make_config("T1", with_embedding=False)
     cell, snv, var, total = (x.numpy() for x in (s.cell, s.snv, s.var, s.total))
@@ -287,7 +296,14 @@ def synth_env():
     total = total.copy(); var = var.copy()
     total[extra] = rng.integers(2, 40, 300)
     var[extra] = rng.integers(0, total[extra] + 1)
-    st = ObservationStore.from_coo(s.n, s.m, cell, snv, var, total)
+    try:
+        st = ObservationStore.from_coo(s.n, s.m, cell, snv, var, total)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
     D = O.DenseData(s.n, s.m, cell, snv, var, total)
     yield s, st, D
     st.close()
@@ -383,3 +399,62 @@ def test_determinism(synth_env):
     c = st.snv_table(lab, 2)
     st.set_group(0, 0)
     assert np.array_equal(a["Nobs"], c["Nobs"]) and rel_close(a["S0"], c["S0"], 1e-13)
+
+
+# ------------------------------------------------------------------------------------------- wide matrices
+@pytest.mark.parametrize("shape", ["many_cells", "many_snvs"])
+def test_wide_matrix_multi_chunk(shape):
+    """More than 65520 indices on the minor axis (three 16-bit chunks, the production layout) and lines long enough
+    (thousands of entries) for the bank-ordered sub-segments; the other orientation has ~2 entries per line (tail only)."""
+    from phertilizer_b200.store import ObservationStore
+    from phertilizer_b200.synth import make_synthetic
+
+    big, small = 150_000, 40
+    n, m = (big, small) if shape == "many_cells" else (small, big)
+    s = make_synthetic(n, m, 0.05, 4, seed=23, with_embedding=False)
+    cell, snv, var, total = (x.numpy() for x in (s.cell, s.snv, s.var, s.total))
+    st = ObservationStore.from_coo(n, m, cell, snv, var, total)
+    info = st.info()
+    assert max(info["chunks_by_snv"], info["chunks_by_cell"]) == 3
+    D = O.DenseData(n, m, cell, snv, var, total)
+    rng = np.random.default_rng(9)
+    for C in (1, 2, 3):
+        lab = np.zeros(n + 16, np.uint8)[:n]
+        lab[:] = rng.integers(0, C + 1, n)
+        groups = [np.nonzero(lab == c)[0] for c in range(1, C + 1)]
+        t = st.snv_table(lab, C)
+        S0, S1, No, Nv = O.snv_table(D, groups, np.arange(m))
+        assert np.array_equal(t["Nobs"], No) and np.array_equal(t["Nvar"], Nv)
+        assert rel_close(t["S0"], S0, TOL) and rel_close(t["S1"], S1, TOL)
+        sl = np.zeros(m + 16, np.uint8)[:m]
+        sl[:] = rng.integers(0, C + 1, m)
+        mg = [np.nonzero(sl == q)[0] for q in range(1, C + 1)]
+        cells = np.sort(rng.choice(n, max(1, n // 3), replace=False))
+        t2 = st.cell_table(sl, C, cells)
+        A0, A1, No2, Nv2 = O.cell_table(D, cells, mg)
+        assert np.array_equal(t2["Nobs"], No2) and np.array_equal(t2["Nvar"], Nv2)
+        assert rel_close(t2["S0"], A0, TOL) and rel_close(t2["S1"], A1, TOL)
+    labA = st.cell_labels(np.nonzero(rng.random(n) < 0.5)[0])
+    lab2, nobs = st.assign_linear(labA, float(labA.sum()))
+    a, b = O.linear_mut_assignment(D, np.nonzero(labA)[0], np.arange(m), nobs_per_cluster=-1)
+    assert np.array_equal(np.nonzero(lab2 == 2)[0], b) and np.array_equal(np.nonzero(lab2 == 1)[0], a)
+    # tree log-likelihood walks the cell-major copy with the SNV labels as the minor axis
+    cell_node = np.zeros(n + 16, np.uint8)[:n]
+    cell_node[:] = s.cell_clone.numpy()
+    snv_node = np.zeros(m + 16, np.uint8)[:m]
+    snv_node[:] = s.snv_node.numpy()
+    anc = s.ancestor_matrix()
+    got = st.tree_loglik(cell_node, snv_node, anc)
+    for k in range(4):
+        present = np.nonzero(anc[k][snv_node.astype(np.int64)])[0]
+        ref = O.variant_likelihood_by_node(D, np.nonzero(cell_node == k)[0], present)
+        assert rel_close(got[k], ref, TOL)
+    # node tables (post_process) on both orientations
+    member = np.zeros((4, 4), np.uint8)
+    member[:] = anc.T   # member[k][r] = 1 iff node k is on the path of cells of node r
+    some = np.sort(rng.choice(m, min(m, 25), replace=False))
+    T = st.snv_node_table(cell_node, member, some)
+    for row, j in zip(T, some):
+        sc = O.snv_node_scores(D, j, {k: member[k][cell_node.astype(np.int64)] for k in range(4)})
+        assert rel_close(row, np.array([sc[k] for k in range(4)]), TOL)
+    st.close()
