@@ -100,26 +100,47 @@ __global__ void k_narrow(const int64_t* __restrict__ in, int64_t n, uint32_t* __
   if (i < n) out[i] = (uint32_t)in[i];
 }
 
-// Position of the r-th (in sorted order) of `cnt` entries inside its padded sub-segment of ng = ceil(cnt/8) groups.
-// bank_order = 0: identity.  bank_order = 1: the sorted (by bank) sequence is cut into 32 runs; run q feeds the groups
-// g with g % 32 == q, so that any 32 consecutive groups -- the 32 lanes of one LDS -- read labels from (nearly) 32
-// different shared-memory banks.
+// bank_order: a sub-segment's entries are laid out in ROUNDS -- round k holds the k-th entry of every shared-memory
+// bank (of the label the entry will gather), in bank order -- and consecutive runs of 32 entries of that sequence become
+// the 32 lanes of one LDS of the pass kernel (group g = lane, same slot e in each group).  A full round has one entry per
+// bank, so those LDS are conflict free wherever the sub-segment starts; only the ragged last rounds can collide.
+//
+// k_round_keys: keys sorted by (segment, bank, idx16) -> keys (segment, rank within bank, bank, idx16).
+__global__ void k_round_keys(const uint64_t* __restrict__ sorted, int64_t nnz, const int64_t* __restrict__ off, int NSUB,
+                             uint64_t* __restrict__ out, int* dup) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < nnz; i += stride) {
+    const uint64_t k = sorted[i];
+    if (i > 0 && sorted[i - 1] == k) *dup = 1;  // the same (line, index) twice
+    const int64_t seg = (int64_t)(k >> 32);
+    if ((int)(seg % (NSUB + 1)) == NSUB) {  // tail entry: unchanged
+      out[i] = k;
+      continue;
+    }
+    const uint64_t kb = k >> 16;  // (segment, bank)
+    int64_t lo = off[seg], hi = i;
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      if ((sorted[mid] >> 16) < kb) lo = mid + 1; else hi = mid;
+    }
+    const uint64_t r = (uint64_t)(i - lo);  // < 2048: a bank holds 2048 bytes of one chunk of the label image
+    out[i] = (k & 0xFFFFFFFF00000000ull) | (r << 21) | (k & 0x1FFFFFull);
+  }
+}
+
+// Position of the r-th entry (in round order) inside its padded sub-segment of ng = ceil(cnt/8) groups.
 __device__ __forceinline__ int64_t place(int64_t r, int64_t cnt, int bank_order) {
   if (!bank_order) return r;
   const int64_t ng = (cnt + 7) >> 3;
-  if (ng < 32) return r;  // short sub-segments: a single LDS row, nothing to spread
-  const int64_t nb = ng >> 5, rem = ng & 31;
-  const int64_t big = 8 * (nb + 1);  // slots of the first `rem` runs
-  int64_t q, col;
-  if (r < big * rem) {
-    q = r / big;
-    col = r - q * big;
-  } else {
-    const int64_t r2 = r - big * rem;
-    q = rem + r2 / (8 * nb);
-    col = r2 - (q - rem) * (8 * nb);
+  const int64_t tf = ng >> 5;  // full blocks of 32 groups = 256 entries
+  if (r < 256 * tf) {
+    const int64_t t = r >> 8, j = (r & 255) >> 5, ln = r & 31;
+    return ((t << 5) + ln) * 8 + j;
   }
-  return (((col >> 3) << 5) + q) * 8 + (col & 7);
+  const int64_t r2 = r - 256 * tf, gl = ng - (tf << 5);  // ragged last block: gl < 32 groups
+  const int64_t e = r2 / gl, ln = r2 - e * gl;
+  return ((tf << 5) + ln) * 8 + e;
 }
 
 __global__ void k_scatter(const uint64_t* __restrict__ keys, int64_t nnz, const int64_t* __restrict__ off, int NSUB,
@@ -202,6 +223,18 @@ int build_orient(ph_handle* h, PhOrient* o, const int32_t* d_major, const int32_
     }
     k_seg_offsets<<<(unsigned)((nseg + 1 + threads - 1) / threads), threads>>>(sorted, nnz, nseg, d_off);
     ph_count_launch();
+    if (nnz > 0 && h->bank_order && NSUB > 0) {
+      // second sort: round order inside every sub-segment (segment sizes, hence d_off, do not change)
+      uint64_t* other = (sorted == kbuf0) ? kbuf1 : kbuf0;
+      k_round_keys<<<blocks, threads>>>(sorted, nnz, d_off, NSUB, other, d_flag + 1);
+      ph_count_launch();
+      cub::DoubleBuffer<uint64_t> db(other, const_cast<uint64_t*>(sorted));
+      int end_bit = 32 + ph_ceil_log2((uint64_t)nseg + 1);
+      if (end_bit > 64) end_bit = 64;
+      PH_CUDA(cub::DeviceRadixSort::SortKeys(d_temp, temp_bytes, db, nnz, 0, end_bit));
+      ph_count_launch(4);
+      sorted = db.Current();
+    }
     if (nseg > 0) {
       k_seg_sizes<<<(unsigned)((nseg + threads - 1) / threads), threads>>>(d_off, n_major, NSUB, d_groups, d_tails);
       ph_count_launch();

@@ -214,12 +214,16 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
         int nacc = 0;
         const uint8_t* maprow = s_map;
 
+        // lanes leave a (line, code) run within a step or two of each other: the ones flushing the same counter
+        // together are summed with REDUX first, so the shared-memory atomic sees one request instead of up to 32
         auto flush = [&]() {
+          const unsigned peers = __match_any_sync(__activemask(), cur_key);
           const uint32_t base = ((cur_key >> 3) * D + (cur_key & 7u)) * NC;
+          const bool leader = lane == __ffs(peers) - 1;
 #pragma unroll
           for (int c = 0; c < NC; ++c) {
-            const uint32_t f = (acc >> (PH_FIELD_BITS * c)) & FM;
-            if (f) atomicAdd(&s_cnt[base + c], f);
+            const uint32_t f = __reduce_add_sync(peers, (acc >> (PH_FIELD_BITS * c)) & FM);
+            if (leader && f) atomicAdd(&s_cnt[base + c], f);
           }
         };
         auto one = [&](uint32_t addr) -> uint32_t {
