@@ -58,7 +58,7 @@ class ClockSampler:
                     self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.02)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -182,7 +182,7 @@ def workload_config(args, w, world, residency):
                         f"(BASELINE.json configs[2]); step = linear-split SNV reassignment pass (K1+K1a) over all observations",
             "nnz": w["nnz_total"], "cells": c["n"], "snvs": c["m"], "coverage": c["cov"], "clones": c["K"],
             "sharding": f"cells sharded over {world} rank(s), all-reduce of the [S0|S1|Nobs] table" if world > 1 else "single GPU",
-            "l2_policy": "inputs larger than L2 (1.6 GB of observations per pass vs 126 MB L2); label vectors rotate every step",
+            "l2_policy": "inputs larger than L2 (0.8 GB of observations streamed per pass vs 126 MB L2); label vectors rotate every step",
             "residency": residency}
 
 
@@ -230,6 +230,7 @@ def run_ours(args):
     packed = torch.empty(3 * m, dtype=torch.float64, device=dev) if world > 1 else None
     lab_out_h = torch.empty(m + 16, dtype=torch.uint8).pin_memory()
     nobs_out_h = torch.empty(m, dtype=torch.int32).pin_memory()
+    lab_out_np, nobs_out_np = lab_out_h.numpy()[:m], nobs_out_h.numpy()
     stream = torch.cuda.current_stream().cuda_stream
 
     kern_ev = []
@@ -258,8 +259,19 @@ def run_ours(args):
     for i in range(args.warmup):
         step_device(i)
     barrier()
-    launches0 = _lib.kernel_launches()
+    # The timed region of K steps lasts a few ms -- shorter than one nvidia-smi poll -- so the sampler also runs over an
+    # untimed ~1 s stretch of the very same steps right before it (clocks "under load"), and stays on through the
+    # timed region.
     with ClockSampler(local) as clk:
+        t_load = time.perf_counter()
+        n_load = 0
+        while time.perf_counter() - t_load < args.clock_seconds:
+            for i in range(50):
+                step_device(n_load + i)
+            n_load += 50
+            torch.cuda.synchronize()
+        barrier()
+        launches0 = _lib.kernel_launches()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
@@ -269,7 +281,7 @@ def run_ours(args):
         barrier()
     ms = e0.elapsed_time(e1)
     launches = _lib.kernel_launches() - launches0
-    if world > 1:
+    if world > 1 and args.exchange == "nccl":
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
@@ -281,7 +293,7 @@ def run_ours(args):
     def step_e2e(i):
         if world == 1:
             # ph_assign_linear(on_device=0): pinned staging, H2D labels, kernel, D2H labels + counts, sync
-            return st.assign_linear(labs_h[i % P].numpy()[:n_loc], lenA[i % P])
+            return st.assign_linear(labs_h[i % P].numpy()[:n_loc], lenA[i % P], out=(lab_out_np, nobs_out_np))
         labs_d[i % P].copy_(labs_h[i % P], non_blocking=True)
         sharded.assign_linear_dev(labs_d[i % P], lenA[i % P], packed, lab_out, nobs_out)
         lab_out_h.copy_(lab_out, non_blocking=True)
@@ -335,6 +347,10 @@ def run_ours(args):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "MEASURED_PEAKS.json hbm_gbs (burst copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         ab = alg_bytes(nnz_loc, n_loc, m, 1)
+        # what the kernel really streams: 2 B per observation incl. 16-byte padding, tail words, sub-segment and tail
+        # offsets, one label image per CTA, the outputs (labels + counts)
+        nsub = info["dense_codes_by_snv"] * info["chunks_by_snv"]
+        phys = info["stream_bytes_by_snv"] + (m * nsub + 1) * 4 + (m + 1) * 8 + n_loc * info["sm_count"] + 5 * m
         achieved = ab / (kernel_ms * 1e-3) / 1e9
         traffic = None
         try:
@@ -354,11 +370,13 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "k_pass<MODE_LINEAR>" if world == 1 else "k_pass<MODE_TABLE>",
-                         "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": ab, "physical_bytes_per_nnz": 4,
-                         "physical_gbs": (4 * nnz_loc + (m * (info['dense_codes_by_snv'] + 1) + 1) * 8) / (kernel_ms * 1e-3) / 1e9,
+                         "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": ab,
+                         "physical_bytes_per_launch": phys, "physical_bytes_per_nnz": phys / max(nnz_loc, 1),
+                         "physical_gbs": phys / (kernel_ms * 1e-3) / 1e9, "physical_frac": phys / (kernel_ms * 1e-3) / 1e9 / peak,
                          "peak_source": peak_src + ", of measured"},
             "cpu_baseline": cpu,
-            "store": {k: info[k] for k in ("dense_codes_by_snv", "group_by_snv", "labels_in_smem_by_snv", "device_bytes")},
+            "store": {k: info[k] for k in ("dense_codes_by_snv", "chunks_by_snv", "group_by_snv", "labels_in_smem_by_snv",
+                                           "stream_bytes_by_snv", "device_bytes")},
         }
         print(json.dumps(line), flush=True)
     st.close()
@@ -375,6 +393,9 @@ def main():
     ap.add_argument("--workload", default="C3")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU baseline budget (N=1 only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--clock-seconds", type=float, default=1.0, help="untimed load stretch sampled for SM clocks")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
+                    help="N>1: how the per-SNV partial tables are combined (peer = fused NVLink peer-memory kernels)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

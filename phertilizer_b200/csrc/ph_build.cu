@@ -44,8 +44,8 @@ __global__ void k_code_hist(const uint16_t* __restrict__ code, int64_t nnz, unsi
 // s = NSUB for the tail.  Payload: idx16 (dense; optionally with the shared-memory bank of its label above it so that
 // the sort groups a sub-segment's entries by bank) or  minor | code << minor_bits  (tail).
 __global__ void k_make_keys(const int32_t* __restrict__ major, const int32_t* __restrict__ minor,
-                            const uint16_t* __restrict__ code, int64_t nnz, int D, int NCH, int CH, int minor_bits,
-                            int n_major, int n_minor, int bank_order, uint64_t* __restrict__ keys, int* bad) {
+                            const uint16_t* __restrict__ code, int64_t nnz, int D, int NCH, int CH, int chunk_bits,
+                            int minor_bits, int n_major, int n_minor, int bank_order, uint64_t* __restrict__ keys, int* bad) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const uint32_t NSUB = (uint32_t)(D * NCH);
@@ -57,14 +57,14 @@ __global__ void k_make_keys(const int32_t* __restrict__ major, const int32_t* __
       mn = 0;
     }
     uint32_t s, payload;
+    const uint32_t ch = mn / (uint32_t)CH;
+    const uint32_t idx = 16u + (mn - ch * (uint32_t)CH);
     if (c < (uint32_t)D) {
-      const uint32_t ch = mn / (uint32_t)CH;
-      const uint32_t idx = 16u + (mn - ch * (uint32_t)CH);
       s = c * (uint32_t)NCH + ch;
       payload = idx | (bank_order ? (((idx >> 2) & 31u) << 16) : 0u);
     } else {
       s = NSUB;
-      payload = mn | (c << minor_bits);
+      payload = ((ch << chunk_bits) | idx) | (c << minor_bits);  // label-image address | code
     }
     keys[i] = ((uint64_t)(mj * (NSUB + 1u) + s) << 32) | payload;
   }
@@ -170,10 +170,14 @@ int build_orient(ph_handle* h, PhOrient* o, const int32_t* d_major, const int32_
   const int64_t nnz = h->nnz;
   o->n_major = n_major;
   o->n_minor = n_minor;
-  o->minor_bits = ph_ceil_log2((uint64_t)n_minor > 1 ? (uint64_t)n_minor : 2);
   o->chunk_bits = h->chunk_bits;
   const int CH = (1 << o->chunk_bits) - 16;
   o->NCH = (n_minor + CH - 1) / CH;
+  {
+    const int last = n_minor - (o->NCH - 1) * CH;
+    o->lab_bytes = (((o->NCH - 1) << o->chunk_bits) + 16 + last + 15) & ~15;
+  }
+  o->minor_bits = ph_ceil_log2((uint64_t)o->lab_bytes);  // a tail word = label-image address | code << minor_bits
   int D = 0;
   while (D < PH_DMAX && D < h->n_codes && (double)code_count[D] >= h->dense_min_avg * (double)n_major) ++D;
   while (D > 0 && D * o->NCH > PH_MAX_SUB) --D;
@@ -181,17 +185,13 @@ int build_orient(ph_handle* h, PhOrient* o, const int32_t* d_major, const int32_
   o->NSUB = D * o->NCH;
   if (h->n_codes > D) {
     if (o->minor_bits >= 32 || (uint64_t)(h->n_codes - 1) >= (1ull << (32 - o->minor_bits)))
-      PH_FAIL(PH_ERR_UNSUPPORTED, "%d (var,total) codes do not fit next to a %d-bit index in a 32-bit word",
+      PH_FAIL(PH_ERR_UNSUPPORTED, "%d (var,total) codes do not fit next to a %d-bit label address in a 32-bit word",
               h->n_codes, o->minor_bits);
   }
   const int NSUB = o->NSUB;
   const int64_t nseg = (int64_t)n_major * (NSUB + 1);
   if (nseg >= (1ll << 31)) PH_FAIL(PH_ERR_UNSUPPORTED, "too many segments (%lld)", (long long)nseg);
-  {
-    const int last = n_minor - (o->NCH - 1) * CH;
-    o->lab_bytes = (((o->NCH - 1) << o->chunk_bits) + 16 + last + 15) & ~15;
-  }
-  o->batch = (n_major > 0 && (double)nnz / n_major >= 512.0) ? 8 : 32;
+  o->batch = 8;  // lines per warp batch (32 was slower on every measured shape; kept as a knob, ph_set_group)
   o->labels_in_smem = 1;
 
   const int threads = 256;
@@ -211,7 +211,7 @@ int build_orient(ph_handle* h, PhOrient* o, const int32_t* d_major, const int32_
     h->device_bytes += (n_sub + 1) * (int64_t)sizeof(uint32_t) + (n_major + 1) * (int64_t)sizeof(int64_t);
     const uint64_t* sorted = kbuf0;
     if (nnz > 0) {
-      k_make_keys<<<blocks, threads>>>(d_major, d_minor, d_code, nnz, D, o->NCH, CH, o->minor_bits, n_major, n_minor,
+      k_make_keys<<<blocks, threads>>>(d_major, d_minor, d_code, nnz, D, o->NCH, CH, o->chunk_bits, o->minor_bits, n_major, n_minor,
                                        h->bank_order, kbuf0, d_flag);
       ph_count_launch();
       cub::DoubleBuffer<uint64_t> db(kbuf0, kbuf1);

@@ -7,6 +7,7 @@
 
 #include "phertilizer_b200.h"
 
+#define PH_MAX_PEERS 8     // GPUs of one NVLink/NVSwitch node
 #define PH_MAX_SUB 32      // max sub-segments (dense codes x chunks) per line
 #define PH_DMAX 4           // max "dense" (var,total) codes that get their own segment per line
 #define PH_FIELD_BITS 10    // packed per-lane counter field width (3 labels x 10 bits, excluded label -> bit 30)
@@ -40,7 +41,8 @@ void ph_count_launch(int n = 1);
 // so a line -- and any run of consecutive lines -- is one contiguous, 16-byte aligned stream of groups.
 //   half    [n_groups * 8]            the stream
 //   sub_off [n_major * NSUB + 1]      first group of every sub-segment (NSUB = D * NCH)
-// Entries with rarer codes go to the "tail": tail_words = minor | code << minor_bits, tail_off per line.
+// Entries with rarer codes go to the "tail": tail_words = (label-image address) | code << minor_bits, sorted by
+// (code, address) inside a line; tail_off per line.
 // The kernels keep a label image of the minor axis in shared memory with the matching layout: chunk c at byte
 // c << chunk_bits, 16 "excluded" bytes (what the padding entries hit) followed by the labels of its indices.
 struct PhOrient {
@@ -53,7 +55,7 @@ struct PhOrient {
   int32_t D;           // dense codes, 0..PH_DMAX
   int32_t NCH, NSUB;   // chunks of the minor axis, sub-segments per line
   int32_t chunk_bits;  // 16 in production (PH_CHUNK_BITS overrides it for tests)
-  int32_t minor_bits;  // bits of the minor index inside a tail word
+  int32_t minor_bits;  // bits of the label-image address inside a tail word
   int32_t lab_bytes;   // size of the label image
   int32_t batch;       // lines per warp batch (8 or 32)
   int32_t labels_in_smem;

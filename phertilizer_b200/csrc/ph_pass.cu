@@ -15,7 +15,7 @@
 
 namespace {
 
-enum { MODE_TABLE = 0, MODE_LINEAR = 1, MODE_BRANCHING = 2, MODE_MAPPED = 3 };
+enum { MODE_TABLE = 0, MODE_LINEAR = 1, MODE_BRANCHING = 2, MODE_MAPPED = 3, MODE_COUNTS = 4 };
 
 constexpr int kBlock = 512;  // threads per CTA of the node-table kernel
 
@@ -42,6 +42,13 @@ struct PassArgs {
   int K;
   double* per_line;                                      // MAPPED
   unsigned* counter;                                     // batch dispenser, zeroed before every launch
+  // COUNTS (cell-sharded K1, ph_peer.cu): every line's (cluster, code) histogram row -> the window of the rank that
+  // owns the line (peer memory over NVLink), then one release flag per peer when the whole grid is done
+  uint16_t* cnt_dst[PH_MAX_PEERS];   // per owner: this rank's source slot in the owner's window
+  uint32_t* flag_dst[PH_MAX_PEERS];  // per peer: where this rank's "partials landed" flag lives
+  unsigned* done;                    // CTA completion counter (local, self-resetting)
+  int blk, ncp, world, row_words;
+  uint32_t epoch;
 };
 
 __device__ __forceinline__ uint4 ld_stream(const uint4* p) {
@@ -96,7 +103,9 @@ __device__ __forceinline__ void fill_label_image(uint8_t* img, const uint8_t* __
 }
 
 // per-warp shared-memory words: sub-segment bounds [B][NSUB+1], counters [B][D][NC], line ids [B], line labels [B]
-__host__ __device__ inline int warp_words(int B, int NSUB, int D, int NC) { return B * (NSUB + 1) + B * D * NC + 2 * B; }
+__host__ __device__ inline int warp_words(int B, int NSUB, int D, int NC) {
+  return (B * (NSUB + 1) + B * D * NC + 2 * B + 3) & ~3;
+}
 
 // One warp walks a batch of B lines handed out by an atomic counter.  After the streaming phase lane (l % B) finishes
 // line l alone ("holder"): rare-code tail, fp64 sums, epilogue, store.
@@ -116,8 +125,10 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
   double* s_L1 = s_L0 + (a.lut_in_smem ? a.n_codes : 0);
   uint8_t* s_vp = reinterpret_cast<uint8_t*>(s_L1 + (a.lut_in_smem ? a.n_codes : 0));
   if (a.lut_in_smem) off += ((size_t)a.n_codes * 17 + 15) & ~(size_t)15;
-  const int wsz = warp_words(B, NSUB, D, NC);
-  uint32_t* s_b = reinterpret_cast<uint32_t*>(smem + off) + (threadIdx.x >> 5) * wsz;
+  const int wsz = warp_words(B, NSUB, D, NC) + a.row_words;  // both terms are multiples of 4 words
+  uint32_t* s_row32 = reinterpret_cast<uint32_t*>(smem + off) + (threadIdx.x >> 5) * wsz;
+  uint16_t* s_row = reinterpret_cast<uint16_t*>(s_row32);  // COUNTS: [B][NC][ncp] histogram rows of the batch
+  uint32_t* s_b = s_row32 + a.row_words;
   uint32_t* s_cnt = s_b + B * NS1;
   int32_t* s_ln = reinterpret_cast<int32_t*>(s_cnt + B * D * NC);
   uint32_t* s_ml = reinterpret_cast<uint32_t*>(s_ln + B);
@@ -148,12 +159,10 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
   const uint8_t* lab = SMEM_LAB ? s_lab : a.minor_label;
 
   constexpr unsigned FULL = 0xffffffffu;
-  constexpr int PARTS = 32 / B;  // lanes sharing the tail of one line
   constexpr unsigned FM = (1u << PH_FIELD_BITS) - 1u;
   const int lane = threadIdx.x & 31;
   const uint32_t mmask = (a.minor_bits >= 32) ? 0xffffffffu : ((1u << a.minor_bits) - 1u);
   const int n_batches = (a.n_work + B - 1) / B;
-  const uint32_t CH = (1u << cb) - 16u;
 
   auto label_at = [&](uint32_t addr) -> uint32_t {
     return SMEM_LAB ? (uint32_t)lab[addr] : (uint32_t)__ldg(lab + addr);
@@ -189,6 +198,8 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
       s_ml[lane] = h_ml;
     }
     for (int k = lane; k < B * D * NC; k += 32) s_cnt[k] = 0;
+    if (MODE == MODE_COUNTS)
+      for (int k = lane; k < a.row_words; k += 32) s_row32[k] = 0;
     __syncwarp();
     for (int k = lane; k < B * NS1; k += 32) {
       const int l = k / NS1, s = k - l * NS1;
@@ -292,48 +303,10 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
     }
     __syncwarp();
 
-    // ---- holders: tail (rare codes, word = minor | code << minor_bits), shared by PARTS lanes per line
-    const uint8_t* h_maprow = (MODE == MODE_MAPPED) ? s_map + h_ml * K2 : nullptr;
-    double t0[NC], t1[NC];
-    unsigned tn[NC], tv[NC];
-#pragma unroll
-    for (int c = 0; c < NC; ++c) { t0[c] = 0.0; t1[c] = 0.0; tn[c] = 0; tv[c] = 0; }
-    if (have) {
-      const int64_t tb = __ldg(a.tail_off + line), te = __ldg(a.tail_off + line + 1);
-      for (int64_t r = tb + lane / B; r < te; r += PARTS) {
-        const uint32_t w = __ldg(a.tail_words + r);
-        const uint32_t code = w >> a.minor_bits;
-        const uint32_t minor = w & mmask;
-        const uint32_t chq = minor / CH;
-        uint32_t sh = label_at((chq << cb) | (16u + minor - chq * CH));
-        if (MODE == MODE_MAPPED) sh = h_maprow[sh];
-        const double l0 = L0[code], l1 = L1[code];
-        const unsigned vp = VP[code] ? 1u : 0u;
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
-          if (sh == (uint32_t)(PH_FIELD_BITS * c)) {
-            t0[c] += l0;
-            t1[c] += l1;
-            tn[c] += 1u;
-            tv[c] += vp;
-          }
-        }
-      }
-    }
-    if (PARTS > 1) {
-#pragma unroll
-      for (int o = B; o < 32; o <<= 1) {
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
-          t0[c] += __shfl_xor_sync(FULL, t0[c], o);
-          t1[c] += __shfl_xor_sync(FULL, t1[c], o);
-          tn[c] += __shfl_xor_sync(FULL, tn[c], o);
-          tv[c] += __shfl_xor_sync(FULL, tv[c], o);
-        }
-      }
-    }
-
-    // ---- holders: integer counts -> fp64 sums in a fixed order, epilogue, store
+    // ---- holders: lane l finishes line l.  Every sum is  sum_code fma(count, L[code])  in ascending code order --
+    // the dense codes from the batch counters, then the rare codes of the tail (words sorted by (code, address), so a
+    // code is one run) -- i.e. a function of the integer (code, cluster) histogram only: the result does not depend on
+    // how the observations were split over lanes, batches or GPUs.
     if (lane < B && have) {
       double s0[NC], s1[NC];
       unsigned nob[NC], nva[NC];
@@ -345,18 +318,46 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
           const unsigned t = s_cnt[(myl * D + d) * NC + c];
+          if (MODE == MODE_COUNTS) s_row[(myl * NC + c) * a.ncp + d] = (uint16_t)t;
           s0[c] = fma((double)t, l0, s0[c]);
           s1[c] = fma((double)t, l1, s1[c]);
           nob[c] += t;
           nva[c] += vp ? t : 0u;
         }
       }
+      {
+        const uint8_t* h_maprow = (MODE == MODE_MAPPED) ? s_map + h_ml * K2 : nullptr;
+        const int64_t tb = __ldg(a.tail_off + line), te = __ldg(a.tail_off + line + 1);
+        uint32_t cur = 0xffffffffu;
+        unsigned rc[NC];
 #pragma unroll
-      for (int c = 0; c < NC; ++c) {
-        s0[c] += t0[c];
-        s1[c] += t1[c];
-        nob[c] += tn[c];
-        nva[c] += tv[c];
+        for (int c = 0; c < NC; ++c) rc[c] = 0;
+        auto fold = [&]() {
+          const double l0 = L0[cur], l1 = L1[cur];
+          const bool vp = VP[cur] != 0;
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            if (MODE == MODE_COUNTS) s_row[(myl * NC + c) * a.ncp + cur] = (uint16_t)rc[c];
+            s0[c] = fma((double)rc[c], l0, s0[c]);
+            s1[c] = fma((double)rc[c], l1, s1[c]);
+            nob[c] += rc[c];
+            nva[c] += vp ? rc[c] : 0u;
+            rc[c] = 0;
+          }
+        };
+        for (int64_t r = tb; r < te; ++r) {
+          const uint32_t w = __ldg(a.tail_words + r);
+          const uint32_t code = w >> a.minor_bits;
+          uint32_t sh = label_at(w & mmask);
+          if (MODE == MODE_MAPPED) sh = h_maprow[sh];
+          if (code != cur) {
+            if (cur != 0xffffffffu) fold();
+            cur = code;
+          }
+#pragma unroll
+          for (int c = 0; c < NC; ++c) rc[c] += (sh == (uint32_t)(PH_FIELD_BITS * c)) ? 1u : 0u;
+        }
+        if (cur != 0xffffffffu) fold();
       }
       const int wi = myw;
       if (MODE == MODE_TABLE) {
@@ -383,11 +384,38 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
         a.label_out[wi] = (cA == mx) ? 1 : ((cB == mx) ? 2 : 3);
         a.nobs_out[2 * (size_t)wi] = (int32_t)nob[0];
         a.nobs_out[2 * (size_t)wi + 1] = (int32_t)nob[NC > 1 ? 1 : 0];
-      } else {  // MODE_MAPPED: absent -> field 0 uses like0, present -> field 1 uses like1
+      } else if (MODE == MODE_MAPPED) {  // absent -> field 0 uses like0, present -> field 1 uses like1
         a.per_line[wi] = h_skip ? 0.0 : s0[0] + s1[NC > 1 ? 1 : 0];
       }
     }
     __syncwarp();
+    if (MODE == MODE_COUNTS) {
+      // the batch's rows are consecutive in the owner's slot: 16-byte stores straight into peer memory
+      const int upl = NC * a.ncp / 8;  // 16-byte units per line
+      for (int u = lane; u < nl * upl; u += 32) {
+        const int l = u / upl;
+        const int k = first + l;
+        const int owner = k / a.blk;
+        uint4* dst = reinterpret_cast<uint4*>(a.cnt_dst[owner] + (size_t)(k - owner * a.blk) * NC * a.ncp) + (u - l * upl);
+        *dst = reinterpret_cast<const uint4*>(s_row)[u];
+      }
+      __syncwarp();
+    }
+  }
+  if (MODE == MODE_COUNTS) {
+    // all partial rows of this rank are on their way: make them visible system-wide, then the last CTA raises this
+    // rank's flag in every peer's window
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned prev = atomicAdd(a.done, 1u);
+      if (prev == gridDim.x - 1) {
+        *a.done = 0;
+        __threadfence_system();
+        for (int p = 0; p < a.world; ++p)
+          asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.flag_dst[p]), "r"(a.epoch) : "memory");
+      }
+    }
   }
 }
 
@@ -474,7 +502,6 @@ __global__ void __launch_bounds__(kBlock, 1) k_node_table(const PassArgs a, cons
   unsigned* cnt = s_cnt + grp * K1;
   const int total_groups = gridDim.x * groups_per_block;
   const int D = a.D, NCH = a.NCH, NSUB = a.NSUB, cb = a.chunk_bits;
-  const uint32_t CH = (1u << cb) - 16u;
   const uint32_t mmask = (a.minor_bits >= 32) ? 0xffffffffu : ((1u << a.minor_bits) - 1u);
   auto node_at = [&](uint32_t addr) -> uint32_t { return SMEM_LAB ? (uint32_t)lab[addr] : (uint32_t)__ldg(lab + addr); };
   for (int wi = blockIdx.x * groups_per_block + grp; wi < a.n_work; wi += total_groups) {
@@ -504,9 +531,7 @@ __global__ void __launch_bounds__(kBlock, 1) k_node_table(const PassArgs a, cons
       for (int64_t p = a.tail_off[line]; p < a.tail_off[line + 1]; ++p) {
         const uint32_t w = a.tail_words[p];
         const uint32_t code = w >> a.minor_bits;
-        const uint32_t minor = w & mmask;
-        const uint32_t chq = minor / CH;
-        const uint32_t r = node_at((chq << cb) | (16u + minor - chq * CH));
+        const uint32_t r = node_at(w & mmask);
         acc0[r] += a.L0[code];
         acc1[r] += a.L1[code];
       }
@@ -528,11 +553,11 @@ __global__ void __launch_bounds__(kBlock, 1) k_node_table(const PassArgs a, cons
 
 // shared memory of one k_pass CTA with `threads` threads; 0 = does not fit
 size_t pass_smem_bytes(const ph_handle* h, const PhOrient* o, int mode, int NC, int K, bool smem_lab, int threads, int B,
-                       int* lut_in_smem) {
+                       int row_words, int* lut_in_smem) {
   size_t b = 0;
   if (smem_lab) b += (size_t)o->lab_bytes;
   if (mode == MODE_MAPPED) b += (((size_t)(K + 2) * (K + 2)) + 15) & ~(size_t)15;
-  const size_t warps = (size_t)(threads / 32) * warp_words(B, o->NSUB, o->D, NC) * 4 + 16;
+  const size_t warps = (size_t)(threads / 32) * (warp_words(B, o->NSUB, o->D, NC) + row_words) * 4 + 16;
   const size_t lut = ((size_t)h->n_codes * 17 + 15) & ~(size_t)15;
   *lut_in_smem = (b + warps + lut <= (size_t)h->max_smem && h->n_codes <= 4096) ? 1 : 0;
   if (*lut_in_smem) b += lut;
@@ -544,12 +569,13 @@ template <int MODE, int NC>
 int launch_pass(ph_handle* h, const PhOrient* o, PassArgs& a, cudaStream_t st) {
   if (a.n_work <= 0) return PH_OK;
   const int B = o->batch == 32 ? 32 : 8;
+  if (MODE == MODE_COUNTS) a.row_words = B * NC * a.ncp / 2;  // ncp is a multiple of 8: whole 16-byte units
   int lut = 0, threads = 0;
   bool smem_lab = true;
   size_t smem = 0;
   for (int pass = 0; pass < 2 && !smem; ++pass) {
     smem_lab = pass == 0;
-    for (threads = 1024; threads >= 256 && !smem; threads >>= 1) smem = pass_smem_bytes(h, o, MODE, NC, a.K, smem_lab, threads, B, &lut);
+    for (threads = 1024; threads >= 256 && !smem; threads >>= 1) smem = pass_smem_bytes(h, o, MODE, NC, a.K, smem_lab, threads, B, a.row_words, &lut);
     if (smem) threads <<= 1;
   }
   if (!smem) PH_FAIL(PH_ERR_UNSUPPORTED, "pass kernel tables do not fit in shared memory (K=%d, %d sub-segments)", a.K, o->NSUB);
@@ -566,7 +592,7 @@ int launch_pass(ph_handle* h, const PhOrient* o, PassArgs& a, cudaStream_t st) {
   int ctas = 1;
   if (h->ctas_per_sm == 2 && threads == 1024) {
     int lut2 = 0;
-    const size_t smem2 = pass_smem_bytes(h, o, MODE, NC, a.K, smem_lab, 512, B, &lut2);
+    const size_t smem2 = pass_smem_bytes(h, o, MODE, NC, a.K, smem_lab, 512, B, a.row_words, &lut2);
     if (smem2 && lut2 == lut && 2 * (smem2 + 1024) <= (size_t)h->smem_per_sm) {
       ctas = 2;
       threads = 512;
@@ -639,9 +665,22 @@ struct Pin {
 };
 
 int check_labels(const uint8_t* lab, int n, int maxv, const char* what) {
+  uint8_t mx = 0;  // branch-free maximum first (vectorises); the scan for the offender only runs on failure
+  for (int i = 0; i < n; ++i) mx = lab[i] > mx ? lab[i] : mx;
+  if (mx <= maxv) return PH_OK;
   for (int i = 0; i < n; ++i)
     if (lab[i] > maxv) PH_FAIL(PH_ERR_ARG, "%s[%d] = %d exceeds %d", what, i, lab[i], maxv);
   return PH_OK;
+}
+
+// page-locked host memory can be the source / target of the async copies directly (no staging memcpy)
+bool is_pinned(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost;
 }
 
 // common driver for the per-line "fast" passes (TABLE / LINEAR / BRANCHING)
@@ -678,8 +717,12 @@ int run_fast(ph_handle* h, PhOrient* o, int mode, const uint8_t* minor_label, in
       if (list[i] < 0 || list[i] >= o->n_major) PH_FAIL(PH_ERR_ARG, "list[%d]=%d out of range", i, list[i]);
   cudaStream_t st = h->stream;
   Pin pin{h->h_stage, h->h_stage_bytes};
-  uint8_t* p_lab = (uint8_t*)pin.take(o->n_minor);
-  memcpy(p_lab, minor_label, o->n_minor);
+  const uint8_t* p_lab = minor_label;
+  if (!is_pinned(minor_label)) {
+    uint8_t* q = (uint8_t*)pin.take(o->n_minor);
+    memcpy(q, minor_label, o->n_minor);
+    p_lab = q;
+  }
   PH_CUDA(cudaMemcpyAsync(h->d_lab_minor, p_lab, o->n_minor, cudaMemcpyHostToDevice, st));
   a.minor_label = h->d_lab_minor;
   if (list) {
@@ -717,13 +760,16 @@ int run_fast(ph_handle* h, PhOrient* o, int mode, const uint8_t* minor_label, in
   a.nobs_out = dNo;
   rc = mode == MODE_LINEAR ? launch_pass<MODE_LINEAR, 1>(h, o, a, st) : launch_pass<MODE_BRANCHING, 2>(h, o, a, st);
   if (rc != PH_OK) return rc;
-  uint8_t* pL = (uint8_t*)pin.take(n_list);
-  int32_t* pN = (int32_t*)pin.take((size_t)n_list * 4 * nobs_per);
+  const bool direct = is_pinned(label_out) && is_pinned(nobs_out);
+  uint8_t* pL = direct ? label_out : (uint8_t*)pin.take(n_list);
+  int32_t* pN = direct ? nobs_out : (int32_t*)pin.take((size_t)n_list * 4 * nobs_per);
   PH_CUDA(cudaMemcpyAsync(pL, h->d_u8, n_list, cudaMemcpyDeviceToHost, st));
   PH_CUDA(cudaMemcpyAsync(pN, dNo, (size_t)n_list * 4 * nobs_per, cudaMemcpyDeviceToHost, st));
   PH_CUDA(cudaStreamSynchronize(st));
-  memcpy(label_out, pL, n_list);
-  memcpy(nobs_out, pN, (size_t)n_list * 4 * nobs_per);
+  if (!direct) {
+    memcpy(label_out, pL, n_list);
+    memcpy(nobs_out, pN, (size_t)n_list * 4 * nobs_per);
+  }
   return PH_OK;
 }
 

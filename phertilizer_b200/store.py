@@ -154,21 +154,21 @@ class ObservationStore:
         """K2: per-cell sums/counts over SNV clusters 1..Q."""
         return self._table(_lib.lib().ph_cell_table, self.n_cells, snv_label, Q, cell_list, want)
 
-    def assign_linear(self, cell_label, lenA, snv_list=None):
+    def assign_linear(self, cell_label, lenA, snv_list=None, out=None):
+        """`out=(labels uint8 [k], nobs int32 [k])` reuses caller buffers; page-locked ones are written by the D2H copy
+        directly (no staging memcpy)."""
         lst = self._list(snv_list)
         k = self.n_snvs if lst is None else len(lst)
-        lab = _padded_u8(k)
-        nobs = np.empty(k, np.int32)
+        lab, nobs = out if out is not None else (_padded_u8(k), np.empty(k, np.int32))
         if k:
             _lib.check(_lib.lib().ph_assign_linear(self._h, _ptr(cell_label), float(lenA), _ptr(lst), k, _ptr(lab),
                                                    _ptr(nobs), 0, None))
         return lab, nobs
 
-    def assign_branching(self, cell_label, snv_list=None):
+    def assign_branching(self, cell_label, snv_list=None, out=None):
         lst = self._list(snv_list)
         k = self.n_snvs if lst is None else len(lst)
-        lab = _padded_u8(k)
-        nobs = np.empty((k, 2), np.int32)
+        lab, nobs = out if out is not None else (_padded_u8(k), np.empty((k, 2), np.int32))
         if k:
             _lib.check(_lib.lib().ph_assign_branching(self._h, _ptr(cell_label), _ptr(lst), k, _ptr(lab), _ptr(nobs), 0,
                                                       None))
