@@ -176,12 +176,13 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, w, world, residency):
+def workload_config(args, w, world, residency, exchange=None):
     c = w["cfg"]
     return {"workload": f"{args.workload}: synthetic {c['n']} cells x {c['m']} SNVs, coverage {c['cov']}, {c['K']} clones "
                         f"(BASELINE.json configs[2]); step = linear-split SNV reassignment pass (K1+K1a) over all observations",
             "nnz": w["nnz_total"], "cells": c["n"], "snvs": c["m"], "coverage": c["cov"], "clones": c["K"],
-            "sharding": f"cells sharded over {world} rank(s), all-reduce of the [S0|S1|Nobs] table" if world > 1 else "single GPU",
+            "sharding": (f"cells sharded over {world} rank(s); " + ("per-SNV integer histograms pushed to the owning rank over NVLink peer memory, labels pushed back (no NCCL)"
+                                                                    if exchange == "peer" else "NCCL all-reduce of the [S0|S1|Nobs] table")) if world > 1 else "single GPU",
             "l2_policy": "inputs larger than L2 (0.8 GB of observations streamed per pass vs 126 MB L2); label vectors rotate every step",
             "residency": residency}
 
@@ -207,8 +208,14 @@ def run_ours(args):
     w = make_workload(args.workload, dev, rank / world, (rank + 1) / world)
     n_loc, m, nnz_loc, nnz_tot = w["n_local"], w["m"], w["nnz_local"], w["nnz_total"]
     pv, pt, code_t = encode_pairs_device(w["var"], w["total"]) if (rank == 0 and world == 1 and not args.no_cpu) else (None, None, None)
-    st = ObservationStore.from_coo(n_loc, m, w["cell"], w["snv"], w["var"], w["total"], device=local)
-    sharded = ShardedStore(CudaBackend(st, dev), w["n"], m, w["lo"], w["hi"]) if world > 1 else None
+    pairs = None
+    if world > 1:  # the ranks must agree on the (var,total) codes: the exchanged histograms are indexed by code
+        from phertilizer_b200.sharded import global_pairs
+
+        pairs = global_pairs(w["var"], w["total"])
+    st = ObservationStore.from_coo(n_loc, m, w["cell"], w["snv"], w["var"], w["total"], device=local, pairs=pairs)
+    sharded = ShardedStore(CudaBackend(st, dev), w["n"], m, w["lo"], w["hi"], exchange=args.exchange) if world > 1 else None
+    exchange = sharded.exchange if sharded is not None else None
     torch.cuda.synchronize()
     info = st.info()
     log(f"[rank {rank}] store ready in {time.time() - t0:.1f}s: {info}")
@@ -238,6 +245,9 @@ def run_ours(args):
     def step_device(i, record=False):
         if world == 1:
             st.assign_linear_dev(labs_d[i % P], lenA[i % P], lab_out, nobs_out, stream=stream)
+        elif exchange == "peer":
+            # pass kernel with peer-memory epilogue + owner finish + collect (csrc/ph_peer.cu); no NCCL in the step
+            sharded.assign_linear_dev(labs_d[i % P], lenA[i % P], packed, lab_out, nobs_out)
         else:
             if record:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -281,7 +291,7 @@ def run_ours(args):
         barrier()
     ms = e0.elapsed_time(e1)
     launches = _lib.kernel_launches() - launches0
-    if world > 1 and args.exchange == "nccl":
+    if world > 1 and exchange == "nccl":
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
@@ -361,15 +371,18 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, w, world, "observations resident in HBM; `value` also has labels resident, `e2e` copies them every step"),
+            "config": workload_config(args, w, world, "observations resident in HBM; `value` also has labels resident, `e2e` copies them every step", exchange),
             "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n_loc) * world, "d2h_bytes_per_step": 5 * m * world,
                     "ms_per_step": 1e3 * e2e_s / args.steps,
                     "path": "ph_assign_linear(on_device=0): host labels -> pinned -> H2D, kernel, D2H SNV labels + Nobs, sync"
-                            if world == 1 else "pinned H2D labels, ph_snv_partial, NCCL all-reduce, ph_finish_linear, D2H labels + Nobs"},
+                            if world == 1 else ("pinned H2D labels, ph_peer_assign_linear, D2H labels + Nobs" if exchange == "peer" else
+                                                "pinned H2D labels, ph_snv_partial, NCCL all-reduce, ph_finish_linear, D2H labels + Nobs")},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "k_pass<MODE_LINEAR>" if world == 1 else "k_pass<MODE_TABLE>",
+                         "traffic": traffic if world == 1 else None,
+                         "kernel": "k_pass<MODE_LINEAR>" if world == 1 else ("k_pass<MODE_TABLE>" if exchange == "nccl" else
+                                   "k_pass<MODE_COUNTS> + k_peer_finish + k_peer_collect (whole step: kernel_ms includes the exchange)"),
                          "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": ab,
                          "physical_bytes_per_launch": phys, "physical_bytes_per_nnz": phys / max(nnz_loc, 1),
                          "physical_gbs": phys / (kernel_ms * 1e-3) / 1e9, "physical_frac": phys / (kernel_ms * 1e-3) / 1e9 / peak,
@@ -379,6 +392,10 @@ def run_ours(args):
                                            "stream_bytes_by_snv", "device_bytes")},
         }
         print(json.dumps(line), flush=True)
+    if sharded is not None and sharded.peer is not None:
+        if sharded.peer.timed_out():
+            log(f"[rank {rank}] WARNING: a peer wait timed out during the run")
+        sharded.peer.close()
     st.close()
     if world > 1:
         dist.destroy_process_group()

@@ -73,7 +73,8 @@ PH_API int64_t ph_kernel_launches(void);
  * (phertilizer/phertilizer.py:153-161, 295-306; data.py:8-20).
  *   cell/snv [nnz]  : COO coordinates, 0 <= cell < n_cells, 0 <= snv < n_snvs, no duplicates
  *   code [nnz]      : index of the observation's (var,total) pair in the likelihood table, 0 <= code < n_codes,
- *                     codes ordered by DESCENDING frequency (code 0 = most frequent pair)
+ *                     codes should be ordered by descending frequency (code 0 = most frequent pair): the leading
+ *                     codes with enough entries per line get the compact 16-bit layout
  *   L0/L1 [n_codes] : log-likelihoods of the pair under y=0 / y=1 (phertilizer.py:121-151)
  *   var_pos[n_codes]: 1 iff var > 0 for the pair (np.count_nonzero(var...) call sites)
  *   coo_on_device   : cell/snv/code are device pointers (they are only read)
@@ -133,6 +134,29 @@ PH_API int ph_snv_partial(ph_handle* h, const uint8_t* cell_label, int32_t C, co
 PH_API int ph_finish_linear(const double* packed, int32_t n_list, double lenA, uint8_t* label_out, int32_t* nobs_out,
                      void* stream);
 PH_API int ph_finish_branching(const double* packed, int32_t n_list, uint8_t* label_out, int32_t* nobs_out, void* stream);
+
+/*
+ * Cell-sharded K1 + K1a over NVLink peer memory (no NCCL on the data path).  Each rank creates a context on its handle,
+ * exports an opaque handle blob of ph_peer_handle_bytes() bytes (a CUDA IPC memory handle), the host language gathers
+ * the blobs of all ranks (rank order) and passes them to ph_peer_connect.  ph_peer_assign_* then behave like
+ * ph_assign_linear / ph_assign_branching on the union of all ranks' cells: `cell_label` are THIS rank's cells, every
+ * rank receives the full label_out / nobs_out.  What travels between the GPUs is the integer (cluster, code) histogram
+ * of every SNV, so the outputs are bit-identical to the single-GPU call for any number of ranks.  Collective: all
+ * ranks must make the same sequence of calls.  Device pointers only, enqueued on `stream`.
+ * Limits: 2..8 ranks of one node, <= 65535 cells per rank, <= 64 (var,total) codes (else PH_ERR_UNSUPPORTED: use
+ * ph_snv_partial + an all-reduce).
+ */
+typedef struct ph_peer ph_peer;
+PH_API int ph_peer_handle_bytes(void);
+PH_API int ph_peer_create(ph_handle* h, int rank, int world, ph_peer** out);
+PH_API int ph_peer_export(ph_peer* p, void* handle_out);
+PH_API int ph_peer_connect(ph_peer* p, const void* all_handles);
+PH_API int ph_peer_assign_linear(ph_peer* p, const uint8_t* cell_label, double lenA, const int32_t* snv_list,
+                          int32_t n_list, uint8_t* label_out, int32_t* nobs_out, void* stream);
+PH_API int ph_peer_assign_branching(ph_peer* p, const uint8_t* cell_label, const int32_t* snv_list, int32_t n_list,
+                             uint8_t* label_out, int32_t* nobs_out, void* stream);
+PH_API int ph_peer_timed_out(ph_peer* p, void* stream); /* 1 if a wait for a peer ever gave up (~3 s) */
+PH_API void ph_peer_destroy(ph_peer* p);
 
 /*
  * K2 -- per-cell table over SNV clusters (transpose of K1).

@@ -39,6 +39,8 @@ EXPORTS = [
     "ph_snv_table", "ph_assign_linear", "ph_assign_branching", "ph_cell_table", "ph_block_sums", "ph_tree_loglik",
     "ph_snv_node_table", "ph_cell_node_table", "ph_gauss_node_ll", "ph_pairwise_dist",
     "ph_snv_partial", "ph_finish_linear", "ph_finish_branching",
+    "ph_peer_handle_bytes", "ph_peer_create", "ph_peer_export", "ph_peer_connect", "ph_peer_assign_linear",
+    "ph_peer_assign_branching", "ph_peer_timed_out", "ph_peer_destroy",
 ]
 
 _lib = None
@@ -74,11 +76,19 @@ def lib():
     L.ph_snv_partial.argtypes = [_vp, _vp, C.c_int32, _vp, C.c_int32, _vp, C.c_int, _vp]
     L.ph_finish_linear.argtypes = [_vp, C.c_int32, C.c_double, _vp, _vp, _vp]
     L.ph_finish_branching.argtypes = [_vp, C.c_int32, _vp, _vp, _vp]
+    L.ph_peer_create.argtypes = [_vp, C.c_int, C.c_int, C.POINTER(_vp)]
+    L.ph_peer_export.argtypes = [_vp, _vp]
+    L.ph_peer_connect.argtypes = [_vp, _vp]
+    L.ph_peer_assign_linear.argtypes = [_vp, _vp, C.c_double, _vp, C.c_int32, _vp, _vp, _vp]
+    L.ph_peer_assign_branching.argtypes = [_vp, _vp, _vp, C.c_int32, _vp, _vp, _vp]
+    L.ph_peer_timed_out.argtypes = [_vp, _vp]
+    L.ph_peer_destroy.argtypes = [_vp]
+    L.ph_peer_destroy.restype = None
     L.ph_gauss_node_ll.argtypes = [_vp, _vp, C.c_int32, _vp, C.c_int32, _vp, _vp, C.c_int, _vp]
     L.ph_pairwise_dist.argtypes = [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, C.c_int, C.c_int, _vp]
     for name in EXPORTS:
         fn = getattr(L, name)
-        if name not in ("ph_last_error", "ph_kernel_launches", "ph_destroy"):
+        if name not in ("ph_last_error", "ph_kernel_launches", "ph_destroy", "ph_peer_destroy"):
             fn.restype = C.c_int
     if L.ph_abi_version() != ABI_VERSION:
         raise PhError(f"ABI version mismatch: library {L.ph_abi_version()} != binding {ABI_VERSION}")

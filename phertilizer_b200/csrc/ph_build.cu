@@ -406,14 +406,6 @@ extern "C" int ph_create(int32_t n_cells, int32_t n_snvs, int64_t nnz, const int
       goto done;
     }
   }
-  for (int c = 1; c < n_codes && c <= PH_DMAX; ++c) {
-    if (h_hist[c] > h_hist[c - 1]) {
-      snprintf(ph_err_msg, sizeof(ph_err_msg), "codes must be ordered by descending frequency (code %d > code %d)", c, c - 1);
-      rc = PH_ERR_ARG;
-      goto done;
-    }
-  }
-
   if (nnz > 0) {
     PH_TRY(cudaMalloc(&kbuf0, nnz * sizeof(uint64_t)));
     PH_TRY(cudaMalloc(&kbuf1, nnz * sizeof(uint64_t)));

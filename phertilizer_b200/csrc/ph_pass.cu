@@ -1075,3 +1075,28 @@ extern "C" int ph_finish_branching(const double* packed, int32_t n_list, uint8_t
   PH_CUDA(cudaGetLastError());
   return PH_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// cell-sharded K1 over peer memory (ph_peer.cu): the COUNTS pass
+// ------------------------------------------------------------------------------------------------
+int ph_pass_counts(ph_handle* h, const uint8_t* cell_label, int C, const int32_t* snv_list, int32_t n_list,
+                   uint16_t* const* cnt_dst, uint32_t* const* flag_dst, unsigned* done, int blk, int ncp, int world,
+                   uint32_t epoch, cudaStream_t st) {
+  PhOrient* o = &h->by_snv;
+  PassArgs a;
+  fill_common(h, o, a);
+  a.C = C;
+  a.n_work = n_list;
+  a.minor_label = cell_label;
+  a.list = snv_list;
+  for (int r = 0; r < world; ++r) {
+    a.cnt_dst[r] = cnt_dst[r];
+    a.flag_dst[r] = flag_dst[r];
+  }
+  a.done = done;
+  a.blk = blk;
+  a.ncp = ncp;
+  a.world = world;
+  a.epoch = epoch;
+  return C == 1 ? launch_pass<MODE_COUNTS, 1>(h, o, a, st) : launch_pass<MODE_COUNTS, 2>(h, o, a, st);
+}

@@ -1,0 +1,306 @@
+// Cell-sharded K1 + K1a over NVLink peer memory -- no NCCL on the data path.
+//
+// Every rank owns a contiguous block of cells (its own ph_handle) and a contiguous block of the listed SNVs.  One step:
+//
+//   A  k_pass<MODE_COUNTS> (ph_pass.cu): the rank's pass over its observations; the (cluster, code) histogram row of
+//      every SNV is stored straight into the window of the rank that OWNS the SNV (16-byte peer stores from the kernel
+//      epilogue, overlapping the streaming of the following batches); the last CTA raises this rank's flag everywhere.
+//   B  k_peer_finish: the owner waits for the world's flags, sums the `world` integer rows of each of its SNVs,
+//      evaluates  sum_code fma(count, L[code])  exactly like the single-GPU holder does, applies the K1a decision rule
+//      and stores label + observation counts into EVERY rank's output window; then raises its second flag everywhere.
+//   C  k_peer_collect: waits for the owners' flags and copies the window to the caller's output buffers.
+//
+// The exchanged quantity is an integer histogram, so the result is bit-identical to the single-GPU kernels for any
+// number of ranks.  Windows are plain cudaMalloc allocations shared through CUDA IPC handles (exchanged by the host
+// language -- torch.distributed in this repository -- as opaque 64-byte blobs).
+#include "ph_common.cuh"
+
+struct ph_peer {
+  ph_handle* h;
+  int rank, world;
+  int32_t max_lines, blk_max, ncp;
+  size_t off_cnt, off_lab, off_nobs, bytes;
+  uint8_t* win[PH_MAX_PEERS];  // win[rank] = own allocation, others = IPC mappings
+  bool opened[PH_MAX_PEERS];
+  unsigned* d_done;            // [2] CTA completion counters (pass, finish) + [1] spin-timeout flag
+  uint32_t epoch;
+};
+
+namespace {
+
+constexpr size_t kFlagBytes = 4096;  // flagA[world] at +0, flagB[world] at +1024
+constexpr long long kSpinLimit = 6000000000ll;  // ~3 s of SM clocks: a lost peer must not hang the GPU
+
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void wait_flags(const uint32_t* flags, int world, uint32_t epoch, unsigned* timeout_flag) {
+  if (threadIdx.x == 0) {
+    const long long t0 = clock64();
+    for (int q = 0; q < world; ++q) {
+      // epochs only grow; signed distance keeps the comparison valid across a 32-bit wrap
+      while ((int32_t)(ld_acquire_sys(flags + q) - epoch) < 0) {
+        if (clock64() - t0 > kSpinLimit) {
+          *timeout_flag = 1;
+          break;
+        }
+        __nanosleep(64);
+      }
+    }
+  }
+  __syncthreads();
+}
+
+struct FinishArgs {
+  const uint8_t* win;  // own window
+  size_t off_cnt;
+  int world, rank, blk, blk_max, ncp, n_codes, n_list, C, mode;  // mode 1 = linear, 2 = branching
+  double lenA;
+  const double* L0;
+  const double* L1;
+  uint8_t* lab_dst[PH_MAX_PEERS];
+  int32_t* nobs_dst[PH_MAX_PEERS];
+  uint32_t* flag_dst[PH_MAX_PEERS];
+  unsigned* done;
+  unsigned* timeout_flag;
+  uint32_t epoch;
+};
+
+template <int C>
+__global__ void __launch_bounds__(256) k_peer_finish(const FinishArgs a) {
+  wait_flags(reinterpret_cast<const uint32_t*>(a.win), a.world, a.epoch, a.timeout_flag);
+  const int first = a.rank * a.blk;
+  const int n_own = min(a.blk, a.n_list - first);
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_own; idx += gridDim.x * blockDim.x) {
+    double s0[C], s1[C];
+    unsigned nob[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) { s0[c] = 0.0; s1[c] = 0.0; nob[c] = 0; }
+    const size_t row = (size_t)C * a.ncp;  // uint16 per line
+    const size_t slot = (size_t)a.blk_max * 3 * a.ncp;  // uint16 per source rank (sized for C = 3)
+    const uint16_t* base = reinterpret_cast<const uint16_t*>(a.win + a.off_cnt) + (size_t)idx * row;
+    for (int c = 0; c < C; ++c) {
+      for (int k8 = 0; k8 < a.ncp; k8 += 8) {
+        unsigned t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int s = 0; s < a.world; ++s) {
+          // written by a peer since the last launch: bypass L1
+          const uint4 v = __ldcv(reinterpret_cast<const uint4*>(base + s * slot + c * a.ncp + k8));
+          t[0] += v.x & 0xFFFFu; t[1] += v.x >> 16; t[2] += v.y & 0xFFFFu; t[3] += v.y >> 16;
+          t[4] += v.z & 0xFFFFu; t[5] += v.z >> 16; t[6] += v.w & 0xFFFFu; t[7] += v.w >> 16;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int code = k8 + j;
+          if (code < a.n_codes) {  // ascending code order, fma(count, L, sum): the holder's arithmetic (ph_pass.cu)
+            s0[c] = fma((double)t[j], a.L0[code], s0[c]);
+            s1[c] = fma((double)t[j], a.L1[code], s1[c]);
+            nob[c] += t[j];
+          }
+        }
+      }
+    }
+    const int k = first + idx;
+    uint8_t label;
+    if (a.mode == 1) {  // linear_split.py:229-234
+      const double m0 = s0[0] / a.lenA, m1 = s1[0] / a.lenA;
+      label = (m0 >= m1) ? 2 : 1;
+    } else {  // branching_split.py:332-346
+      const double cA = s1[0] + s0[C > 1 ? 1 : 0];
+      const double cB = s0[0] + s1[C > 1 ? 1 : 0];
+      const double cC = s1[0] + s1[C > 1 ? 1 : 0];
+      const double mx = fmax(cA, fmax(cB, cC));
+      label = (cA == mx) ? 1 : ((cB == mx) ? 2 : 3);
+    }
+    for (int p = 0; p < a.world; ++p) {
+      a.lab_dst[p][k] = label;
+#pragma unroll
+      for (int c = 0; c < C; ++c) a.nobs_dst[p][(size_t)k * C + c] = (int32_t)nob[c];
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(a.done, 1u);
+    if (prev == gridDim.x - 1) {
+      *a.done = 0;
+      __threadfence_system();
+      for (int p = 0; p < a.world; ++p)
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.flag_dst[p]), "r"(a.epoch) : "memory");
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_peer_collect(const uint8_t* win, size_t off_lab, size_t off_nobs, int world,
+                                                     uint32_t epoch, int n_list, int C, uint8_t* label_out,
+                                                     int32_t* nobs_out, unsigned* timeout_flag) {
+  wait_flags(reinterpret_cast<const uint32_t*>(win + 1024), world, epoch, timeout_flag);
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  const uint32_t* src_n = reinterpret_cast<const uint32_t*>(win + off_nobs);
+  for (int i = tid; i < n_list * C; i += nt) nobs_out[i] = (int32_t)__ldcv(src_n + i);
+  const uint8_t* src_l = win + off_lab;
+  for (int i = tid; i < n_list; i += nt) label_out[i] = __ldcv(src_l + i);
+}
+
+}  // namespace
+
+// implemented in ph_pass.cu: the COUNTS pass with its peer destinations
+int ph_pass_counts(ph_handle* h, const uint8_t* cell_label, int C, const int32_t* snv_list, int32_t n_list,
+                   uint16_t* const* cnt_dst, uint32_t* const* flag_dst, unsigned* done, int blk, int ncp, int world,
+                   uint32_t epoch, cudaStream_t st);
+
+extern "C" int ph_peer_handle_bytes(void) { return (int)sizeof(cudaIpcMemHandle_t); }
+
+extern "C" void ph_peer_destroy(ph_peer* p) {
+  if (!p) return;
+  cudaSetDevice(p->h->device);
+  for (int r = 0; r < p->world; ++r) {
+    if (r == p->rank) continue;
+    if (p->opened[r]) cudaIpcCloseMemHandle(p->win[r]);
+  }
+  cudaFree(p->win[p->rank]);
+  cudaFree(p->d_done);
+  delete p;
+}
+
+extern "C" int ph_peer_create(ph_handle* h, int rank, int world, ph_peer** out) {
+  if (!h || !out) PH_FAIL(PH_ERR_ARG, "null argument");
+  *out = nullptr;
+  if (world < 2 || world > PH_MAX_PEERS || rank < 0 || rank >= world)
+    PH_FAIL(PH_ERR_ARG, "rank %d / world %d outside 2..%d", rank, world, PH_MAX_PEERS);
+  if (h->n_cells > 65535)
+    PH_FAIL(PH_ERR_UNSUPPORTED, "%d local cells: the exchanged histogram rows are 16-bit (at most 65535 cells per rank)", h->n_cells);
+  if (h->n_codes > 64) PH_FAIL(PH_ERR_UNSUPPORTED, "%d (var,total) codes: histogram exchange supports up to 64", h->n_codes);
+  PH_CUDA(cudaSetDevice(h->device));
+  ph_peer* p = new ph_peer();
+  memset(p, 0, sizeof(*p));
+  p->h = h;
+  p->rank = rank;
+  p->world = world;
+  p->max_lines = h->n_snvs;
+  p->blk_max = (h->n_snvs + world - 1) / world;
+  p->ncp = (h->n_codes + 7) & ~7;
+  p->off_cnt = kFlagBytes;
+  const size_t cnt_bytes = (size_t)world * p->blk_max * 3 * p->ncp * sizeof(uint16_t);
+  p->off_lab = (p->off_cnt + cnt_bytes + 255) & ~(size_t)255;
+  p->off_nobs = (p->off_lab + (size_t)p->max_lines + 255) & ~(size_t)255;
+  p->bytes = p->off_nobs + (size_t)p->max_lines * 3 * sizeof(int32_t) + 256;
+  cudaError_t e = cudaMalloc(&p->win[rank], p->bytes);
+  if (e == cudaSuccess) e = cudaMemset(p->win[rank], 0, p->bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&p->d_done, 16);
+  if (e == cudaSuccess) e = cudaMemset(p->d_done, 0, 16);
+  if (e != cudaSuccess) {
+    snprintf(ph_err_msg, sizeof(ph_err_msg), "peer window allocation failed: %s", cudaGetErrorString(e));
+    ph_peer_destroy(p);
+    return PH_ERR_CUDA;
+  }
+  *out = p;
+  return PH_OK;
+}
+
+extern "C" int ph_peer_export(ph_peer* p, void* handle_out) {
+  if (!p || !handle_out) PH_FAIL(PH_ERR_ARG, "null argument");
+  PH_CUDA(cudaSetDevice(p->h->device));
+  cudaIpcMemHandle_t hd;
+  PH_CUDA(cudaIpcGetMemHandle(&hd, p->win[p->rank]));
+  memcpy(handle_out, &hd, sizeof(hd));
+  return PH_OK;
+}
+
+extern "C" int ph_peer_connect(ph_peer* p, const void* all_handles) {
+  if (!p || !all_handles) PH_FAIL(PH_ERR_ARG, "null argument");
+  PH_CUDA(cudaSetDevice(p->h->device));
+  for (int r = 0; r < p->world; ++r) {
+    if (r == p->rank || p->opened[r]) continue;
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, (const uint8_t*)all_handles + (size_t)r * sizeof(hd), sizeof(hd));
+    void* ptr = nullptr;
+    PH_CUDA(cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+    p->win[r] = (uint8_t*)ptr;
+    p->opened[r] = true;
+  }
+  return PH_OK;
+}
+
+namespace {
+int peer_assign(ph_peer* p, int mode, const uint8_t* cell_label, double lenA, const int32_t* snv_list, int32_t n_list,
+                uint8_t* label_out, int32_t* nobs_out, void* stream) {
+  if (!p) PH_FAIL(PH_ERR_ARG, "null peer context");
+  if (!cell_label || !label_out || !nobs_out) PH_FAIL(PH_ERR_ARG, "null pointer");
+  ph_handle* h = p->h;
+  if (!snv_list) n_list = h->n_snvs;
+  if (n_list <= 0 || n_list > p->max_lines) PH_FAIL(PH_ERR_ARG, "n_list=%d outside 1..%d", n_list, p->max_lines);
+  for (int r = 0; r < p->world; ++r)
+    if (!p->win[r]) PH_FAIL(PH_ERR_ARG, "ph_peer_connect has not been called (rank %d missing)", r);
+  PH_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int C = mode == 1 ? 1 : 2;
+  const int blk = (n_list + p->world - 1) / p->world;
+  const uint32_t epoch = ++p->epoch;
+  const size_t slot = (size_t)p->blk_max * 3 * p->ncp;  // uint16 per source rank
+
+  uint16_t* cnt_dst[PH_MAX_PEERS] = {};
+  uint32_t* flagA_dst[PH_MAX_PEERS] = {};
+  FinishArgs f;
+  memset(&f, 0, sizeof(f));
+  for (int r = 0; r < p->world; ++r) {
+    cnt_dst[r] = reinterpret_cast<uint16_t*>(p->win[r] + p->off_cnt) + (size_t)p->rank * slot;
+    flagA_dst[r] = reinterpret_cast<uint32_t*>(p->win[r]) + p->rank;
+    f.lab_dst[r] = p->win[r] + p->off_lab;
+    f.nobs_dst[r] = reinterpret_cast<int32_t*>(p->win[r] + p->off_nobs);
+    f.flag_dst[r] = reinterpret_cast<uint32_t*>(p->win[r] + 1024) + p->rank;
+  }
+  int rc = ph_pass_counts(h, cell_label, C, snv_list, n_list, cnt_dst, flagA_dst, p->d_done, blk, p->ncp, p->world, epoch, st);
+  if (rc != PH_OK) return rc;
+
+  f.win = p->win[p->rank];
+  f.off_cnt = p->off_cnt;
+  f.world = p->world;
+  f.rank = p->rank;
+  f.blk = blk;
+  f.blk_max = p->blk_max;
+  f.ncp = p->ncp;
+  f.n_codes = h->n_codes;
+  f.n_list = n_list;
+  f.C = C;
+  f.mode = mode;
+  f.lenA = lenA;
+  f.L0 = h->d_L0;
+  f.L1 = h->d_L1;
+  f.done = p->d_done + 1;
+  f.timeout_flag = p->d_done + 2;
+  f.epoch = epoch;
+  const int fb = (blk + 255) / 256 < h->sm_count * 4 ? (blk + 255) / 256 : h->sm_count * 4;
+  if (C == 1) k_peer_finish<1><<<fb > 0 ? fb : 1, 256, 0, st>>>(f);
+  else k_peer_finish<2><<<fb > 0 ? fb : 1, 256, 0, st>>>(f);
+  ph_count_launch();
+  const int cb = (n_list * C + 255) / 256 < h->sm_count * 2 ? (n_list * C + 255) / 256 : h->sm_count * 2;
+  k_peer_collect<<<cb, 256, 0, st>>>(p->win[p->rank], p->off_lab, p->off_nobs, p->world, epoch, n_list, C, label_out,
+                                     nobs_out, p->d_done + 2);
+  ph_count_launch();
+  PH_CUDA(cudaGetLastError());
+  return PH_OK;
+}
+}  // namespace
+
+extern "C" int ph_peer_assign_linear(ph_peer* p, const uint8_t* cell_label, double lenA, const int32_t* snv_list,
+                                     int32_t n_list, uint8_t* label_out, int32_t* nobs_out, void* stream) {
+  return peer_assign(p, 1, cell_label, lenA, snv_list, n_list, label_out, nobs_out, stream);
+}
+
+extern "C" int ph_peer_assign_branching(ph_peer* p, const uint8_t* cell_label, const int32_t* snv_list, int32_t n_list,
+                                        uint8_t* label_out, int32_t* nobs_out, void* stream) {
+  return peer_assign(p, 2, cell_label, 1.0, snv_list, n_list, label_out, nobs_out, stream);
+}
+
+// 1 if a spin-wait of this context ever gave up (a peer never arrived); synchronises the stream
+extern "C" int ph_peer_timed_out(ph_peer* p, void* stream) {
+  if (!p) return 0;
+  unsigned v = 0;
+  cudaSetDevice(p->h->device);
+  cudaStreamSynchronize((cudaStream_t)stream);
+  cudaMemcpy(&v, p->d_done + 2, sizeof(v), cudaMemcpyDeviceToHost);
+  return v ? 1 : 0;
+}

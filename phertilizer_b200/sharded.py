@@ -1,9 +1,14 @@
 """Cell-sharded observation store: one process per GPU, cells partitioned contiguously, all SNVs on every rank.
 
-SURVEY.md section 8e: per-SNV tables (K1) are sums over cells, so every rank computes the partial table of its block of
-cells (`ph_snv_partial`) and ONE sum all-reduce of the packed `[S0 | S1 | Nobs]` float64 table (NCCL over NVLink)
-gives every rank the full table; the K1a decision (`ph_finish_linear` / `ph_finish_branching`) then runs redundantly
-on every rank.  Per-cell tables (K2) need no exchange.  Block sums all-reduce a handful of scalars.
+SURVEY.md section 8e: per-SNV tables (K1) are sums over cells.  Two transports combine the ranks' partial tables:
+
+* `exchange="peer"` (default when it can be set up): the pass kernel stores every SNV's integer (cluster, code)
+  histogram straight into the NVLink peer window of the rank owning the SNV, the owner decides and pushes label +
+  counts to every rank (csrc/ph_peer.cu).  No NCCL on the data path; bit-identical to the single-GPU kernels.
+* `exchange="nccl"`: every rank computes the partial `[S0 | S1 | Nobs]` float64 table (`ph_snv_partial`), ONE NCCL sum
+  all-reduce, then the K1a decision (`ph_finish_linear` / `ph_finish_branching`) redundantly on every rank.
+
+Per-cell tables (K2) need no exchange.  Block sums all-reduce a handful of scalars.
 
 `torch.distributed` is plumbing only.  The `backend` indirection exists so the partition / exchange logic can be tested
 with the gloo backend on a CPU-only box (tests/test_sharded_gloo.py) with a CPU stand-in for the two kernels.
@@ -16,6 +21,28 @@ import numpy as np
 def cell_block(n_cells: int, rank: int, world: int):
     """Contiguous block [lo, hi) of cells owned by `rank`."""
     return (n_cells * rank) // world, (n_cells * (rank + 1)) // world
+
+
+def global_pairs(var, total, group=None):
+    """One (var,total) code table for all ranks: the local pair counts are gathered and merged, then ordered by global
+    frequency.  The peer-memory exchange sums integer histograms indexed by code, so the codes must mean the same
+    pair everywhere."""
+    import torch.distributed as dist
+
+    from .store import order_pairs, pair_counts
+
+    pv, pt, cnt = pair_counts(var, total)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return order_pairs(pv, pt, cnt)
+    parts = [None] * dist.get_world_size(group)
+    dist.all_gather_object(parts, (pv.tolist(), pt.tolist(), cnt.tolist()), group=group)
+    merged = {}
+    for a, b, c in parts:
+        for v, t, k in zip(a, b, c):
+            merged[(v, t)] = merged.get((v, t), 0) + k
+    keys = list(merged)
+    return order_pairs(np.array([k[0] for k in keys], np.int64), np.array([k[1] for k in keys], np.int64),
+                       np.array([merged[k] for k in keys], np.int64))
 
 
 class CudaBackend:
@@ -47,8 +74,55 @@ class CudaBackend:
         self.store.finish_branching_dev(packed_t, k, lab_t, nobs_t, stream=self.stream())
 
 
+class PeerExchange:
+    """NVLink peer-memory windows of the fused sharded K1 (include/phertilizer_b200.h, ph_peer_*).  torch.distributed
+    only carries the 64-byte IPC handle of every rank's window once, at set-up."""
+
+    def __init__(self, store, rank, world, group=None):
+        import ctypes as C
+
+        import torch
+        import torch.distributed as dist
+
+        from . import _lib
+
+        L = _lib.lib()
+        self._lib, self._L = _lib, L
+        self._p = C.c_void_p()
+        _lib.check(L.ph_peer_create(store._h, int(rank), int(world), C.byref(self._p)))
+        nb = L.ph_peer_handle_bytes()
+        mine = C.create_string_buffer(nb)
+        _lib.check(L.ph_peer_export(self._p, mine))
+        blobs = [None] * world
+        dist.all_gather_object(blobs, bytes(mine.raw), group=group)
+        allb = C.create_string_buffer(b"".join(blobs), nb * world)
+        _lib.check(L.ph_peer_connect(self._p, allb))
+        dist.barrier(group=group)  # every window is mapped everywhere before the first kernel stores into one
+        torch.cuda.synchronize()
+
+    def assign_linear(self, label_t, lenA, lab_out_t, nobs_out_t, list_t=None, k=0, stream=None):
+        from .store import _ptr
+
+        self._lib.check(self._L.ph_peer_assign_linear(self._p, _ptr(label_t), float(lenA), _ptr(list_t), int(k),
+                                                      _ptr(lab_out_t), _ptr(nobs_out_t), stream))
+
+    def assign_branching(self, label_t, lab_out_t, nobs_out_t, list_t=None, k=0, stream=None):
+        from .store import _ptr
+
+        self._lib.check(self._L.ph_peer_assign_branching(self._p, _ptr(label_t), _ptr(list_t), int(k), _ptr(lab_out_t),
+                                                         _ptr(nobs_out_t), stream))
+
+    def timed_out(self, stream=None) -> bool:
+        return bool(self._L.ph_peer_timed_out(self._p, stream))
+
+    def close(self):
+        if self._p is not None:
+            self._L.ph_peer_destroy(self._p)
+            self._p = None
+
+
 class ShardedStore:
-    def __init__(self, backend, n_cells, n_snvs, lo, hi, group=None):
+    def __init__(self, backend, n_cells, n_snvs, lo, hi, group=None, exchange="auto"):
         import torch
         import torch.distributed as dist
 
@@ -58,9 +132,31 @@ class ShardedStore:
         self.lo, self.hi = int(lo), int(hi)
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.peer = None
+        self.exchange = "nccl"
+        if exchange in ("auto", "peer") and self.world > 1 and isinstance(backend, CudaBackend):
+            # every rank must take the same branch: agree on the outcome of the set-up
+            ok, err = 1, None
+            try:
+                self.peer = PeerExchange(backend.store, dist.get_rank(group), self.world, group)
+            except Exception as e:  # PhError (unsupported shape, IPC not permitted) -> the NCCL transport
+                ok, err = 0, e
+            flag = torch.tensor([ok], dtype=torch.int32, device=backend.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            if int(flag.item()) == 1:
+                self.exchange = "peer"
+            else:
+                if self.peer is not None:
+                    self.peer.close()
+                    self.peer = None
+                if exchange == "peer":
+                    raise RuntimeError(f"peer-memory exchange unavailable: {err}")
+                if err is not None:
+                    print(f"[phertilizer_b200] peer-memory exchange unavailable ({err}); using the NCCL all-reduce")
 
     @classmethod
-    def from_coo(cls, n_cells, n_snvs, cell, snv, var, total, rank, world, device, alpha=0.001, max_copies=5, group=None):
+    def from_coo(cls, n_cells, n_snvs, cell, snv, var, total, rank, world, device, alpha=0.001, max_copies=5, group=None,
+                 exchange="auto"):
         """Every rank passes the observations it has (the full COO or any superset of its block); rows outside
         [lo, hi) are dropped and the rest is re-indexed to local cell ids."""
         import torch
@@ -75,9 +171,10 @@ class ShardedStore:
             keep = (cell >= lo) & (cell < hi)
             cell, snv, var, total = (cell[keep] - lo).contiguous(), snv[keep].contiguous(), var[keep].contiguous(), total[keep].contiguous()
         st = ObservationStore.from_coo(hi - lo, n_snvs, cell, snv, var, total, alpha=alpha, max_copies=max_copies,
-                                       device=device if isinstance(device, int) else device.index)
+                                       device=device if isinstance(device, int) else device.index,
+                                       pairs=global_pairs(var, total, group))
         dev = torch.device("cuda", device) if isinstance(device, int) else device
-        return cls(CudaBackend(st, dev), n_cells, n_snvs, lo, hi, group)
+        return cls(CudaBackend(st, dev), n_cells, n_snvs, lo, hi, group, exchange)
 
     # ------------------------------------------------------------------ helpers
     def local_labels(self, cell_label_global: np.ndarray):
@@ -95,12 +192,16 @@ class ShardedStore:
     def assign_linear_dev(self, label_t, lenA, packed_t, lab_out_t, nobs_out_t, list_t=None):
         """label_t: this rank's local labels; lenA: GLOBAL |cellsA|; packed_t: float64 [3*k] scratch."""
         k = self.n_snvs if list_t is None else int(list_t.numel())
+        if self.peer is not None:
+            return self.peer.assign_linear(label_t, lenA, lab_out_t, nobs_out_t, list_t, k, stream=self.b.stream())
         self.b.snv_partial(label_t, 1, packed_t, list_t)
         self._allreduce(packed_t)
         self.b.finish_linear(packed_t, k, lenA, lab_out_t, nobs_out_t)
 
     def assign_branching_dev(self, label_t, packed_t, lab_out_t, nobs_out_t, list_t=None):
         k = self.n_snvs if list_t is None else int(list_t.numel())
+        if self.peer is not None:
+            return self.peer.assign_branching(label_t, lab_out_t, nobs_out_t, list_t, k, stream=self.b.stream())
         self.b.snv_partial(label_t, 2, packed_t, list_t)
         self._allreduce(packed_t)
         self.b.finish_branching(packed_t, k, lab_out_t, nobs_out_t)

@@ -61,6 +61,48 @@ def encode_pairs_device(var, total):
     return (u % width).astype(np.int64), (u // width).astype(np.int64), code
 
 
+def pair_counts(var, total):
+    """Distinct (var, total) pairs of a COO block with their counts (host arrays); inputs numpy or torch."""
+    if isinstance(var, np.ndarray):
+        pv, pt, cnt, _ = encode_pairs(var, total)
+        return pv, pt, cnt
+    import torch
+
+    width = int(var.max().item()) + 1 if var.numel() else 1
+    key = total.to(torch.int64) * width + var.to(torch.int64)
+    uniq, cnt = torch.unique(key, return_counts=True)
+    u = uniq.cpu().numpy()
+    return (u % width).astype(np.int64), (u // width).astype(np.int64), cnt.cpu().numpy().astype(np.int64)
+
+
+def order_pairs(pv, pt, cnt):
+    """Code order: descending frequency, ties by ascending (total, var) -- like_lut.encode_pairs."""
+    order = np.lexsort((pv, pt, -np.asarray(cnt)))
+    return np.asarray(pv)[order], np.asarray(pt)[order]
+
+
+def encode_with_table(var, total, pv, pt):
+    """Codes of every observation in a GIVEN (var, total) table (all ranks of a sharded store share one table)."""
+    width = int(max(int(pv.max()) if len(pv) else 0, int(var.max()) if len(var) else 0)) + 1
+    tkey = np.asarray(pt, np.int64) * width + np.asarray(pv, np.int64)
+    order = np.argsort(tkey)
+    if isinstance(var, np.ndarray):
+        key = np.asarray(total, np.int64) * width + np.asarray(var, np.int64)
+        pos = np.searchsorted(tkey[order], key)
+        pos = np.minimum(pos, len(order) - 1)
+        if len(key) and not np.array_equal(tkey[order][pos], key):
+            raise _lib.PhError("an observation's (var,total) pair is missing from the given table")
+        return order[pos].astype(np.uint16)
+    import torch
+
+    key = total.to(torch.int64) * width + var.to(torch.int64)
+    skey = torch.from_numpy(tkey[order]).to(key.device)
+    pos = torch.searchsorted(skey, key).clamp_(max=len(order) - 1)
+    if key.numel() and not bool((skey[pos] == key).all().item()):
+        raise _lib.PhError("an observation's (var,total) pair is missing from the given table")
+    return torch.from_numpy(order.astype(np.int16)).to(key.device)[pos].contiguous()
+
+
 class ObservationStore:
     def __init__(self, handle, n_cells, n_snvs, pair_var, pair_total, L0, L1, device):
         self._h = handle
@@ -74,18 +116,28 @@ class ObservationStore:
 
     # ------------------------------------------------------------------ construction
     @classmethod
-    def from_coo(cls, n_cells, n_snvs, cell, snv, var, total, alpha=0.001, max_copies=5, device=0):
-        """cell/snv/var/total: numpy arrays (host) or torch CUDA tensors (stay on the device)."""
+    def from_coo(cls, n_cells, n_snvs, cell, snv, var, total, alpha=0.001, max_copies=5, device=0, pairs=None):
+        """cell/snv/var/total: numpy arrays (host) or torch CUDA tensors (stay on the device).
+        pairs=(pair_var, pair_total): use this (var,total) table and code order instead of deriving it from the data
+        (the ranks of a cell-sharded store must agree on the codes)."""
         L = _lib.lib()
         on_dev = not isinstance(cell, np.ndarray)
         if on_dev:
-            pv, pt, code = encode_pairs_device(var, total)
+            if pairs is None:
+                pv, pt, code = encode_pairs_device(var, total)
+            else:
+                pv, pt = (np.asarray(x, np.int64) for x in pairs)
+                code = encode_with_table(var, total, pv, pt)
             cell = cell.to(torch_int32()).contiguous()
             snv = snv.to(torch_int32()).contiguous()
             nnz = int(cell.numel())
         else:
-            pv, pt, _, code32 = encode_pairs(var, total)
-            code = code32.astype(np.uint16)
+            if pairs is None:
+                pv, pt, _, code32 = encode_pairs(var, total)
+                code = code32.astype(np.uint16)
+            else:
+                pv, pt = (np.asarray(x, np.int64) for x in pairs)
+                code = encode_with_table(np.asarray(var), np.asarray(total), pv, pt)
             cell = np.ascontiguousarray(cell, dtype=np.int32)
             snv = np.ascontiguousarray(snv, dtype=np.int32)
             nnz = int(cell.shape[0])
