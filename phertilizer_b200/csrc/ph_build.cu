@@ -82,7 +82,7 @@ __global__ void k_seg_offsets(const uint64_t* __restrict__ keys, int64_t nnz, in
   off[s] = lo;
 }
 
-// per sub-segment: groups of 8 entries (rounded up); per line: tail entries
+// per sub-segment: groups of PH_GE entries (rounded up); per line: tail entries
 __global__ void k_seg_sizes(const int64_t* __restrict__ off, int64_t n_major, int NSUB, int64_t* __restrict__ groups,
                             int64_t* __restrict__ tails) {
   int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -91,7 +91,7 @@ __global__ void k_seg_sizes(const int64_t* __restrict__ off, int64_t n_major, in
   const int64_t line = k / (NSUB + 1);
   const int s = (int)(k - line * (NSUB + 1));
   const int64_t cnt = off[k + 1] - off[k];
-  if (s < NSUB) groups[line * NSUB + s] = (cnt + 7) >> 3;
+  if (s < NSUB) groups[line * NSUB + s] = (cnt + PH_GE - 1) / PH_GE;
   else tails[line] = cnt;
 }
 
@@ -129,18 +129,20 @@ __global__ void k_round_keys(const uint64_t* __restrict__ sorted, int64_t nnz, c
   }
 }
 
-// Position of the r-th entry (in round order) inside its padded sub-segment of ng = ceil(cnt/8) groups.
+// Position of the r-th entry (in round order) inside its padded sub-segment of ng = ceil(cnt / PH_GE) groups: run j
+// of 32 entries of the round sequence becomes slot (j % PH_GE) of the 32 groups of block (j / PH_GE).
 __device__ __forceinline__ int64_t place(int64_t r, int64_t cnt, int bank_order) {
   if (!bank_order) return r;
-  const int64_t ng = (cnt + 7) >> 3;
-  const int64_t tf = ng >> 5;  // full blocks of 32 groups = 256 entries
-  if (r < 256 * tf) {
-    const int64_t t = r >> 8, j = (r & 255) >> 5, ln = r & 31;
-    return ((t << 5) + ln) * 8 + j;
+  const int64_t ng = (cnt + PH_GE - 1) / PH_GE;
+  const int64_t tf = ng >> 5;  // full blocks of 32 groups
+  constexpr int64_t BE = 32 * PH_GE;  // entries of a full block
+  if (r < BE * tf) {
+    const int64_t t = r / BE, j = (r % BE) >> 5, ln = r & 31;
+    return ((t << 5) + ln) * PH_GE + j;
   }
-  const int64_t r2 = r - 256 * tf, gl = ng - (tf << 5);  // ragged last block: gl < 32 groups
+  const int64_t r2 = r - BE * tf, gl = ng - (tf << 5);  // ragged last block: gl < 32 groups
   const int64_t e = r2 / gl, ln = r2 - e * gl;
-  return ((tf << 5) + ln) * 8 + e;
+  return ((tf << 5) + ln) * PH_GE + e;
 }
 
 __global__ void k_scatter(const uint64_t* __restrict__ keys, int64_t nnz, const int64_t* __restrict__ off, int NSUB,
@@ -157,7 +159,7 @@ __global__ void k_scatter(const uint64_t* __restrict__ keys, int64_t nnz, const 
     const int64_t r = i - off[seg];
     if (s < NSUB) {
       const int64_t cnt = off[seg + 1] - off[seg];
-      half[(int64_t)sub_off[line * NSUB + s] * 8 + place(r, cnt, bank_order)] = (uint16_t)k;
+      half[(int64_t)sub_off[line * NSUB + s] * PH_GE + place(r, cnt, bank_order)] = (uint16_t)k;
     } else {
       tail_words[tail_off[line] + r] = (uint32_t)k;
     }
@@ -256,8 +258,7 @@ int build_orient(ph_handle* h, PhOrient* o, const int32_t* d_major, const int32_
     k_narrow<<<(unsigned)((n_sub + 1 + threads - 1) / threads), threads>>>(d_groups, n_sub + 1, o->sub_off);
     ph_count_launch();
     PH_CUDA(cudaMemcpy(o->tail_off, d_tails, (size_t)(n_major + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice));
-    // the stream is over-read by up to 3 prefetched steps of 32 groups past a batch: keep 160 zero groups of slack
-    const size_t half_bytes = (size_t)(o->n_groups + 160) * 16;
+    const size_t half_bytes = (size_t)(o->n_groups + 160) * PH_GE * sizeof(uint16_t);  // with some zero slack
     PH_CUDA(cudaMalloc(&o->half, half_bytes));
     PH_CUDA(cudaMemset(o->half, 0, half_bytes));
     PH_CUDA(cudaMalloc(&o->tail_words, (size_t)(o->n_tail + 8) * sizeof(uint32_t)));
@@ -488,8 +489,8 @@ extern "C" int ph_get_info(const ph_handle* h, ph_info* out) {
   out->group_by_cell = h->by_cell.batch;
   out->chunks_by_snv = h->by_snv.NCH;
   out->chunks_by_cell = h->by_cell.NCH;
-  out->stream_bytes_by_snv = h->by_snv.n_groups * 16 + h->by_snv.n_tail * 4;
-  out->stream_bytes_by_cell = h->by_cell.n_groups * 16 + h->by_cell.n_tail * 4;
+  out->stream_bytes_by_snv = h->by_snv.n_groups * PH_GE * 2 + h->by_snv.n_tail * 4;
+  out->stream_bytes_by_cell = h->by_cell.n_groups * PH_GE * 2 + h->by_cell.n_tail * 4;
   out->labels_in_smem_by_snv = h->by_snv.labels_in_smem;
   out->labels_in_smem_by_cell = h->by_cell.labels_in_smem;
   return PH_OK;

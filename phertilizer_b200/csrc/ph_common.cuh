@@ -11,6 +11,7 @@
 #define PH_MAX_SUB 32      // max sub-segments (dense codes x chunks) per line
 #define PH_DMAX 4           // max "dense" (var,total) codes that get their own segment per line
 #define PH_FIELD_BITS 10    // packed per-lane counter field width (3 labels x 10 bits, excluded label -> bit 30)
+#define PH_GE 8             // entries per group: a lane consumes one 16-byte group per step (32-byte groups were not faster)
 #define PH_FLUSH_GROUPS 127 // 8 increments per group -> a field gains <= 1016 < 1024 between flushes
 
 extern thread_local char ph_err_msg[512];
@@ -37,9 +38,9 @@ void ph_count_launch(int n = 1);
 // The minor axis is cut into chunks of CH = 2^chunk_bits - 16 indices, so that an entry is ONE 16-bit half-word
 //   idx16 = 16 + (minor - chunk * CH)            (values 0..15 never occur; 0 is the padding entry)
 // A line's entries with one of the D most frequent ("dense") (var,total) codes are stored as D * NCH sub-segments
-// ordered by (code, chunk); every sub-segment is padded with idx16 = 0 to a whole number of 16-byte GROUPS (8 entries),
-// so a line -- and any run of consecutive lines -- is one contiguous, 16-byte aligned stream of groups.
-//   half    [n_groups * 8]            the stream
+// ordered by (code, chunk); every sub-segment is padded with idx16 = 0 to a whole number of 16-byte GROUPS (PH_GE = 8
+// entries), so a line -- and any run of consecutive lines -- is one contiguous, 16-byte aligned stream of groups.
+//   half    [n_groups * PH_GE]        the stream
 //   sub_off [n_major * NSUB + 1]      first group of every sub-segment (NSUB = D * NCH)
 // Entries with rarer codes go to the "tail": tail_words = (label-image address) | code << minor_bits, sorted by
 // (code, address) inside a line; tail_off per line.

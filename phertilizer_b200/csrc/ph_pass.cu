@@ -164,6 +164,9 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
   const uint32_t mmask = (a.minor_bits >= 32) ? 0xffffffffu : ((1u << a.minor_bits) - 1u);
   const int n_batches = (a.n_work + B - 1) / B;
 
+  const uint32_t magic_nch = (65536u + (uint32_t)NCH - 1u) / (uint32_t)NCH;      // exact k / NCH for k < 256 * 32 / NCH
+  const uint32_t magic_d = D > 0 ? (65536u + (uint32_t)D - 1u) / (uint32_t)D : 0u;  // exact key / D
+
   auto label_at = [&](uint32_t addr) -> uint32_t {
     return SMEM_LAB ? (uint32_t)lab[addr] : (uint32_t)__ldg(lab + addr);
   };
@@ -201,11 +204,15 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
     if (MODE == MODE_COUNTS)
       for (int k = lane; k < a.row_words; k += 32) s_row32[k] = 0;
     __syncwarp();
-    for (int k = lane; k < B * NS1; k += 32) {
-      const int l = k / NS1, s = k - l * NS1;
+    // s_e[k]: end (in groups) of sub-segment k = l * NSUB + s of the batch; s_start[l]: first group of line l
+    uint32_t* s_e = s_b;
+    uint32_t* s_start = s_b + B * NSUB;
+    for (int k = lane; k < B * NSUB; k += 32) {
+      const int l = k / NSUB, s = k - l * NSUB;
       const int ln = s_ln[l];
-      s_b[k] = ln >= 0 ? __ldg(a.sub_off + (size_t)ln * NSUB + s) : 0u;
+      s_e[k] = ln >= 0 ? __ldg(a.sub_off + (size_t)ln * NSUB + s + 1) : 0u;
     }
+    if (lane < B) s_start[lane] = (line >= 0 && NSUB > 0) ? __ldg(a.sub_off + (size_t)line * NSUB) : 0u;
     __syncwarp();
 
     // ---- dense part: maximal runs of lines that are contiguous in memory are streamed as one range of groups
@@ -213,29 +220,43 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
       int l0 = 0;
       while (l0 < nl) {
         int l1 = l0 + 1;
-        while (l1 < nl && s_b[l1 * NS1] == s_b[(l1 - 1) * NS1 + NSUB]) ++l1;
-        const uint32_t gbeg = s_b[l0 * NS1], gend = s_b[(l1 - 1) * NS1 + NSUB];
+        while (l1 < nl && s_start[l1] == s_e[l1 * NSUB - 1]) ++l1;
+        const uint32_t gbeg = s_start[l0], gend = s_e[l1 * NSUB - 1];
         uint32_t g = gbeg + lane;
         const uint4* gp = reinterpret_cast<const uint4*>(a.half) + g;
-        // cursor over the sub-segments: (l, s = d * NCH + ch), *bp = end of the current sub-segment
-        int l = l0, s = 0, d = 0, ch = 0;
-        const uint32_t* bp = s_b + l0 * NS1 + 1;
-        uint32_t nb = *bp;
-        uint32_t cur_key = 0xffffffffu, acc = 0;
-        int nacc = 0;
+        // Per-lane cursor: k = current sub-segment.  Everything derived from it -- the counter key = k / NCH =
+        // line * D + code, the chunk base of the label address -- only changes when the lane's group index passes
+        // nb_eff = min(end of sub-segment k, overflow deadline of the packed counters), so the common path of a
+        // group is one compare; the slow path advances k, flushes the counters if the (line, code) key changed.
+        int k = l0 * NSUB;
+        uint32_t nb_eff = 0, cur_key = 0xffffffffu, cbase = 0, acc = 0, gflush = gbeg;
         const uint8_t* maprow = s_map;
+        constexpr uint32_t kDeadline = PH_FLUSH_GROUPS * 32u;
 
         // lanes leave a (line, code) run within a step or two of each other: the ones flushing the same counter
         // together are summed with REDUX first, so the shared-memory atomic sees one request instead of up to 32
         auto flush = [&]() {
           const unsigned peers = __match_any_sync(__activemask(), cur_key);
-          const uint32_t base = ((cur_key >> 3) * D + (cur_key & 7u)) * NC;
           const bool leader = lane == __ffs(peers) - 1;
 #pragma unroll
           for (int c = 0; c < NC; ++c) {
             const uint32_t f = __reduce_add_sync(peers, (acc >> (PH_FIELD_BITS * c)) & FM);
-            if (leader && f) atomicAdd(&s_cnt[base + c], f);
+            if (leader && f) atomicAdd(&s_cnt[cur_key * NC + c], f);
           }
+        };
+        auto slow = [&](uint32_t gg) {
+          uint32_t nb = s_e[k];
+          while (gg >= nb) nb = s_e[++k];
+          const uint32_t key = ((uint32_t)k * magic_nch) >> 16;  // k / NCH
+          if (key != cur_key || gg - gflush >= kDeadline) {
+            if (acc) flush();
+            acc = 0;
+            cur_key = key;
+            gflush = gg;
+            if (MODE == MODE_MAPPED) maprow = s_map + s_ml[(key * magic_d) >> 16] * K2;  // line = key / D
+          }
+          cbase = ((uint32_t)k - key * (uint32_t)NCH) << cb;
+          nb_eff = min(nb, gflush + kDeadline);
         };
         auto one = [&](uint32_t addr) -> uint32_t {
           uint32_t sh = label_at(addr);
@@ -243,22 +264,7 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
           return 1u << sh;
         };
         auto consume = [&](const uint4& w, uint32_t gg) {
-          while (gg >= nb) {
-            ++s; ++ch; ++bp;
-            if (ch == NCH) { ch = 0; ++d; }
-            if (s == NSUB) { s = 0; d = 0; ++l; ++bp; }
-            nb = *bp;
-          }
-          const uint32_t key = ((uint32_t)l << 3) | (uint32_t)d;
-          if (key != cur_key || nacc == PH_FLUSH_GROUPS) {
-            if (acc) flush();
-            acc = 0;
-            nacc = 0;
-            cur_key = key;
-            if (MODE == MODE_MAPPED) maprow = s_map + s_ml[l] * K2;
-          }
-          ++nacc;
-          const uint32_t cbase = (uint32_t)ch << cb;
+          if (gg >= nb_eff) slow(gg);
           uint32_t a0, a1, a2, a3, a4, a5, a6, a7;
           if (S16) {
             a0 = __byte_perm(w.x, cbase, 0x7610); a1 = __byte_perm(w.x, cbase, 0x7632);
@@ -511,7 +517,7 @@ __global__ void __launch_bounds__(kBlock, 1) k_node_table(const PassArgs a, cons
     __syncwarp(gmask);
     for (int d = 0; d < D; ++d) {
       for (int ch = 0; ch < NCH; ++ch) {
-        const int64_t pb = (int64_t)so[d * NCH + ch] * 8, pe = (int64_t)so[d * NCH + ch + 1] * 8;
+        const int64_t pb = (int64_t)so[d * NCH + ch] * PH_GE, pe = (int64_t)so[d * NCH + ch + 1] * PH_GE;
         for (int64_t p = pb + g; p < pe; p += G) {
           const uint32_t idx = a.half[p];
           if (idx) atomicAdd(&cnt[node_at(((uint32_t)ch << cb) | idx)], 1u);  // idx 0 = padding
