@@ -212,6 +212,28 @@ PH_API int ph_gauss_node_ll(ph_handle* h, const double* X, int32_t D, const uint
                      double* per_node, double* per_cell, int on_device, void* stream);
 
 /*
+ * Cell-clustering step (linear_split.py:277-390, branching_split.py:175-291,
+ * utils.py:131-150).  The context keeps `copy_distance = squareform(pdist(embedding))` (phertilizer.py:286) in HBM.
+ * ph_affinity_build forms, for a set of cells and their mutation-burden features, the reference's affinity
+ *     W = exp(-1*d_mat/kw) * (exp(-1*c_mat/kwc) with entries c_mat > r (strict: >= r) zeroed)        [use_copy_kernel]
+ *     d_mat = squareform(pdist(feats)), c_mat = copy_distance[ix_(cells, cells)], kw/kwc = 0.2*(max-min),
+ *     r = np.quantile(c_mat, radius)
+ * and overwrites it with the normalised graph Laplacian sklearn's spectral_embedding builds from it
+ * (scipy csgraph_laplacian(normed=True) + unit diagonal); dd_out [k] receives its sqrt-degree vector.
+ * ph_affinity_matmat then serves Y = L @ X (X, Y: k x c row-major, c <= 8) to the host eigensolver (scipy LOBPCG, as
+ * in the reference).  stats_out [8] = kw, kwc, r, has_nan, max d, max c, q_lo, q_hi.  Host pointers; synchronous.
+ * ph_affinity_rows copies rows of copy_distance (rows == NULL and n_rows == n: the whole matrix).
+ */
+typedef struct ph_affinity ph_affinity;
+PH_API int ph_affinity_create(const double* embedding, int32_t n, int32_t D, int device, ph_affinity** out);
+PH_API int ph_affinity_rows(ph_affinity* a, const int32_t* rows, int32_t n_rows, double* out);
+PH_API int ph_affinity_build(ph_affinity* a, const int32_t* cells, int32_t k, const double* feats, int32_t F,
+                      int use_copy_kernel, double radius, int strict, double* stats_out, double* dd_out);
+PH_API int ph_affinity_matmat(ph_affinity* a, const double* X, int32_t c, double* Y);
+PH_API int ph_affinity_matrix(ph_affinity* a, double* out); /* the k x k Laplacian (tests) */
+PH_API void ph_affinity_destroy(ph_affinity* a);
+
+/*
  * K5 -- pairwise Euclidean distance of the embedding, `squareform(pdist(X))` (phertilizer.py:286):
  *   out[i*n + j] = sqrt(sum_d (X[i,d]-X[j,d])^2) computed by direct differences in float64, rows
  *   [row_begin, row_end) only (row-block sharding);  out has (row_end-row_begin) * n entries.

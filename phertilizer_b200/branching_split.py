@@ -12,11 +12,10 @@ from __future__ import annotations
 
 import numpy as np
 import pandas as pd
-from scipy.spatial.distance import pdist, squareform
 
 from .clonal_tree import BranchingTree
 from .clonal_tree_list import ClonalTreeList
-from .utils import cnv_kernel_width, impute_mut_features, normalizedMinCut, snv_kernel_width
+from .utils import impute_mut_features, split_by_labels
 
 np.seterr(invalid="ignore", divide="ignore")
 
@@ -50,32 +49,30 @@ class Branching_split:
         return (t["Nvar"][:, 0] / t["Nobs"][:, 0]).reshape(-1, 1)
 
     def create_affinity(self, mutsA, mutsB, cells):
+        """Features of the affinity (branching_split.py:175-215): per-cell burden over mutsA and mutsB, imputed."""
         if len(mutsA) == 0 or len(mutsB) == 0:
-            return None, None
+            return None
         t = self.store.cell_table(self.store.snv_labels(mutsA, mutsB), 2, cells, want=("Nobs", "Nvar"))
         mut_features = t["Nvar"] / t["Nobs"]          # columns: tmb over mutsA, tmb over mutsB
         mut_features = impute_mut_features(self.data.copy_distance, mut_features, cells)
         if np.any(np.isnan(mut_features)):
-            return None, None
-        mut_features_df = pd.DataFrame(mut_features, cells)
-        d_mat = squareform(pdist(mut_features, metric="euclidean"))
-        kernel = np.exp(-1 * d_mat / snv_kernel_width(d_mat))
-        c_mat = self.data.copy_distance[np.ix_(cells, cells)]
-        r = np.quantile(c_mat, self.radius)
-        if self.use_copy_kernel:
-            copy_kernel = np.exp(-1 * c_mat / cnv_kernel_width(c_mat))
-            copy_kernel[c_mat >= r] = 0
-            kernel = np.multiply(copy_kernel, kernel)
-        return kernel, mut_features_df
+            return None
+        return mut_features
 
     def cluster_cells(self, mutsA, mutsB, cells):
-        W, feats = self.create_affinity(mutsA, mutsB, cells)
-        if W is None:
+        mut_features = self.create_affinity(mutsA, mutsB, cells)
+        if mut_features is None:
             return cells, np.empty(shape=0, dtype=int)
-        if np.any(np.isnan(W)):
-            print("Terminating cell clustering due to NANs in affinity matrix")
-            return cells, np.empty(shape=0, dtype=int)
-        (cells1, cells2), _, _, _ = normalizedMinCut(W, cells, self.np_rng)
+        if len(cells) == 1:                     # utils.py:133-135
+            cells1, cells2 = cells, np.empty(shape=0)
+        else:
+            # branching kernel: copy-distance entries >= r are cut (branching_split.py:228)
+            labels = self.data.copy_distance.min_cut(cells, mut_features, self.use_copy_kernel, self.radius, True, self.np_rng)
+            if labels is None:
+                print("Terminating cell clustering due to NANs in affinity matrix")
+                return cells, np.empty(shape=0, dtype=int)
+            cells1, cells2 = split_by_labels(cells, labels)
+        feats = pd.DataFrame(mut_features, cells)
         avg = feats[feats.index.isin(cells1)].mean(axis=0)
         # the cluster whose mutsA burden exceeds its mutsB burden becomes cellsA (branching_split.py:275-286)
         return (cells1, cells2) if avg[0] > avg[1] else (cells2, cells1)

@@ -1,0 +1,122 @@
+"""Cell clustering of the tree operations on the GPU.
+
+The reference builds a dense affinity between the cells of a seed -- `exp(-pdist(tmb)/kw)` times an optional kernel on
+the copy-number (embedding) distance -- and cuts it in two with sklearn's `spectral_clustering(assign_labels=
+"cluster_qr", eigen_solver="lobpcg")` (linear_split.py:277-390, branching_split.py:175-291, utils.py:131-150).  Here
+the n x n embedding distance, the affinity and its normalised Laplacian live in HBM (`csrc/ph_affinity.cu`); the
+eigensolver is still scipy's LOBPCG -- the reference's own third-party code, fed with the same initial block drawn from
+the same `RandomState` -- but its operator is the GPU product `L @ X`.  Everything after the eigenvectors
+(`_deterministic_vector_sign_flip`, `cluster_qr`) is sklearn's.
+
+For sets of fewer than `SMALL` cells the (tiny) Laplacian is copied to the host and handed to the same scipy routines
+as a dense array -- LOBPCG itself switches to a dense solver below 15 nodes, sklearn to `eigh` below 11.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+SMALL = 64
+
+
+def _dptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class CopyDistance:
+    """`squareform(pdist(embedding))` (phertilizer.py:286) resident on the GPU, with the affinity workspace."""
+
+    def __init__(self, embedding, device=0):
+        emb = np.ascontiguousarray(embedding, dtype=np.float64)
+        self.n, self.D = emb.shape
+        self._h = C.c_void_p()
+        self._L = _lib.lib()
+        _lib.check(self._L.ph_affinity_create(_dptr(emb), self.n, self.D, int(device), C.byref(self._h)))
+        self._full = None
+        self._k = 0
+
+    shape = property(lambda self: (self.n, self.n))
+
+    def close(self):
+        if self._h is not None:
+            self._L.ph_affinity_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ distance access
+    def rows(self, idx) -> np.ndarray:
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        out = np.empty((len(idx), self.n), np.float64)
+        if len(idx):
+            _lib.check(self._L.ph_affinity_rows(self._h, _dptr(idx), len(idx), _dptr(out)))
+        return out
+
+    def full(self) -> np.ndarray:
+        """The whole n x n matrix on the host (small inputs, tests, the < MIN_GPU_CELLS path)."""
+        if self._full is None:
+            out = np.empty((self.n, self.n), np.float64)
+            _lib.check(self._L.ph_affinity_rows(self._h, None, self.n, _dptr(out)))
+            self._full = out
+        return self._full
+
+    # ------------------------------------------------------------------ affinity + Laplacian + cut
+    def build(self, cells, feats, use_copy_kernel, radius, strict):
+        """Affinity of `cells` from features [k, F] -> (stats dict, dd) ; the Laplacian stays on the device."""
+        cells = np.ascontiguousarray(cells, dtype=np.int32)
+        feats = np.ascontiguousarray(feats, dtype=np.float64).reshape(len(cells), -1)
+        stats = np.zeros(8, np.float64)
+        dd = np.empty(len(cells), np.float64)
+        _lib.check(self._L.ph_affinity_build(self._h, _dptr(cells), len(cells), _dptr(feats), feats.shape[1],
+                                             int(bool(use_copy_kernel)), float(radius), int(bool(strict)), _dptr(stats),
+                                             _dptr(dd)))
+        self._k = len(cells)
+        names = ("kw", "kwc", "r", "has_nan", "max_d", "max_c", "q_lo", "q_hi")
+        return dict(zip(names, stats.tolist())), dd
+
+    def matmat(self, X) -> np.ndarray:
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        if X.ndim == 1:
+            X = X.reshape(-1, 1)
+        Y = np.empty_like(X)
+        _lib.check(self._L.ph_affinity_matmat(self._h, _dptr(X), X.shape[1], _dptr(Y)))
+        return Y
+
+    def laplacian(self) -> np.ndarray:
+        out = np.empty((self._k, self._k), np.float64)
+        _lib.check(self._L.ph_affinity_matrix(self._h, _dptr(out)))
+        return out
+
+    def min_cut(self, cells, feats, use_copy_kernel, radius, strict, random_state):
+        """Two-way normalised cut of `cells` -> labels (0/1 per cell), or None when the affinity contains NaN (the
+        reference then terminates the clustering).  Mirrors sklearn.cluster.spectral_clustering(n_clusters=2,
+        assign_labels="cluster_qr", eigen_solver="lobpcg") -> _spectral_embedding(drop_first=False)."""
+        from scipy.sparse.linalg import lobpcg
+        from sklearn.cluster._spectral import cluster_qr
+        from sklearn.utils.extmath import _deterministic_vector_sign_flip
+
+        from scipy.linalg import eigh
+
+        stats, dd = self.build(cells, feats, use_copy_kernel, radius, strict)
+        if stats["has_nan"]:
+            return None
+        k, n_components = len(cells), 2
+        if k < 5 * n_components + 1:
+            # sklearn short-circuits LOBPCG for tiny graphs (manifold/_spectral_embedding.py, lobpcg branch)
+            _, diffusion_map = eigh(self.laplacian(), check_finite=False)
+        else:
+            X = random_state.standard_normal(size=(k, n_components + 1))
+            X[:, 0] = dd.ravel()
+            A = self.laplacian() if k < SMALL else (lambda V: self.matmat(V))
+            _, diffusion_map = lobpcg(A, X, tol=None, largest=False, maxiter=2000)
+        embedding = diffusion_map.T[:n_components]
+        embedding = embedding / dd          # recover u = D^-1/2 x
+        embedding = _deterministic_vector_sign_flip(embedding)
+        return cluster_qr(embedding[:n_components].T)

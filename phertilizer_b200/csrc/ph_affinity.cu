@@ -1,0 +1,385 @@
+// Cell-clustering step on the GPU: the dense k x k affinity of a set of cells and its
+// normalised graph Laplacian stay in HBM; the host eigensolver (scipy's LOBPCG, as in the reference) only sees
+// "L @ X" products.
+//
+// Replaces, for one call of `create_affinity` + `normalizedMinCut`
+// (linear_split.py:277-338, branching_split.py:175-232, utils.py:131-150, sklearn spectral_embedding):
+//   d_mat   = squareform(pdist(features))                 kernel   = exp(-1 * d_mat / (0.2 * (max d - min d)))
+//   c_mat   = copy_distance[np.ix_(cells, cells)]         r        = quantile(c_mat, radius)
+//   copy_k  = exp(-1 * c_mat / (0.2 * (max c - min c)));  copy_k[c_mat > r] = 0   (branching: >= r)
+//   W       = kernel * copy_k
+//   L       = csgraph_laplacian(W, normed=True): zero diagonal, w = column sums (rows added in order), dd = sqrt(w)
+//             (1 where w == 0), L = -(W / dd) / dd[:, None], unit diagonal
+// with the reference's operation order (separately rounded divide / multiply), so that W, dd and L agree with numpy up
+// to the last-ulp difference between CUDA's and glibc's exp().
+#include <cub/device/device_radix_sort.cuh>
+#include <math.h>
+
+#include <new>
+
+#include "ph_common.cuh"
+
+struct ph_affinity {
+  int device;
+  int32_t n, D;
+  double* d_copy;    // [n*n] pairwise Euclidean distance of the embedding (phertilizer.py:286)
+  double* d_W;       // [cap*cap] affinity, then Laplacian of the current cell set
+  double* d_tmp;     // [cap*cap] sort scratch (quantile), allocated on first use
+  double* d_feat;    // [cap*8]
+  double* d_dd;      // [cap]
+  double* d_x;       // [cap*8] matmat operand / result
+  double* d_y;
+  int32_t* d_cells;  // [cap]
+  unsigned long long* d_red;  // [4]: max d bits, max c bits, nan flag, spare
+  void* d_sort_tmp;
+  size_t sort_tmp_bytes;
+  double* h_pin;     // [cap*16] pinned staging
+  int32_t cap, k;    // capacity (= n), current cell-set size
+  cudaStream_t st;
+};
+
+namespace {
+
+constexpr int kMaxF = 8, kMaxCols = 8;
+
+// d(i,j) = sqrt(sum_f (x_if - x_jf)^2), multiply and add rounded separately like scipy's C loop
+__device__ __forceinline__ double feat_dist(const double* __restrict__ f, int F, int i, int j) {
+  double s = 0.0;
+  for (int q = 0; q < F; ++q) {
+    const double t = __dsub_rn(f[(size_t)i * F + q], f[(size_t)j * F + q]);
+    s = __dadd_rn(s, __dmul_rn(t, t));
+  }
+  return sqrt(s);
+}
+
+// pass 1: max of d and of c over all pairs (their minima are the zero diagonals), NaN flag
+__global__ void k_aff_stats(const double* __restrict__ feat, int F, const double* __restrict__ copy, int n,
+                            const int32_t* __restrict__ cells, int k, int use_copy, unsigned long long* red) {
+  double md = 0.0, mc = 0.0;
+  int nan = 0;
+  const size_t total = (size_t)k * k;
+  for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < total; p += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(p / k), j = (int)(p - (size_t)i * k);
+    const double d = feat_dist(feat, F, i, j);
+    if (d != d) nan = 1;
+    md = fmax(md, d);
+    if (use_copy) {
+      const double c = copy[(size_t)cells[i] * n + cells[j]];
+      if (c != c) nan = 1;
+      mc = fmax(mc, c);
+    }
+  }
+  // non-negative doubles order like their bit patterns
+  for (int o = 16; o > 0; o >>= 1) {
+    md = fmax(md, __shfl_xor_sync(0xffffffffu, md, o));
+    mc = fmax(mc, __shfl_xor_sync(0xffffffffu, mc, o));
+    nan |= __shfl_xor_sync(0xffffffffu, nan, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(red + 0, (unsigned long long)__double_as_longlong(md));
+    atomicMax(red + 1, (unsigned long long)__double_as_longlong(mc));
+    if (nan) atomicMax(red + 2, 1ull);
+  }
+}
+
+__global__ void k_aff_gather_c(const double* __restrict__ copy, int n, const int32_t* __restrict__ cells, int k,
+                               double* __restrict__ out) {
+  const size_t total = (size_t)k * k;
+  for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < total; p += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(p / k), j = (int)(p - (size_t)i * k);
+    out[p] = copy[(size_t)cells[i] * n + cells[j]];
+  }
+}
+
+// pass 2: W = exp(-1*d/kw) * copy_kernel
+__global__ void k_aff_build(const double* __restrict__ feat, int F, const double* __restrict__ copy, int n,
+                            const int32_t* __restrict__ cells, int k, int use_copy, double kw, double kwc, double r,
+                            int strict, double* __restrict__ W, unsigned long long* red) {
+  const size_t total = (size_t)k * k;
+  int nan = 0;
+  for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < total; p += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(p / k), j = (int)(p - (size_t)i * k);
+    const double d = feat_dist(feat, F, i, j);
+    double w = exp(__ddiv_rn(__dmul_rn(-1.0, d), kw));
+    if (use_copy) {
+      const double c = copy[(size_t)cells[i] * n + cells[j]];
+      double ck = exp(__ddiv_rn(__dmul_rn(-1.0, c), kwc));
+      if (strict ? (c >= r) : (c > r)) ck = 0.0;
+      w = __dmul_rn(w, ck);
+    }
+    if (w != w) nan = 1;
+    W[p] = w;
+  }
+  if (__any_sync(0xffffffffu, nan) && (threadIdx.x & 31) == 0) atomicMax(red + 2, 1ull);
+}
+
+// w_j = sum_i W_ij with a zero diagonal, rows added in order (numpy's axis-0 reduction); dd = sqrt(w), 1 if isolated
+__global__ void k_aff_degree(const double* __restrict__ W, int k, double* __restrict__ dd) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= k) return;
+  double s = 0.0;
+  for (int i = 0; i < k; ++i) s = __dadd_rn(s, i == j ? 0.0 : W[(size_t)i * k + j]);
+  dd[j] = (s == 0.0) ? 1.0 : sqrt(s);
+}
+
+// L = -((W / dd[None, :]) / dd[:, None]), unit diagonal (csgraph_laplacian + _set_diag)
+__global__ void k_aff_laplacian(double* __restrict__ W, int k, const double* __restrict__ dd) {
+  const size_t total = (size_t)k * k;
+  for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < total; p += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(p / k), j = (int)(p - (size_t)i * k);
+    W[p] = (i == j) ? 1.0 : __dmul_rn(__ddiv_rn(__ddiv_rn(W[p], dd[j]), dd[i]), -1.0);
+  }
+}
+
+// Y[i, :] = L[i, :] @ X  (X: k x c row-major, c <= 8); one warp per row, lanes stride the row, fixed reduction order
+template <int C>
+__global__ void k_aff_matmat(const double* __restrict__ L, int k, const double* __restrict__ X, double* __restrict__ Y) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= k) return;
+  const double* row = L + (size_t)warp * k;
+  double acc[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) acc[c] = 0.0;
+  for (int j = lane; j < k; j += 32) {
+    const double l = row[j];
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = fma(l, X[(size_t)j * C + c], acc[c]);
+  }
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+    if (lane == 0) Y[(size_t)warp * C + c] = acc[c];
+  }
+}
+
+__global__ void k_gather_rows(const double* __restrict__ copy, int n, const int32_t* __restrict__ rows, int nr,
+                              double* __restrict__ out) {
+  const size_t total = (size_t)nr * n;
+  for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < total; p += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(p / n), j = (int)(p - (size_t)i * n);
+    out[p] = copy[(size_t)rows[i] * n + j];
+  }
+}
+
+}  // namespace
+
+extern "C" void ph_affinity_destroy(ph_affinity* a) {
+  if (!a) return;
+  cudaSetDevice(a->device);
+  cudaFree(a->d_copy); cudaFree(a->d_W); cudaFree(a->d_tmp); cudaFree(a->d_feat); cudaFree(a->d_dd); cudaFree(a->d_x);
+  cudaFree(a->d_y); cudaFree(a->d_cells); cudaFree(a->d_red); cudaFree(a->d_sort_tmp);
+  if (a->h_pin) cudaFreeHost(a->h_pin);
+  if (a->st) cudaStreamDestroy(a->st);
+  delete a;
+}
+
+extern "C" int ph_affinity_create(const double* embedding, int32_t n, int32_t D, int device, ph_affinity** out) {
+  if (!embedding || !out) PH_FAIL(PH_ERR_ARG, "null pointer");
+  *out = nullptr;
+  if (n < 1 || D < 1) PH_FAIL(PH_ERR_ARG, "bad shape n=%d D=%d", n, D);
+  int ndev = 0;
+  PH_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) PH_FAIL(PH_ERR_CUDA, "device %d not available (%d CUDA devices)", device, ndev);
+  PH_CUDA(cudaSetDevice(device));
+  size_t free_b = 0, total_b = 0;
+  PH_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  const size_t nn = (size_t)n * n * sizeof(double);
+  if (2 * nn + ((size_t)1 << 28) > free_b)
+    PH_FAIL(PH_ERR_UNSUPPORTED, "%d cells need %.1f GB for the dense distance + affinity matrices (%.1f GB free)", n,
+            2.0 * nn / 1e9, free_b / 1e9);
+  ph_affinity* a = new (std::nothrow) ph_affinity();
+  if (!a) PH_FAIL(PH_ERR_ARG, "out of host memory");
+  memset(a, 0, sizeof(*a));
+  a->device = device;
+  a->n = n;
+  a->D = D;
+  a->cap = n;
+  double* d_emb = nullptr;
+  auto body = [&]() -> int {
+    PH_CUDA(cudaStreamCreateWithFlags(&a->st, cudaStreamNonBlocking));
+    PH_CUDA(cudaMalloc(&a->d_copy, nn));
+    PH_CUDA(cudaMalloc(&a->d_W, nn));
+    PH_CUDA(cudaMalloc(&a->d_feat, (size_t)n * kMaxF * 8));
+    PH_CUDA(cudaMalloc(&a->d_dd, (size_t)n * 8));
+    PH_CUDA(cudaMalloc(&a->d_x, (size_t)n * kMaxCols * 8));
+    PH_CUDA(cudaMalloc(&a->d_y, (size_t)n * kMaxCols * 8));
+    PH_CUDA(cudaMalloc(&a->d_cells, (size_t)n * 4));
+    PH_CUDA(cudaMalloc(&a->d_red, 4 * 8));
+    PH_CUDA(cudaMallocHost(&a->h_pin, (size_t)n * 16 * 8));
+    PH_CUDA(cudaMalloc(&d_emb, (size_t)n * D * 8));
+    PH_CUDA(cudaMemcpyAsync(d_emb, embedding, (size_t)n * D * 8, cudaMemcpyHostToDevice, a->st));
+    int rc = ph_pairwise_dist(d_emb, n, D, 0, n, a->d_copy, device, 1, a->st);
+    if (rc != PH_OK) return rc;
+    PH_CUDA(cudaStreamSynchronize(a->st));
+    return PH_OK;
+  };
+  int rc = body();
+  cudaFree(d_emb);
+  if (rc != PH_OK) {
+    ph_affinity_destroy(a);
+    return rc;
+  }
+  *out = a;
+  return PH_OK;
+}
+
+// rows of the copy-distance matrix (impute_mut_features reads a few rows; `copy_distance` itself is an output only for
+// small inputs / tests)
+extern "C" int ph_affinity_rows(ph_affinity* a, const int32_t* rows, int32_t n_rows, double* out) {
+  if (!a || !out || (!rows && n_rows != a->n)) PH_FAIL(PH_ERR_ARG, "null pointer");
+  PH_CUDA(cudaSetDevice(a->device));
+  if (!rows) {  // the whole matrix
+    PH_CUDA(cudaMemcpy(out, a->d_copy, (size_t)a->n * a->n * 8, cudaMemcpyDeviceToHost));
+    return PH_OK;
+  }
+  if (n_rows <= 0) return PH_OK;
+  for (int i = 0; i < n_rows; ++i)
+    if (rows[i] < 0 || rows[i] >= a->n) PH_FAIL(PH_ERR_ARG, "row %d out of range", rows[i]);
+  // stage through the W buffer in slabs of at most n rows
+  int done = 0;
+  while (done < n_rows) {
+    const int nr = n_rows - done < a->n ? n_rows - done : a->n;
+    PH_CUDA(cudaMemcpyAsync(a->d_cells, rows + done, (size_t)nr * 4, cudaMemcpyHostToDevice, a->st));
+    k_gather_rows<<<1184, 256, 0, a->st>>>(a->d_copy, a->n, a->d_cells, nr, a->d_W);
+    ph_count_launch();
+    PH_CUDA(cudaMemcpyAsync(out + (size_t)done * a->n, a->d_W, (size_t)nr * a->n * 8, cudaMemcpyDeviceToHost, a->st));
+    PH_CUDA(cudaStreamSynchronize(a->st));
+    done += nr;
+  }
+  a->k = 0;  // the W buffer no longer holds a Laplacian
+  return PH_OK;
+}
+
+/*
+ * Affinity + normalised Laplacian of `cells` (k of them) from their features [k*F]; see the header for the formulas.
+ *   stats_out[8] = kw, kwc, r, has_nan (0/1), max d, max c, and the two order statistics r was interpolated from
+ * When has_nan is set the Laplacian is not built (the reference terminates the clustering, linear_split.py:364-369).
+ */
+extern "C" int ph_affinity_build(ph_affinity* a, const int32_t* cells, int32_t k, const double* feats, int32_t F,
+                                 int use_copy_kernel, double radius, int strict, double* stats_out, double* dd_out) {
+  if (!a || !cells || !feats || !stats_out) PH_FAIL(PH_ERR_ARG, "null pointer");
+  if (k < 1 || k > a->cap || F < 1 || F > kMaxF) PH_FAIL(PH_ERR_ARG, "bad shape k=%d F=%d", k, F);
+  for (int i = 0; i < k; ++i)
+    if (cells[i] < 0 || cells[i] >= a->n) PH_FAIL(PH_ERR_ARG, "cells[%d]=%d out of range", i, cells[i]);
+  PH_CUDA(cudaSetDevice(a->device));
+  cudaStream_t st = a->st;
+  a->k = 0;
+  memcpy(a->h_pin, feats, (size_t)k * F * 8);
+  memcpy(a->h_pin + (size_t)k * F, cells, (size_t)k * 4);
+  PH_CUDA(cudaMemcpyAsync(a->d_feat, a->h_pin, (size_t)k * F * 8, cudaMemcpyHostToDevice, st));
+  PH_CUDA(cudaMemcpyAsync(a->d_cells, a->h_pin + (size_t)k * F, (size_t)k * 4, cudaMemcpyHostToDevice, st));
+  PH_CUDA(cudaMemsetAsync(a->d_red, 0, 4 * 8, st));
+  const int blocks = 1184;
+  k_aff_stats<<<blocks, 256, 0, st>>>(a->d_feat, F, a->d_copy, a->n, a->d_cells, k, use_copy_kernel, a->d_red);
+  ph_count_launch();
+  unsigned long long red[4];
+  PH_CUDA(cudaMemcpyAsync(red, a->d_red, sizeof(red), cudaMemcpyDeviceToHost, st));
+  PH_CUDA(cudaStreamSynchronize(st));
+  double maxd, maxc;
+  memcpy(&maxd, &red[0], 8);
+  memcpy(&maxc, &red[1], 8);
+  // utils.py:75-84  kernel width = 0.2 * (max - min), min = 0 (the diagonal)
+  const double kw = 0.2 * (maxd - 0.0), kwc = 0.2 * (maxc - 0.0);
+  double r = maxc, q_lo = maxc, q_hi = maxc;
+  if (use_copy_kernel && radius < 1.0) {
+    // np.quantile(c_mat, radius), method "linear": sort the k*k distances, interpolate between two order statistics
+    const size_t N = (size_t)k * k;
+    if (N >= ((size_t)1 << 31)) PH_FAIL(PH_ERR_UNSUPPORTED, "quantile over %zu distances", N);
+    if (!a->d_tmp) PH_CUDA(cudaMalloc(&a->d_tmp, (size_t)a->cap * a->cap * 8));
+    size_t need = 0;
+    cub::DoubleBuffer<double> db(a->d_W, a->d_tmp);
+    PH_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, need, db, (int)N, 0, 64, st));
+    if (need > a->sort_tmp_bytes) {
+      cudaFree(a->d_sort_tmp);
+      a->d_sort_tmp = nullptr;
+      PH_CUDA(cudaMalloc(&a->d_sort_tmp, need));
+      a->sort_tmp_bytes = need;
+    }
+    k_aff_gather_c<<<blocks, 256, 0, st>>>(a->d_copy, a->n, a->d_cells, k, a->d_W);
+    PH_CUDA(cub::DeviceRadixSort::SortKeys(a->d_sort_tmp, need, db, (int)N, 0, 64, st));
+    ph_count_launch(5);
+    // numpy _compute_virtual_index(n, q, alpha=1, beta=1) and _lerp
+    const double nq = (double)N, q = radius;
+    double vi = nq * q + (1.0 + q * (1.0 - 1.0 - 1.0)) - 1.0;
+    double prev = floor(vi);
+    long long lo = (long long)prev, hi = lo + 1;
+    if (lo < 0) lo = 0;
+    if (hi < 0) hi = 0;
+    if (lo > (long long)N - 1) lo = (long long)N - 1;
+    if (hi > (long long)N - 1) hi = (long long)N - 1;
+    const double gamma = vi - prev;
+    PH_CUDA(cudaMemcpyAsync(&q_lo, db.Current() + lo, 8, cudaMemcpyDeviceToHost, st));
+    PH_CUDA(cudaMemcpyAsync(&q_hi, db.Current() + hi, 8, cudaMemcpyDeviceToHost, st));
+    PH_CUDA(cudaStreamSynchronize(st));
+    const double diff = q_hi - q_lo;
+    r = q_lo + diff * gamma;
+    if (gamma >= 0.5) r = q_hi - diff * (1.0 - gamma);
+  }
+  stats_out[0] = kw;
+  stats_out[1] = kwc;
+  stats_out[2] = r;
+  stats_out[4] = maxd;
+  stats_out[5] = maxc;
+  stats_out[6] = q_lo;
+  stats_out[7] = q_hi;
+  if (red[2]) {  // NaN features / distances
+    stats_out[3] = 1.0;
+    return PH_OK;
+  }
+  k_aff_build<<<blocks, 256, 0, st>>>(a->d_feat, F, a->d_copy, a->n, a->d_cells, k, use_copy_kernel, kw, kwc, r, strict,
+                                      a->d_W, a->d_red);
+  ph_count_launch();
+  PH_CUDA(cudaMemcpyAsync(red, a->d_red, sizeof(red), cudaMemcpyDeviceToHost, st));
+  PH_CUDA(cudaStreamSynchronize(st));
+  stats_out[3] = red[2] ? 1.0 : 0.0;
+  if (red[2]) return PH_OK;
+  k_aff_degree<<<(k + 127) / 128, 128, 0, st>>>(a->d_W, k, a->d_dd);
+  k_aff_laplacian<<<blocks, 256, 0, st>>>(a->d_W, k, a->d_dd);
+  ph_count_launch(2);
+  PH_CUDA(cudaGetLastError());
+  if (dd_out) {
+    PH_CUDA(cudaMemcpyAsync(a->h_pin, a->d_dd, (size_t)k * 8, cudaMemcpyDeviceToHost, st));
+    PH_CUDA(cudaStreamSynchronize(st));
+    memcpy(dd_out, a->h_pin, (size_t)k * 8);
+  }
+  a->k = k;
+  return PH_OK;
+}
+
+// Y = L @ X for the Laplacian built by the last ph_affinity_build; X, Y: k x c row-major host arrays, c <= 8
+extern "C" int ph_affinity_matmat(ph_affinity* a, const double* X, int32_t c, double* Y) {
+  if (!a || !X || !Y) PH_FAIL(PH_ERR_ARG, "null pointer");
+  if (a->k < 1) PH_FAIL(PH_ERR_ARG, "no Laplacian: call ph_affinity_build first");
+  if (c < 1 || c > kMaxCols) PH_FAIL(PH_ERR_ARG, "c=%d outside 1..%d", c, kMaxCols);
+  PH_CUDA(cudaSetDevice(a->device));
+  cudaStream_t st = a->st;
+  const int k = a->k;
+  memcpy(a->h_pin, X, (size_t)k * c * 8);
+  PH_CUDA(cudaMemcpyAsync(a->d_x, a->h_pin, (size_t)k * c * 8, cudaMemcpyHostToDevice, st));
+  const int threads = 256, blocks = (k * 32 + threads - 1) / threads;
+  switch (c) {
+    case 1: k_aff_matmat<1><<<blocks, threads, 0, st>>>(a->d_W, k, a->d_x, a->d_y); break;
+    case 2: k_aff_matmat<2><<<blocks, threads, 0, st>>>(a->d_W, k, a->d_x, a->d_y); break;
+    case 3: k_aff_matmat<3><<<blocks, threads, 0, st>>>(a->d_W, k, a->d_x, a->d_y); break;
+    case 4: k_aff_matmat<4><<<blocks, threads, 0, st>>>(a->d_W, k, a->d_x, a->d_y); break;
+    case 5: k_aff_matmat<5><<<blocks, threads, 0, st>>>(a->d_W, k, a->d_x, a->d_y); break;
+    case 6: k_aff_matmat<6><<<blocks, threads, 0, st>>>(a->d_W, k, a->d_x, a->d_y); break;
+    case 7: k_aff_matmat<7><<<blocks, threads, 0, st>>>(a->d_W, k, a->d_x, a->d_y); break;
+    default: k_aff_matmat<8><<<blocks, threads, 0, st>>>(a->d_W, k, a->d_x, a->d_y); break;
+  }
+  ph_count_launch();
+  PH_CUDA(cudaGetLastError());
+  PH_CUDA(cudaMemcpyAsync(a->h_pin + (size_t)k * kMaxCols, a->d_y, (size_t)k * c * 8, cudaMemcpyDeviceToHost, st));
+  PH_CUDA(cudaStreamSynchronize(st));
+  memcpy(Y, a->h_pin + (size_t)k * kMaxCols, (size_t)k * c * 8);
+  return PH_OK;
+}
+
+// the k x k matrix currently held (affinity-derived Laplacian) -- tests and small inputs only
+extern "C" int ph_affinity_matrix(ph_affinity* a, double* out) {
+  if (!a || !out) PH_FAIL(PH_ERR_ARG, "null pointer");
+  if (a->k < 1) PH_FAIL(PH_ERR_ARG, "no Laplacian: call ph_affinity_build first");
+  PH_CUDA(cudaSetDevice(a->device));
+  PH_CUDA(cudaMemcpy(out, a->d_W, (size_t)a->k * a->k * 8, cudaMemcpyDeviceToHost));
+  return PH_OK;
+}

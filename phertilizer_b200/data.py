@@ -1,6 +1,7 @@
 """`Data`: what the tree operations read.  The reference's `Data` (phertilizer/data.py:8-20) carries four dense
-n x m matrices; here the observations live on the GPU inside an `ObservationStore` and only the lookups, the embedding
-and the n x n copy distance (computed by the K5 kernel) stay on the host."""
+n x m matrices and the n x n copy distance; here the observations live on the GPU inside an `ObservationStore`, the copy
+distance inside a `cluster.CopyDistance` (K5 kernel; `.full()` gives the host matrix), and only the lookups and the
+embedding stay on the host."""
 from __future__ import annotations
 
 from dataclasses import dataclass
@@ -17,7 +18,7 @@ class Data:
     mut_lookup: pd.Series
     store: ObservationStore
     read_depth: np.ndarray
-    copy_distance: np.ndarray = None
+    copy_distance: object = None   # cluster.CopyDistance
     use_read_depth: bool = True
     like1_dict: dict = None   # kept for attribute compatibility (always None, as in the live reference path)
     cna_hmm: object = None    # idem ("depreciated" in the reference)

@@ -9,7 +9,8 @@ live methods only); every reduction over the observation matrices goes to the GP
   check_metrics / check_reads (393-425)-> K1 / K2 count tables
   compute_norm_likelihood   (523-556)  -> block sums                    : ObservationStore.block_sums     (K3)
 
-The cell clustering itself (affinity kernels + sklearn normalized cut, 308-390) stays on the host, as in the reference.
+The cell clustering (308-390): the affinity and its normalised Laplacian are built on the GPU from the mutation-burden
+features (`cluster.CopyDistance.min_cut`); the eigenvectors come from scipy's LOBPCG as in the reference.
 """
 from __future__ import annotations
 
@@ -17,11 +18,10 @@ import logging
 
 import numpy as np
 import pandas as pd
-from scipy.spatial.distance import pdist, squareform
 
 from .clonal_tree import LinearTree
 from .clonal_tree_list import ClonalTreeList
-from .utils import check_obs, cnv_kernel_width, impute_mut_features, normalizedMinCut, snv_kernel_width
+from .utils import check_obs, impute_mut_features, split_by_labels
 
 np.seterr(invalid="ignore", divide="ignore")
 
@@ -67,6 +67,8 @@ class Linear_split:
 
     # ------------------------------------------------------------------ cell step
     def create_affinity(self, cells, mutsB=None):
+        """Per-cell mutation burden over mutsB (linear_split.py:301-310) -> the features of the affinity; the affinity
+        matrix itself (308-335) is formed on the GPU by `cluster_cells`."""
         if mutsB is None:
             return None, None
         t = self.store.cell_table(self.store.snv_labels(mutsB), 1, cells, want=("Nobs", "Nvar"))
@@ -74,25 +76,23 @@ class Linear_split:
         tmb = (mb_mut_count / t["Nobs"][:, 0]).reshape(-1, 1)
         if np.any(np.isnan(tmb)):
             tmb = impute_mut_features(self.copy_distance_matrix, tmb, cells)
-        d_mat = squareform(pdist(tmb, metric="euclidean"))
-        kernel = np.exp(-1 * d_mat / snv_kernel_width(d_mat))
-        counts = pd.Series(mb_mut_count.reshape(-1), index=cells)
-        c_mat = self.copy_distance_matrix[np.ix_(cells, cells)]
-        r = np.quantile(c_mat, self.radius)
-        if self.use_copy_kernel:
-            copy_kernel = np.exp(-1 * c_mat / cnv_kernel_width(c_mat))
-            copy_kernel[c_mat > r] = 0
-            kernel = np.multiply(kernel, copy_kernel)
-        return kernel, counts
+        return tmb, pd.Series(mb_mut_count.reshape(-1), index=cells)
 
     def cluster_cells(self, cells, mutsB):
-        W, counts = self.create_affinity(cells, mutsB)
-        if W is None:
+        tmb, counts = self.create_affinity(cells, mutsB)
+        if tmb is None:
             return cells, np.empty(shape=0, dtype=int), None
-        if np.any(np.isnan(W)):
-            print("Terminating cell clustering due to NANs in affinity matrix")
-            return cells, np.empty(shape=0, dtype=int), None
-        (cells1, cells2), _, _, stats = normalizedMinCut(W, cells, self.np_rng)
+        stats = {}
+        if len(cells) == 1:                     # utils.py:133-135
+            cells1, cells2 = cells, np.empty(shape=0)
+        else:
+            # linear kernel: copy-distance entries > r are cut (linear_split.py:329)
+            labels = self.copy_distance_matrix.min_cut(cells, tmb, self.use_copy_kernel, self.radius, False, self.np_rng)
+            if labels is None:
+                print("Terminating cell clustering due to NANs in affinity matrix")
+                return cells, np.empty(shape=0, dtype=int), None
+            cells1, cells2 = split_by_labels(cells, labels)
+            stats.update(jump_perc=0.08, first_gap=0.03, largest_gap=0.5, spectral_num_k=2)
         mean1, mean2 = counts[cells1].mean(), counts[cells2].mean()
         if np.isnan(mean1) or np.isnan(mean2):
             print("warning mut count mean is Nan")

@@ -19,7 +19,8 @@ from .clonal_tree import IdentityTree, Seed
 from .clonal_tree_list import ClonalTreeList
 from .data import Data
 from .params import Params
-from .store import ObservationStore, pairwise_dist
+from .cluster import CopyDistance
+from .store import ObservationStore
 from .utils import check_obs, power_calc
 
 
@@ -63,7 +64,7 @@ class Phertilizer:
         bc["cell_index"] = cell_series[bc["cell"]].values
         bc = bc.sort_values(by=["cell_index"]).drop(["cell", "cell_index"], axis=1).to_numpy()
         embedding = _embed(bc, dim_reduce)
-        copy_distance = pairwise_dist(np.asarray(embedding, dtype=np.float64), device=device)
+        copy_distance = CopyDistance(np.asarray(embedding, dtype=np.float64), device=device)
 
         # per-observation likelihoods become a (var,total) -> (like0, like1) table inside the store (295-306)
         store = ObservationStore.from_coo(len(self.cells), len(self.muts), cell_idx, mut_idx, vc["var"].to_numpy(),

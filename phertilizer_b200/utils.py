@@ -22,9 +22,10 @@ def cnv_kernel_width(dmat):
 def impute_mut_features(c_mat, mut_features, cells):
     """Fill NaN feature rows with the features of the closest (copy distance) cell of `cells` that has features
     (utils.py:87-129).  The reference argsorts a masked copy of the whole n x n matrix and reads column 0 of the
-    rows it needs; only those rows are sorted here.  The row content (NaN on the diagonal, on cells outside `cells` and
-    on cells that themselves need imputation) and the sort call are the reference's, so exact distance ties -- which do
-    occur with integer bin counts -- resolve to the same neighbour.
+    rows it needs; only those rows are fetched (`c_mat.rows`, from the GPU-resident distance matrix) and sorted here.
+    The row content (NaN on the diagonal, on cells outside `cells` and on cells that themselves need imputation) and
+    the sort call are the reference's, so exact distance ties -- which do occur with integer bin counts -- resolve to
+    the same neighbour.
     """
     cells = np.asarray(cells)
     na = np.isnan(mut_features.sum(axis=1).reshape(-1))
@@ -35,27 +36,23 @@ def impute_mut_features(c_mat, mut_features, cells):
     donor_mask = np.zeros(c_mat.shape[0], dtype=bool)
     donor_mask[cells[~na]] = True
     row_of = {int(c): i for i, c in enumerate(cells)}
-    for row in np.nonzero(na)[0]:
-        c = cells[row]
-        d = np.where(donor_mask, c_mat[c, :].astype(float), np.nan)
-        d[c] = np.nan
-        nearest = int(np.argsort(d)[0])
-        mut_features[row, :] = mut_features[row_of[nearest], :]
+    need = np.nonzero(na)[0]
+    for lo in range(0, len(need), 2048):   # bounded slabs of distance rows
+        part = need[lo:lo + 2048]
+        dist = c_mat.rows(cells[part])
+        for row, drow in zip(part, dist):
+            c = cells[row]
+            d = np.where(donor_mask, drow.astype(float), np.nan)
+            d[c] = np.nan
+            nearest = int(np.argsort(d)[0])
+            mut_features[row, :] = mut_features[row_of[nearest], :]
     assert not np.any(np.isnan(mut_features))
     return mut_features
 
 
-def normalizedMinCut(W, index, random_state=None):
-    """Two-way normalized min cut by sklearn spectral clustering (utils.py:131-150)."""
-    from sklearn.cluster import spectral_clustering
-
-    stats = {}
-    if W.shape[0] == 1 or np.any(np.isnan(W)):
-        return (index, np.empty(shape=0)), None, None, stats
-    labels = spectral_clustering(W, n_clusters=2, random_state=random_state, assign_labels="cluster_qr",
-                                 eigen_solver="lobpcg")
-    stats.update(jump_perc=0.08, first_gap=0.03, largest_gap=0.5, spectral_num_k=2)
-    return (index[labels == 0], index[labels == 1]), None, labels, stats
+def split_by_labels(index, labels):
+    """utils.py:146-150: the two sides of the cut as index arrays."""
+    return index[labels == 0], index[labels == 1]
 
 
 def success_prob(N, parts, d):

@@ -103,9 +103,48 @@ class OracleStore:
         return T
 
 
+class HostCopyDistance:
+    """TEST DOUBLE of phertilizer_b200.cluster.CopyDistance: the reference's own host arithmetic (scipy pdist, numpy
+    exp / quantile, sklearn spectral_clustering -- linear_split.py:308-335, branching_split.py:215-232, utils.py:131-150)."""
+
+    def __init__(self, embedding, device=0):
+        self._full = O.pairwise_dist(np.asarray(embedding, np.float64))
+        self.n = self._full.shape[0]
+        self.shape = self._full.shape
+
+    def full(self):
+        return self._full
+
+    def rows(self, idx):
+        return self._full[np.asarray(idx, np.int64), :]
+
+    def affinity(self, cells, feats, use_copy_kernel, radius, strict):
+        from scipy.spatial.distance import pdist, squareform
+
+        feats = np.asarray(feats, np.float64).reshape(len(cells), -1)
+        d_mat = squareform(pdist(feats, metric="euclidean"))
+        kernel = np.exp(-1 * d_mat / (0.2 * (np.max(d_mat) - np.min(d_mat))))
+        c_mat = self._full[np.ix_(cells, cells)]
+        r = np.quantile(c_mat, radius)
+        if use_copy_kernel:
+            copy_kernel = np.exp(-1 * c_mat / (0.2 * (np.max(c_mat) - np.min(c_mat))))
+            copy_kernel[(c_mat >= r) if strict else (c_mat > r)] = 0
+            kernel = np.multiply(kernel, copy_kernel)
+        return kernel
+
+    def min_cut(self, cells, feats, use_copy_kernel, radius, strict, random_state):
+        from sklearn.cluster import spectral_clustering
+
+        W = self.affinity(cells, feats, use_copy_kernel, radius, strict)
+        if np.any(np.isnan(W)):
+            return None
+        return spectral_clustering(W, n_clusters=2, random_state=random_state, assign_labels="cluster_qr",
+                                   eigen_solver="lobpcg")
+
+
 def patch_phertilizer(monkeypatch):
-    """Route phertilizer_b200.phertilizer's data layer to the CPU test double."""
+    """Route phertilizer_b200.phertilizer's data layer to the CPU test doubles."""
     import phertilizer_b200.phertilizer as P
 
     monkeypatch.setattr(P, "ObservationStore", OracleStore)
-    monkeypatch.setattr(P, "pairwise_dist", lambda X, device=0: O.pairwise_dist(X))
+    monkeypatch.setattr(P, "CopyDistance", HostCopyDistance)
