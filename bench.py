@@ -275,7 +275,13 @@ def run_ours(args):
     with ClockSampler(local) as clk:
         t_load = time.perf_counter()
         n_load = 0
-        while time.perf_counter() - t_load < args.clock_seconds:
+        while True:
+            # every rank must run the SAME number of (collective) steps: rank 0's clock decides, the others follow
+            go = torch.tensor([1 if time.perf_counter() - t_load < args.clock_seconds else 0], dtype=torch.int32, device=dev)
+            if world > 1:
+                dist.broadcast(go, 0)
+            if int(go.item()) == 0:
+                break
             for i in range(50):
                 step_device(n_load + i)
             n_load += 50

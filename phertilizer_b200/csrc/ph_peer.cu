@@ -120,9 +120,9 @@ __global__ void __launch_bounds__(256) k_peer_finish(const FinishArgs a) {
       for (int c = 0; c < C; ++c) a.nobs_dst[p][(size_t)k * C + c] = (int32_t)nob[c];
     }
   }
-  __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence_system();
     const unsigned prev = atomicAdd(a.done, 1u);
     if (prev == gridDim.x - 1) {
       *a.done = 0;

@@ -83,6 +83,17 @@ def encode_pairs(var: np.ndarray, total: np.ndarray):
     total = np.asarray(total, dtype=np.int64)
     width = int(var.max()) + 1 if len(var) else 1
     key = total * width + var
+    kmax = int(key.max()) + 1 if len(key) else 1
+    if kmax <= (1 << 24):
+        # read counts are small: a counting pass instead of a sort of all observations
+        hist = np.bincount(key, minlength=kmax)
+        uniq = np.nonzero(hist)[0]
+        cnt = hist[uniq]
+        order = np.lexsort((uniq, -cnt))
+        lut = np.zeros(kmax, dtype=np.int32)
+        lut[uniq[order]] = np.arange(len(order), dtype=np.int32)
+        u = uniq[order]
+        return (u % width).astype(np.int64), (u // width).astype(np.int64), cnt[order].astype(np.int64), lut[key]
     uniq, inv, cnt = np.unique(key, return_inverse=True, return_counts=True)
     order = np.lexsort((uniq, -cnt))
     rank = np.empty_like(order)

@@ -53,11 +53,14 @@ for name in ("snv_table", "cell_table", "assign_linear", "assign_branching", "bl
              "cell_node_table", "gauss_node_ll"):
     timed(ObservationStore, name, "gpu:" + name)
 # the modules bind these helpers by name: patch them where they are used
+from phertilizer_b200.cluster import CopyDistance
 for mod in (LS, BS):
     timed(mod, "impute_mut_features", "host:impute_mut_features")
-    timed(mod, "normalizedMinCut", "host:normalizedMinCut")
-timed(LS.Linear_split, "create_affinity", "host:create_affinity(total)")
-timed(BS.Branching_split, "create_affinity", "host:create_affinity(total)")
+timed(CopyDistance, "min_cut", "cluster:min_cut(total: GPU affinity + Laplacian, LOBPCG with GPU matmat)")
+timed(CopyDistance, "build", "gpu:affinity_build")
+timed(CopyDistance, "matmat", "gpu:laplacian_matmat")
+timed(LS.Linear_split, "cluster_cells", "split:cluster_cells(total)")
+timed(BS.Branching_split, "cluster_cells", "split:cluster_cells(total)")
 timed(ClonalTree, "compute_likelihood", "tree:compute_likelihood(total)")
 timed(ClonalTree, "post_process", "tree:post_process(total)")
 
@@ -72,7 +75,7 @@ with redirect_stdout(buf):
 t_run = time.time() - t0
 if not args.quiet:
     sys.stderr.write(buf.getvalue()[-1500:])
-gpu = sum(v for k, v in acc.items() if k.startswith("gpu:"))
+gpu = sum(v for k, v in acc.items() if k.startswith("gpu:") and "affinity" not in k and "matmat" not in k)
 out = {"config": args.config, "n": s.n, "m": s.m, "nnz": s.nnz, "starts": args.starts, "iterations": args.iterations,
        "post_process": args.post, "synth_s": round(t_data, 2), "init_s": round(t_init, 2), "phertilize_s": round(t_run, 2),
        "gpu_store_calls_s": round(gpu, 3), "gpu_store_calls": int(sum(c for k, c in cnt.items() if k.startswith("gpu:"))),

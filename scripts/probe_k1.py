@@ -10,7 +10,10 @@ GS = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [8, 32]
 REPS = int(sys.argv[3]) if len(sys.argv) > 3 else 10
 dev = torch.device("cuda:0")
 t = time.time()
-s = make_config(name, device=dev, with_embedding=False)
+over = {}
+if len(sys.argv) > 4:
+    over["n"] = int(sys.argv[4])   # e.g. C3 with n = 12500: the shard one rank of an 8-GPU run walks
+s = make_config(name, device=dev, with_embedding=False, **over)
 torch.cuda.synchronize()
 print("synth", name, s.nnz, "nnz", round(time.time() - t, 2), "s", flush=True)
 t = time.time()
