@@ -181,7 +181,11 @@ int build_orient(ph_handle* h, PhOrient* o, const int32_t* d_major, const int32_
   }
   o->minor_bits = ph_ceil_log2((uint64_t)o->lab_bytes);  // a tail word = label-image address | code << minor_bits
   int D = 0;
-  while (D < PH_DMAX && D < h->n_codes && (double)code_count[D] >= h->dense_min_avg * (double)n_major) ++D;
+  // a code gets its own sub-segments when it has >= dense_min_avg entries per line on average AND >= 2 % of all
+  // observations (a rarer code costs more in sub-segment bookkeeping than its tail entries do)
+  while (D < PH_DMAX && D < h->n_codes && (double)code_count[D] >= h->dense_min_avg * (double)n_major &&
+         (double)code_count[D] >= h->dense_min_share * (double)nnz)
+    ++D;
   while (D > 0 && D * o->NCH > PH_MAX_SUB) --D;
   o->D = D;
   o->NSUB = D * o->NCH;
@@ -338,7 +342,9 @@ extern "C" int ph_create(int32_t n_cells, int32_t n_snvs, int64_t nnz, const int
   h->nnz = nnz;
   {
     const char* e = getenv("PH_DENSE_MIN_AVG");  // tuning knob: minimum average entries per line of a dense code
-    h->dense_min_avg = e ? atof(e) : 32.0;
+    h->dense_min_avg = e ? atof(e) : 8.0;
+    e = getenv("PH_DENSE_MIN_SHARE");
+    h->dense_min_share = e ? atof(e) : 0.02;
     e = getenv("PH_CHUNK_BITS");  // test knob: log2 of the label-image stride of one chunk of the minor axis
     h->chunk_bits = e ? atoi(e) : 16;
     if (h->chunk_bits < 6 || h->chunk_bits > 16) h->chunk_bits = 16;

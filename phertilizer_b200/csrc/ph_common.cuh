@@ -75,7 +75,7 @@ struct ph_handle {
   uint8_t* d_varpos; // [n_codes]
   int64_t device_bytes;
   int chunk_bits, bank_order, ctas_per_sm;
-  double dense_min_avg;  // a (var,total) code gets its own segment when it has >= this many entries per line on average
+  double dense_min_avg, dense_min_share;  // a (var,total) code gets its own segment when it has >= this many entries per line on average
   // scratch (device)
   uint8_t* d_lab_minor;  // [max(n,m)] staged labels of the minor axis
   uint8_t* d_lab_major;  // [max(n,m)]

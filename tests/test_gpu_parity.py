@@ -283,8 +283,8 @@ def synth_env(request):
     from phertilizer_b200.store import ObservationStore
     from phertilizer_b200.synth import make_config
 
-    knobs = {"default": {}, "chunks512": {"PH_CHUNK_BITS": "9", "PH_DENSE_MIN_AVG": "4"},
-             "chunks64_nobank": {"PH_CHUNK_BITS": "8", "PH_BANK_ORDER": "0", "PH_DENSE_MIN_AVG": "2"}}[request.param]
+    knobs = {"default": {}, "chunks512": {"PH_CHUNK_BITS": "9", "PH_DENSE_MIN_AVG": "4", "PH_DENSE_MIN_SHARE": "0"},
+             "chunks64_nobank": {"PH_CHUNK_BITS": "8", "PH_BANK_ORDER": "0", "PH_DENSE_MIN_AVG": "2", "PH_DENSE_MIN_SHARE": "0"}}[request.param]
     saved = {k: os.environ.get(k) for k in knobs}
     os.environ.update(knobs)
 
