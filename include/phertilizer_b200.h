@@ -68,6 +68,9 @@ PH_API int ph_abi_version(void);
 /* Number of CUDA kernels this library has launched in this process (bench.py's gpu_launches). */
 PH_API int64_t ph_kernel_launches(void);
 
+/* CUDA devices visible to the process (the `--runs` fan-out puts one worker on each). */
+PH_API int ph_device_count(int* out);
+
 /*
  * Build the device-resident observation store.  Replaces `sparse_matrix()` + the four dense matrices of `Data`
  * (phertilizer/phertilizer.py:153-161, 295-306; data.py:8-20).

@@ -35,7 +35,7 @@ class PhInfo(C.Structure):
 
 # every symbol include/phertilizer_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
-    "ph_last_error", "ph_abi_version", "ph_kernel_launches", "ph_create", "ph_destroy", "ph_get_info", "ph_set_group",
+    "ph_last_error", "ph_abi_version", "ph_kernel_launches", "ph_device_count", "ph_create", "ph_destroy", "ph_get_info", "ph_set_group",
     "ph_snv_table", "ph_assign_linear", "ph_assign_branching", "ph_cell_table", "ph_block_sums", "ph_tree_loglik",
     "ph_snv_node_table", "ph_cell_node_table", "ph_gauss_node_ll", "ph_pairwise_dist",
     "ph_snv_partial", "ph_finish_linear", "ph_finish_branching",
@@ -63,6 +63,7 @@ def lib():
     L.ph_kernel_launches.restype = C.c_int64
     L.ph_create.argtypes = [C.c_int32, C.c_int32, C.c_int64, _vp, _vp, _vp, C.c_int, C.c_int32, _vp, _vp, _vp, C.c_int,
                             C.POINTER(_vp)]
+    L.ph_device_count.argtypes = [C.POINTER(C.c_int)]
     L.ph_destroy.argtypes = [_vp]
     L.ph_destroy.restype = None
     L.ph_get_info.argtypes = [_vp, C.POINTER(PhInfo)]

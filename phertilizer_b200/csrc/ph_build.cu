@@ -16,6 +16,11 @@ void ph_count_launch(int n) { g_launches += n; }
 extern "C" const char* ph_last_error(void) { return ph_err_msg; }
 extern "C" int ph_abi_version(void) { return PH_ABI_VERSION; }
 extern "C" int64_t ph_kernel_launches(void) { return g_launches; }
+extern "C" int ph_device_count(int* out) {
+  if (!out) PH_FAIL(PH_ERR_ARG, "null pointer");
+  PH_CUDA(cudaGetDeviceCount(out));
+  return PH_OK;
+}
 
 namespace {
 

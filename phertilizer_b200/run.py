@@ -6,6 +6,7 @@ import sys
 import numpy as np
 import pandas as pd
 
+from .fanout import run_many, visible_devices
 from .phertilizer import Phertilizer
 from .utils import pickle_save
 
@@ -21,25 +22,41 @@ def main(args):
     print("\nInput binned read count data:")
     print(bin_count_data.head())
 
-    ph = Phertilizer(variant_data, bin_count_data, alpha=args.alpha, max_copies=args.copies, mode="rd",
-                     dim_reduce=not args.no_umap)
-    if args.embedding is not None:
-        ph.save_embedding(args.embedding)
+    ctor = dict(alpha=args.alpha, max_copies=args.copies, mode="rd", dim_reduce=not args.no_umap)
 
+    def run_kwargs(i):
+        return dict(max_iterations=args.iterations, starts=args.starts, seed=100 * args.seed + i, radius=args.radius,
+                    gamma=args.gamma, d=args.min_obs, use_copy_kernel=True, post_process=args.post_process,
+                    low_cmb=args.low_cmb, high_cmb=args.high_cmb, nobs_per_cluster=args.nobs_per_cluster)
+
+    devices = visible_devices()
     best_like = -np.inf
     best_tree = best_list = best_loglikes = None
-    for i in range(args.runs):
-        print(f"Run {i + 1}")
-        tree, tree_list, loglikes = ph.phertilize(max_iterations=args.iterations, starts=args.starts, seed=100 * args.seed + i,
-                                                   radius=args.radius, gamma=args.gamma, d=args.min_obs, use_copy_kernel=True,
-                                                   post_process=args.post_process, low_cmb=args.low_cmb, high_cmb=args.high_cmb,
-                                                   nobs_per_cluster=args.nobs_per_cluster)
-        if tree.norm_loglikelihood > best_like:
-            best_like = tree.norm_loglikelihood
-            best_tree, best_list, best_loglikes = tree, tree_list, loglikes
-        print(f"\nRun {i + 1} complete: Normalized Log Likelihood: {best_like}")
+    if args.runs > 1 and len(devices) > 1 and args.embedding is None:
+        # independent runs, one worker process per GPU (fanout.py); same winner as the sequential loop below
+        print(f"Spreading {args.runs} runs over devices {devices}")
+        results, (cell_lookup, mut_lookup) = run_many(variant_data, bin_count_data, ctor,
+                                                      [run_kwargs(i) for i in range(args.runs)], devices)
+        for i, (tree, tree_list, loglikes, text) in enumerate(results):
+            print(f"Run {i + 1}")
+            sys.stdout.write(text)
+            if tree.norm_loglikelihood > best_like:
+                best_like = tree.norm_loglikelihood
+                best_tree, best_list, best_loglikes = tree, tree_list, loglikes
+            print(f"\nRun {i + 1} complete: Normalized Log Likelihood: {best_like}")
+    else:
+        ph = Phertilizer(variant_data, bin_count_data, **ctor)
+        if args.embedding is not None:
+            ph.save_embedding(args.embedding)
+        for i in range(args.runs):
+            print(f"Run {i + 1}")
+            tree, tree_list, loglikes = ph.phertilize(**run_kwargs(i))
+            if tree.norm_loglikelihood > best_like:
+                best_like = tree.norm_loglikelihood
+                best_tree, best_list, best_loglikes = tree, tree_list, loglikes
+            print(f"\nRun {i + 1} complete: Normalized Log Likelihood: {best_like}")
+        cell_lookup, mut_lookup = ph.get_id_mappings()
 
-    cell_lookup, mut_lookup = ph.get_id_mappings()
     print("\nPhertilizer Tree")
     print(f"Normalized log likelihood: {best_like}")
     print(best_tree)

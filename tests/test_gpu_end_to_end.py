@@ -83,3 +83,38 @@ def test_pairwise_distance_bitwise_vs_scipy():
     frac_exact = float(np.mean(got == ref))
     print("pairwise distance bit-exact fraction:", frac_exact)
     assert frac_exact > 0.5
+
+
+def test_runs_fanout_equals_sequential_loop():
+    """`--runs` spread over worker processes (two workers; on a 1-GPU box both share device 0) must return, run by run,
+    what the reference's sequential loop (run.py:55-74) returns, and pick the same winner."""
+    import torch
+
+    from phertilizer_b200.fanout import best_run, run_many
+    from phertilizer_b200.phertilizer import Phertilizer
+
+    g = load_golden("synth_t0")
+    vc, bc = frames_from_golden(g)
+    ctor = dict(alpha=0.001, max_copies=5, mode="rd", dim_reduce=False)
+    kws = [dict(max_iterations=4, starts=2, seed=100 * 7 + i, radius=1, gamma=0.95, d=10, use_copy_kernel=True,
+                post_process=False) for i in range(3)]
+    devices = [0, 1] if torch.cuda.device_count() > 1 else [0, 0]
+    results, (cell_lookup, mut_lookup) = run_many(vc, bc, ctor, kws, devices)
+    ph = Phertilizer(vc, bc, **ctor)
+    assert list(cell_lookup) == list(ph.get_id_mappings()[0]) and list(mut_lookup) == list(ph.get_id_mappings()[1])
+    seq = []
+    for kw in kws:
+        with redirect_stdout(io.StringIO()):
+            seq.append(ph.phertilize(**kw))
+    for (tree, tl, ll, _), (t2, tl2, ll2) in zip(results, seq):
+        assert tree.norm_loglikelihood == t2.norm_loglikelihood and tl.size() == tl2.size()
+        assert sorted(tree.tree.edges()) == sorted(t2.tree.edges())
+        for k in tree.tree.nodes():
+            assert np.array_equal(tree.get_tip_cells(k), t2.get_tip_cells(k))
+            assert np.array_equal(tree.get_tip_muts(k), t2.get_tip_muts(k))
+        assert np.array_equal(ll.to_numpy(), ll2.to_numpy())
+    best_seq, bl = None, -np.inf
+    for i, r in enumerate(seq):
+        if r[0].norm_loglikelihood > bl:
+            bl, best_seq = r[0].norm_loglikelihood, i
+    assert best_run(results) == best_seq
