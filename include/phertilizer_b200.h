@@ -230,6 +230,10 @@ PH_API int ph_gauss_node_ll(ph_handle* h, const double* X, int32_t D, const uint
 typedef struct ph_affinity ph_affinity;
 PH_API int ph_affinity_create(const double* embedding, int32_t n, int32_t D, int device, ph_affinity** out);
 PH_API int ph_affinity_rows(ph_affinity* a, const int32_t* rows, int32_t n_rows, double* out);
+/* impute_mut_features (utils.py:87-129): for every listed cell c the donor j (donor_mask[j] != 0, j != c) with the
+ * smallest copy_distance[c][j] (lowest j among equals) and how many donors share that minimum. */
+PH_API int ph_affinity_nearest(ph_affinity* a, const int32_t* rows, int32_t n_rows, const uint8_t* donor_mask,
+                        int32_t* out_idx, int32_t* out_ties);
 PH_API int ph_affinity_build(ph_affinity* a, const int32_t* cells, int32_t k, const double* feats, int32_t F,
                       int use_copy_kernel, double radius, int strict, double* stats_out, double* dd_out);
 PH_API int ph_affinity_matmat(ph_affinity* a, const double* X, int32_t c, double* Y);

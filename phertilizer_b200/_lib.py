@@ -41,7 +41,7 @@ EXPORTS = [
     "ph_snv_partial", "ph_finish_linear", "ph_finish_branching",
     "ph_peer_handle_bytes", "ph_peer_create", "ph_peer_export", "ph_peer_connect", "ph_peer_assign_linear",
     "ph_peer_assign_branching", "ph_peer_timed_out", "ph_peer_destroy",
-    "ph_affinity_create", "ph_affinity_rows", "ph_affinity_build", "ph_affinity_matmat", "ph_affinity_matrix",
+    "ph_affinity_create", "ph_affinity_rows", "ph_affinity_nearest", "ph_affinity_build", "ph_affinity_matmat", "ph_affinity_matrix",
     "ph_affinity_destroy",
 ]
 
@@ -89,6 +89,7 @@ def lib():
     L.ph_peer_destroy.restype = None
     L.ph_affinity_create.argtypes = [_vp, C.c_int32, C.c_int32, C.c_int, C.POINTER(_vp)]
     L.ph_affinity_rows.argtypes = [_vp, _vp, C.c_int32, _vp]
+    L.ph_affinity_nearest.argtypes = [_vp, _vp, C.c_int32, _vp, _vp, _vp]
     L.ph_affinity_build.argtypes = [_vp, _vp, C.c_int32, _vp, C.c_int32, C.c_int, C.c_double, C.c_int, _vp, _vp]
     L.ph_affinity_matmat.argtypes = [_vp, _vp, C.c_int32, _vp]
     L.ph_affinity_matrix.argtypes = [_vp, _vp]

@@ -59,6 +59,18 @@ class CopyDistance:
             _lib.check(self._L.ph_affinity_rows(self._h, _dptr(idx), len(idx), _dptr(out)))
         return out
 
+    def nearest(self, rows, donor_mask):
+        """For every cell of `rows`: the donor (donor_mask) at the smallest copy distance and the number of donors tied
+        at that distance (GPU masked arg-min; replaces the full-row argsort of utils.py:100-112)."""
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        mask = np.ascontiguousarray(donor_mask, dtype=np.uint8)
+        idx = np.empty(len(rows), np.int32)
+        ties = np.empty(len(rows), np.int32)
+        for lo in range(0, len(rows), self.n):
+            part = rows[lo:lo + self.n]
+            _lib.check(self._L.ph_affinity_nearest(self._h, _dptr(part), len(part), _dptr(mask), _dptr(idx[lo:]), _dptr(ties[lo:])))
+        return idx, ties
+
     def full(self) -> np.ndarray:
         """The whole n x n matrix on the host (small inputs, tests, the < MIN_GPU_CELLS path)."""
         if self._full is None:

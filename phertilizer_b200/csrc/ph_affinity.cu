@@ -14,6 +14,7 @@
 // to the last-ulp difference between CUDA's and glibc's exp().
 #include <cub/device/device_radix_sort.cuh>
 #include <math.h>
+#include <stdlib.h>
 
 #include <new>
 
@@ -22,7 +23,9 @@
 struct ph_affinity {
   int device;
   int32_t n, D;
-  double* d_copy;    // [n*n] pairwise Euclidean distance of the embedding (phertilizer.py:286)
+  double* d_copy;    // [n*n] pairwise Euclidean distance of the embedding (phertilizer.py:286); NULL = not stored:
+                     // entries are recomputed from d_emb on the fly (low-dimensional embeddings of many cells)
+  double* d_emb;     // [n*D]
   double* d_W;       // [cap*cap] affinity, then Laplacian of the current cell set
   double* d_tmp;     // [cap*cap] sort scratch (quantile), allocated on first use
   double* d_feat;    // [cap*8]
@@ -52,8 +55,24 @@ __device__ __forceinline__ double feat_dist(const double* __restrict__ f, int F,
   return sqrt(s);
 }
 
+// copy_distance[ci][cj]: from the stored matrix, or recomputed with the arithmetic of ph_pairwise_dist (k_pdist)
+struct CopySrc {
+  const double* copy;
+  const double* emb;
+  int n, D;
+};
+__device__ __forceinline__ double copy_at(const CopySrc& s, int ci, int cj) {
+  if (s.copy) return s.copy[(size_t)ci * s.n + cj];
+  double acc = 0.0;
+  for (int q = 0; q < s.D; ++q) {
+    const double t = __dsub_rn(s.emb[(size_t)ci * s.D + q], s.emb[(size_t)cj * s.D + q]);
+    acc = __dadd_rn(acc, __dmul_rn(t, t));
+  }
+  return sqrt(acc);
+}
+
 // pass 1: max of d and of c over all pairs (their minima are the zero diagonals), NaN flag
-__global__ void k_aff_stats(const double* __restrict__ feat, int F, const double* __restrict__ copy, int n,
+__global__ void k_aff_stats(const double* __restrict__ feat, int F, const CopySrc src,
                             const int32_t* __restrict__ cells, int k, int use_copy, unsigned long long* red) {
   double md = 0.0, mc = 0.0;
   int nan = 0;
@@ -64,7 +83,7 @@ __global__ void k_aff_stats(const double* __restrict__ feat, int F, const double
     if (d != d) nan = 1;
     md = fmax(md, d);
     if (use_copy) {
-      const double c = copy[(size_t)cells[i] * n + cells[j]];
+      const double c = copy_at(src, cells[i], cells[j]);
       if (c != c) nan = 1;
       mc = fmax(mc, c);
     }
@@ -82,17 +101,16 @@ __global__ void k_aff_stats(const double* __restrict__ feat, int F, const double
   }
 }
 
-__global__ void k_aff_gather_c(const double* __restrict__ copy, int n, const int32_t* __restrict__ cells, int k,
-                               double* __restrict__ out) {
+__global__ void k_aff_gather_c(const CopySrc src, const int32_t* __restrict__ cells, int k, double* __restrict__ out) {
   const size_t total = (size_t)k * k;
   for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < total; p += (size_t)gridDim.x * blockDim.x) {
     const int i = (int)(p / k), j = (int)(p - (size_t)i * k);
-    out[p] = copy[(size_t)cells[i] * n + cells[j]];
+    out[p] = copy_at(src, cells[i], cells[j]);
   }
 }
 
 // pass 2: W = exp(-1*d/kw) * copy_kernel
-__global__ void k_aff_build(const double* __restrict__ feat, int F, const double* __restrict__ copy, int n,
+__global__ void k_aff_build(const double* __restrict__ feat, int F, const CopySrc src,
                             const int32_t* __restrict__ cells, int k, int use_copy, double kw, double kwc, double r,
                             int strict, double* __restrict__ W, unsigned long long* red) {
   const size_t total = (size_t)k * k;
@@ -102,7 +120,7 @@ __global__ void k_aff_build(const double* __restrict__ feat, int F, const double
     const double d = feat_dist(feat, F, i, j);
     double w = exp(__ddiv_rn(__dmul_rn(-1.0, d), kw));
     if (use_copy) {
-      const double c = copy[(size_t)cells[i] * n + cells[j]];
+      const double c = copy_at(src, cells[i], cells[j]);
       double ck = exp(__ddiv_rn(__dmul_rn(-1.0, c), kwc));
       if (strict ? (c >= r) : (c > r)) ck = 0.0;
       w = __dmul_rn(w, ck);
@@ -152,21 +170,94 @@ __global__ void k_aff_matmat(const double* __restrict__ L, int k, const double* 
   }
 }
 
-__global__ void k_gather_rows(const double* __restrict__ copy, int n, const int32_t* __restrict__ rows, int nr,
+// rows == NULL: rows row0, row0+1, ...
+__global__ void k_gather_rows(const CopySrc src, const int32_t* __restrict__ rows, int row0, int nr,
                               double* __restrict__ out) {
+  const int n = src.n;
   const size_t total = (size_t)nr * n;
   for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < total; p += (size_t)gridDim.x * blockDim.x) {
     const int i = (int)(p / n), j = (int)(p - (size_t)i * n);
-    out[p] = copy[(size_t)rows[i] * n + j];
+    out[p] = copy_at(src, rows ? rows[i] : row0 + i, j);
+  }
+}
+
+// nearest donor of every listed cell (impute_mut_features, utils.py:87-129): argmin over donors j != c of
+// copy_distance[c][j]; ties[r] = number of donors at that minimum (the caller resolves real ties the reference's way)
+__global__ void __launch_bounds__(256) k_nearest(const CopySrc src, const int32_t* __restrict__ rows, int nr,
+                                                 const uint8_t* __restrict__ donor, int32_t* __restrict__ out_idx,
+                                                 int32_t* __restrict__ out_ties) {
+  const int r = blockIdx.x;
+  if (r >= nr) return;
+  const int c = rows[r];
+  double best = INFINITY;
+  int bj = -1, cnt = 0;
+  for (int j = threadIdx.x; j < src.n; j += blockDim.x) {
+    if (!donor[j] || j == c) continue;
+    const double d = copy_at(src, c, j);
+    if (d < best) {
+      best = d;
+      bj = j;
+      cnt = 1;
+    } else if (d == best) {
+      ++cnt;
+    }
+  }
+  __shared__ double sd[256];
+  __shared__ int sj[256], sc[256];
+  sd[threadIdx.x] = best; sj[threadIdx.x] = bj; sc[threadIdx.x] = cnt;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      const double d2 = sd[threadIdx.x + o];
+      const int j2 = sj[threadIdx.x + o], c2 = sc[threadIdx.x + o];
+      if (j2 >= 0) {
+        if (sj[threadIdx.x] < 0 || d2 < sd[threadIdx.x]) {
+          sd[threadIdx.x] = d2; sj[threadIdx.x] = j2; sc[threadIdx.x] = c2;
+        } else if (d2 == sd[threadIdx.x]) {
+          sc[threadIdx.x] += c2;
+          if (j2 < sj[threadIdx.x]) sj[threadIdx.x] = j2;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    out_idx[r] = sj[0];
+    out_ties[r] = sc[0];
   }
 }
 
 }  // namespace
 
+extern "C" int ph_affinity_nearest(ph_affinity* a, const int32_t* rows, int32_t n_rows, const uint8_t* donor_mask,
+                                   int32_t* out_idx, int32_t* out_ties) {
+  if (!a || !rows || !donor_mask || !out_idx || !out_ties) PH_FAIL(PH_ERR_ARG, "null pointer");
+  if (n_rows <= 0) return PH_OK;
+  if (n_rows > a->n) PH_FAIL(PH_ERR_ARG, "n_rows=%d exceeds the number of cells", n_rows);
+  for (int i = 0; i < n_rows; ++i)
+    if (rows[i] < 0 || rows[i] >= a->n) PH_FAIL(PH_ERR_ARG, "row %d out of range", rows[i]);
+  PH_CUDA(cudaSetDevice(a->device));
+  cudaStream_t st = a->st;
+  // scratch: rows -> d_cells, donor mask + outputs -> the x / y vectors (n * 8 doubles each)
+  uint8_t* d_mask = reinterpret_cast<uint8_t*>(a->d_x);
+  int32_t* d_idx = reinterpret_cast<int32_t*>(a->d_y);
+  int32_t* d_ties = d_idx + a->n;
+  PH_CUDA(cudaMemcpyAsync(a->d_cells, rows, (size_t)n_rows * 4, cudaMemcpyHostToDevice, st));
+  PH_CUDA(cudaMemcpyAsync(d_mask, donor_mask, (size_t)a->n, cudaMemcpyHostToDevice, st));
+  const CopySrc src{a->d_copy, a->d_emb, a->n, a->D};
+  k_nearest<<<n_rows, 256, 0, st>>>(src, a->d_cells, n_rows, d_mask, d_idx, d_ties);
+  ph_count_launch();
+  PH_CUDA(cudaGetLastError());
+  PH_CUDA(cudaMemcpyAsync(out_idx, d_idx, (size_t)n_rows * 4, cudaMemcpyDeviceToHost, st));
+  PH_CUDA(cudaMemcpyAsync(out_ties, d_ties, (size_t)n_rows * 4, cudaMemcpyDeviceToHost, st));
+  PH_CUDA(cudaStreamSynchronize(st));
+  return PH_OK;
+}
+
 extern "C" void ph_affinity_destroy(ph_affinity* a) {
   if (!a) return;
   cudaSetDevice(a->device);
-  cudaFree(a->d_copy); cudaFree(a->d_W); cudaFree(a->d_tmp); cudaFree(a->d_feat); cudaFree(a->d_dd); cudaFree(a->d_x);
+  cudaFree(a->d_copy); cudaFree(a->d_emb); cudaFree(a->d_W); cudaFree(a->d_tmp); cudaFree(a->d_feat); cudaFree(a->d_dd); cudaFree(a->d_x);
   cudaFree(a->d_y); cudaFree(a->d_cells); cudaFree(a->d_red); cudaFree(a->d_sort_tmp);
   if (a->h_pin) cudaFreeHost(a->h_pin);
   if (a->st) cudaStreamDestroy(a->st);
@@ -184,9 +275,17 @@ extern "C" int ph_affinity_create(const double* embedding, int32_t n, int32_t D,
   size_t free_b = 0, total_b = 0;
   PH_CUDA(cudaMemGetInfo(&free_b, &total_b));
   const size_t nn = (size_t)n * n * sizeof(double);
-  if (2 * nn + ((size_t)1 << 28) > free_b)
-    PH_FAIL(PH_ERR_UNSUPPORTED, "%d cells need %.1f GB for the dense distance + affinity matrices (%.1f GB free)", n,
-            2.0 * nn / 1e9, free_b / 1e9);
+  const size_t margin = (size_t)1 << 30;
+  // the distance matrix is kept next to the affinity when both fit (and a third n x n block remains for the quantile
+  // sort); otherwise a low-dimensional embedding is re-evaluated entry by entry
+  bool store = 3 * nn + margin <= free_b;
+  if (const char* e = getenv("PH_AFFINITY_STORE")) store = atoi(e) != 0;
+  if (!store && D > 16 && 2 * nn + margin <= free_b) store = true;
+  if ((store ? 2 : 1) * nn + margin > free_b)
+    PH_FAIL(PH_ERR_UNSUPPORTED, "%d cells need %.1f GB for the dense affinity matrix (%.1f GB free)", n,
+            (store ? 2.0 : 1.0) * nn / 1e9, free_b / 1e9);
+  if (!store && D > 16)
+    PH_FAIL(PH_ERR_UNSUPPORTED, "%d cells x %d embedding dimensions: the distance matrix neither fits nor can be recomputed cheaply", n, D);
   ph_affinity* a = new (std::nothrow) ph_affinity();
   if (!a) PH_FAIL(PH_ERR_ARG, "out of host memory");
   memset(a, 0, sizeof(*a));
@@ -194,10 +293,9 @@ extern "C" int ph_affinity_create(const double* embedding, int32_t n, int32_t D,
   a->n = n;
   a->D = D;
   a->cap = n;
-  double* d_emb = nullptr;
   auto body = [&]() -> int {
     PH_CUDA(cudaStreamCreateWithFlags(&a->st, cudaStreamNonBlocking));
-    PH_CUDA(cudaMalloc(&a->d_copy, nn));
+    if (store) PH_CUDA(cudaMalloc(&a->d_copy, nn));
     PH_CUDA(cudaMalloc(&a->d_W, nn));
     PH_CUDA(cudaMalloc(&a->d_feat, (size_t)n * kMaxF * 8));
     PH_CUDA(cudaMalloc(&a->d_dd, (size_t)n * 8));
@@ -206,15 +304,16 @@ extern "C" int ph_affinity_create(const double* embedding, int32_t n, int32_t D,
     PH_CUDA(cudaMalloc(&a->d_cells, (size_t)n * 4));
     PH_CUDA(cudaMalloc(&a->d_red, 4 * 8));
     PH_CUDA(cudaMallocHost(&a->h_pin, (size_t)n * 16 * 8));
-    PH_CUDA(cudaMalloc(&d_emb, (size_t)n * D * 8));
-    PH_CUDA(cudaMemcpyAsync(d_emb, embedding, (size_t)n * D * 8, cudaMemcpyHostToDevice, a->st));
-    int rc = ph_pairwise_dist(d_emb, n, D, 0, n, a->d_copy, device, 1, a->st);
-    if (rc != PH_OK) return rc;
+    PH_CUDA(cudaMalloc(&a->d_emb, (size_t)n * D * 8));
+    PH_CUDA(cudaMemcpyAsync(a->d_emb, embedding, (size_t)n * D * 8, cudaMemcpyHostToDevice, a->st));
+    if (store) {
+      int rc = ph_pairwise_dist(a->d_emb, n, D, 0, n, a->d_copy, device, 1, a->st);
+      if (rc != PH_OK) return rc;
+    }
     PH_CUDA(cudaStreamSynchronize(a->st));
     return PH_OK;
   };
   int rc = body();
-  cudaFree(d_emb);
   if (rc != PH_OK) {
     ph_affinity_destroy(a);
     return rc;
@@ -228,19 +327,17 @@ extern "C" int ph_affinity_create(const double* embedding, int32_t n, int32_t D,
 extern "C" int ph_affinity_rows(ph_affinity* a, const int32_t* rows, int32_t n_rows, double* out) {
   if (!a || !out || (!rows && n_rows != a->n)) PH_FAIL(PH_ERR_ARG, "null pointer");
   PH_CUDA(cudaSetDevice(a->device));
-  if (!rows) {  // the whole matrix
-    PH_CUDA(cudaMemcpy(out, a->d_copy, (size_t)a->n * a->n * 8, cudaMemcpyDeviceToHost));
-    return PH_OK;
-  }
+  const CopySrc src{a->d_copy, a->d_emb, a->n, a->D};
+  if (rows)
+    for (int i = 0; i < n_rows; ++i)
+      if (rows[i] < 0 || rows[i] >= a->n) PH_FAIL(PH_ERR_ARG, "row %d out of range", rows[i]);
   if (n_rows <= 0) return PH_OK;
-  for (int i = 0; i < n_rows; ++i)
-    if (rows[i] < 0 || rows[i] >= a->n) PH_FAIL(PH_ERR_ARG, "row %d out of range", rows[i]);
-  // stage through the W buffer in slabs of at most n rows
+  // staged through the W buffer in slabs of at most n rows
   int done = 0;
   while (done < n_rows) {
     const int nr = n_rows - done < a->n ? n_rows - done : a->n;
-    PH_CUDA(cudaMemcpyAsync(a->d_cells, rows + done, (size_t)nr * 4, cudaMemcpyHostToDevice, a->st));
-    k_gather_rows<<<1184, 256, 0, a->st>>>(a->d_copy, a->n, a->d_cells, nr, a->d_W);
+    if (rows) PH_CUDA(cudaMemcpyAsync(a->d_cells, rows + done, (size_t)nr * 4, cudaMemcpyHostToDevice, a->st));
+    k_gather_rows<<<1184, 256, 0, a->st>>>(src, rows ? a->d_cells : nullptr, done, nr, a->d_W);
     ph_count_launch();
     PH_CUDA(cudaMemcpyAsync(out + (size_t)done * a->n, a->d_W, (size_t)nr * a->n * 8, cudaMemcpyDeviceToHost, a->st));
     PH_CUDA(cudaStreamSynchronize(a->st));
@@ -270,7 +367,8 @@ extern "C" int ph_affinity_build(ph_affinity* a, const int32_t* cells, int32_t k
   PH_CUDA(cudaMemcpyAsync(a->d_cells, a->h_pin + (size_t)k * F, (size_t)k * 4, cudaMemcpyHostToDevice, st));
   PH_CUDA(cudaMemsetAsync(a->d_red, 0, 4 * 8, st));
   const int blocks = 1184;
-  k_aff_stats<<<blocks, 256, 0, st>>>(a->d_feat, F, a->d_copy, a->n, a->d_cells, k, use_copy_kernel, a->d_red);
+  const CopySrc src{a->d_copy, a->d_emb, a->n, a->D};
+  k_aff_stats<<<blocks, 256, 0, st>>>(a->d_feat, F, src, a->d_cells, k, use_copy_kernel, a->d_red);
   ph_count_launch();
   unsigned long long red[4];
   PH_CUDA(cudaMemcpyAsync(red, a->d_red, sizeof(red), cudaMemcpyDeviceToHost, st));
@@ -295,7 +393,7 @@ extern "C" int ph_affinity_build(ph_affinity* a, const int32_t* cells, int32_t k
       PH_CUDA(cudaMalloc(&a->d_sort_tmp, need));
       a->sort_tmp_bytes = need;
     }
-    k_aff_gather_c<<<blocks, 256, 0, st>>>(a->d_copy, a->n, a->d_cells, k, a->d_W);
+    k_aff_gather_c<<<blocks, 256, 0, st>>>(src, a->d_cells, k, a->d_W);
     PH_CUDA(cub::DeviceRadixSort::SortKeys(a->d_sort_tmp, need, db, (int)N, 0, 64, st));
     ph_count_launch(5);
     // numpy _compute_virtual_index(n, q, alpha=1, beta=1) and _lerp
@@ -326,7 +424,7 @@ extern "C" int ph_affinity_build(ph_affinity* a, const int32_t* cells, int32_t k
     stats_out[3] = 1.0;
     return PH_OK;
   }
-  k_aff_build<<<blocks, 256, 0, st>>>(a->d_feat, F, a->d_copy, a->n, a->d_cells, k, use_copy_kernel, kw, kwc, r, strict,
+  k_aff_build<<<blocks, 256, 0, st>>>(a->d_feat, F, src, a->d_cells, k, use_copy_kernel, kw, kwc, r, strict,
                                       a->d_W, a->d_red);
   ph_count_launch();
   PH_CUDA(cudaMemcpyAsync(red, a->d_red, sizeof(red), cudaMemcpyDeviceToHost, st));

@@ -56,7 +56,16 @@ class Phertilizer:
         chr_codes, chr_uniques = pd.factorize(vc["chr"], sort=False)
         mid_codes, mid_uniques = pd.factorize(vc["mutation_id"], sort=False)
         pair = chr_codes.astype(np.int64) * max(len(mid_uniques), 1) + mid_codes.astype(np.int64)
-        pair_u, pair_inv = np.unique(pair, return_inverse=True)
+        n_pair_space = len(chr_uniques) * max(len(mid_uniques), 1)
+        if n_pair_space <= (1 << 27):
+            # counting pass instead of sorting all observations
+            seen = np.bincount(pair, minlength=n_pair_space) > 0
+            pair_u = np.nonzero(seen)[0]
+            lut = np.zeros(n_pair_space, dtype=np.int64)
+            lut[pair_u] = np.arange(len(pair_u))
+            pair_inv = lut[pair]
+        else:
+            pair_u, pair_inv = np.unique(pair, return_inverse=True)
         pair_str = (pd.Series(np.asarray(chr_uniques)[pair_u // max(len(mid_uniques), 1)]).astype("str") + "_"
                     + pd.Series(np.asarray(mid_uniques)[pair_u % max(len(mid_uniques), 1)]).astype(str)).to_numpy()
         mut_labels = np.sort(pd.unique(pair_str))

@@ -37,6 +37,14 @@ def impute_mut_features(c_mat, mut_features, cells):
     donor_mask[cells[~na]] = True
     row_of = {int(c): i for i, c in enumerate(cells)}
     need = np.nonzero(na)[0]
+    if hasattr(c_mat, "nearest"):
+        # masked arg-min on the GPU; only rows whose minimum is shared by several donors (exact distance ties) go through
+        # the reference's argsort below, which decides such ties
+        near, ties = c_mat.nearest(cells[need], donor_mask)
+        uniq = ties == 1
+        src = np.fromiter((row_of[int(j)] for j in near[uniq]), dtype=np.int64, count=int(uniq.sum()))
+        mut_features[need[uniq], :] = mut_features[src, :]
+        need = need[~uniq]
     for lo in range(0, len(need), 2048):   # bounded slabs of distance rows
         part = need[lo:lo + 2048]
         dist = c_mat.rows(cells[part])

@@ -34,7 +34,8 @@ over = {}
 if args.n: over["n"] = args.n
 if args.m: over["m"] = args.m
 t0 = time.time()
-s = make_config(args.config, **over)
+import torch
+s = make_config(args.config, device="cuda" if torch.cuda.is_available() else "cpu", **over)
 vc, bc = to_dataframes(s)
 t_data = time.time() - t0
 

@@ -12,13 +12,27 @@ from tests.oracle_store import HostCopyDistance
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", params=["example", "synth_t1"])
+@pytest.fixture(scope="module", params=["example", "synth_t1", "synth_t1_recompute"])
 def env(request):
+    """`_recompute`: the n x n distance matrix is NOT kept in HBM (PH_AFFINITY_STORE=0, what happens automatically for
+    ~100k cells with a low-dimensional embedding); its entries are re-evaluated inside the affinity kernels."""
+    import os
+
     from phertilizer_b200.cluster import CopyDistance
 
-    g = load_golden(request.param)
+    stem = request.param.replace("_recompute", "")
+    g = load_golden(stem)
     X = g.inputs["read_depth"].astype(np.float64)
-    gpu = CopyDistance(X)
+    saved = os.environ.get("PH_AFFINITY_STORE")
+    if request.param.endswith("_recompute"):
+        os.environ["PH_AFFINITY_STORE"] = "0"
+    try:
+        gpu = CopyDistance(X)
+    finally:
+        if saved is None:
+            os.environ.pop("PH_AFFINITY_STORE", None)
+        else:
+            os.environ["PH_AFFINITY_STORE"] = saved
     host = HostCopyDistance(X)
     yield g, gpu, host
     gpu.close()
@@ -96,3 +110,32 @@ def test_nan_affinity_terminates(env):
     feats = np.linspace(0, 1, 50).reshape(-1, 1)
     feats[3] = np.nan
     assert gpu.min_cut(cells, feats, False, 1.0, False, np.random.RandomState(1)) is None
+
+
+def test_nearest_donor_matches_reference_argsort(env):
+    """impute_mut_features (utils.py:87-129): masked arg-min on the GPU == position 0 of the reference's argsort whenever
+    the minimum is unique; the tie count flags the rows the host resolves."""
+    g, gpu, host = env
+    rng = np.random.default_rng(3)
+    full = gpu.full()
+    donor = rng.random(g.n) < 0.6
+    rows = np.nonzero(~donor)[0][:200]
+    idx, ties = gpu.nearest(rows, donor)
+    for c, j, t in zip(rows, idx, ties):
+        d = np.where(donor, full[c], np.nan)
+        d[c] = np.nan
+        dmin = np.nanmin(d)
+        assert t == int(np.sum(d == dmin))
+        assert d[j] == dmin and j == int(np.nonzero(d == dmin)[0][0])
+        if t == 1:
+            assert j == int(np.argsort(d)[0])
+    # and through the host helper: identical features to the all-host path
+    from phertilizer_b200.utils import impute_mut_features
+
+    cells = np.sort(rng.choice(g.n, size=min(g.n, 500), replace=False))
+    feats = rng.random((len(cells), 2))
+    feats[rng.random(len(cells)) < 0.3] = np.nan
+    a = impute_mut_features(gpu, feats.copy(), cells)
+    host._full = full
+    b = impute_mut_features(host, feats.copy(), cells)
+    assert np.array_equal(a, b)
