@@ -38,8 +38,25 @@ class ClonalTreeList:
     def get_all_trees(self):
         return self.stack
 
+    @staticmethod
+    def _signature(tree):
+        """Invariant of the reference's tree equality (isomorphism with matching `ncells`, clonal_tree.py:187-192): the
+        sorted (ncells, out-degree, in-degree) triples of the nodes.  Different signatures => not equal, so the
+        quadratic number of `nx.is_isomorphic` calls of `grow` (phertilizer.py:558-614) shrinks to the real candidates."""
+        g = tree.tree
+        return tuple(sorted((d.get("ncells"), g.out_degree(v), g.in_degree(v)) for v, d in g.nodes(data=True)))
+
+    def _cached_signature(self, tree):
+        # trees are not edited once they sit in a list; a relabel/merge replaces `tree.tree`, which invalidates the entry
+        ent = getattr(tree, "_sig_cache", None)
+        if ent is None or ent[0] is not tree.tree or ent[1] != tree.tree.number_of_nodes():
+            ent = (tree.tree, tree.tree.number_of_nodes(), self._signature(tree))
+            tree._sig_cache = ent
+        return ent[2]
+
     def contains(self, obj):
-        return any(t == obj for t in self.stack)
+        sig = self._signature(obj)
+        return any(self._cached_signature(t) == sig and t == obj for t in self.stack)
 
     def find_best_tree(self, data):
         """Score every candidate on the GPU and keep the first maximum of the normalised log-likelihood

@@ -83,4 +83,14 @@ out = {"config": args.config, "n": s.n, "m": s.m, "nnz": s.nnz, "starts": args.s
        "stages_s": {k: [round(v, 3), cnt[k]] for k, v in sorted(acc.items(), key=lambda kv: -kv[1])},
        "tree_nodes": int(tree.tree.number_of_nodes()), "n_trees": int(trees.size()),
        "norm_loglikelihood": float(tree.norm_loglikelihood)}
+try:  # agreement of the inferred cell clusters with the generator's clones (sanity, not parity)
+    from sklearn.metrics import adjusted_rand_score
+
+    pred = np.full(s.n, -1)
+    for node in tree.tree.nodes():
+        pred[np.asarray(tree.get_tip_cells(node), dtype=np.int64)] = node
+    out["cell_ari_vs_truth"] = round(float(adjusted_rand_score(s.cell_clone.cpu().numpy(), pred)), 4)
+    out["true_clones"] = int(len(s.parent))
+except Exception as e:  # pragma: no cover
+    out["cell_ari_vs_truth"] = f"n/a ({e})"
 print(json.dumps(out))
