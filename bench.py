@@ -181,8 +181,11 @@ def workload_config(args, w, world, residency, exchange=None):
     return {"workload": f"{args.workload}: synthetic {c['n']} cells x {c['m']} SNVs, coverage {c['cov']}, {c['K']} clones "
                         f"(BASELINE.json configs[2]); step = linear-split SNV reassignment pass (K1+K1a) over all observations",
             "nnz": w["nnz_total"], "cells": c["n"], "snvs": c["m"], "coverage": c["cov"], "clones": c["K"],
-            "sharding": (f"cells sharded over {world} rank(s); " + ("per-SNV integer histograms pushed to the owning rank over NVLink peer memory, labels pushed back (no NCCL)"
-                                                                    if exchange == "peer" else "NCCL all-reduce of the [S0|S1|Nobs] table")) if world > 1 else "single GPU",
+            "sharding": ((f"SNVs sharded over {world} rank(s), all cells on every rank: per-SNV tables are independent, no partial-table "
+                          "exchange; labels + counts pushed to every rank over NVLink peer memory from the kernel epilogue (no NCCL)")
+                         if exchange == "snv-peer" else
+                         (f"cells sharded over {world} rank(s); " + ("per-SNV integer histograms pushed to the owning rank over NVLink peer memory, labels pushed back (no NCCL)"
+                                                                    if exchange == "peer" else "NCCL all-reduce of the [S0|S1|Nobs] table"))) if world > 1 else "single GPU",
             "l2_policy": "inputs larger than L2 (0.8 GB of observations streamed per pass vs 126 MB L2); label vectors rotate every step",
             "residency": residency}
 
@@ -205,7 +208,11 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     t0 = time.time()
-    w = make_workload(args.workload, dev, rank / world, (rank + 1) / world)
+    snv_sharded = world > 1 and args.shard == "snvs"
+    if snv_sharded:
+        w = make_workload(args.workload, dev)            # all cells; the SNV block is cut below
+    else:
+        w = make_workload(args.workload, dev, rank / world, (rank + 1) / world)
     n_loc, m, nnz_loc, nnz_tot = w["n_local"], w["m"], w["nnz_local"], w["nnz_total"]
     pv, pt, code_t = encode_pairs_device(w["var"], w["total"]) if (rank == 0 and world == 1 and not args.no_cpu) else (None, None, None)
     pairs = None
@@ -213,9 +220,18 @@ def run_ours(args):
         from phertilizer_b200.sharded import global_pairs
 
         pairs = global_pairs(w["var"], w["total"])
-    st = ObservationStore.from_coo(n_loc, m, w["cell"], w["snv"], w["var"], w["total"], device=local, pairs=pairs)
-    sharded = ShardedStore(CudaBackend(st, dev), w["n"], m, w["lo"], w["hi"], exchange=args.exchange) if world > 1 else None
-    exchange = sharded.exchange if sharded is not None else None
+    snv_store = None
+    if snv_sharded:
+        from phertilizer_b200.sharded import SnvShardedStore
+
+        snv_store = SnvShardedStore.from_coo(w["n"], m, w["cell"], w["snv"], w["var"], w["total"], rank, world, local)
+        st = snv_store.store
+        nnz_loc = int(st.info()["nnz"])
+        sharded, exchange = None, "snv-peer"
+    else:
+        st = ObservationStore.from_coo(n_loc, m, w["cell"], w["snv"], w["var"], w["total"], device=local, pairs=pairs)
+        sharded = ShardedStore(CudaBackend(st, dev), w["n"], m, w["lo"], w["hi"], exchange=args.exchange) if world > 1 else None
+        exchange = sharded.exchange if sharded is not None else None
     torch.cuda.synchronize()
     info = st.info()
     log(f"[rank {rank}] store ready in {time.time() - t0:.1f}s: {info}")
@@ -229,7 +245,7 @@ def run_ours(args):
         full = (torch.rand(w["n"], generator=g) < 0.5).to(torch.uint8)
         lenA.append(float(full.sum()))
         loc = torch.zeros(n_loc + 16, dtype=torch.uint8)
-        loc[:n_loc] = full[w["lo"]:w["hi"]]
+        loc[:n_loc] = full[w["lo"]:w["hi"]]          # SNV-sharded: lo..hi = all cells
         labs_h.append(loc.pin_memory())
         labs_d.append(loc.to(dev))
     lab_out = torch.empty(m + 16, dtype=torch.uint8, device=dev)
@@ -245,6 +261,9 @@ def run_ours(args):
     def step_device(i, record=False):
         if world == 1:
             st.assign_linear_dev(labs_d[i % P], lenA[i % P], lab_out, nobs_out, stream=stream)
+        elif exchange == "snv-peer":
+            # each rank: the fused single-GPU kernel on its SNVs, epilogue pushes label + counts to every rank; collect
+            snv_store.assign_linear_dev(labs_d[i % P], lenA[i % P], lab_out, nobs_out)
         elif exchange == "peer":
             # pass kernel with peer-memory epilogue + owner finish + collect (csrc/ph_peer.cu); no NCCL in the step
             sharded.assign_linear_dev(labs_d[i % P], lenA[i % P], packed, lab_out, nobs_out)
@@ -311,7 +330,10 @@ def run_ours(args):
             # ph_assign_linear(on_device=0): pinned staging, H2D labels, kernel, D2H labels + counts, sync
             return st.assign_linear(labs_h[i % P].numpy()[:n_loc], lenA[i % P], out=(lab_out_np, nobs_out_np))
         labs_d[i % P].copy_(labs_h[i % P], non_blocking=True)
-        sharded.assign_linear_dev(labs_d[i % P], lenA[i % P], packed, lab_out, nobs_out)
+        if snv_store is not None:
+            snv_store.assign_linear_dev(labs_d[i % P], lenA[i % P], lab_out, nobs_out)
+        else:
+            sharded.assign_linear_dev(labs_d[i % P], lenA[i % P], packed, lab_out, nobs_out)
         lab_out_h.copy_(lab_out, non_blocking=True)
         nobs_out_h.copy_(nobs_out, non_blocking=True)
         torch.cuda.synchronize()
@@ -362,11 +384,12 @@ def run_ours(args):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "MEASURED_PEAKS.json hbm_gbs (burst copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        ab = alg_bytes(nnz_loc, n_loc, m, 1)
+        m_loc = int(info["n_snvs"])      # SNVs this rank walks (all of them unless SNV-sharded)
+        ab = alg_bytes(nnz_loc, n_loc, m_loc, 1)
         # what the kernel really streams: 2 B per observation incl. 16-byte padding, tail words, sub-segment and tail
         # offsets, one label image per CTA, the outputs (labels + counts)
         nsub = info["dense_codes_by_snv"] * info["chunks_by_snv"]
-        phys = info["stream_bytes_by_snv"] + (m * nsub + 1) * 4 + (m + 1) * 8 + n_loc * info["sm_count"] + 5 * m
+        phys = info["stream_bytes_by_snv"] + (m_loc * nsub + 1) * 4 + (m_loc + 1) * 8 + n_loc * info["sm_count"] + 5 * m_loc
         achieved = ab / (kernel_ms * 1e-3) / 1e9
         traffic = None
         try:
@@ -382,13 +405,14 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n_loc) * world, "d2h_bytes_per_step": 5 * m * world,
                     "ms_per_step": 1e3 * e2e_s / args.steps,
                     "path": "ph_assign_linear(on_device=0): host labels -> pinned -> H2D, kernel, D2H SNV labels + Nobs, sync"
-                            if world == 1 else ("pinned H2D labels, ph_peer_assign_linear, D2H labels + Nobs" if exchange == "peer" else
+                            if world == 1 else ("pinned H2D labels, ph_peer_assign_linear(_snv), D2H labels + Nobs" if exchange in ("peer", "snv-peer") else
                                                 "pinned H2D labels, ph_snv_partial, NCCL all-reduce, ph_finish_linear, D2H labels + Nobs")},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic if world == 1 else None,
                          "kernel": "k_pass<MODE_LINEAR>" if world == 1 else ("k_pass<MODE_TABLE>" if exchange == "nccl" else
-                                   "k_pass<MODE_COUNTS> + k_peer_finish + k_peer_collect (whole step: kernel_ms includes the exchange)"),
+                                   ("k_pass<MODE_LINEAR, push> + k_peer_collect (whole step)" if exchange == "snv-peer" else
+                                    "k_pass<MODE_COUNTS> + k_peer_finish + k_peer_collect (whole step: kernel_ms includes the exchange)")),
                          "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": ab,
                          "physical_bytes_per_launch": phys, "physical_bytes_per_nnz": phys / max(nnz_loc, 1),
                          "physical_gbs": phys / (kernel_ms * 1e-3) / 1e9, "physical_frac": phys / (kernel_ms * 1e-3) / 1e9 / peak,
@@ -398,10 +422,11 @@ def run_ours(args):
                                            "stream_bytes_by_snv", "device_bytes")},
         }
         print(json.dumps(line), flush=True)
-    if sharded is not None and sharded.peer is not None:
-        if sharded.peer.timed_out():
+    peer = snv_store.peer if snv_store is not None else (sharded.peer if sharded is not None else None)
+    if peer is not None:
+        if peer.timed_out():
             log(f"[rank {rank}] WARNING: a peer wait timed out during the run")
-        sharded.peer.close()
+        peer.close()
     st.close()
     if world > 1:
         dist.destroy_process_group()
@@ -417,6 +442,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU baseline budget (N=1 only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--clock-seconds", type=float, default=1.0, help="untimed load stretch sampled for SM clocks")
+    ap.add_argument("--shard", default="snvs", choices=["snvs", "cells"],
+                    help="N>1: which axis is split across ranks for the SNV-reassignment step (DESIGN.md section 5)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
                     help="N>1: how the per-SNV partial tables are combined (peer = fused NVLink peer-memory kernels)")
     args = ap.parse_args()

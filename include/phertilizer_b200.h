@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PH_ABI_VERSION 2
+#define PH_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define PH_API __attribute__((visibility("default")))
@@ -151,13 +151,23 @@ PH_API int ph_finish_branching(const double* packed, int32_t n_list, uint8_t* la
  */
 typedef struct ph_peer ph_peer;
 PH_API int ph_peer_handle_bytes(void);
-PH_API int ph_peer_create(ph_handle* h, int rank, int world, ph_peer** out);
+PH_API int ph_peer_create(ph_handle* h, int rank, int world, int32_t total_snvs /* 0: every rank holds all SNVs */, ph_peer** out);
 PH_API int ph_peer_export(ph_peer* p, void* handle_out);
 PH_API int ph_peer_connect(ph_peer* p, const void* all_handles);
 PH_API int ph_peer_assign_linear(ph_peer* p, const uint8_t* cell_label, double lenA, const int32_t* snv_list,
                           int32_t n_list, uint8_t* label_out, int32_t* nobs_out, void* stream);
 PH_API int ph_peer_assign_branching(ph_peer* p, const uint8_t* cell_label, const int32_t* snv_list, int32_t n_list,
                              uint8_t* label_out, int32_t* nobs_out, void* stream);
+/*
+ * SNV-sharded variant: every rank holds ALL cells and the SNVs [snv_offset, snv_offset + n_snvs) of `total_snvs`
+ * (ph_peer_create).  Per-SNV tables are independent across SNVs, so the pass needs no exchange of partial tables: the
+ * kernel epilogue stores every SNV's label and counts into all ranks' output windows and label_out / nobs_out
+ * [total_snvs (* 2)] are complete on every rank after the call.  `cell_label` covers all cells.
+ */
+PH_API int ph_peer_assign_linear_snv(ph_peer* p, const uint8_t* cell_label, double lenA, int32_t snv_offset,
+                              uint8_t* label_out, int32_t* nobs_out, void* stream);
+PH_API int ph_peer_assign_branching_snv(ph_peer* p, const uint8_t* cell_label, int32_t snv_offset, uint8_t* label_out,
+                                 int32_t* nobs_out, void* stream);
 PH_API int ph_peer_timed_out(ph_peer* p, void* stream); /* 1 if a wait for a peer ever gave up (~3 s) */
 PH_API void ph_peer_destroy(ph_peer* p);
 

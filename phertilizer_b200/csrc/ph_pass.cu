@@ -49,6 +49,11 @@ struct PassArgs {
   unsigned* done;                    // CTA completion counter (local, self-resetting)
   int blk, ncp, world, row_words;
   uint32_t epoch;
+  // LINEAR / BRANCHING with push != 0 (SNV-sharded K1, ph_peer.cu): the line's label and counts go to position
+  // out_off + line of EVERY rank's output window instead of label_out / nobs_out; then the flag, as for COUNTS
+  uint8_t* label_dst[PH_MAX_PEERS];
+  int32_t* nobs_dst[PH_MAX_PEERS];
+  int push, out_off;
 };
 
 __device__ __forceinline__ uint4 ld_stream(const uint4* p) {
@@ -379,17 +384,34 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
       } else if (MODE == MODE_LINEAR) {
         // linear_split.py:229-234  like0.mean(axis=0) >= like1.mean(axis=0) -> mutsB (ties -> mutsB)
         const double m0 = s0[0] / a.lenA, m1 = s1[0] / a.lenA;
-        a.label_out[wi] = (m0 >= m1) ? 2 : 1;
-        a.nobs_out[wi] = (int32_t)nob[0];
+        const uint8_t lb = (m0 >= m1) ? 2 : 1;
+        if (a.push) {
+          for (int p = 0; p < a.world; ++p) {
+            a.label_dst[p][a.out_off + wi] = lb;
+            a.nobs_dst[p][a.out_off + wi] = (int32_t)nob[0];
+          }
+        } else {
+          a.label_out[wi] = lb;
+          a.nobs_out[wi] = (int32_t)nob[0];
+        }
       } else if (MODE == MODE_BRANCHING) {
         // branching_split.py:332-346
         const double cA = s1[0] + s0[NC > 1 ? 1 : 0];
         const double cB = s0[0] + s1[NC > 1 ? 1 : 0];
         const double cC = s1[0] + s1[NC > 1 ? 1 : 0];
         const double mx = fmax(cA, fmax(cB, cC));
-        a.label_out[wi] = (cA == mx) ? 1 : ((cB == mx) ? 2 : 3);
-        a.nobs_out[2 * (size_t)wi] = (int32_t)nob[0];
-        a.nobs_out[2 * (size_t)wi + 1] = (int32_t)nob[NC > 1 ? 1 : 0];
+        const uint8_t lb = (cA == mx) ? 1 : ((cB == mx) ? 2 : 3);
+        if (a.push) {
+          for (int p = 0; p < a.world; ++p) {
+            a.label_dst[p][a.out_off + wi] = lb;
+            a.nobs_dst[p][2 * (size_t)(a.out_off + wi)] = (int32_t)nob[0];
+            a.nobs_dst[p][2 * (size_t)(a.out_off + wi) + 1] = (int32_t)nob[NC > 1 ? 1 : 0];
+          }
+        } else {
+          a.label_out[wi] = lb;
+          a.nobs_out[2 * (size_t)wi] = (int32_t)nob[0];
+          a.nobs_out[2 * (size_t)wi + 1] = (int32_t)nob[NC > 1 ? 1 : 0];
+        }
       } else if (MODE == MODE_MAPPED) {  // absent -> field 0 uses like0, present -> field 1 uses like1
         a.per_line[wi] = h_skip ? 0.0 : s0[0] + s1[NC > 1 ? 1 : 0];
       }
@@ -408,8 +430,8 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
       __syncwarp();
     }
   }
-  if (MODE == MODE_COUNTS) {
-    // all partial rows of this rank are on their way: make them visible system-wide, then the last CTA raises this
+  if (MODE == MODE_COUNTS || ((MODE == MODE_LINEAR || MODE == MODE_BRANCHING) && a.push)) {
+    // all partial rows (or pushed outputs) of this rank are on their way: make them visible system-wide, then the last CTA raises this
     // rank's flag in every peer's window
     __threadfence_system();
     __syncthreads();
@@ -1105,4 +1127,28 @@ int ph_pass_counts(ph_handle* h, const uint8_t* cell_label, int C, const int32_t
   a.world = world;
   a.epoch = epoch;
   return C == 1 ? launch_pass<MODE_COUNTS, 1>(h, o, a, st) : launch_pass<MODE_COUNTS, 2>(h, o, a, st);
+}
+
+// SNV-sharded K1 + K1a (ph_peer.cu): this rank's SNVs, outputs pushed to every rank's window at out_off + line
+int ph_pass_assign_push(ph_handle* h, int mode, const uint8_t* cell_label, double lenA, uint8_t* const* label_dst,
+                        int32_t* const* nobs_dst, uint32_t* const* flag_dst, unsigned* done, int out_off, int world,
+                        uint32_t epoch, cudaStream_t st) {
+  PhOrient* o = &h->by_snv;
+  PassArgs a;
+  fill_common(h, o, a);
+  a.C = mode == MODE_LINEAR ? 1 : 2;
+  a.lenA = lenA;
+  a.n_work = o->n_major;
+  a.minor_label = cell_label;
+  for (int r = 0; r < world; ++r) {
+    a.label_dst[r] = label_dst[r];
+    a.nobs_dst[r] = nobs_dst[r];
+    a.flag_dst[r] = flag_dst[r];
+  }
+  a.done = done;
+  a.world = world;
+  a.epoch = epoch;
+  a.push = 1;
+  a.out_off = out_off;
+  return mode == MODE_LINEAR ? launch_pass<MODE_LINEAR, 1>(h, o, a, st) : launch_pass<MODE_BRANCHING, 2>(h, o, a, st);
 }

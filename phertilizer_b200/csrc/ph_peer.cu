@@ -19,7 +19,7 @@ struct ph_peer {
   ph_handle* h;
   int rank, world;
   int32_t max_lines, blk_max, ncp;
-  size_t off_cnt, off_lab, off_nobs, bytes;
+  size_t off_cnt, off_lab, off_nobs, off_lab2, off_nobs2, bytes;  // *2: second output buffer (SNV-sharded steps alternate)
   uint8_t* win[PH_MAX_PEERS];  // win[rank] = own allocation, others = IPC mappings
   bool opened[PH_MAX_PEERS];
   unsigned* d_done;            // [2] CTA completion counters (pass, finish) + [1] spin-timeout flag
@@ -133,10 +133,10 @@ __global__ void __launch_bounds__(256) k_peer_finish(const FinishArgs a) {
   }
 }
 
-__global__ void __launch_bounds__(256) k_peer_collect(const uint8_t* win, size_t off_lab, size_t off_nobs, int world,
-                                                     uint32_t epoch, int n_list, int C, uint8_t* label_out,
+__global__ void __launch_bounds__(256) k_peer_collect(const uint8_t* win, size_t off_flags, size_t off_lab, size_t off_nobs,
+                                                     int world, uint32_t epoch, int n_list, int C, uint8_t* label_out,
                                                      int32_t* nobs_out, unsigned* timeout_flag) {
-  wait_flags(reinterpret_cast<const uint32_t*>(win + 1024), world, epoch, timeout_flag);
+  wait_flags(reinterpret_cast<const uint32_t*>(win + off_flags), world, epoch, timeout_flag);
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
   const uint32_t* src_n = reinterpret_cast<const uint32_t*>(win + off_nobs);
   for (int i = tid; i < n_list * C; i += nt) nobs_out[i] = (int32_t)__ldcv(src_n + i);
@@ -150,6 +150,10 @@ __global__ void __launch_bounds__(256) k_peer_collect(const uint8_t* win, size_t
 int ph_pass_counts(ph_handle* h, const uint8_t* cell_label, int C, const int32_t* snv_list, int32_t n_list,
                    uint16_t* const* cnt_dst, uint32_t* const* flag_dst, unsigned* done, int blk, int ncp, int world,
                    uint32_t epoch, cudaStream_t st);
+
+int ph_pass_assign_push(ph_handle* h, int mode, const uint8_t* cell_label, double lenA, uint8_t* const* label_dst,
+                        int32_t* const* nobs_dst, uint32_t* const* flag_dst, unsigned* done, int out_off, int world,
+                        uint32_t epoch, cudaStream_t st);
 
 extern "C" int ph_peer_handle_bytes(void) { return (int)sizeof(cudaIpcMemHandle_t); }
 
@@ -165,28 +169,30 @@ extern "C" void ph_peer_destroy(ph_peer* p) {
   delete p;
 }
 
-extern "C" int ph_peer_create(ph_handle* h, int rank, int world, ph_peer** out) {
+extern "C" int ph_peer_create(ph_handle* h, int rank, int world, int32_t total_snvs, ph_peer** out) {
   if (!h || !out) PH_FAIL(PH_ERR_ARG, "null argument");
   *out = nullptr;
   if (world < 2 || world > PH_MAX_PEERS || rank < 0 || rank >= world)
     PH_FAIL(PH_ERR_ARG, "rank %d / world %d outside 2..%d", rank, world, PH_MAX_PEERS);
-  if (h->n_cells > 65535)
-    PH_FAIL(PH_ERR_UNSUPPORTED, "%d local cells: the exchanged histogram rows are 16-bit (at most 65535 cells per rank)", h->n_cells);
-  if (h->n_codes > 64) PH_FAIL(PH_ERR_UNSUPPORTED, "%d (var,total) codes: histogram exchange supports up to 64", h->n_codes);
+  if (total_snvs <= 0) total_snvs = h->n_snvs;  // cell-sharded: every rank holds all SNVs
+  if (total_snvs < h->n_snvs) PH_FAIL(PH_ERR_ARG, "total_snvs=%d is less than the %d local SNVs", total_snvs, h->n_snvs);
   PH_CUDA(cudaSetDevice(h->device));
   ph_peer* p = new ph_peer();
   memset(p, 0, sizeof(*p));
   p->h = h;
   p->rank = rank;
   p->world = world;
-  p->max_lines = h->n_snvs;
+  p->max_lines = total_snvs;
   p->blk_max = (h->n_snvs + world - 1) / world;
   p->ncp = (h->n_codes + 7) & ~7;
+  if (p->ncp > 64) p->ncp = 64;  // histogram exchange (cell-sharded) is refused above 64 codes, see peer_assign
   p->off_cnt = kFlagBytes;
   const size_t cnt_bytes = (size_t)world * p->blk_max * 3 * p->ncp * sizeof(uint16_t);
   p->off_lab = (p->off_cnt + cnt_bytes + 255) & ~(size_t)255;
   p->off_nobs = (p->off_lab + (size_t)p->max_lines + 255) & ~(size_t)255;
-  p->bytes = p->off_nobs + (size_t)p->max_lines * 3 * sizeof(int32_t) + 256;
+  p->off_lab2 = (p->off_nobs + (size_t)p->max_lines * 3 * sizeof(int32_t) + 255) & ~(size_t)255;
+  p->off_nobs2 = (p->off_lab2 + (size_t)p->max_lines + 255) & ~(size_t)255;
+  p->bytes = p->off_nobs2 + (size_t)p->max_lines * 3 * sizeof(int32_t) + 256;
   cudaError_t e = cudaMalloc(&p->win[rank], p->bytes);
   if (e == cudaSuccess) e = cudaMemset(p->win[rank], 0, p->bytes);
   if (e == cudaSuccess) e = cudaMalloc(&p->d_done, 16);
@@ -231,7 +237,10 @@ int peer_assign(ph_peer* p, int mode, const uint8_t* cell_label, double lenA, co
   if (!cell_label || !label_out || !nobs_out) PH_FAIL(PH_ERR_ARG, "null pointer");
   ph_handle* h = p->h;
   if (!snv_list) n_list = h->n_snvs;
-  if (n_list <= 0 || n_list > p->max_lines) PH_FAIL(PH_ERR_ARG, "n_list=%d outside 1..%d", n_list, p->max_lines);
+  if (n_list <= 0 || n_list > h->n_snvs) PH_FAIL(PH_ERR_ARG, "n_list=%d outside 1..%d", n_list, h->n_snvs);
+  if (h->n_cells > 65535)
+    PH_FAIL(PH_ERR_UNSUPPORTED, "%d local cells: the exchanged histogram rows are 16-bit (at most 65535 cells per rank)", h->n_cells);
+  if (h->n_codes > 64) PH_FAIL(PH_ERR_UNSUPPORTED, "%d (var,total) codes: histogram exchange supports up to 64", h->n_codes);
   for (int r = 0; r < p->world; ++r)
     if (!p->win[r]) PH_FAIL(PH_ERR_ARG, "ph_peer_connect has not been called (rank %d missing)", r);
   PH_CUDA(cudaSetDevice(h->device));
@@ -277,8 +286,8 @@ int peer_assign(ph_peer* p, int mode, const uint8_t* cell_label, double lenA, co
   else k_peer_finish<2><<<fb > 0 ? fb : 1, 256, 0, st>>>(f);
   ph_count_launch();
   const int cb = (n_list * C + 255) / 256 < h->sm_count * 2 ? (n_list * C + 255) / 256 : h->sm_count * 2;
-  k_peer_collect<<<cb, 256, 0, st>>>(p->win[p->rank], p->off_lab, p->off_nobs, p->world, epoch, n_list, C, label_out,
-                                     nobs_out, p->d_done + 2);
+  k_peer_collect<<<cb, 256, 0, st>>>(p->win[p->rank], (size_t)1024, p->off_lab, p->off_nobs, p->world, epoch, n_list, C,
+                                     label_out, nobs_out, p->d_done + 2);
   ph_count_launch();
   PH_CUDA(cudaGetLastError());
   return PH_OK;
@@ -293,6 +302,58 @@ extern "C" int ph_peer_assign_linear(ph_peer* p, const uint8_t* cell_label, doub
 extern "C" int ph_peer_assign_branching(ph_peer* p, const uint8_t* cell_label, const int32_t* snv_list, int32_t n_list,
                                         uint8_t* label_out, int32_t* nobs_out, void* stream) {
   return peer_assign(p, 2, cell_label, 1.0, snv_list, n_list, label_out, nobs_out, stream);
+}
+
+// ---- SNV-sharded K1 + K1a: every rank holds ALL cells and the SNVs [snv_offset, snv_offset + n_snvs) of total_snvs.
+// Per-SNV tables are independent across SNVs, so the pass itself needs no exchange: the kernel epilogue stores each
+// SNV's label and counts straight into every rank's output window (NVLink peer stores), the last CTA raises the flag,
+// and k_peer_collect copies the assembled window out once all ranks' flags are up.  Two launches per step.
+namespace {
+int peer_assign_snv(ph_peer* p, int mode, const uint8_t* cell_label, double lenA, int32_t snv_offset, uint8_t* label_out,
+                    int32_t* nobs_out, void* stream) {
+  if (!p) PH_FAIL(PH_ERR_ARG, "null peer context");
+  if (!cell_label || !label_out || !nobs_out) PH_FAIL(PH_ERR_ARG, "null pointer");
+  ph_handle* h = p->h;
+  if (snv_offset < 0 || snv_offset + h->n_snvs > p->max_lines)
+    PH_FAIL(PH_ERR_ARG, "SNV block [%d, %d) outside 0..%d", snv_offset, snv_offset + h->n_snvs, p->max_lines);
+  for (int r = 0; r < p->world; ++r)
+    if (!p->win[r]) PH_FAIL(PH_ERR_ARG, "ph_peer_connect has not been called (rank %d missing)", r);
+  PH_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int C = mode == 1 ? 1 : 2;
+  if (h->n_snvs <= 0) PH_FAIL(PH_ERR_ARG, "this rank holds no SNVs");
+  const uint32_t epoch = ++p->epoch;
+  // Outputs alternate between two buffers: a fast rank may already push step e+1 into a peer whose collect kernel
+  // still copies step e (its own step e+2 cannot start before that peer has finished step e, see the flag order).
+  const size_t off_lab = (epoch & 1) ? p->off_lab2 : p->off_lab, off_nobs = (epoch & 1) ? p->off_nobs2 : p->off_nobs;
+  uint8_t* lab_dst[PH_MAX_PEERS] = {};
+  int32_t* nobs_dst[PH_MAX_PEERS] = {};
+  uint32_t* flag_dst[PH_MAX_PEERS] = {};
+  for (int r = 0; r < p->world; ++r) {
+    lab_dst[r] = p->win[r] + off_lab;
+    nobs_dst[r] = reinterpret_cast<int32_t*>(p->win[r] + off_nobs);
+    flag_dst[r] = reinterpret_cast<uint32_t*>(p->win[r]) + p->rank;
+  }
+  int rc = ph_pass_assign_push(h, mode, cell_label, lenA, lab_dst, nobs_dst, flag_dst, p->d_done, snv_offset, p->world, epoch, st);
+  if (rc != PH_OK) return rc;
+  const int total = p->max_lines;
+  const int cb = (total * C + 255) / 256 < h->sm_count * 2 ? (total * C + 255) / 256 : h->sm_count * 2;
+  k_peer_collect<<<cb, 256, 0, st>>>(p->win[p->rank], (size_t)0, off_lab, off_nobs, p->world, epoch, total, C, label_out,
+                                     nobs_out, p->d_done + 2);
+  ph_count_launch();
+  PH_CUDA(cudaGetLastError());
+  return PH_OK;
+}
+}  // namespace
+
+extern "C" int ph_peer_assign_linear_snv(ph_peer* p, const uint8_t* cell_label, double lenA, int32_t snv_offset,
+                                         uint8_t* label_out, int32_t* nobs_out, void* stream) {
+  return peer_assign_snv(p, 1, cell_label, lenA, snv_offset, label_out, nobs_out, stream);
+}
+
+extern "C" int ph_peer_assign_branching_snv(ph_peer* p, const uint8_t* cell_label, int32_t snv_offset, uint8_t* label_out,
+                                            int32_t* nobs_out, void* stream) {
+  return peer_assign_snv(p, 2, cell_label, 1.0, snv_offset, label_out, nobs_out, stream);
 }
 
 // 1 if a spin-wait of this context ever gave up (a peer never arrived); synchronises the stream

@@ -78,7 +78,7 @@ class PeerExchange:
     """NVLink peer-memory windows of the fused sharded K1 (include/phertilizer_b200.h, ph_peer_*).  torch.distributed
     only carries the 64-byte IPC handle of every rank's window once, at set-up."""
 
-    def __init__(self, store, rank, world, group=None):
+    def __init__(self, store, rank, world, group=None, total_snvs=0):
         import ctypes as C
 
         import torch
@@ -89,7 +89,7 @@ class PeerExchange:
         L = _lib.lib()
         self._lib, self._L = _lib, L
         self._p = C.c_void_p()
-        _lib.check(L.ph_peer_create(store._h, int(rank), int(world), C.byref(self._p)))
+        _lib.check(L.ph_peer_create(store._h, int(rank), int(world), int(total_snvs), C.byref(self._p)))
         nb = L.ph_peer_handle_bytes()
         mine = C.create_string_buffer(nb)
         _lib.check(L.ph_peer_export(self._p, mine))
@@ -111,6 +111,18 @@ class PeerExchange:
 
         self._lib.check(self._L.ph_peer_assign_branching(self._p, _ptr(label_t), _ptr(list_t), int(k), _ptr(lab_out_t),
                                                          _ptr(nobs_out_t), stream))
+
+    def assign_linear_snv(self, label_t, lenA, snv_offset, lab_out_t, nobs_out_t, stream=None):
+        from .store import _ptr
+
+        self._lib.check(self._L.ph_peer_assign_linear_snv(self._p, _ptr(label_t), float(lenA), int(snv_offset),
+                                                          _ptr(lab_out_t), _ptr(nobs_out_t), stream))
+
+    def assign_branching_snv(self, label_t, snv_offset, lab_out_t, nobs_out_t, stream=None):
+        from .store import _ptr
+
+        self._lib.check(self._L.ph_peer_assign_branching_snv(self._p, _ptr(label_t), int(snv_offset), _ptr(lab_out_t),
+                                                             _ptr(nobs_out_t), stream))
 
     def timed_out(self, stream=None) -> bool:
         return bool(self._L.ph_peer_timed_out(self._p, stream))
@@ -240,3 +252,80 @@ class ShardedStore:
         self.snv_table_dev(self.local_labels(cell_label_global), C, packed, lst)
         p = packed.cpu().numpy().reshape(3, k, C)
         return {"S0": p[0], "S1": p[1], "Nobs": p[2].astype(np.int32)}
+
+
+
+def snv_block(n_snvs: int, rank: int, world: int):
+    """Contiguous block [lo, hi) of SNVs owned by `rank`."""
+    return (n_snvs * rank) // world, (n_snvs * (rank + 1)) // world
+
+
+class SnvShardedStore:
+    """SNVs partitioned across ranks, every rank holds all cells of its SNV block.
+
+    Per-SNV tables (K1) are independent across SNVs, so this sharding needs NO exchange of partial tables for the SNV
+    reassignment: each rank runs the single-GPU fused kernel on its SNVs and the kernel epilogue stores label + counts
+    into every rank's output window over NVLink peer memory (`ph_peer_assign_*_snv`).  What would need an exchange under
+    this sharding is K2 (per-cell tables: a sum all-reduce of `n x Q` integer counts), the mirror image of the
+    cell-sharded layout.  Results are those of the single-GPU kernel bit for bit (it IS that kernel, on a slice)."""
+
+    def __init__(self, store, n_cells, n_snvs, lo, hi, device, group=None):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist = torch, dist
+        self.store, self.device, self.group = store, device, group
+        self.n_cells, self.n_snvs, self.lo, self.hi = int(n_cells), int(n_snvs), int(lo), int(hi)
+        self.world = dist.get_world_size(group)
+        self.peer = PeerExchange(store, dist.get_rank(group), self.world, group, total_snvs=self.n_snvs)
+
+    @classmethod
+    def from_coo(cls, n_cells, n_snvs, cell, snv, var, total, rank, world, device, alpha=0.001, max_copies=5, group=None):
+        import torch
+
+        from .store import ObservationStore
+
+        lo, hi = snv_block(n_snvs, rank, world)
+        keep = (snv >= lo) & (snv < hi)
+        if isinstance(cell, np.ndarray):
+            cell, snv, var, total = cell[keep], snv[keep] - lo, var[keep], total[keep]
+        else:
+            cell, snv, var, total = cell[keep].contiguous(), (snv[keep] - lo).contiguous(), var[keep].contiguous(), total[keep].contiguous()
+        dev_index = device if isinstance(device, int) else device.index
+        st = ObservationStore.from_coo(n_cells, hi - lo, cell, snv, var, total, alpha=alpha, max_copies=max_copies,
+                                       device=dev_index, pairs=global_pairs(var, total, group))
+        dev = torch.device("cuda", dev_index)
+        return cls(st, n_cells, n_snvs, lo, hi, dev, group)
+
+    def _stream(self):
+        return self.torch.cuda.current_stream().cuda_stream
+
+    def assign_linear_dev(self, label_t, lenA, lab_out_t, nobs_out_t):
+        """label_t: labels of ALL cells (uint8, device); outputs cover all n_snvs SNVs on every rank."""
+        self.peer.assign_linear_snv(label_t, lenA, self.lo, lab_out_t, nobs_out_t, stream=self._stream())
+
+    def assign_branching_dev(self, label_t, lab_out_t, nobs_out_t):
+        self.peer.assign_branching_snv(label_t, self.lo, lab_out_t, nobs_out_t, stream=self._stream())
+
+    def _labels_dev(self, cell_label):
+        buf = np.zeros(self.n_cells + 16, np.uint8)
+        buf[: self.n_cells] = cell_label
+        return self.torch.from_numpy(buf).to(self.device)
+
+    def assign_linear(self, cell_label, lenA):
+        t = self.torch
+        lab = t.empty(self.n_snvs + 16, dtype=t.uint8, device=self.device)
+        nobs = t.empty(self.n_snvs, dtype=t.int32, device=self.device)
+        self.assign_linear_dev(self._labels_dev(cell_label), lenA, lab, nobs)
+        return lab[: self.n_snvs].cpu().numpy(), nobs.cpu().numpy()
+
+    def assign_branching(self, cell_label):
+        t = self.torch
+        lab = t.empty(self.n_snvs + 16, dtype=t.uint8, device=self.device)
+        nobs = t.empty(2 * self.n_snvs, dtype=t.int32, device=self.device)
+        self.assign_branching_dev(self._labels_dev(cell_label), lab, nobs)
+        return lab[: self.n_snvs].cpu().numpy(), nobs.cpu().numpy().reshape(self.n_snvs, 2)
+
+    def close(self):
+        self.peer.close()
+        self.store.close()

@@ -6,7 +6,7 @@ import os, sys
 import numpy as np
 import torch, torch.distributed as dist
 sys.path.insert(0, ".")
-from phertilizer_b200.sharded import ShardedStore
+from phertilizer_b200.sharded import ShardedStore, SnvShardedStore
 from phertilizer_b200.store import ObservationStore
 from phertilizer_b200.synth import make_config
 from tests.golden_util import load_golden
@@ -65,6 +65,22 @@ for stem, n, m, cell, snv, var, total in datasets():
             ok &= not sh.peer.timed_out()
             sh.peer.close()
         sh.b.store.close()
+    # SNV-sharded: the single-GPU kernel on a slice of the SNVs, outputs pushed to every rank -> exact equality
+    ss = SnvShardedStore.from_coo(n, m, cell, snv, var, total, rank, world, local)
+    used.add("snv-sharded peer")
+    rng = np.random.default_rng(12)
+    for trial in range(4):
+        lab = np.zeros(n + 16, np.uint8)[:n]; lab[:] = rng.integers(0, 3, n)
+        labA = np.zeros(n + 16, np.uint8)[:n]; labA[:] = (lab == 1)
+        l1, n1 = full.assign_linear(labA, float(labA.sum()))
+        l2, n2 = ss.assign_linear(labA, float(labA.sum()))
+        b1, m1 = full.assign_branching(lab)
+        b2, m2 = ss.assign_branching(lab)
+        good = np.array_equal(l1, l2) and np.array_equal(n1, n2) and np.array_equal(b1, b2) and np.array_equal(m1, m2)
+        if not good: print(f"[rank {rank}] SNV-sharded mismatch", stem, trial)
+        ok &= good
+    ok &= not ss.peer.timed_out()
+    ss.close()
     full.close()
 t = torch.tensor([1 if ok else 0], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0:
