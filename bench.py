@@ -206,7 +206,18 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL announces its version on STDOUT when the first communicator comes up; stdout must carry the JSON line only
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     t0 = time.time()
     snv_sharded = world > 1 and args.shard == "snvs"
     if snv_sharded:
@@ -259,8 +270,11 @@ def run_ours(args):
     kern_ev = []
 
     def step_device(i, record=False):
+        if graphs is not None:
+            graphs[i % P].replay()
+            return
         if world == 1:
-            st.assign_linear_dev(labs_d[i % P], lenA[i % P], lab_out, nobs_out, stream=stream)
+            st.assign_linear_dev(labs_d[i % P], lenA[i % P], lab_out, nobs_out, stream=torch.cuda.current_stream().cuda_stream)
         elif exchange == "snv-peer":
             # each rank: the fused single-GPU kernel on its SNVs, epilogue pushes label + counts to every rank; collect
             snv_store.assign_linear_dev(labs_d[i % P], lenA[i % P], lab_out, nobs_out)
@@ -285,9 +299,31 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---------------- device-resident throughput (value) ----------------
+    graphs = None
     for i in range(args.warmup):
         step_device(i)
     barrier()
+    l0 = _lib.kernel_launches()
+    step_device(0)
+    launches_per_step = _lib.kernel_launches() - l0 + (1 if exchange == "nccl" else 0)
+    barrier()
+    if args.cuda_graphs and exchange != "nccl":
+        # one CUDA graph per label set (memset of the batch counter + the step's kernels): the step is launch-bound at
+        # N > 1 (tens of microseconds of GPU work), so the host-side launch path is taken out of the loop
+        try:
+            captured = []
+            for j in range(P):
+                g_ = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_):
+                    step_device(j)
+                captured.append(g_)
+            graphs = captured
+            for i in range(args.warmup):
+                step_device(i)
+            barrier()
+        except Exception as e:  # capture not possible: stay eager
+            log(f"[rank {rank}] CUDA graph capture failed ({e}); running eagerly")
+            graphs = None
     # The timed region of K steps lasts a few ms -- shorter than one nvidia-smi poll -- so the sampler also runs over an
     # untimed ~1 s stretch of the very same steps right before it (clocks "under load"), and stays on through the
     # timed region.
@@ -315,12 +351,11 @@ def run_ours(args):
         e1.record()
         barrier()
     ms = e0.elapsed_time(e1)
-    launches = _lib.kernel_launches() - launches0
-    if world > 1 and exchange == "nccl":
+    launches = launches_per_step * args.steps
+    if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-        launches += args.steps  # the NCCL all-reduce kernel of every step
     value = args.steps * nnz_tot / (ms * 1e-3)
     kernel_ms = (sum(a.elapsed_time(b) for a, b in kern_ev) / len(kern_ev)) if kern_ev else ms / args.steps
 
@@ -407,7 +442,7 @@ def run_ours(args):
                     "path": "ph_assign_linear(on_device=0): host labels -> pinned -> H2D, kernel, D2H SNV labels + Nobs, sync"
                             if world == 1 else ("pinned H2D labels, ph_peer_assign_linear(_snv), D2H labels + Nobs" if exchange in ("peer", "snv-peer") else
                                                 "pinned H2D labels, ph_snv_partial, NCCL all-reduce, ph_finish_linear, D2H labels + Nobs")},
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches), "cuda_graphs": graphs is not None,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic if world == 1 else None,
                          "kernel": "k_pass<MODE_LINEAR>" if world == 1 else ("k_pass<MODE_TABLE>" if exchange == "nccl" else
@@ -442,6 +477,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU baseline budget (N=1 only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--clock-seconds", type=float, default=1.0, help="untimed load stretch sampled for SM clocks")
+    ap.add_argument("--no-cuda-graphs", dest="cuda_graphs", action="store_false",
+                    help="launch every step eagerly instead of replaying a captured CUDA graph")
     ap.add_argument("--shard", default="snvs", choices=["snvs", "cells"],
                     help="N>1: which axis is split across ranks for the SNV-reassignment step (DESIGN.md section 5)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],

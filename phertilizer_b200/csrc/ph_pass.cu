@@ -48,12 +48,12 @@ struct PassArgs {
   uint32_t* flag_dst[PH_MAX_PEERS];  // per peer: where this rank's "partials landed" flag lives
   unsigned* done;                    // CTA completion counter (local, self-resetting)
   int blk, ncp, world, row_words;
-  uint32_t epoch;
   // LINEAR / BRANCHING with push != 0 (SNV-sharded K1, ph_peer.cu): the line's label and counts go to position
   // out_off + line of EVERY rank's output window instead of label_out / nobs_out; then the flag, as for COUNTS
-  uint8_t* label_dst[PH_MAX_PEERS];
-  int32_t* nobs_dst[PH_MAX_PEERS];
+  uint8_t* label_dst[2][PH_MAX_PEERS];  // [parity of the step][rank]: outputs alternate between two windows
+  int32_t* nobs_dst[2][PH_MAX_PEERS];
   int push, out_off;
+  const uint32_t* epoch_ptr;  // step counter in device memory (step = *epoch_ptr + 1): launches are CUDA-graph replayable
 };
 
 __device__ __forceinline__ uint4 ld_stream(const uint4* p) {
@@ -169,6 +169,8 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
   const uint32_t mmask = (a.minor_bits >= 32) ? 0xffffffffu : ((1u << a.minor_bits) - 1u);
   const int n_batches = (a.n_work + B - 1) / B;
 
+  const uint32_t epoch = a.epoch_ptr ? *a.epoch_ptr + 1u : 0u;  // this step (peer modes)
+  const int par = (int)(epoch & 1u);
   const uint32_t magic_nch = (65536u + (uint32_t)NCH - 1u) / (uint32_t)NCH;      // exact k / NCH for k < 256 * 32 / NCH
   const uint32_t magic_d = D > 0 ? (65536u + (uint32_t)D - 1u) / (uint32_t)D : 0u;  // exact key / D
 
@@ -387,8 +389,8 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
         const uint8_t lb = (m0 >= m1) ? 2 : 1;
         if (a.push) {
           for (int p = 0; p < a.world; ++p) {
-            a.label_dst[p][a.out_off + wi] = lb;
-            a.nobs_dst[p][a.out_off + wi] = (int32_t)nob[0];
+            a.label_dst[par][p][a.out_off + wi] = lb;
+            a.nobs_dst[par][p][a.out_off + wi] = (int32_t)nob[0];
           }
         } else {
           a.label_out[wi] = lb;
@@ -403,9 +405,9 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
         const uint8_t lb = (cA == mx) ? 1 : ((cB == mx) ? 2 : 3);
         if (a.push) {
           for (int p = 0; p < a.world; ++p) {
-            a.label_dst[p][a.out_off + wi] = lb;
-            a.nobs_dst[p][2 * (size_t)(a.out_off + wi)] = (int32_t)nob[0];
-            a.nobs_dst[p][2 * (size_t)(a.out_off + wi) + 1] = (int32_t)nob[NC > 1 ? 1 : 0];
+            a.label_dst[par][p][a.out_off + wi] = lb;
+            a.nobs_dst[par][p][2 * (size_t)(a.out_off + wi)] = (int32_t)nob[0];
+            a.nobs_dst[par][p][2 * (size_t)(a.out_off + wi) + 1] = (int32_t)nob[NC > 1 ? 1 : 0];
           }
         } else {
           a.label_out[wi] = lb;
@@ -441,7 +443,7 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
         *a.done = 0;
         __threadfence_system();
         for (int p = 0; p < a.world; ++p)
-          asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.flag_dst[p]), "r"(a.epoch) : "memory");
+          asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.flag_dst[p]), "r"(epoch) : "memory");
       }
     }
   }
@@ -1109,7 +1111,7 @@ extern "C" int ph_finish_branching(const double* packed, int32_t n_list, uint8_t
 // ------------------------------------------------------------------------------------------------
 int ph_pass_counts(ph_handle* h, const uint8_t* cell_label, int C, const int32_t* snv_list, int32_t n_list,
                    uint16_t* const* cnt_dst, uint32_t* const* flag_dst, unsigned* done, int blk, int ncp, int world,
-                   uint32_t epoch, cudaStream_t st) {
+                   const uint32_t* epoch_ptr, cudaStream_t st) {
   PhOrient* o = &h->by_snv;
   PassArgs a;
   fill_common(h, o, a);
@@ -1125,14 +1127,14 @@ int ph_pass_counts(ph_handle* h, const uint8_t* cell_label, int C, const int32_t
   a.blk = blk;
   a.ncp = ncp;
   a.world = world;
-  a.epoch = epoch;
+  a.epoch_ptr = epoch_ptr;
   return C == 1 ? launch_pass<MODE_COUNTS, 1>(h, o, a, st) : launch_pass<MODE_COUNTS, 2>(h, o, a, st);
 }
 
 // SNV-sharded K1 + K1a (ph_peer.cu): this rank's SNVs, outputs pushed to every rank's window at out_off + line
-int ph_pass_assign_push(ph_handle* h, int mode, const uint8_t* cell_label, double lenA, uint8_t* const* label_dst,
-                        int32_t* const* nobs_dst, uint32_t* const* flag_dst, unsigned* done, int out_off, int world,
-                        uint32_t epoch, cudaStream_t st) {
+int ph_pass_assign_push(ph_handle* h, int mode, const uint8_t* cell_label, double lenA, uint8_t* const (*label_dst)[PH_MAX_PEERS],
+                        int32_t* const (*nobs_dst)[PH_MAX_PEERS], uint32_t* const* flag_dst, unsigned* done, int out_off,
+                        int world, const uint32_t* epoch_ptr, cudaStream_t st) {
   PhOrient* o = &h->by_snv;
   PassArgs a;
   fill_common(h, o, a);
@@ -1141,13 +1143,15 @@ int ph_pass_assign_push(ph_handle* h, int mode, const uint8_t* cell_label, doubl
   a.n_work = o->n_major;
   a.minor_label = cell_label;
   for (int r = 0; r < world; ++r) {
-    a.label_dst[r] = label_dst[r];
-    a.nobs_dst[r] = nobs_dst[r];
+    for (int q = 0; q < 2; ++q) {
+      a.label_dst[q][r] = label_dst[q][r];
+      a.nobs_dst[q][r] = nobs_dst[q][r];
+    }
     a.flag_dst[r] = flag_dst[r];
   }
   a.done = done;
   a.world = world;
-  a.epoch = epoch;
+  a.epoch_ptr = epoch_ptr;
   a.push = 1;
   a.out_off = out_off;
   return mode == MODE_LINEAR ? launch_pass<MODE_LINEAR, 1>(h, o, a, st) : launch_pass<MODE_BRANCHING, 2>(h, o, a, st);

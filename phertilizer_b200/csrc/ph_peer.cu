@@ -22,8 +22,10 @@ struct ph_peer {
   size_t off_cnt, off_lab, off_nobs, off_lab2, off_nobs2, bytes;  // *2: second output buffer (SNV-sharded steps alternate)
   uint8_t* win[PH_MAX_PEERS];  // win[rank] = own allocation, others = IPC mappings
   bool opened[PH_MAX_PEERS];
-  unsigned* d_done;            // [2] CTA completion counters (pass, finish) + [1] spin-timeout flag
-  uint32_t epoch;
+  unsigned* d_done;            // [0],[1] CTA completion counters (pass, finish), [2] spin-timeout flag,
+                               // [3] collect completion counter, [4] step counter ("epoch"), advanced by the last
+                               // block of every collect kernel: no launch parameter changes from step to step, so a
+                               // step can be captured in a CUDA graph and replayed
 };
 
 namespace {
@@ -66,12 +68,13 @@ struct FinishArgs {
   uint32_t* flag_dst[PH_MAX_PEERS];
   unsigned* done;
   unsigned* timeout_flag;
-  uint32_t epoch;
+  const uint32_t* epoch_ptr;
 };
 
 template <int C>
 __global__ void __launch_bounds__(256) k_peer_finish(const FinishArgs a) {
-  wait_flags(reinterpret_cast<const uint32_t*>(a.win), a.world, a.epoch, a.timeout_flag);
+  const uint32_t epoch = *a.epoch_ptr + 1u;
+  wait_flags(reinterpret_cast<const uint32_t*>(a.win), a.world, epoch, a.timeout_flag);
   const int first = a.rank * a.blk;
   const int n_own = min(a.blk, a.n_list - first);
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_own; idx += gridDim.x * blockDim.x) {
@@ -128,20 +131,36 @@ __global__ void __launch_bounds__(256) k_peer_finish(const FinishArgs a) {
       *a.done = 0;
       __threadfence_system();
       for (int p = 0; p < a.world; ++p)
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.flag_dst[p]), "r"(a.epoch) : "memory");
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.flag_dst[p]), "r"(epoch) : "memory");
     }
   }
 }
 
+// waits for the step's flags, copies the output window (parity buffer of the step when `off_lab2` != 0) to the caller,
+// and the last block to finish advances the step counter
 __global__ void __launch_bounds__(256) k_peer_collect(const uint8_t* win, size_t off_flags, size_t off_lab, size_t off_nobs,
-                                                     int world, uint32_t epoch, int n_list, int C, uint8_t* label_out,
+                                                     size_t off_lab2, size_t off_nobs2, int world, uint32_t* epoch_ptr,
+                                                     unsigned* done, int n_list, int C, uint8_t* label_out,
                                                      int32_t* nobs_out, unsigned* timeout_flag) {
+  const uint32_t epoch = *epoch_ptr + 1u;
   wait_flags(reinterpret_cast<const uint32_t*>(win + off_flags), world, epoch, timeout_flag);
+  if (off_lab2 && (epoch & 1u)) {
+    off_lab = off_lab2;
+    off_nobs = off_nobs2;
+  }
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
   const uint32_t* src_n = reinterpret_cast<const uint32_t*>(win + off_nobs);
   for (int i = tid; i < n_list * C; i += nt) nobs_out[i] = (int32_t)__ldcv(src_n + i);
   const uint8_t* src_l = win + off_lab;
   for (int i = tid; i < n_list; i += nt) label_out[i] = __ldcv(src_l + i);
+  __syncthreads();  // every thread of the block has read the counter
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(done, 1u);
+    if (prev == gridDim.x - 1) {
+      *done = 0;
+      *epoch_ptr = epoch;
+    }
+  }
 }
 
 }  // namespace
@@ -149,11 +168,11 @@ __global__ void __launch_bounds__(256) k_peer_collect(const uint8_t* win, size_t
 // implemented in ph_pass.cu: the COUNTS pass with its peer destinations
 int ph_pass_counts(ph_handle* h, const uint8_t* cell_label, int C, const int32_t* snv_list, int32_t n_list,
                    uint16_t* const* cnt_dst, uint32_t* const* flag_dst, unsigned* done, int blk, int ncp, int world,
-                   uint32_t epoch, cudaStream_t st);
+                   const uint32_t* epoch_ptr, cudaStream_t st);
 
-int ph_pass_assign_push(ph_handle* h, int mode, const uint8_t* cell_label, double lenA, uint8_t* const* label_dst,
-                        int32_t* const* nobs_dst, uint32_t* const* flag_dst, unsigned* done, int out_off, int world,
-                        uint32_t epoch, cudaStream_t st);
+int ph_pass_assign_push(ph_handle* h, int mode, const uint8_t* cell_label, double lenA, uint8_t* const (*label_dst)[PH_MAX_PEERS],
+                        int32_t* const (*nobs_dst)[PH_MAX_PEERS], uint32_t* const* flag_dst, unsigned* done, int out_off,
+                        int world, const uint32_t* epoch_ptr, cudaStream_t st);
 
 extern "C" int ph_peer_handle_bytes(void) { return (int)sizeof(cudaIpcMemHandle_t); }
 
@@ -195,8 +214,8 @@ extern "C" int ph_peer_create(ph_handle* h, int rank, int world, int32_t total_s
   p->bytes = p->off_nobs2 + (size_t)p->max_lines * 3 * sizeof(int32_t) + 256;
   cudaError_t e = cudaMalloc(&p->win[rank], p->bytes);
   if (e == cudaSuccess) e = cudaMemset(p->win[rank], 0, p->bytes);
-  if (e == cudaSuccess) e = cudaMalloc(&p->d_done, 16);
-  if (e == cudaSuccess) e = cudaMemset(p->d_done, 0, 16);
+  if (e == cudaSuccess) e = cudaMalloc(&p->d_done, 64);
+  if (e == cudaSuccess) e = cudaMemset(p->d_done, 0, 64);
   if (e != cudaSuccess) {
     snprintf(ph_err_msg, sizeof(ph_err_msg), "peer window allocation failed: %s", cudaGetErrorString(e));
     ph_peer_destroy(p);
@@ -247,7 +266,7 @@ int peer_assign(ph_peer* p, int mode, const uint8_t* cell_label, double lenA, co
   cudaStream_t st = (cudaStream_t)stream;
   const int C = mode == 1 ? 1 : 2;
   const int blk = (n_list + p->world - 1) / p->world;
-  const uint32_t epoch = ++p->epoch;
+  const uint32_t* epoch_ptr = reinterpret_cast<const uint32_t*>(p->d_done + 4);
   const size_t slot = (size_t)p->blk_max * 3 * p->ncp;  // uint16 per source rank
 
   uint16_t* cnt_dst[PH_MAX_PEERS] = {};
@@ -261,7 +280,7 @@ int peer_assign(ph_peer* p, int mode, const uint8_t* cell_label, double lenA, co
     f.nobs_dst[r] = reinterpret_cast<int32_t*>(p->win[r] + p->off_nobs);
     f.flag_dst[r] = reinterpret_cast<uint32_t*>(p->win[r] + 1024) + p->rank;
   }
-  int rc = ph_pass_counts(h, cell_label, C, snv_list, n_list, cnt_dst, flagA_dst, p->d_done, blk, p->ncp, p->world, epoch, st);
+  int rc = ph_pass_counts(h, cell_label, C, snv_list, n_list, cnt_dst, flagA_dst, p->d_done, blk, p->ncp, p->world, epoch_ptr, st);
   if (rc != PH_OK) return rc;
 
   f.win = p->win[p->rank];
@@ -280,14 +299,15 @@ int peer_assign(ph_peer* p, int mode, const uint8_t* cell_label, double lenA, co
   f.L1 = h->d_L1;
   f.done = p->d_done + 1;
   f.timeout_flag = p->d_done + 2;
-  f.epoch = epoch;
+  f.epoch_ptr = epoch_ptr;
   const int fb = (blk + 255) / 256 < h->sm_count * 4 ? (blk + 255) / 256 : h->sm_count * 4;
   if (C == 1) k_peer_finish<1><<<fb > 0 ? fb : 1, 256, 0, st>>>(f);
   else k_peer_finish<2><<<fb > 0 ? fb : 1, 256, 0, st>>>(f);
   ph_count_launch();
   const int cb = (n_list * C + 255) / 256 < h->sm_count * 2 ? (n_list * C + 255) / 256 : h->sm_count * 2;
-  k_peer_collect<<<cb, 256, 0, st>>>(p->win[p->rank], (size_t)1024, p->off_lab, p->off_nobs, p->world, epoch, n_list, C,
-                                     label_out, nobs_out, p->d_done + 2);
+  k_peer_collect<<<cb, 256, 0, st>>>(p->win[p->rank], (size_t)1024, p->off_lab, p->off_nobs, (size_t)0, (size_t)0, p->world,
+                                     reinterpret_cast<uint32_t*>(p->d_done + 4), p->d_done + 3, n_list, C, label_out, nobs_out,
+                                     p->d_done + 2);
   ph_count_launch();
   PH_CUDA(cudaGetLastError());
   return PH_OK;
@@ -322,24 +342,26 @@ int peer_assign_snv(ph_peer* p, int mode, const uint8_t* cell_label, double lenA
   cudaStream_t st = (cudaStream_t)stream;
   const int C = mode == 1 ? 1 : 2;
   if (h->n_snvs <= 0) PH_FAIL(PH_ERR_ARG, "this rank holds no SNVs");
-  const uint32_t epoch = ++p->epoch;
-  // Outputs alternate between two buffers: a fast rank may already push step e+1 into a peer whose collect kernel
-  // still copies step e (its own step e+2 cannot start before that peer has finished step e, see the flag order).
-  const size_t off_lab = (epoch & 1) ? p->off_lab2 : p->off_lab, off_nobs = (epoch & 1) ? p->off_nobs2 : p->off_nobs;
-  uint8_t* lab_dst[PH_MAX_PEERS] = {};
-  int32_t* nobs_dst[PH_MAX_PEERS] = {};
+  // Outputs alternate between two buffers (parity of the step counter): a fast rank may already push step e+1 into a
+  // peer whose collect kernel still copies step e (its own step e+2 cannot start before that peer has finished step e,
+  // see the flag order).
+  uint8_t* lab_dst[2][PH_MAX_PEERS] = {};
+  int32_t* nobs_dst[2][PH_MAX_PEERS] = {};
   uint32_t* flag_dst[PH_MAX_PEERS] = {};
   for (int r = 0; r < p->world; ++r) {
-    lab_dst[r] = p->win[r] + off_lab;
-    nobs_dst[r] = reinterpret_cast<int32_t*>(p->win[r] + off_nobs);
+    lab_dst[0][r] = p->win[r] + p->off_lab;
+    lab_dst[1][r] = p->win[r] + p->off_lab2;
+    nobs_dst[0][r] = reinterpret_cast<int32_t*>(p->win[r] + p->off_nobs);
+    nobs_dst[1][r] = reinterpret_cast<int32_t*>(p->win[r] + p->off_nobs2);
     flag_dst[r] = reinterpret_cast<uint32_t*>(p->win[r]) + p->rank;
   }
-  int rc = ph_pass_assign_push(h, mode, cell_label, lenA, lab_dst, nobs_dst, flag_dst, p->d_done, snv_offset, p->world, epoch, st);
+  uint32_t* epoch_ptr = reinterpret_cast<uint32_t*>(p->d_done + 4);
+  int rc = ph_pass_assign_push(h, mode, cell_label, lenA, lab_dst, nobs_dst, flag_dst, p->d_done, snv_offset, p->world, epoch_ptr, st);
   if (rc != PH_OK) return rc;
   const int total = p->max_lines;
   const int cb = (total * C + 255) / 256 < h->sm_count * 2 ? (total * C + 255) / 256 : h->sm_count * 2;
-  k_peer_collect<<<cb, 256, 0, st>>>(p->win[p->rank], (size_t)0, off_lab, off_nobs, p->world, epoch, total, C, label_out,
-                                     nobs_out, p->d_done + 2);
+  k_peer_collect<<<cb, 256, 0, st>>>(p->win[p->rank], (size_t)0, p->off_lab, p->off_nobs, p->off_lab2, p->off_nobs2, p->world,
+                                     epoch_ptr, p->d_done + 3, total, C, label_out, nobs_out, p->d_done + 2);
   ph_count_launch();
   PH_CUDA(cudaGetLastError());
   return PH_OK;
