@@ -221,6 +221,8 @@ PH_API int ph_cell_node_table(ph_handle* h, const uint8_t* snv_node, const uint8
  * dims with var <= eps dropped, rank-dependent normaliser, -inf for rows off the support).
  *   X [n_cells * D] row-major float64 ; cell_node [n_cells], 255 = skip ; per_node [K] (0 for empty nodes)
  */
+/* Register the embedding once; ph_gauss_node_ll(X = NULL, on_device = 0) then uses the device copy. */
+PH_API int ph_set_embedding(ph_handle* h, const double* X, int32_t D);
 PH_API int ph_gauss_node_ll(ph_handle* h, const double* X, int32_t D, const uint8_t* cell_node, int32_t K,
                      double* per_node, double* per_cell, int on_device, void* stream);
 

@@ -300,6 +300,8 @@ extern "C" void ph_destroy(ph_handle* h) {
     cudaFree(o->tail_off);
   }
   cudaFree(h->d_lab_img);
+  cudaFree(h->d_emb);
+  cudaFree(h->d_gauss);
   cudaFree(h->d_L0);
   cudaFree(h->d_L1);
   cudaFree(h->d_varpos);

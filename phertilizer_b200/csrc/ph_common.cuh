@@ -70,6 +70,10 @@ struct ph_handle {
   int32_t n_cells, n_snvs, n_codes;
   int64_t nnz;
   PhOrient by_snv, by_cell;
+  uint8_t* d_gauss;  // scratch of ph_gauss_node_ll (grown on demand)
+  size_t gauss_bytes;
+  double* d_emb;     // [n_cells * emb_D] optional cached embedding (ph_set_embedding)
+  int emb_D;
   double* d_L0;      // [n_codes]
   double* d_L1;      // [n_codes]
   uint8_t* d_varpos; // [n_codes]

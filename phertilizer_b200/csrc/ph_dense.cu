@@ -14,18 +14,21 @@ namespace {
 // ---------------------------------------------------------------- K4
 // rows[] lists the cells of every node consecutively (stable order), node_off[k]..node_off[k+1].
 // stat pass: column sums of f(x) over the rows of node k, f = x (pass 0) or (x-mean)^2 (pass 1).
-// block = 32 dims x 8 row lanes, grid = (ceil(D/32), K).  Fixed summation order -> deterministic.
-__global__ void k_gauss_stat(const double* __restrict__ X, int D, const int32_t* __restrict__ rows,
-                             const int32_t* __restrict__ node_off, const double* __restrict__ mean, int pass,
-                             double* __restrict__ out) {
+// block = DX dims x RL row lanes (32 x 8 for wide embeddings, 4 x 64 for the 2-D UMAP case), grid = (ceil(D/DX), K).
+// Fixed summation order -> deterministic.
+template <int DX, int RL>
+__global__ void __launch_bounds__(DX * RL) k_gauss_stat(const double* __restrict__ X, int D, const int32_t* __restrict__ rows,
+                                                        const int32_t* __restrict__ node_off,
+                                                        const double* __restrict__ mean, int pass,
+                                                        double* __restrict__ out) {
   const int k = blockIdx.y;
-  const int d = blockIdx.x * 32 + threadIdx.x;
+  const int d = blockIdx.x * DX + threadIdx.x;
   const int beg = node_off[k], end = node_off[k + 1];
   const int cnt = end - beg;
   double acc = 0.0;
   if (d < D && cnt > 0) {
     const double mu = pass ? mean[(size_t)k * D + d] : 0.0;
-    for (int r = beg + threadIdx.y; r < end; r += 8) {
+    for (int r = beg + threadIdx.y; r < end; r += RL) {
       const double x = X[(size_t)rows[r] * D + d];
       if (pass) {
         const double t = x - mu;
@@ -35,13 +38,13 @@ __global__ void k_gauss_stat(const double* __restrict__ X, int D, const int32_t*
       }
     }
   }
-  __shared__ double sh[8][33];
+  __shared__ double sh[RL][DX + 1];
   sh[threadIdx.y][threadIdx.x] = acc;
   __syncthreads();
   if (threadIdx.y == 0 && d < D) {
     double t = sh[0][threadIdx.x];
 #pragma unroll
-    for (int y = 1; y < 8; ++y) t += sh[y][threadIdx.x];
+    for (int y = 1; y < RL; ++y) t += sh[y][threadIdx.x];
     out[(size_t)k * D + d] = cnt > 0 ? t / (double)cnt : 0.0;
   }
 }
@@ -210,7 +213,14 @@ __global__ void __launch_bounds__(256) k_pdist(const double* __restrict__ X, int
 extern "C" int ph_gauss_node_ll(ph_handle* h, const double* X, int32_t D, const uint8_t* cell_node, int32_t K,
                                 double* per_node, double* per_cell, int on_device, void* stream) {
   if (!h) PH_FAIL(PH_ERR_ARG, "null handle");
-  if (!X || !cell_node || !per_node) PH_FAIL(PH_ERR_ARG, "null pointer");
+  if (!cell_node || !per_node) PH_FAIL(PH_ERR_ARG, "null pointer");
+  bool cached = false;
+  if (!X) {  // the embedding registered with ph_set_embedding
+    if (!h->d_emb || on_device) PH_FAIL(PH_ERR_ARG, "X is NULL and no embedding was registered (ph_set_embedding)");
+    X = h->d_emb;
+    D = h->emb_D;
+    cached = true;
+  }
   if (D < 1 || K < 1 || K > PH_MAX_TREE_NODES) PH_FAIL(PH_ERR_ARG, "D=%d K=%d out of range", D, K);
   PH_CUDA(cudaSetDevice(h->device));
   const int n = h->n_cells;
@@ -232,37 +242,58 @@ extern "C" int ph_gauss_node_ll(ph_handle* h, const double* X, int32_t D, const 
     for (int i = 0; i < n; ++i)
       if (lab[i] < K) rows[pos[lab[i]]++] = i;
   }
+  // scratch lives in the handle (grown on demand): with tens of GB allocated next to it, a cudaMalloc / cudaFree pair per
+  // buffer per call cost milliseconds, and find_best_tree scores hundreds of trees
   double *dX = nullptr, *d_mean = nullptr, *d_var = nullptr, *d_inv = nullptr, *d_cst = nullptr, *d_pc = nullptr, *d_pn = nullptr;
   int32_t *d_rows = nullptr, *d_off = nullptr;
   uint8_t* d_lab = nullptr;
   int rc = PH_OK;
   auto body = [&]() -> int {
     const size_t kd = (size_t)K * D;
-    PH_CUDA(cudaMalloc(&d_mean, kd * 8));
-    PH_CUDA(cudaMalloc(&d_var, kd * 8));
-    PH_CUDA(cudaMalloc(&d_inv, kd * 8));
-    PH_CUDA(cudaMalloc(&d_cst, (size_t)K * 4 * 8));
-    PH_CUDA(cudaMalloc(&d_rows, (size_t)(n > 0 ? n : 1) * 4));
-    PH_CUDA(cudaMalloc(&d_off, (size_t)(K + 1) * 4));
+    auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const bool need_x = !on_device && !cached;
+    const size_t need = 3 * up(kd * 8) + up((size_t)K * 4 * 8) + up((size_t)(n > 0 ? n : 1) * 4) + up((size_t)(K + 1) * 4) +
+                        up((size_t)n + 16) + up((size_t)K * 8) + up((size_t)n * 8) + (need_x ? up((size_t)n * D * 8) : 0);
+    if (need > h->gauss_bytes) {
+      cudaFree(h->d_gauss);
+      h->d_gauss = nullptr;
+      h->gauss_bytes = 0;
+      PH_CUDA(cudaMalloc(&h->d_gauss, need));
+      h->gauss_bytes = need;
+    }
+    uint8_t* cur = h->d_gauss;
+    auto take = [&](size_t b) { uint8_t* r = cur; cur += up(b); return r; };
+    d_mean = (double*)take(kd * 8);
+    d_var = (double*)take(kd * 8);
+    d_inv = (double*)take(kd * 8);
+    d_cst = (double*)take((size_t)K * 4 * 8);
+    d_rows = (int32_t*)take((size_t)(n > 0 ? n : 1) * 4);
+    d_off = (int32_t*)take((size_t)(K + 1) * 4);
+    d_lab = (uint8_t*)take((size_t)n + 16);
+    d_pn = (double*)take((size_t)K * 8);
+    d_pc = (double*)take((size_t)n * 8);
+    if (need_x) dX = (double*)take((size_t)n * D * 8);
     PH_CUDA(cudaMemcpyAsync(d_rows, rows.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
     PH_CUDA(cudaMemcpyAsync(d_off, off.data(), (size_t)(K + 1) * 4, cudaMemcpyHostToDevice, st));
     const double* Xd = X;
     const uint8_t* labd = cell_node;
     if (!on_device) {
-      PH_CUDA(cudaMalloc(&dX, (size_t)n * D * 8));
-      PH_CUDA(cudaMemcpyAsync(dX, X, (size_t)n * D * 8, cudaMemcpyHostToDevice, st));
-      PH_CUDA(cudaMalloc(&d_lab, (size_t)n + 16));
+      if (!cached) PH_CUDA(cudaMemcpyAsync(dX, X, (size_t)n * D * 8, cudaMemcpyHostToDevice, st));
       PH_CUDA(cudaMemcpyAsync(d_lab, lab.data(), n, cudaMemcpyHostToDevice, st));
-      Xd = dX;
+      Xd = cached ? X : dX;
       labd = d_lab;
-      PH_CUDA(cudaMalloc(&d_pn, (size_t)K * 8));
     }
-    if (!on_device || !per_cell) PH_CUDA(cudaMalloc(&d_pc, (size_t)n * 8));
     double* pc = (on_device && per_cell) ? per_cell : d_pc;
     double* pn = on_device ? per_node : d_pn;
     dim3 gs((D + 31) / 32, K), bs(32, 8);
-    k_gauss_stat<<<gs, bs, 0, st>>>(Xd, D, d_rows, d_off, nullptr, 0, d_mean);
-    k_gauss_stat<<<gs, bs, 0, st>>>(Xd, D, d_rows, d_off, d_mean, 1, d_var);
+    if (D <= 4) {
+      dim3 gs4((D + 3) / 4, K), bs4(4, 64);
+      k_gauss_stat<4, 64><<<gs4, bs4, 0, st>>>(Xd, D, d_rows, d_off, nullptr, 0, d_mean);
+      k_gauss_stat<4, 64><<<gs4, bs4, 0, st>>>(Xd, D, d_rows, d_off, d_mean, 1, d_var);
+    } else {
+      k_gauss_stat<32, 8><<<gs, bs, 0, st>>>(Xd, D, d_rows, d_off, nullptr, 0, d_mean);
+      k_gauss_stat<32, 8><<<gs, bs, 0, st>>>(Xd, D, d_rows, d_off, d_mean, 1, d_var);
+    }
     k_gauss_consts<<<K, 1024, 0, st>>>(d_var, D, d_inv, d_cst);
     k_gauss_logpdf<<<(n * 32 + 255) / 256, 256, 0, st>>>(Xd, n, D, labd, K, d_mean, d_inv, d_cst, pc);
     k_node_reduce_d<<<K, 1024, 0, st>>>(pc, d_rows, d_off, pn);
@@ -272,13 +303,25 @@ extern "C" int ph_gauss_node_ll(ph_handle* h, const double* X, int32_t D, const 
       PH_CUDA(cudaMemcpyAsync(per_node, pn, (size_t)K * 8, cudaMemcpyDeviceToHost, st));
       if (per_cell) PH_CUDA(cudaMemcpyAsync(per_cell, pc, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
     }
-    PH_CUDA(cudaStreamSynchronize(st));  // temporaries are freed below
+    PH_CUDA(cudaStreamSynchronize(st));  // host staging vectors go out of scope; the scratch is reused by the next call
     return PH_OK;
   };
   rc = body();
-  cudaFree(dX); cudaFree(d_mean); cudaFree(d_var); cudaFree(d_inv); cudaFree(d_cst); cudaFree(d_pc); cudaFree(d_pn);
-  cudaFree(d_rows); cudaFree(d_off); cudaFree(d_lab);
   return rc;
+}
+
+// keep the embedding (read_depth, data.py:14) on the device: ph_gauss_node_ll(X = NULL) then scores trees without
+// re-uploading it (find_best_tree scores hundreds of candidate trees, clonal_tree_list.py:196-234)
+extern "C" int ph_set_embedding(ph_handle* h, const double* X, int32_t D) {
+  if (!h || !X) PH_FAIL(PH_ERR_ARG, "null pointer");
+  if (D < 1) PH_FAIL(PH_ERR_ARG, "D=%d out of range", D);
+  PH_CUDA(cudaSetDevice(h->device));
+  cudaFree(h->d_emb);
+  h->d_emb = nullptr;
+  PH_CUDA(cudaMalloc(&h->d_emb, (size_t)h->n_cells * D * 8));
+  PH_CUDA(cudaMemcpy(h->d_emb, X, (size_t)h->n_cells * D * 8, cudaMemcpyHostToDevice));
+  h->emb_D = D;
+  return PH_OK;
 }
 
 extern "C" int ph_pairwise_dist(const double* X, int32_t n, int32_t D, int32_t row_begin, int32_t row_end, double* out,

@@ -87,6 +87,8 @@ class Phertilizer:
         # per-observation likelihoods become a (var,total) -> (like0, like1) table inside the store (295-306)
         store = ObservationStore.from_coo(len(self.cells), len(self.muts), cell_idx, mut_idx, vc["var"].to_numpy(),
                                           vc["total"].to_numpy(), alpha=alpha, max_copies=max_copies, device=device)
+        if hasattr(store, "set_embedding"):
+            store.set_embedding(embedding)       # tree scoring (K4) reads it hundreds of times
         self.data = Data(cell_lookup, mut_lookup, store, embedding, copy_distance, use_read_depth)
 
     # ------------------------------------------------------------------ small accessors

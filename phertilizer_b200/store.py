@@ -261,12 +261,21 @@ class ObservationStore:
             _lib.check(fn(self._h, _ptr(minor_node), _ptr(member), K, _ptr(lst), k, _ptr(T), 0, None))
         return T
 
+    def set_embedding(self, X):
+        """Keep the embedding on the device: `gauss_node_ll(X)` with the SAME array object then skips the upload."""
+        Xc = np.ascontiguousarray(X, dtype=np.float64)
+        _lib.check(_lib.lib().ph_set_embedding(self._h, _ptr(Xc), Xc.shape[1]))
+        self._emb = X
+
     def gauss_node_ll(self, X, cell_node, K, per_cell=False):
-        X = np.ascontiguousarray(X, dtype=np.float64)
         out = np.empty(K, np.float64)
         pc = np.empty(self.n_cells, np.float64) if per_cell else None
-        _lib.check(_lib.lib().ph_gauss_node_ll(self._h, _ptr(X), X.shape[1], _ptr(cell_node), K, _ptr(out), _ptr(pc), 0,
-                                               None))
+        if X is getattr(self, "_emb", None):
+            _lib.check(_lib.lib().ph_gauss_node_ll(self._h, None, 0, _ptr(cell_node), K, _ptr(out), _ptr(pc), 0, None))
+        else:
+            X = np.ascontiguousarray(X, dtype=np.float64)
+            _lib.check(_lib.lib().ph_gauss_node_ll(self._h, _ptr(X), X.shape[1], _ptr(cell_node), K, _ptr(out), _ptr(pc), 0,
+                                                   None))
         return (out, pc) if per_cell else out
 
     # ------------------------------------------------------------------ device-pointer calls (torch tensors, async)
