@@ -88,6 +88,16 @@ def _worker(rank, world, port, q):
         ok &= np.array_equal(nobs2, No)
         t = sh.snv_table(lab, 2, sub)
         ok &= np.array_equal(t["Nobs"], No) and np.allclose(t["S0"], S0, rtol=1e-12, atol=0) and np.allclose(t["S1"], S1, rtol=1e-12, atol=0)
+        # one (var,total) code table for all ranks (the peer exchange sums histograms indexed by code): the merged table of
+        # the ranks' blocks must be the table of the whole data set, in the same order, on every rank
+        from phertilizer_b200.sharded import global_pairs
+        from phertilizer_b200.store import encode_with_table, order_pairs, pair_counts
+
+        gv, gt = global_pairs(i["var"][keep], i["total"][keep])
+        ev, et = order_pairs(*pair_counts(i["var"], i["total"]))
+        ok &= np.array_equal(gv, ev) and np.array_equal(gt, et)
+        code = encode_with_table(i["var"][keep], i["total"][keep], gv, gt)
+        ok &= np.array_equal(gv[code], i["var"][keep]) and np.array_equal(gt[code], i["total"][keep])
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
@@ -107,10 +117,11 @@ def test_two_rank_gloo_sharded_assignment():
 
 
 def test_cell_blocks_cover_all_cells():
-    from phertilizer_b200.sharded import cell_block
+    from phertilizer_b200.sharded import cell_block, snv_block
 
     for n in (1, 7, 1427, 100000):
         for w in (1, 2, 3, 8):
+            assert [snv_block(n, r, w) for r in range(w)] == [cell_block(n, r, w) for r in range(w)]
             blocks = [cell_block(n, r, w) for r in range(w)]
             assert blocks[0][0] == 0 and blocks[-1][1] == n
             assert all(blocks[r][1] == blocks[r + 1][0] for r in range(w - 1))
