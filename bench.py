@@ -140,10 +140,11 @@ def run_reference(args):
         return
     import torch
 
-    from oracle.oracle_sparse import SparseOracle, threads
+    from oracle.oracle_sparse import SparseOracle, threads, use_all_cores
     from phertilizer_b200.like_lut import like_tables
     from phertilizer_b200.store import encode_pairs_device
 
+    use_all_cores()   # torchrun exports OMP_NUM_THREADS=1: the reference arm still gets every host core
     dev = "cuda:0" if torch.cuda.is_available() else "cpu"
     t0 = time.time()
     w = make_workload(args.workload, dev)
@@ -235,7 +236,14 @@ def run_ours(args):
     if snv_sharded:
         from phertilizer_b200.sharded import SnvShardedStore
 
-        snv_store = SnvShardedStore.from_coo(w["n"], m, w["cell"], w["snv"], w["var"], w["total"], rank, world, local)
+        try:
+            snv_store = SnvShardedStore.from_coo(w["n"], m, w["cell"], w["snv"], w["var"], w["total"], rank, world, local)
+        except _lib.PhError as e:   # raised on every rank alike (sharded.PeerExchange): fall back to cell sharding
+            log(f"[rank {rank}] SNV-sharded peer path unavailable ({e}); using --shard cells")
+            snv_sharded = False
+            w = make_workload(args.workload, dev, rank / world, (rank + 1) / world)
+            n_loc, m, nnz_loc, nnz_tot = w["n_local"], w["m"], w["nnz_local"], w["nnz_total"]
+    if snv_store is not None:
         st = snv_store.store
         nnz_loc = int(st.info()["nnz"])
         sharded, exchange = None, "snv-peer"
@@ -391,9 +399,10 @@ def run_ours(args):
     # ---------------- CPU baseline (rank 0, N = 1): the oracle port on the host cores, and a parity spot check ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        from oracle.oracle_sparse import SparseOracle, threads
+        from oracle.oracle_sparse import SparseOracle, threads, use_all_cores
         from phertilizer_b200.like_lut import like_tables
 
+        use_all_cores()
         t0 = time.time()
         L0, L1 = like_tables(pv, pt)
         colptr, row, code = host_csc(w, code_t)

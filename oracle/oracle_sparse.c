@@ -20,6 +20,15 @@
 #include <omp.h>
 #endif
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the baseline legs of bench.py ask for all host cores explicitly */
+void orc_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int orc_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

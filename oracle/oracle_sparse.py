@@ -103,3 +103,13 @@ class SparseOracle:
 
 def threads():
     return int(lib().orc_threads())
+
+
+def use_all_cores():
+    """All cores this process may run on, whatever OMP_NUM_THREADS says (torchrun sets it to 1 for its workers)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    lib().orc_set_threads(int(n))
+    return threads()

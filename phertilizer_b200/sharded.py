@@ -89,16 +89,33 @@ class PeerExchange:
         L = _lib.lib()
         self._lib, self._L = _lib, L
         self._p = C.c_void_p()
-        _lib.check(L.ph_peer_create(store._h, int(rank), int(world), int(total_snvs), C.byref(self._p)))
+        # Set-up is collective; a rank whose local step fails (unsupported shape, IPC not permitted in this container)
+        # must still take part in every collective below, or the others would wait forever.  Everyone learns the outcome.
         nb = L.ph_peer_handle_bytes()
-        mine = C.create_string_buffer(nb)
-        _lib.check(L.ph_peer_export(self._p, mine))
+        blob, err = None, None
+        try:
+            _lib.check(L.ph_peer_create(store._h, int(rank), int(world), int(total_snvs), C.byref(self._p)))
+            mine = C.create_string_buffer(nb)
+            _lib.check(L.ph_peer_export(self._p, mine))
+            blob = bytes(mine.raw)
+        except _lib.PhError as e:
+            err = str(e)
         blobs = [None] * world
-        dist.all_gather_object(blobs, bytes(mine.raw), group=group)
-        allb = C.create_string_buffer(b"".join(blobs), nb * world)
-        _lib.check(L.ph_peer_connect(self._p, allb))
-        dist.barrier(group=group)  # every window is mapped everywhere before the first kernel stores into one
+        dist.all_gather_object(blobs, blob, group=group)
+        if err is None and all(b is not None for b in blobs):
+            try:
+                _lib.check(L.ph_peer_connect(self._p, C.create_string_buffer(b"".join(blobs), nb * world)))
+            except _lib.PhError as e:
+                err = str(e)
+        elif err is None:
+            err = "a peer could not create its window"
+        errs = [None] * world
+        dist.all_gather_object(errs, err, group=group)  # also the barrier: every window is mapped before any kernel stores
         torch.cuda.synchronize()
+        bad = [f"rank {r}: {e}" for r, e in enumerate(errs) if e is not None]
+        if bad:
+            self.close()
+            raise _lib.PhError("peer-memory exchange unavailable (" + "; ".join(bad) + ")")
 
     def assign_linear(self, label_t, lenA, lab_out_t, nobs_out_t, list_t=None, k=0, stream=None):
         from .store import _ptr
@@ -147,24 +164,14 @@ class ShardedStore:
         self.peer = None
         self.exchange = "nccl"
         if exchange in ("auto", "peer") and self.world > 1 and isinstance(backend, CudaBackend):
-            # every rank must take the same branch: agree on the outcome of the set-up
-            ok, err = 1, None
+            # PeerExchange raises on EVERY rank if any rank failed, so all ranks take the same branch
             try:
                 self.peer = PeerExchange(backend.store, dist.get_rank(group), self.world, group)
-            except Exception as e:  # PhError (unsupported shape, IPC not permitted) -> the NCCL transport
-                ok, err = 0, e
-            flag = torch.tensor([ok], dtype=torch.int32, device=backend.device)
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
-            if int(flag.item()) == 1:
                 self.exchange = "peer"
-            else:
-                if self.peer is not None:
-                    self.peer.close()
-                    self.peer = None
+            except Exception as e:  # PhError (unsupported shape, IPC not permitted) -> the NCCL transport
                 if exchange == "peer":
-                    raise RuntimeError(f"peer-memory exchange unavailable: {err}")
-                if err is not None:
-                    print(f"[phertilizer_b200] peer-memory exchange unavailable ({err}); using the NCCL all-reduce")
+                    raise
+                print(f"[phertilizer_b200] {e}; using the NCCL all-reduce")
 
     @classmethod
     def from_coo(cls, n_cells, n_snvs, cell, snv, var, total, rank, world, device, alpha=0.001, max_copies=5, group=None,
@@ -295,7 +302,11 @@ class SnvShardedStore:
         st = ObservationStore.from_coo(n_cells, hi - lo, cell, snv, var, total, alpha=alpha, max_copies=max_copies,
                                        device=dev_index, pairs=global_pairs(var, total, group))
         dev = torch.device("cuda", dev_index)
-        return cls(st, n_cells, n_snvs, lo, hi, dev, group)
+        try:
+            return cls(st, n_cells, n_snvs, lo, hi, dev, group)
+        except Exception:
+            st.close()
+            raise
 
     def _stream(self):
         return self.torch.cuda.current_stream().cuda_stream
