@@ -12,6 +12,8 @@
  *   - a "label" array assigns every cell (or SNV) to a cluster: 0 = not in any cluster (excluded from the
  *     np.ix_ subset), 1..C = cluster index.  This is how `cells`, `cellsA`, `cellsB`, `muts`, ... index arrays of
  *     the reference are passed.
+ *   - label / node arrays are read 4 bytes at a time: device buffers passed with `on_device != 0` must be 4-byte
+ *     aligned and readable up to the next multiple of 4 bytes (any cudaMalloc'd or torch-allocated buffer is).
  *   - `on_device != 0`: every data pointer of the call is a device pointer on the handle's GPU and the call is
  *     enqueued on `stream` (a cudaStream_t passed as void*, may be NULL) WITHOUT synchronising.
  *     `on_device == 0`: pointers are host memory; the call stages them through pinned buffers, runs, copies
