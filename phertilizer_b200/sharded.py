@@ -260,6 +260,42 @@ class ShardedStore:
         p = packed.cpu().numpy().reshape(3, k, C)
         return {"S0": p[0], "S1": p[1], "Nobs": p[2].astype(np.int32)}
 
+    # ------------------------------------------------------------------ the rest of the store API under cell sharding
+    # (SURVEY 8e): K2 is local to the rank owning the cells, K3 and the tree log-likelihood all-reduce a handful of
+    # scalars.  Only CudaBackend: these go through the rank's ObservationStore host-buffer calls.
+    def cell_table(self, snv_label, Q, want=("S0", "S1", "Nobs", "Nvar")):
+        """Per-cell table of ALL cells on every rank: each rank computes its block, the blocks are all-gathered."""
+        t, d = self.torch, self.dist
+        loc = self.b.store.cell_table(snv_label, Q, want=want)
+        out = {}
+        for k, a in loc.items():
+            parts = [None] * self.world
+            if self.world > 1:
+                d.all_gather_object(parts, a, group=self.group)
+            else:
+                parts = [a]
+            out[k] = np.concatenate(parts, axis=0)
+        return out
+
+    def _sum(self, arr):
+        if self.world == 1:
+            return arr
+        t = self.torch.from_numpy(np.ascontiguousarray(arr)).to(self.b.device)
+        self.dist.all_reduce(t, group=self.group)
+        return t.cpu().numpy()
+
+    def block_sums(self, cell_label_global, C, snv_label, Q):
+        """K3 over all ranks: (sum0, sum1, nobs, nvar) [Q, C]; counts exact, sums = sum of per-rank partials."""
+        lab = np.zeros(self.hi - self.lo + 16, np.uint8)[: self.hi - self.lo]
+        lab[:] = np.asarray(cell_label_global, np.uint8)[self.lo:self.hi]
+        s0, s1, no, nv = self.b.store.block_sums(lab, C, snv_label, Q)
+        return self._sum(s0), self._sum(s1), self._sum(no), self._sum(nv)
+
+    def tree_loglik(self, cell_node_global, snv_node, present):
+        """Variant log-likelihood per tree node (clonal_tree.py:932-944) over all ranks."""
+        node = np.full(self.hi - self.lo + 16, 255, np.uint8)[: self.hi - self.lo]
+        node[:] = np.asarray(cell_node_global, np.uint8)[self.lo:self.hi]
+        return self._sum(self.b.store.tree_loglik(node, snv_node, present))
 
 
 def snv_block(n_snvs: int, rank: int, world: int):

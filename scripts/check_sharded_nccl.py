@@ -61,6 +61,20 @@ for stem, n, m, cell, snv, var, total in datasets():
             if not exact:
                 t1 = full.snv_table(lab, 2, sub); t2 = sh.snv_table(lab, 2, sub)
                 ok &= np.array_equal(t1["Nobs"], t2["Nobs"]) and np.allclose(t1["S0"], t2["S0"], rtol=1e-12, atol=0) and np.allclose(t1["S1"], t2["S1"], rtol=1e-12, atol=0)
+        if exchange == "peer":
+            # the rest of the store API under cell sharding: K2 (local + gather), K3 and tree log-likelihood (scalar all-reduce)
+            lab = np.zeros(n + 16, np.uint8)[:n]; lab[:] = rng.integers(0, 3, n)
+            sl = np.zeros(m + 16, np.uint8)[:m]; sl[:] = rng.integers(0, 3, m)
+            c1, c2 = full.cell_table(sl, 2), sh.cell_table(sl, 2)
+            ok &= all(np.array_equal(c1[k], c2[k]) for k in c1)
+            b1, b2 = full.block_sums(lab, 2, sl, 2), sh.block_sums(lab, 2, sl, 2)
+            ok &= np.array_equal(b1[2], b2[2]) and np.array_equal(b1[3], b2[3])
+            ok &= np.allclose(b1[0], b2[0], rtol=1e-12, atol=0) and np.allclose(b1[1], b2[1], rtol=1e-12, atol=0)
+            cn = np.full(n + 16, 255, np.uint8)[:n]; cn[lab > 0] = lab[lab > 0] - 1
+            sn = np.full(m + 16, 255, np.uint8)[:m]; sn[sl > 0] = sl[sl > 0] - 1
+            pres = np.array([[1, 0], [1, 1]], np.uint8)
+            ok &= np.allclose(full.tree_loglik(cn, sn, pres), sh.tree_loglik(cn, sn, pres), rtol=1e-12, atol=0)
+            if not ok: print(f"[rank {rank}] K2/K3/tree mismatch", stem)
         if sh.peer is not None:
             ok &= not sh.peer.timed_out()
             sh.peer.close()

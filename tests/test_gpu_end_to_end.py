@@ -118,3 +118,41 @@ def test_runs_fanout_equals_sequential_loop():
         if r[0].norm_loglikelihood > bl:
             bl, best_seq = r[0].norm_loglikelihood, i
     assert best_run(results) == best_seq
+
+
+def test_mid_size_run_matches_reference():
+    """4000 cells x 20000 SNVs (3.9 M observations): the unmodified reference's end-to-end result
+    (tests/golden/make_golden_mid.py, dense path) vs phertilizer_b200 on the GPU -- same candidate trees, same cell and SNV
+    assignments, log-likelihoods to 1e-9."""
+    import json
+    import os
+
+    from phertilizer_b200.phertilizer import Phertilizer
+    from tests.golden.make_golden_mid import RUN, make_inputs
+
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    if not os.path.exists(os.path.join(here, "mid_e2e.npz")):
+        pytest.skip("mid-size golden not generated")
+    meta = json.load(open(os.path.join(here, "mid_e2e.json")))
+    gold = np.load(os.path.join(here, "mid_e2e.npz"))
+    s, (vc, bc), digest = make_inputs()
+    if digest != meta["inputs_sha256"]:
+        pytest.skip("the seeded generator produced different inputs on this machine (torch CPU RNG): golden not comparable")
+    ph = Phertilizer(vc, bc, alpha=0.001, max_copies=5, mode="rd", dim_reduce=False)
+    with redirect_stdout(io.StringIO()):
+        tree, tree_list, loglikes = ph.phertilize(**RUN)
+    assert ph.params.minobs == meta["minobs"] and tree_list.size() == meta["n_trees"]
+    assert rel_close(loglikes.to_numpy(), gold["loglikes"], 1e-9)
+
+    def same(prefix, t):
+        assert sorted(int(v) for v in t.tree.nodes()) == list(gold[prefix + "nodes"])
+        assert sorted((int(a), int(b)) for a, b in t.tree.edges()) == [tuple(e) for e in gold[prefix + "edges"]]
+        for k in gold[prefix + "nodes"]:
+            assert np.array_equal(np.asarray(t.get_tip_cells(int(k)), np.int64), gold[f"{prefix}cells_{k}"])
+            assert np.array_equal(np.asarray(t.get_tip_muts(int(k))).astype(np.int64), gold[f"{prefix}muts_{k}"])
+
+    for i, t in enumerate(tree_list.get_all_trees()):
+        same(f"cand{i}_", t)
+    same("final_", tree)
+    assert rel_close(tree.norm_loglikelihood, float(meta["norm"]), 1e-9)
+    assert rel_close(tree.variant_likelihood, float(meta["variant_likelihood"]), 1e-9)
