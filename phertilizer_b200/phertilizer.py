@@ -24,6 +24,16 @@ from .store import ObservationStore
 from .utils import check_obs, power_calc
 
 
+def _factorize(col):
+    """(codes, uniques) with codes[i] the index of col[i] in uniques (any bijection: callers re-rank the uniques).
+    Small non-negative integer ids -- the usual case -- take a counting pass instead of pandas' hash table."""
+    a = col.to_numpy()
+    if a.dtype.kind in "iu" and len(a) and int(a.min()) >= 0 and int(a.max()) < (1 << 27):
+        seen = np.bincount(a, minlength=int(a.max()) + 1) > 0
+        return (np.cumsum(seen) - 1)[a], np.nonzero(seen)[0].astype(a.dtype)
+    return pd.factorize(col, sort=False)
+
+
 def _embed(bin_counts: np.ndarray, dim_reduce: bool) -> np.ndarray:
     """Row-normalise + UMAP (phertilizer.py:267-279) or the raw bins (284-285).  UMAP is third-party and stays so."""
     if not dim_reduce:
@@ -49,12 +59,12 @@ class Phertilizer:
         # Same labels and order as the reference; the per-observation string concatenation and label lookups (tens of
         # seconds at 2.4e7 observations) are done on the distinct (chr, mutation_id) pairs / cell ids only.
         vc = variant_count_data
-        cell_codes, cell_uniques = pd.factorize(vc["cell_id"], sort=False)
+        cell_codes, cell_uniques = _factorize(vc["cell_id"])
         cell_labels = np.sort(np.asarray(cell_uniques))
         cell_rank = pd.Series(np.arange(len(cell_labels)), index=cell_labels)[np.asarray(cell_uniques)].to_numpy()
         cell_idx = cell_rank[cell_codes]
-        chr_codes, chr_uniques = pd.factorize(vc["chr"], sort=False)
-        mid_codes, mid_uniques = pd.factorize(vc["mutation_id"], sort=False)
+        chr_codes, chr_uniques = _factorize(vc["chr"])
+        mid_codes, mid_uniques = _factorize(vc["mutation_id"])
         pair = chr_codes.astype(np.int64) * max(len(mid_uniques), 1) + mid_codes.astype(np.int64)
         n_pair_space = len(chr_uniques) * max(len(mid_uniques), 1)
         if n_pair_space <= (1 << 27):

@@ -120,22 +120,24 @@ def test_runs_fanout_equals_sequential_loop():
     assert best_run(results) == best_seq
 
 
-def test_mid_size_run_matches_reference():
-    """4000 cells x 20000 SNVs (3.9 M observations): the unmodified reference's end-to-end result
-    (tests/golden/make_golden_mid.py, dense path) vs phertilizer_b200 on the GPU -- same candidate trees, same cell and SNV
-    assignments, log-likelihoods to 1e-9."""
+@pytest.mark.parametrize("case", ["mid", "c2"])
+def test_mid_size_run_matches_reference(case):
+    """4000 x 20000 (3.9 M observations) and BASELINE config 2 itself, 10000 x 50000 (24 M): the unmodified reference's
+    end-to-end result (tests/golden/make_golden_mid.py, dense path) vs phertilizer_b200 on the GPU -- same candidate trees,
+    same cell and SNV assignments, log-likelihoods to 1e-9."""
     import json
     import os
 
     from phertilizer_b200.phertilizer import Phertilizer
-    from tests.golden.make_golden_mid import RUN, make_inputs
+    from tests.golden.make_golden_mid import CASES, make_inputs
 
+    RUN = CASES[case][1]
     here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-    if not os.path.exists(os.path.join(here, "mid_e2e.npz")):
-        pytest.skip("mid-size golden not generated")
-    meta = json.load(open(os.path.join(here, "mid_e2e.json")))
-    gold = np.load(os.path.join(here, "mid_e2e.npz"))
-    s, (vc, bc), digest = make_inputs()
+    if not os.path.exists(os.path.join(here, f"{case}_e2e.npz")):
+        pytest.skip(f"golden '{case}' not generated (tests/golden/make_golden_mid.py {case})")
+    meta = json.load(open(os.path.join(here, f"{case}_e2e.json")))
+    gold = np.load(os.path.join(here, f"{case}_e2e.npz"))
+    s, (vc, bc), digest = make_inputs(case)
     if digest != meta["inputs_sha256"]:
         pytest.skip("the seeded generator produced different inputs on this machine (torch CPU RNG): golden not comparable")
     ph = Phertilizer(vc, bc, alpha=0.001, max_copies=5, mode="rd", dim_reduce=False)
