@@ -16,9 +16,8 @@ g = load_golden(stem)
 vc, bc = frames_from_golden(g)
 ph = Phertilizer(vc, bc, mode="rd", dim_reduce=False)
 ref = squareform(pdist(np.asarray(ph.data.read_depth, float)))
-print("copy_distance exact fraction", np.mean(ph.data.copy_distance == ref), "max rel", np.max(np.abs(ph.data.copy_distance - ref) / np.maximum(ref, 1e-300)))
-if len(sys.argv) > 2 and sys.argv[2] == "scipydist":
-    ph.data.copy_distance = ref
+cd = ph.data.copy_distance.full()
+print("copy_distance exact fraction", np.mean(cd == ref), "max rel", np.max(np.abs(cd - ref) / np.maximum(ref, 1e-300)))
 pos = {}
 first = []
 
