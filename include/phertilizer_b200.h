@@ -148,8 +148,8 @@ PH_API int ph_finish_branching(const double* packed, int32_t n_list, uint8_t* la
  * rank receives the full label_out / nobs_out.  What travels between the GPUs is the integer (cluster, code) histogram
  * of every SNV, so the outputs are bit-identical to the single-GPU call for any number of ranks.  Collective: all
  * ranks must make the same sequence of calls.  Device pointers only, enqueued on `stream`.
- * Limits: 2..8 ranks of one node, <= 65535 cells per rank, <= 64 (var,total) codes (else PH_ERR_UNSUPPORTED: use
- * ph_snv_partial + an all-reduce).
+ * Limits: 1..8 ranks of one node (1 = the same kernels on a local window), <= 65535 cells per rank, <= 64 (var,total)
+ * codes (else PH_ERR_UNSUPPORTED: use ph_snv_partial + an all-reduce).
  */
 typedef struct ph_peer ph_peer;
 PH_API int ph_peer_handle_bytes(void);
@@ -163,8 +163,10 @@ PH_API int ph_peer_assign_branching(ph_peer* p, const uint8_t* cell_label, const
 /*
  * SNV-sharded variant: every rank holds ALL cells and the SNVs [snv_offset, snv_offset + n_snvs) of `total_snvs`
  * (ph_peer_create).  Per-SNV tables are independent across SNVs, so the pass needs no exchange of partial tables: the
- * kernel epilogue stores every SNV's label and counts into all ranks' output windows and label_out / nobs_out
- * [total_snvs (* 2)] are complete on every rank after the call.  `cell_label` covers all cells.
+ * kernel stores the labels and counts of every batch of 8 SNVs as one 64/128-byte record into all ranks' windows
+ * while it streams the next batch, and label_out / nobs_out [total_snvs (* 2)] are complete on every rank after the
+ * call.  `cell_label` covers all cells.  Blocks must be balanced: at most ceil(total_snvs / world) + 8 SNVs per rank
+ * (PH_ERR_UNSUPPORTED otherwise) and must not overlap.
  */
 PH_API int ph_peer_assign_linear_snv(ph_peer* p, const uint8_t* cell_label, double lenA, int32_t snv_offset,
                               uint8_t* label_out, int32_t* nobs_out, void* stream);

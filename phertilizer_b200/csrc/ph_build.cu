@@ -462,6 +462,7 @@ extern "C" int ph_create(int32_t n_cells, int32_t n_snvs, int64_t nnz, const int
   PH_TRY(cudaMalloc(&h->d_small, 4096 * sizeof(double)));
   PH_TRY(cudaMalloc(&h->d_map, 65 * 65 + 64));
   PH_TRY(cudaMalloc(&h->d_counter, 64));
+  PH_TRY(cudaMemset(h->d_counter, 0, 64));  // [0] batch dispenser, [1] CTA completion counter: both re-arm themselves
   h->device_bytes += (int64_t)nmax * (3 + 4 + 2 * PH_MAX_FAST_CLUSTERS * 12) + 4096 * 8;
   h->h_stage_bytes = (size_t)nmax * (2 * PH_MAX_FAST_CLUSTERS * 12 + 8) + (1 << 16);
   PH_TRY(cudaMallocHost(&h->h_stage, h->h_stage_bytes));
@@ -482,6 +483,7 @@ done:
     ph_destroy(h);
     return rc;
   }
+  cudaDeviceSynchronize();  // scratch initialisation (legacy stream) is complete before any caller stream uses it
   *out = h;
   return PH_OK;
 #undef PH_TRY

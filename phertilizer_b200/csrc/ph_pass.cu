@@ -41,17 +41,19 @@ struct PassArgs {
   const uint8_t* __restrict__ map;                       // MAPPED: [K+1][K+1] bytes, != 0 -> "present"
   int K;
   double* per_line;                                      // MAPPED
-  unsigned* counter;                                     // batch dispenser, zeroed before every launch
+  unsigned* counter;                                     // batch dispenser: zero at creation, re-armed by the last CTA of every launch
   // COUNTS (cell-sharded K1, ph_peer.cu): every line's (cluster, code) histogram row -> the window of the rank that
   // owns the line (peer memory over NVLink), then one release flag per peer when the whole grid is done
   uint16_t* cnt_dst[PH_MAX_PEERS];   // per owner: this rank's source slot in the owner's window
   uint32_t* flag_dst[PH_MAX_PEERS];  // per peer: where this rank's "partials landed" flag lives
   unsigned* done;                    // CTA completion counter (local, self-resetting)
   int blk, ncp, world, row_words;
-  // LINEAR / BRANCHING with push != 0 (SNV-sharded K1, ph_peer.cu): the line's label and counts go to position
-  // out_off + line of EVERY rank's output window instead of label_out / nobs_out; then the flag, as for COUNTS
-  uint8_t* label_dst[2][PH_MAX_PEERS];  // [parity of the step][rank]: outputs alternate between two windows
-  int32_t* nobs_dst[2][PH_MAX_PEERS];
+  // LINEAR / BRANCHING with push != 0 (SNV-sharded K1, ph_peer.cu): the outputs of a batch of 8 lines form one RECORD
+  // of 64 * Cq bytes (Cq = counts per line: 1 linear, 2 branching) -- labels at bytes 0..7, the int32 counts from byte
+  // 16 -- which the warp stores into this rank's region of EVERY rank's window with one 16-byte store per lane
+  // (a 64-byte NVLink write per peer and batch instead of 16 scattered 1- and 4-byte stores); then the flag, as for COUNTS
+  uint8_t* rec_dst[2][PH_MAX_PEERS];  // [parity of the step][rank]: records alternate between two regions
+  int32_t* hdr_dst[PH_MAX_PEERS];     // {out_off, n_work} of this rank in every rank's window (read by the collect kernel)
   int push, out_off;
   const uint32_t* epoch_ptr;  // step counter in device memory (step = *epoch_ptr + 1): launches are CUDA-graph replayable
 };
@@ -97,10 +99,23 @@ __device__ __forceinline__ void fill_label_image(uint8_t* img, const uint8_t* __
   for (int c = 0; c < NCH; ++c) {
     const int cnt = min(CH, n_minor - c * CH);
     const int nw = (cnt + 3) >> 2;
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(raw + (size_t)c * CH);  // buffers are padded to 4 B
+    const uint8_t* srcb = raw + (size_t)c * CH;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(srcb);  // buffers are padded to 4 B
     uint32_t* dst = reinterpret_cast<uint32_t*>(img + ((size_t)c << cb));
     if (tid < 4) dst[tid] = excl * 0x01010101u;
-    for (int i = tid; i < nw; i += nthreads) {
+    // whole 16-byte units of an aligned source go through 128-bit loads and stores (4x fewer round trips on the
+    // start-up path of every CTA); the rest, and unaligned sources, word by word
+    const int nv = (reinterpret_cast<uintptr_t>(srcb) & 15) == 0 ? (cnt >> 4) : 0;
+    for (int i = tid; i < nv; i += nthreads) {
+      const uint4 w = __ldg(reinterpret_cast<const uint4*>(srcb) + i);
+      uint4 o;
+      o.x = NODES ? clamp_nodes4(w.x, (uint32_t)K) : scale_labels4<NC>(w.x);
+      o.y = NODES ? clamp_nodes4(w.y, (uint32_t)K) : scale_labels4<NC>(w.y);
+      o.z = NODES ? clamp_nodes4(w.z, (uint32_t)K) : scale_labels4<NC>(w.z);
+      o.w = NODES ? clamp_nodes4(w.w, (uint32_t)K) : scale_labels4<NC>(w.w);
+      reinterpret_cast<uint4*>(dst + 4)[i] = o;
+    }
+    for (int i = 4 * nv + tid; i < nw; i += nthreads) {
       const uint32_t w = src[i];
       dst[4 + i] = NODES ? clamp_nodes4(w, (uint32_t)K) : scale_labels4<NC>(w);
     }
@@ -138,6 +153,8 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
   int32_t* s_ln = reinterpret_cast<int32_t*>(s_cnt + B * D * NC);
   uint32_t* s_ml = reinterpret_cast<uint32_t*>(s_ln + B);
 
+  unsigned bidx0 = 0;
+  if ((threadIdx.x & 31) == 0) bidx0 = atomicAdd(a.counter, 1u);  // first batch of this warp, consumed after the staging
   if (SMEM_LAB) fill_label_image<MODE == MODE_MAPPED, NC>(s_lab, a.minor_label, a.n_minor, NCH, cb, a.K, threadIdx.x, nthreads);
   if (MODE == MODE_MAPPED) {
     // rows: node of the line (K, K+1: not in the tree -> nothing counts); columns: node of the minor index
@@ -178,11 +195,10 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
     return SMEM_LAB ? (uint32_t)lab[addr] : (uint32_t)__ldg(lab + addr);
   };
 
-  for (;;) {
-    unsigned bidx = 0;
-    if (lane == 0) bidx = atomicAdd(a.counter, 1u);
-    bidx = __shfl_sync(FULL, bidx, 0);
-    if (bidx >= (unsigned)n_batches) break;
+  // The dispenser round trip never sits on the critical path: the first batch is drawn before the staging above is
+  // published (see `bidx0`), every following one while the holders finish the current batch.
+  unsigned bidx = __shfl_sync(FULL, bidx0, 0);
+  while (bidx < (unsigned)n_batches) {
     const int first = (int)bidx * B;
     const int nl = min(B, a.n_work - first);
 
@@ -206,6 +222,14 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
     if (lane < B) {
       s_ln[lane] = line;
       s_ml[lane] = h_ml;
+    }
+    // the holder's tail range: offsets loaded now, words pulled into L2 while the dense part streams
+    int64_t h_tb = 0, h_te = 0;
+    if (lane < B && have) {
+      h_tb = __ldg(a.tail_off + line);
+      h_te = __ldg(a.tail_off + line + 1);
+      for (int64_t r = h_tb; r < h_te; r += 32)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.tail_words + r));
     }
     for (int k = lane; k < B * D * NC; k += 32) s_cnt[k] = 0;
     if (MODE == MODE_COUNTS)
@@ -315,6 +339,8 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
       }
     }
     __syncwarp();
+    unsigned bnext = 0;
+    if (lane == 0) bnext = atomicAdd(a.counter, 1u);  // next batch: the round trip overlaps the holders' work
 
     // ---- holders: lane l finishes line l.  Every sum is  sum_code fma(count, L[code])  in ascending code order --
     // the dense codes from the batch counters, then the rare codes of the tail (words sorted by (code, address), so a
@@ -340,7 +366,7 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
       }
       {
         const uint8_t* h_maprow = (MODE == MODE_MAPPED) ? s_map + h_ml * K2 : nullptr;
-        const int64_t tb = __ldg(a.tail_off + line), te = __ldg(a.tail_off + line + 1);
+        const int64_t tb = h_tb, te = h_te;
         uint32_t cur = 0xffffffffu;
         unsigned rc[NC];
 #pragma unroll
@@ -387,11 +413,9 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
         // linear_split.py:229-234  like0.mean(axis=0) >= like1.mean(axis=0) -> mutsB (ties -> mutsB)
         const double m0 = s0[0] / a.lenA, m1 = s1[0] / a.lenA;
         const uint8_t lb = (m0 >= m1) ? 2 : 1;
-        if (a.push) {
-          for (int p = 0; p < a.world; ++p) {
-            a.label_dst[par][p][a.out_off + wi] = lb;
-            a.nobs_dst[par][p][a.out_off + wi] = (int32_t)nob[0];
-          }
+        if (B == 8 && a.push) {
+          reinterpret_cast<uint8_t*>(s_row32)[myl] = lb;
+          reinterpret_cast<int32_t*>(s_row32)[4 + myl] = (int32_t)nob[0];
         } else {
           a.label_out[wi] = lb;
           a.nobs_out[wi] = (int32_t)nob[0];
@@ -403,12 +427,10 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
         const double cC = s1[0] + s1[NC > 1 ? 1 : 0];
         const double mx = fmax(cA, fmax(cB, cC));
         const uint8_t lb = (cA == mx) ? 1 : ((cB == mx) ? 2 : 3);
-        if (a.push) {
-          for (int p = 0; p < a.world; ++p) {
-            a.label_dst[par][p][a.out_off + wi] = lb;
-            a.nobs_dst[par][p][2 * (size_t)(a.out_off + wi)] = (int32_t)nob[0];
-            a.nobs_dst[par][p][2 * (size_t)(a.out_off + wi) + 1] = (int32_t)nob[NC > 1 ? 1 : 0];
-          }
+        if (B == 8 && a.push) {
+          reinterpret_cast<uint8_t*>(s_row32)[myl] = lb;
+          reinterpret_cast<int32_t*>(s_row32)[4 + 2 * myl] = (int32_t)nob[0];
+          reinterpret_cast<int32_t*>(s_row32)[4 + 2 * myl + 1] = (int32_t)nob[NC > 1 ? 1 : 0];
         } else {
           a.label_out[wi] = lb;
           a.nobs_out[2 * (size_t)wi] = (int32_t)nob[0];
@@ -419,6 +441,16 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
       }
     }
     __syncwarp();
+    if (B == 8 && (MODE == MODE_LINEAR || MODE == MODE_BRANCHING) && a.push) {
+      // the batch's record -> every rank's window: lane = (peer, 16-byte piece)
+      constexpr int PIECES = MODE == MODE_LINEAR ? 4 : 8;
+      const uint4* src = reinterpret_cast<const uint4*>(s_row32);
+      for (int u = lane; u < a.world * PIECES; u += 32) {
+        const int p = u / PIECES, q = u - p * PIECES;
+        reinterpret_cast<uint4*>(a.rec_dst[par][p] + (size_t)bidx * (16 * PIECES))[q] = src[q];
+      }
+      __syncwarp();
+    }
     if (MODE == MODE_COUNTS) {
       // the batch's rows are consecutive in the owner's slot: 16-byte stores straight into peer memory
       const int upl = NC * a.ncp / 8;  // 16-byte units per line
@@ -431,16 +463,25 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
       }
       __syncwarp();
     }
+    bidx = __shfl_sync(FULL, bnext, 0);
   }
-  if (MODE == MODE_COUNTS || ((MODE == MODE_LINEAR || MODE == MODE_BRANCHING) && a.push)) {
-    // all partial rows (or pushed outputs) of this rank are on their way: make them visible system-wide, then the last CTA raises this
-    // rank's flag in every peer's window
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      const unsigned prev = atomicAdd(a.done, 1u);
-      if (prev == gridDim.x - 1) {
-        *a.done = 0;
+  // The last CTA to finish re-arms the batch dispenser for the next launch (no memset between launches).  Peer modes:
+  // all partial rows (or pushed records) of this rank are on their way -- make them visible system-wide first; the last
+  // CTA then raises this rank's flag in every peer's window.
+  const bool peer_mode = MODE == MODE_COUNTS || ((MODE == MODE_LINEAR || MODE == MODE_BRANCHING) && a.push);
+  if (peer_mode) __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(a.done, 1u);
+    if (prev == gridDim.x - 1) {
+      *a.done = 0;
+      *a.counter = 0;
+      if (peer_mode) {
+        if (MODE != MODE_COUNTS)
+          for (int p = 0; p < a.world; ++p) {
+            a.hdr_dst[p][0] = a.out_off;
+            a.hdr_dst[p][1] = a.n_work;
+          }
         __threadfence_system();
         for (int p = 0; p < a.world; ++p)
           asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.flag_dst[p]), "r"(epoch) : "memory");
@@ -598,8 +639,9 @@ size_t pass_smem_bytes(const ph_handle* h, const PhOrient* o, int mode, int NC, 
 template <int MODE, int NC>
 int launch_pass(ph_handle* h, const PhOrient* o, PassArgs& a, cudaStream_t st) {
   if (a.n_work <= 0) return PH_OK;
-  const int B = o->batch == 32 ? 32 : 8;
+  const int B = (o->batch == 32 && !a.push) ? 32 : 8;  // pushed records hold the 8 lines of a batch
   if (MODE == MODE_COUNTS) a.row_words = B * NC * a.ncp / 2;  // ncp is a multiple of 8: whole 16-byte units
+  if (a.push) a.row_words = MODE == MODE_LINEAR ? 16 : 32;     // one record
   int lut = 0, threads = 0;
   bool smem_lab = true;
   size_t smem = 0;
@@ -630,12 +672,16 @@ int launch_pass(ph_handle* h, const PhOrient* o, PassArgs& a, cudaStream_t st) {
     }
   }
   const int grid = h->sm_count * ctas;
-  a.counter = h->d_counter;
-  PH_CUDA(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned), st));
+  a.counter = h->d_counter;  // zero at creation, re-armed by the last CTA of every launch
+  if (!a.done) a.done = h->d_counter + 1;
 #define PH_LAUNCH(BB, SL, SS)                                                                                    \
   do {                                                                                                           \
     auto kern = k_pass<BB, MODE, NC, SL, SS>;                                                                    \
-    PH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->max_smem));          \
+    static int attr_dev = -1; /* opt-in shared memory: once per instantiation and device */                     \
+    if (attr_dev != h->device) {                                                                                 \
+      PH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->max_smem));        \
+      attr_dev = h->device;                                                                                      \
+    }                                                                                                            \
     kern<<<grid, threads, smem, st>>>(a);                                                                        \
   } while (0)
 #define PH_LAUNCH_B(BB)                                                        \
@@ -1131,10 +1177,10 @@ int ph_pass_counts(ph_handle* h, const uint8_t* cell_label, int C, const int32_t
   return C == 1 ? launch_pass<MODE_COUNTS, 1>(h, o, a, st) : launch_pass<MODE_COUNTS, 2>(h, o, a, st);
 }
 
-// SNV-sharded K1 + K1a (ph_peer.cu): this rank's SNVs, outputs pushed to every rank's window at out_off + line
-int ph_pass_assign_push(ph_handle* h, int mode, const uint8_t* cell_label, double lenA, uint8_t* const (*label_dst)[PH_MAX_PEERS],
-                        int32_t* const (*nobs_dst)[PH_MAX_PEERS], uint32_t* const* flag_dst, unsigned* done, int out_off,
-                        int world, const uint32_t* epoch_ptr, cudaStream_t st) {
+// SNV-sharded K1 + K1a (ph_peer.cu): this rank's SNVs, one record per batch of 8 lines pushed to every rank's window
+int ph_pass_assign_push(ph_handle* h, int mode, const uint8_t* cell_label, double lenA, uint8_t* const (*rec_dst)[PH_MAX_PEERS],
+                        int32_t* const* hdr_dst, uint32_t* const* flag_dst, unsigned* done, int out_off, int world,
+                        const uint32_t* epoch_ptr, cudaStream_t st) {
   PhOrient* o = &h->by_snv;
   PassArgs a;
   fill_common(h, o, a);
@@ -1143,10 +1189,8 @@ int ph_pass_assign_push(ph_handle* h, int mode, const uint8_t* cell_label, doubl
   a.n_work = o->n_major;
   a.minor_label = cell_label;
   for (int r = 0; r < world; ++r) {
-    for (int q = 0; q < 2; ++q) {
-      a.label_dst[q][r] = label_dst[q][r];
-      a.nobs_dst[q][r] = nobs_dst[q][r];
-    }
+    for (int q = 0; q < 2; ++q) a.rec_dst[q][r] = rec_dst[q][r];
+    a.hdr_dst[r] = hdr_dst[r];
     a.flag_dst[r] = flag_dst[r];
   }
   a.done = done;

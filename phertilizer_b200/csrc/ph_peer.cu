@@ -19,7 +19,8 @@ struct ph_peer {
   ph_handle* h;
   int rank, world;
   int32_t max_lines, blk_max, ncp;
-  size_t off_cnt, off_lab, off_nobs, off_lab2, off_nobs2, bytes;  // *2: second output buffer (SNV-sharded steps alternate)
+  size_t off_cnt, off_lab, off_nobs, off_rec[2], bytes;  // off_rec: the two record regions of the SNV-sharded steps
+  int32_t cap_recs;            // records (batches of 8 SNVs) one rank may push per step
   uint8_t* win[PH_MAX_PEERS];  // win[rank] = own allocation, others = IPC mappings
   bool opened[PH_MAX_PEERS];
   unsigned* d_done;            // [0],[1] CTA completion counters (pass, finish), [2] spin-timeout flag,
@@ -30,7 +31,9 @@ struct ph_peer {
 
 namespace {
 
-constexpr size_t kFlagBytes = 4096;  // flagA[world] at +0, flagB[world] at +1024
+constexpr size_t kFlagBytes = 4096;  // flagA[world] at +0, flagB[world] at +1024, SNV block headers {offset, count}[world] at +2048
+constexpr size_t kHdrOff = 2048;
+constexpr size_t kRecStride = 128;   // bytes reserved per record (64 used by linear steps, 128 by branching)
 constexpr long long kSpinLimit = 6000000000ll;  // ~3 s of SM clocks: a lost peer must not hang the GPU
 
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
@@ -163,6 +166,40 @@ __global__ void __launch_bounds__(256) k_peer_collect(const uint8_t* win, size_t
   }
 }
 
+// SNV-sharded steps: waits for the step's flags, unpacks the records of every rank's SNV block (ph_pass.cu, PassArgs::
+// rec_dst: 8 label bytes, then 8 * C int32 counts from byte 16) into the caller's arrays; the last block advances the step
+__global__ void __launch_bounds__(256) k_peer_collect_rec(const uint8_t* win, size_t off_rec0, size_t off_rec1, int cap_recs,
+                                                         int world, uint32_t* epoch_ptr, unsigned* done, int C, int max_lines,
+                                                         uint8_t* label_out, int32_t* nobs_out, unsigned* timeout_flag) {
+  __shared__ int s_hdr[2 * PH_MAX_PEERS];
+  const uint32_t epoch = *epoch_ptr + 1u;
+  wait_flags(reinterpret_cast<const uint32_t*>(win), world, epoch, timeout_flag);
+  if (threadIdx.x < 2 * world) s_hdr[threadIdx.x] = (int)__ldcv(reinterpret_cast<const uint32_t*>(win + kHdrOff) + threadIdx.x);
+  __syncthreads();
+  const uint8_t* rec = win + ((epoch & 1u) ? off_rec1 : off_rec0);
+  const int cap_lines = cap_recs * 8;
+  const int rb = 64 * C;  // record bytes in use
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  for (int idx = tid; idx < world * cap_lines; idx += nt) {
+    const int r = idx / cap_lines, j = idx - r * cap_lines;
+    const int off = s_hdr[2 * r], cnt = s_hdr[2 * r + 1];
+    if (j >= cnt || off + j >= max_lines) continue;
+    const uint8_t* b = rec + ((size_t)r * cap_recs) * kRecStride + (size_t)(j >> 3) * rb;
+    const int s = j & 7;
+    label_out[off + j] = __ldcv(b + s);
+    const uint32_t* cn = reinterpret_cast<const uint32_t*>(b + 16) + s * C;
+    for (int c = 0; c < C; ++c) nobs_out[(size_t)(off + j) * C + c] = (int32_t)__ldcv(cn + c);
+  }
+  __syncthreads();  // every thread of the block has read the counter
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(done, 1u);
+    if (prev == gridDim.x - 1) {
+      *done = 0;
+      *epoch_ptr = epoch;
+    }
+  }
+}
+
 }  // namespace
 
 // implemented in ph_pass.cu: the COUNTS pass with its peer destinations
@@ -170,9 +207,9 @@ int ph_pass_counts(ph_handle* h, const uint8_t* cell_label, int C, const int32_t
                    uint16_t* const* cnt_dst, uint32_t* const* flag_dst, unsigned* done, int blk, int ncp, int world,
                    const uint32_t* epoch_ptr, cudaStream_t st);
 
-int ph_pass_assign_push(ph_handle* h, int mode, const uint8_t* cell_label, double lenA, uint8_t* const (*label_dst)[PH_MAX_PEERS],
-                        int32_t* const (*nobs_dst)[PH_MAX_PEERS], uint32_t* const* flag_dst, unsigned* done, int out_off,
-                        int world, const uint32_t* epoch_ptr, cudaStream_t st);
+int ph_pass_assign_push(ph_handle* h, int mode, const uint8_t* cell_label, double lenA, uint8_t* const (*rec_dst)[PH_MAX_PEERS],
+                        int32_t* const* hdr_dst, uint32_t* const* flag_dst, unsigned* done, int out_off, int world,
+                        const uint32_t* epoch_ptr, cudaStream_t st);
 
 extern "C" int ph_peer_handle_bytes(void) { return (int)sizeof(cudaIpcMemHandle_t); }
 
@@ -191,8 +228,9 @@ extern "C" void ph_peer_destroy(ph_peer* p) {
 extern "C" int ph_peer_create(ph_handle* h, int rank, int world, int32_t total_snvs, ph_peer** out) {
   if (!h || !out) PH_FAIL(PH_ERR_ARG, "null argument");
   *out = nullptr;
-  if (world < 2 || world > PH_MAX_PEERS || rank < 0 || rank >= world)
-    PH_FAIL(PH_ERR_ARG, "rank %d / world %d outside 2..%d", rank, world, PH_MAX_PEERS);
+  // world = 1 is a degenerate but valid context (the window is local): the same kernels, no NVLink traffic
+  if (world < 1 || world > PH_MAX_PEERS || rank < 0 || rank >= world)
+    PH_FAIL(PH_ERR_ARG, "rank %d / world %d outside 1..%d", rank, world, PH_MAX_PEERS);
   if (total_snvs <= 0) total_snvs = h->n_snvs;  // cell-sharded: every rank holds all SNVs
   if (total_snvs < h->n_snvs) PH_FAIL(PH_ERR_ARG, "total_snvs=%d is less than the %d local SNVs", total_snvs, h->n_snvs);
   PH_CUDA(cudaSetDevice(h->device));
@@ -209,9 +247,12 @@ extern "C" int ph_peer_create(ph_handle* h, int rank, int world, int32_t total_s
   const size_t cnt_bytes = (size_t)world * p->blk_max * 3 * p->ncp * sizeof(uint16_t);
   p->off_lab = (p->off_cnt + cnt_bytes + 255) & ~(size_t)255;
   p->off_nobs = (p->off_lab + (size_t)p->max_lines + 255) & ~(size_t)255;
-  p->off_lab2 = (p->off_nobs + (size_t)p->max_lines * 3 * sizeof(int32_t) + 255) & ~(size_t)255;
-  p->off_nobs2 = (p->off_lab2 + (size_t)p->max_lines + 255) & ~(size_t)255;
-  p->bytes = p->off_nobs2 + (size_t)p->max_lines * 3 * sizeof(int32_t) + 256;
+  // SNV-sharded steps: every rank pushes its block as records of 8 SNVs into its own region of each window; blocks are
+  // expected to be balanced (at most ceil(total / world) + 8 SNVs per rank)
+  p->cap_recs = ((total_snvs + world - 1) / world + 8 + 7) / 8;
+  p->off_rec[0] = (p->off_nobs + (size_t)p->max_lines * 3 * sizeof(int32_t) + 255) & ~(size_t)255;
+  p->off_rec[1] = p->off_rec[0] + (size_t)world * p->cap_recs * kRecStride;
+  p->bytes = p->off_rec[1] + (size_t)world * p->cap_recs * kRecStride + 256;
   cudaError_t e = cudaMalloc(&p->win[rank], p->bytes);
   if (e == cudaSuccess) e = cudaMemset(p->win[rank], 0, p->bytes);
   if (e == cudaSuccess) e = cudaMalloc(&p->d_done, 64);
@@ -326,8 +367,8 @@ extern "C" int ph_peer_assign_branching(ph_peer* p, const uint8_t* cell_label, c
 
 // ---- SNV-sharded K1 + K1a: every rank holds ALL cells and the SNVs [snv_offset, snv_offset + n_snvs) of total_snvs.
 // Per-SNV tables are independent across SNVs, so the pass itself needs no exchange: the kernel epilogue stores each
-// SNV's label and counts straight into every rank's output window (NVLink peer stores), the last CTA raises the flag,
-// and k_peer_collect copies the assembled window out once all ranks' flags are up.  Two launches per step.
+// batch's labels and counts as one 64/128-byte record into every rank's window (NVLink peer stores), the last CTA raises
+// the flag, and k_peer_collect_rec unpacks the assembled window once all ranks' flags are up.  Two launches per step.
 namespace {
 int peer_assign_snv(ph_peer* p, int mode, const uint8_t* cell_label, double lenA, int32_t snv_offset, uint8_t* label_out,
                     int32_t* nobs_out, void* stream) {
@@ -342,26 +383,27 @@ int peer_assign_snv(ph_peer* p, int mode, const uint8_t* cell_label, double lenA
   cudaStream_t st = (cudaStream_t)stream;
   const int C = mode == 1 ? 1 : 2;
   if (h->n_snvs <= 0) PH_FAIL(PH_ERR_ARG, "this rank holds no SNVs");
-  // Outputs alternate between two buffers (parity of the step counter): a fast rank may already push step e+1 into a
-  // peer whose collect kernel still copies step e (its own step e+2 cannot start before that peer has finished step e,
+  if (h->n_snvs > p->cap_recs * 8)
+    PH_FAIL(PH_ERR_UNSUPPORTED, "%d local SNVs exceed the %d a balanced block may hold (ceil(total / world) + 8)", h->n_snvs,
+            p->cap_recs * 8);
+  // Records alternate between two regions (parity of the step counter): a fast rank may already push step e+1 into a
+  // peer whose collect kernel still unpacks step e (its own step e+2 cannot start before that peer has finished step e,
   // see the flag order).
-  uint8_t* lab_dst[2][PH_MAX_PEERS] = {};
-  int32_t* nobs_dst[2][PH_MAX_PEERS] = {};
+  uint8_t* rec_dst[2][PH_MAX_PEERS] = {};
+  int32_t* hdr_dst[PH_MAX_PEERS] = {};
   uint32_t* flag_dst[PH_MAX_PEERS] = {};
   for (int r = 0; r < p->world; ++r) {
-    lab_dst[0][r] = p->win[r] + p->off_lab;
-    lab_dst[1][r] = p->win[r] + p->off_lab2;
-    nobs_dst[0][r] = reinterpret_cast<int32_t*>(p->win[r] + p->off_nobs);
-    nobs_dst[1][r] = reinterpret_cast<int32_t*>(p->win[r] + p->off_nobs2);
+    for (int q = 0; q < 2; ++q) rec_dst[q][r] = p->win[r] + p->off_rec[q] + (size_t)p->rank * p->cap_recs * kRecStride;
+    hdr_dst[r] = reinterpret_cast<int32_t*>(p->win[r] + kHdrOff) + 2 * p->rank;
     flag_dst[r] = reinterpret_cast<uint32_t*>(p->win[r]) + p->rank;
   }
   uint32_t* epoch_ptr = reinterpret_cast<uint32_t*>(p->d_done + 4);
-  int rc = ph_pass_assign_push(h, mode, cell_label, lenA, lab_dst, nobs_dst, flag_dst, p->d_done, snv_offset, p->world, epoch_ptr, st);
+  int rc = ph_pass_assign_push(h, mode, cell_label, lenA, rec_dst, hdr_dst, flag_dst, p->d_done, snv_offset, p->world, epoch_ptr, st);
   if (rc != PH_OK) return rc;
-  const int total = p->max_lines;
-  const int cb = (total * C + 255) / 256 < h->sm_count * 2 ? (total * C + 255) / 256 : h->sm_count * 2;
-  k_peer_collect<<<cb, 256, 0, st>>>(p->win[p->rank], (size_t)0, p->off_lab, p->off_nobs, p->off_lab2, p->off_nobs2, p->world,
-                                     epoch_ptr, p->d_done + 3, total, C, label_out, nobs_out, p->d_done + 2);
+  const int total = p->world * p->cap_recs * 8;
+  const int cb = (total + 255) / 256 < h->sm_count * 2 ? (total + 255) / 256 : h->sm_count * 2;
+  k_peer_collect_rec<<<cb, 256, 0, st>>>(p->win[p->rank], p->off_rec[0], p->off_rec[1], p->cap_recs, p->world, epoch_ptr,
+                                         p->d_done + 3, C, p->max_lines, label_out, nobs_out, p->d_done + 2);
   ph_count_launch();
   PH_CUDA(cudaGetLastError());
   return PH_OK;
