@@ -359,6 +359,8 @@ extern "C" int ph_create(int32_t n_cells, int32_t n_snvs, int64_t nnz, const int
     h->bank_order = e ? atoi(e) : 1;
     e = getenv("PH_CTAS");  // pass kernels: CTAs per SM (1 x 1024 threads, or 2 x 512 when two label images fit)
     h->ctas_per_sm = e ? atoi(e) : 1;
+    e = getenv("PH_ALIGNED_IMAGE");  // pass kernels: label image at a 2^16-aligned shared address when it fits (default on)
+    h->aligned_image = e ? atoi(e) : 1;
   }
 
   int rc = PH_OK;

@@ -25,6 +25,7 @@ struct PassArgs {
   const uint32_t* __restrict__ tail_words;
   const int64_t* __restrict__ tail_off;
   int D, NCH, NSUB, chunk_bits, minor_bits, n_minor, lab_bytes;
+  int tab_bytes;  // LAY = 2: bytes of everything but the label image (they go below the image when they fit)
   const uint8_t* __restrict__ minor_label;  // raw labels [n_minor] (SMEM_LAB) or the prepared label image (global)
   const int32_t* __restrict__ list;         // optional list of lines
   int n_work;
@@ -129,16 +130,25 @@ __host__ __device__ inline int warp_words(int B, int NSUB, int D, int NC) {
 
 // One warp walks a batch of B lines handed out by an atomic counter.  After the streaming phase lane (l % B) finishes
 // line l alone ("holder"): rare-code tail, fp64 sums, epilogue, store.
-// NC = counted classes; S16 = production layout (chunk stride 2^16: the label address is one PRMT).
-template <int B, int MODE, int NC, bool SMEM_LAB, bool S16>
+// NC = counted classes.  LAY = 0: any chunk stride; 1: production layout (chunk stride 2^16: the label address is one
+// PRMT of the entry and the chunk base); 2: as 1 with the label image placed at a shared-memory address that is a
+// multiple of 2^16, so that the PRMT yields the complete shared-window address and the gather is a bare LDS.U8 [reg]
+// (no base add per observation).  The bytes below the image hold the per-warp tables.
+template <int B, int MODE, int NC, bool SMEM_LAB, int LAY>
 __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
+  constexpr bool S16 = LAY >= 1;
+  constexpr bool AL = LAY == 2;
   const int nthreads = blockDim.x;
   const int D = a.D, NCH = a.NCH, NSUB = a.NSUB, NS1 = NSUB + 1, cb = a.chunk_bits;
   const int K2 = a.K + 2;
-  // ---- shared memory carve-up: [label image][map][L0][L1][varpos][per-warp tables]
-  uint8_t* s_lab = smem;
+  // ---- shared memory carve-up: [label image][map][L0][L1][varpos][per-warp tables]; LAY = 2: the image starts at the
+  // next multiple of 2^16 of the shared window and the tables sit below it when they fit there (else behind it)
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
+  const uint32_t img_base = AL ? ((sbase + 0xFFFFu) & ~0xFFFFu) : sbase;  // shared-window address of the image
+  uint8_t* s_lab = smem + (img_base - sbase);
   size_t off = SMEM_LAB ? (size_t)a.lab_bytes : 0;
+  if (AL) off = (img_base - sbase) >= (uint32_t)a.tab_bytes ? 0 : (size_t)(img_base - sbase) + (size_t)a.lab_bytes;
   uint8_t* s_map = smem + off;
   if (MODE == MODE_MAPPED) off += ((size_t)K2 * K2 + 15) & ~(size_t)15;
   double* s_L0 = reinterpret_cast<double*>(smem + off);
@@ -191,8 +201,16 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
   const uint32_t magic_nch = (65536u + (uint32_t)NCH - 1u) / (uint32_t)NCH;      // exact k / NCH for k < 256 * 32 / NCH
   const uint32_t magic_d = D > 0 ? (65536u + (uint32_t)D - 1u) / (uint32_t)D : 0u;  // exact key / D
 
-  auto label_at = [&](uint32_t addr) -> uint32_t {
+  auto label_at = [&](uint32_t addr) -> uint32_t {  // addr = offset into the label image
     return SMEM_LAB ? (uint32_t)lab[addr] : (uint32_t)__ldg(lab + addr);
+  };
+  auto label_dense = [&](uint32_t addr) -> uint32_t {  // LAY = 2: addr is the complete shared-window address
+    if (AL) {
+      uint32_t v;
+      asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));  // pure: the image is read-only after the staging barrier
+      return v;
+    }
+    return label_at(addr);
   };
 
   // The dispenser round trip never sits on the critical path: the first batch is drawn before the staging above is
@@ -286,11 +304,11 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
             gflush = gg;
             if (MODE == MODE_MAPPED) maprow = s_map + s_ml[(key * magic_d) >> 16] * K2;  // line = key / D
           }
-          cbase = ((uint32_t)k - key * (uint32_t)NCH) << cb;
+          cbase = (((uint32_t)k - key * (uint32_t)NCH) << cb) + (AL ? img_base : 0u);
           nb_eff = min(nb, gflush + kDeadline);
         };
         auto one = [&](uint32_t addr) -> uint32_t {
-          uint32_t sh = label_at(addr);
+          uint32_t sh = label_dense(addr);
           if (MODE == MODE_MAPPED) sh = maprow[sh];
           return 1u << sh;
         };
@@ -643,8 +661,19 @@ int launch_pass(ph_handle* h, const PhOrient* o, PassArgs& a, cudaStream_t st) {
   if (MODE == MODE_COUNTS) a.row_words = B * NC * a.ncp / 2;  // ncp is a multiple of 8: whole 16-byte units
   if (a.push) a.row_words = MODE == MODE_LINEAR ? 16 : 32;     // one record
   int lut = 0, threads = 0;
-  bool smem_lab = true;
+  bool smem_lab = true, aligned = false;
   size_t smem = 0;
+  // first choice: the label image at a 2^16-aligned shared address (LAY = 2).  Costs up to 64 KB of address space below
+  // the image (the tables live there), so it needs  64 KB + image + tables  to fit -- true for up to ~150 k minor indices.
+  if (o->chunk_bits == 16 && h->aligned_image) {
+    const size_t full = pass_smem_bytes(h, o, MODE, NC, a.K, true, 1024, B, a.row_words, &lut);
+    if (full && full + 65536 <= (size_t)h->max_smem) {
+      smem = full + 65536;
+      threads = 1024;
+      aligned = true;
+      a.tab_bytes = (int)(full - (size_t)o->lab_bytes);
+    }
+  }
   for (int pass = 0; pass < 2 && !smem; ++pass) {
     smem_lab = pass == 0;
     for (threads = 1024; threads >= 256 && !smem; threads >>= 1) smem = pass_smem_bytes(h, o, MODE, NC, a.K, smem_lab, threads, B, a.row_words, &lut);
@@ -662,7 +691,7 @@ int launch_pass(ph_handle* h, const PhOrient* o, PassArgs& a, cudaStream_t st) {
   }
   // one CTA of up to 32 warps per SM; PH_CTAS=2 halves the CTA instead when two copies of the image fit
   int ctas = 1;
-  if (h->ctas_per_sm == 2 && threads == 1024) {
+  if (h->ctas_per_sm == 2 && threads == 1024 && !aligned) {
     int lut2 = 0;
     const size_t smem2 = pass_smem_bytes(h, o, MODE, NC, a.K, smem_lab, 512, B, a.row_words, &lut2);
     if (smem2 && lut2 == lut && 2 * (smem2 + 1024) <= (size_t)h->smem_per_sm) {
@@ -686,9 +715,10 @@ int launch_pass(ph_handle* h, const PhOrient* o, PassArgs& a, cudaStream_t st) {
   } while (0)
 #define PH_LAUNCH_B(BB)                                                        \
   do {                                                                         \
-    if (!smem_lab) PH_LAUNCH(BB, false, false);                                \
-    else if (o->chunk_bits == 16) PH_LAUNCH(BB, true, true);                   \
-    else PH_LAUNCH(BB, true, false);                                           \
+    if (!smem_lab) PH_LAUNCH(BB, false, 0);                                    \
+    else if (aligned) PH_LAUNCH(BB, true, 2);                                  \
+    else if (o->chunk_bits == 16) PH_LAUNCH(BB, true, 1);                      \
+    else PH_LAUNCH(BB, true, 0);                                               \
   } while (0)
   if (B == 32) PH_LAUNCH_B(32);
   else PH_LAUNCH_B(8);
