@@ -183,7 +183,8 @@ def workload_config(args, w, world, residency, exchange=None, l2_policy=None):
                         f"(BASELINE.json configs[2]); step = linear-split SNV reassignment pass (K1+K1a) over all observations",
             "nnz": w["nnz_total"], "cells": c["n"], "snvs": c["m"], "coverage": c["cov"], "clones": c["K"],
             "sharding": ((f"SNVs sharded over {world} rank(s), all cells on every rank: per-SNV tables are independent, no partial-table "
-                          "exchange; labels + counts pushed to every rank over NVLink peer memory from the kernel epilogue (no NCCL)")
+                          "exchange; each batch's labels + counts pushed as one record to every rank over NVLink peer memory while the kernel streams on, "
+                          "the same launch then waits for the world's flags and unpacks the window (one kernel per step, no NCCL)")
                          if exchange == "snv-peer" else
                          (f"cells sharded over {world} rank(s); " + ("per-SNV integer histograms pushed to the owning rank over NVLink peer memory, labels pushed back (no NCCL)"
                                                                     if exchange == "peer" else "NCCL all-reduce of the [S0|S1|Nobs] table"))) if world > 1 else "single GPU",
@@ -262,7 +263,7 @@ def run_ours(args):
     flush_buf = torch.empty(2 * l2_bytes, dtype=torch.uint8, device=dev) if flush_l2 else None
     if flush_l2:
         l2_policy = (f"per-rank stream of {info['stream_bytes_by_snv'] / 1e6:.0f} MB is below 2 x L2 ({l2_bytes / 1e6:.0f} MB): L2 flushed (write of a "
-                     f"{2 * l2_bytes / 1e6:.0f} MB buffer, untimed) before every timed step, each step timed by its own CUDA event pair; label vectors rotate every step")
+                     f"{2 * l2_bytes / 1e6:.0f} MB buffer, untimed) before every timed step, each step timed by its own CUDA event pair after a device-side rendez-vous of the ranks; label vectors rotate every step")
     else:
         l2_policy = (f"inputs larger than L2 ({info['stream_bytes_by_snv'] / 1e9:.2f} GB of observations streamed per pass and rank vs "
                      f"{l2_bytes / 1e6:.0f} MB L2); label vectors rotate every step")
@@ -328,9 +329,21 @@ def run_ours(args):
     launches_per_step = _lib.kernel_launches() - l0 + (1 if exchange == "nccl" else 0)
     barrier()
     if args.cuda_graphs and exchange != "nccl":
-        # one CUDA graph per label set (memset of the batch counter + the step's kernels): the step is launch-bound at
-        # N > 1 (tens of microseconds of GPU work), so the host-side launch path is taken out of the loop
+        # One CUDA graph per label set (the step's kernel).  A step is one launch of tens of microseconds: graph replay
+        # takes the host launch path out of the loop, but graph-to-graph hand-over costs a few microseconds that plain
+        # back-to-back launches do not pay -- a short untimed trial of both decides (rank 0's verdict, for all ranks).
+        def trial(n=40):
+            barrier()
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record()
+            for i in range(n):
+                step_device(i)
+            b_.record()
+            barrier()
+            return a_.elapsed_time(b_) / n
+
         try:
+            t_eager = trial()
             captured = []
             for j in range(P):
                 g_ = torch.cuda.CUDAGraph()
@@ -340,6 +353,13 @@ def run_ours(args):
             graphs = captured
             for i in range(args.warmup):
                 step_device(i)
+            t_graph = trial()
+            keep = torch.tensor([1 if t_graph <= t_eager else 0], dtype=torch.int32, device=dev)
+            if world > 1:
+                dist.broadcast(keep, 0)
+            log(f"[rank {rank}] step trial: eager {1e3 * t_eager:.1f} us, graph replay {1e3 * t_graph:.1f} us")
+            if int(keep.item()) == 0:
+                graphs = None
             barrier()
         except Exception as e:  # capture not possible: stay eager
             log(f"[rank {rank}] CUDA graph capture failed ({e}); running eagerly")
@@ -367,8 +387,11 @@ def run_ours(args):
             # the rank's share of the observations would (partly) stay in L2 from one step to the next: every timed step
             # is preceded by an untimed write of a buffer twice the size of L2 and bracketed by its own pair of events
             pairs_ev = []
+            sync_t = torch.zeros(1, dtype=torch.int32, device=dev)
             for i in range(args.steps):
                 flush_buf.zero_()
+                if world > 1:
+                    dist.all_reduce(sync_t)   # device-side rendez-vous: the ranks' flushes end at different times, the step starts together
                 a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a_.record()
                 step_device(args.warmup + i, record=True)
@@ -490,7 +513,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic if world == 1 else None,
                          "kernel": "k_pass<MODE_LINEAR>" if world == 1 else ("k_pass<MODE_TABLE>" if exchange == "nccl" else
-                                   ("k_pass<MODE_LINEAR, push> + k_peer_collect (whole step)" if exchange == "snv-peer" else
+                                   ("k_pass<MODE_LINEAR, push + collect> (whole step = one launch)" if exchange == "snv-peer" else
                                     "k_pass<MODE_COUNTS> + k_peer_finish + k_peer_collect (whole step: kernel_ms includes the exchange)")),
                          "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": ab,
                          "physical_bytes_per_launch": phys, "physical_bytes_per_nnz": phys / max(nnz_loc, 1),

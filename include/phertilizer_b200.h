@@ -90,7 +90,8 @@ PH_API int ph_create(int32_t n_cells, int32_t n_snvs, int64_t nnz, const int32_t
 PH_API void ph_destroy(ph_handle* h);
 PH_API int ph_get_info(const ph_handle* h, ph_info* out);
 
-/* Tuning knob for experiments: SNVs / cells per warp batch (8 or 32; 16 means 8) ; 0 = keep. */
+/* Tuning knob: SNVs / cells per warp batch (4, 8 or 32; 16 means 8); -1 = automatic (4 for launches with fewer than
+ * two batches of 8 per warp of the grid, else 8); 0 = keep. */
 PH_API int ph_set_group(ph_handle* h, int group_by_snv, int group_by_cell);
 
 /*

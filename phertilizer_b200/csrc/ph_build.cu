@@ -202,7 +202,7 @@ int build_orient(ph_handle* h, PhOrient* o, const int32_t* d_major, const int32_
   const int NSUB = o->NSUB;
   const int64_t nseg = (int64_t)n_major * (NSUB + 1);
   if (nseg >= (1ll << 31)) PH_FAIL(PH_ERR_UNSUPPORTED, "too many segments (%lld)", (long long)nseg);
-  o->batch = 8;  // lines per warp batch (32 was slower on every measured shape; kept as a knob, ph_set_group)
+  o->batch = 0;  // lines per warp batch: automatic (8, or 4 in the quantisation band, see launch_pass); 4 / 8 / 32 via ph_set_group
   o->labels_in_smem = 1;
 
   const int threads = 256;
@@ -515,10 +515,12 @@ extern "C" int ph_get_info(const ph_handle* h, ph_info* out) {
 
 extern "C" int ph_set_group(ph_handle* h, int group_by_snv, int group_by_cell) {
   if (!h) PH_FAIL(PH_ERR_ARG, "null handle");
-  auto ok = [](int g) { return g == 0 || g == 8 || g == 16 || g == 32; };
-  if (!ok(group_by_snv) || !ok(group_by_cell)) PH_FAIL(PH_ERR_ARG, "group must be 0, 8, 16 or 32");
-  // lines per warp batch: 32 for short lines, 8 otherwise (16 is accepted for ABI compatibility and means 8)
-  if (group_by_snv) h->by_snv.batch = group_by_snv == 32 ? 32 : 8;
-  if (group_by_cell) h->by_cell.batch = group_by_cell == 32 ? 32 : 8;
+  auto ok = [](int g) { return g == 0 || g == -1 || g == 4 || g == 8 || g == 16 || g == 32; };
+  if (!ok(group_by_snv) || !ok(group_by_cell)) PH_FAIL(PH_ERR_ARG, "group must be -1, 0, 4, 8, 16 or 32");
+  // lines per warp batch: 4, 8 or 32 (16 is accepted for ABI compatibility and means 8); -1 = automatic (4 when the
+  // launch has fewer than two batches of 8 per warp, else 8); 0 = leave unchanged
+  auto val = [](int g) { return g == -1 ? 0 : (g == 32 ? 32 : (g == 4 ? 4 : 8)); };
+  if (group_by_snv) h->by_snv.batch = val(group_by_snv);
+  if (group_by_cell) h->by_cell.batch = val(group_by_cell);
   return PH_OK;
 }

@@ -98,6 +98,67 @@ struct ph_handle {
   cudaStream_t stream;   // private stream for host-pointer calls
 };
 
+// ---- peer-memory exchange helpers shared by ph_pass.cu and ph_peer.cu
+constexpr size_t kPeerHdrOff = 2048;   // window: flagA[world] at +0, flagB[world] at +1024, SNV block headers {offset, count, B, record bytes}[world] at +2048
+constexpr size_t kPeerRecStride = 128; // bytes reserved per 8 lines of a rank's record region (a record of B lines takes <= 16 B per line)
+constexpr long long kSpinLimit = 6000000000ll;  // ~3 s of SM clocks: a lost peer must not hang the GPU
+
+// what the collect phase of an SNV-sharded step needs (ph_peer.cu fills it, the pass kernel runs it)
+struct PhCollect {
+  const uint8_t* win;     // this rank's window
+  size_t off_rec[2];      // the two record regions (parity of the step)
+  int cap_recs, max_lines, C;
+  uint8_t* label_out;
+  int32_t* nobs_out;
+  unsigned* done;         // completion counter of the collect phase (self-resetting)
+  unsigned* timeout_flag;
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// thread 0 of the block polls `world` flags until each has reached `epoch`; ends with a block barrier
+__device__ __forceinline__ void wait_flags(const uint32_t* flags, int world, uint32_t epoch, unsigned* timeout_flag) {
+  if (threadIdx.x == 0) {
+    const long long t0 = clock64();
+    for (int q = 0; q < world; ++q) {
+      // epochs only grow; signed distance keeps the comparison valid across a 32-bit wrap
+      while ((int32_t)(ld_acquire_sys(flags + q) - epoch) < 0) {
+        if (clock64() - t0 > kSpinLimit) {
+          *timeout_flag = 1;
+          break;
+        }
+        __nanosleep(64);
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// Unpacks the records of every rank's SNV block (ph_pass.cu, PassArgs::rec_dst: B label bytes, then B * C int32 counts
+// from byte 16; B and the record size come with the block's header) into the caller's arrays.  s_hdr: 4 * world ints.
+__device__ __forceinline__ void unpack_records(const PhCollect& c, int world, uint32_t epoch, int* s_hdr, int tid, int nt) {
+  if (threadIdx.x < 4 * world) s_hdr[threadIdx.x] = (int)__ldcv(reinterpret_cast<const uint32_t*>(c.win + kPeerHdrOff) + threadIdx.x);
+  __syncthreads();
+  const uint8_t* rec = c.win + c.off_rec[epoch & 1u];
+  const int cap_lines = c.cap_recs * 8;
+  for (int idx = tid; idx < world * cap_lines; idx += nt) {
+    const int r = idx / cap_lines, j = idx - r * cap_lines;
+    const int off = s_hdr[4 * r], cnt = s_hdr[4 * r + 1], B = s_hdr[4 * r + 2], rb = s_hdr[4 * r + 3];
+    if (j >= cnt || off + j >= c.max_lines) continue;
+    const int q = j / B, s = j - q * B;
+    const uint8_t* b = rec + ((size_t)r * c.cap_recs) * kPeerRecStride + (size_t)q * rb;
+    c.label_out[off + j] = __ldcv(b + s);
+    const uint32_t* cn = reinterpret_cast<const uint32_t*>(b + 16) + s * c.C;
+    for (int k = 0; k < c.C; ++k) c.nobs_out[(size_t)(off + j) * c.C + k] = (int32_t)__ldcv(cn + k);
+  }
+}
+#endif
+
 static inline int ph_ceil_log2(uint64_t x) {
   int b = 0;
   while ((1ull << b) < x) ++b;

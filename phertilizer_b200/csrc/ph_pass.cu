@@ -49,13 +49,16 @@ struct PassArgs {
   uint32_t* flag_dst[PH_MAX_PEERS];  // per peer: where this rank's "partials landed" flag lives
   unsigned* done;                    // CTA completion counter (local, self-resetting)
   int blk, ncp, world, row_words;
-  // LINEAR / BRANCHING with push != 0 (SNV-sharded K1, ph_peer.cu): the outputs of a batch of 8 lines form one RECORD
-  // of 64 * Cq bytes (Cq = counts per line: 1 linear, 2 branching) -- labels at bytes 0..7, the int32 counts from byte
-  // 16 -- which the warp stores into this rank's region of EVERY rank's window with one 16-byte store per lane
-  // (a 64-byte NVLink write per peer and batch instead of 16 scattered 1- and 4-byte stores); then the flag, as for COUNTS
+  // LINEAR / BRANCHING with push != 0 (SNV-sharded K1, ph_peer.cu): the outputs of a batch of B <= 8 lines form one
+  // RECORD of 16 + 4 * B * Cq bytes rounded up to 16 (Cq = counts per line: 1 linear, 2 branching) -- labels at bytes
+  // 0..B-1, the int32 counts from byte 16 -- which the warp stores into this rank's region of EVERY rank's window with
+  // one 16-byte store per lane (one contiguous NVLink write per peer and batch instead of 2 * B scattered 1- and 4-byte
+  // stores); then the flag, as for COUNTS
   uint8_t* rec_dst[2][PH_MAX_PEERS];  // [parity of the step][rank]: records alternate between two regions
-  int32_t* hdr_dst[PH_MAX_PEERS];     // {out_off, n_work} of this rank in every rank's window (read by the collect kernel)
+  int32_t* hdr_dst[PH_MAX_PEERS];     // {out_off, n_work, B, record bytes} of this rank in every rank's window (for the collect kernel)
   int push, out_off;
+  PhCollect col;              // push: the collect phase, run by every CTA of the same launch once all flags are up
+  uint32_t* epoch_w;          // push: the step counter, advanced by the last CTA out of the collect phase
   const uint32_t* epoch_ptr;  // step counter in device memory (step = *epoch_ptr + 1): launches are CUDA-graph replayable
 };
 
@@ -156,7 +159,8 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
   uint8_t* s_vp = reinterpret_cast<uint8_t*>(s_L1 + (a.lut_in_smem ? a.n_codes : 0));
   if (a.lut_in_smem) off += ((size_t)a.n_codes * 17 + 15) & ~(size_t)15;
   const int wsz = warp_words(B, NSUB, D, NC) + a.row_words;  // both terms are multiples of 4 words
-  uint32_t* s_row32 = reinterpret_cast<uint32_t*>(smem + off) + (threadIdx.x >> 5) * wsz;
+  uint32_t* s_tab0 = reinterpret_cast<uint32_t*>(smem + off);  // start of the per-warp tables
+  uint32_t* s_row32 = s_tab0 + (threadIdx.x >> 5) * wsz;
   uint16_t* s_row = reinterpret_cast<uint16_t*>(s_row32);  // COUNTS: [B][NC][ncp] histogram rows of the batch
   uint32_t* s_b = s_row32 + a.row_words;
   uint32_t* s_cnt = s_b + B * NS1;
@@ -431,7 +435,7 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
         // linear_split.py:229-234  like0.mean(axis=0) >= like1.mean(axis=0) -> mutsB (ties -> mutsB)
         const double m0 = s0[0] / a.lenA, m1 = s1[0] / a.lenA;
         const uint8_t lb = (m0 >= m1) ? 2 : 1;
-        if (B == 8 && a.push) {
+        if (B <= 8 && a.push) {
           reinterpret_cast<uint8_t*>(s_row32)[myl] = lb;
           reinterpret_cast<int32_t*>(s_row32)[4 + myl] = (int32_t)nob[0];
         } else {
@@ -445,7 +449,7 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
         const double cC = s1[0] + s1[NC > 1 ? 1 : 0];
         const double mx = fmax(cA, fmax(cB, cC));
         const uint8_t lb = (cA == mx) ? 1 : ((cB == mx) ? 2 : 3);
-        if (B == 8 && a.push) {
+        if (B <= 8 && a.push) {
           reinterpret_cast<uint8_t*>(s_row32)[myl] = lb;
           reinterpret_cast<int32_t*>(s_row32)[4 + 2 * myl] = (int32_t)nob[0];
           reinterpret_cast<int32_t*>(s_row32)[4 + 2 * myl + 1] = (int32_t)nob[NC > 1 ? 1 : 0];
@@ -459,9 +463,9 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
       }
     }
     __syncwarp();
-    if (B == 8 && (MODE == MODE_LINEAR || MODE == MODE_BRANCHING) && a.push) {
+    if (B <= 8 && (MODE == MODE_LINEAR || MODE == MODE_BRANCHING) && a.push) {
       // the batch's record -> every rank's window: lane = (peer, 16-byte piece)
-      constexpr int PIECES = MODE == MODE_LINEAR ? 4 : 8;
+      constexpr int PIECES = (16 + 4 * B * (MODE == MODE_LINEAR ? 1 : 2) + 15) / 16;
       const uint4* src = reinterpret_cast<const uint4*>(s_row32);
       for (int u = lane; u < a.world * PIECES; u += 32) {
         const int p = u / PIECES, q = u - p * PIECES;
@@ -487,9 +491,10 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
   // all partial rows (or pushed records) of this rank are on their way -- make them visible system-wide first; the last
   // CTA then raises this rank's flag in every peer's window.
   const bool peer_mode = MODE == MODE_COUNTS || ((MODE == MODE_LINEAR || MODE == MODE_BRANCHING) && a.push);
-  if (peer_mode) __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
+    // one system-scope fence per CTA: the barrier orders the other threads' peer stores before it (cumulativity)
+    if (peer_mode) __threadfence_system();
     const unsigned prev = atomicAdd(a.done, 1u);
     if (prev == gridDim.x - 1) {
       *a.done = 0;
@@ -499,10 +504,27 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
           for (int p = 0; p < a.world; ++p) {
             a.hdr_dst[p][0] = a.out_off;
             a.hdr_dst[p][1] = a.n_work;
+            a.hdr_dst[p][2] = B;
+            a.hdr_dst[p][3] = 16 * ((16 + 4 * B * (MODE == MODE_LINEAR ? 1 : 2) + 15) / 16);
           }
         __threadfence_system();
         for (int p = 0; p < a.world; ++p)
           asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.flag_dst[p]), "r"(epoch) : "memory");
+      }
+    }
+  }
+  if ((MODE == MODE_LINEAR || MODE == MODE_BRANCHING) && a.push) {
+    // ---- collect phase, same launch: every CTA (all are resident: one per SM) waits until every rank's block has
+    // landed in this rank's window, then unpacks its slice of the records into the caller's arrays
+    wait_flags(reinterpret_cast<const uint32_t*>(a.col.win), a.world, epoch, a.col.timeout_flag);
+    int* s_hdr = reinterpret_cast<int*>(s_tab0);  // the per-warp tables are free now (all warps passed the barrier above)
+    unpack_records(a.col, a.world, epoch, s_hdr, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned prev = atomicAdd(a.col.done, 1u);
+      if (prev == gridDim.x - 1) {
+        *a.col.done = 0;
+        *a.epoch_w = epoch;  // next step
       }
     }
   }
@@ -657,9 +679,17 @@ size_t pass_smem_bytes(const ph_handle* h, const PhOrient* o, int mode, int NC, 
 template <int MODE, int NC>
 int launch_pass(ph_handle* h, const PhOrient* o, PassArgs& a, cudaStream_t st) {
   if (a.n_work <= 0) return PH_OK;
-  const int B = (o->batch == 32 && !a.push) ? 32 : 8;  // pushed records hold the 8 lines of a batch
+  // lines per warp batch: 8; 32 and 4 are knobs (ph_set_group).  Pushed records hold at most 8 lines.
+  int B = o->batch == 32 ? (a.push ? 8 : 32) : (o->batch == 4 ? 4 : 8);
+  if (o->batch == 0) {
+    // automatic: between one and two batches of 8 per warp of the grid the work quantises badly (some warps stream two
+    // batches, most one: 6250 batches on 4736 warps when 4 GPUs share C3, 71 -> 63 us) -- halve the batch there.  With
+    // fewer batches than warps, or many per warp, 8 is faster (measured, scripts/probe_snv_shard.py).
+    const int64_t nb8 = ((int64_t)a.n_work + 7) / 8, warps = (int64_t)h->sm_count * 32;
+    B = (nb8 > warps && nb8 < 2 * warps) ? 4 : 8;
+  }
   if (MODE == MODE_COUNTS) a.row_words = B * NC * a.ncp / 2;  // ncp is a multiple of 8: whole 16-byte units
-  if (a.push) a.row_words = MODE == MODE_LINEAR ? 16 : 32;     // one record
+  if (a.push) a.row_words = 4 * ((16 + 4 * B * (MODE == MODE_LINEAR ? 1 : 2) + 15) / 16);  // one record
   int lut = 0, threads = 0;
   bool smem_lab = true, aligned = false;
   size_t smem = 0;
@@ -721,6 +751,7 @@ int launch_pass(ph_handle* h, const PhOrient* o, PassArgs& a, cudaStream_t st) {
     else PH_LAUNCH(BB, true, 0);                                               \
   } while (0)
   if (B == 32) PH_LAUNCH_B(32);
+  else if (B == 4) PH_LAUNCH_B(4);
   else PH_LAUNCH_B(8);
 #undef PH_LAUNCH_B
 #undef PH_LAUNCH
@@ -1210,7 +1241,7 @@ int ph_pass_counts(ph_handle* h, const uint8_t* cell_label, int C, const int32_t
 // SNV-sharded K1 + K1a (ph_peer.cu): this rank's SNVs, one record per batch of 8 lines pushed to every rank's window
 int ph_pass_assign_push(ph_handle* h, int mode, const uint8_t* cell_label, double lenA, uint8_t* const (*rec_dst)[PH_MAX_PEERS],
                         int32_t* const* hdr_dst, uint32_t* const* flag_dst, unsigned* done, int out_off, int world,
-                        const uint32_t* epoch_ptr, cudaStream_t st) {
+                        uint32_t* epoch_ptr, const PhCollect& col, cudaStream_t st) {
   PhOrient* o = &h->by_snv;
   PassArgs a;
   fill_common(h, o, a);
@@ -1226,6 +1257,8 @@ int ph_pass_assign_push(ph_handle* h, int mode, const uint8_t* cell_label, doubl
   a.done = done;
   a.world = world;
   a.epoch_ptr = epoch_ptr;
+  a.epoch_w = epoch_ptr;
+  a.col = col;
   a.push = 1;
   a.out_off = out_off;
   return mode == MODE_LINEAR ? launch_pass<MODE_LINEAR, 1>(h, o, a, st) : launch_pass<MODE_BRANCHING, 2>(h, o, a, st);

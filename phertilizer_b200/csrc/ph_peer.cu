@@ -31,34 +31,9 @@ struct ph_peer {
 
 namespace {
 
-constexpr size_t kFlagBytes = 4096;  // flagA[world] at +0, flagB[world] at +1024, SNV block headers {offset, count}[world] at +2048
-constexpr size_t kHdrOff = 2048;
-constexpr size_t kRecStride = 128;   // bytes reserved per record (64 used by linear steps, 128 by branching)
-constexpr long long kSpinLimit = 6000000000ll;  // ~3 s of SM clocks: a lost peer must not hang the GPU
-
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-
-__device__ __forceinline__ void wait_flags(const uint32_t* flags, int world, uint32_t epoch, unsigned* timeout_flag) {
-  if (threadIdx.x == 0) {
-    const long long t0 = clock64();
-    for (int q = 0; q < world; ++q) {
-      // epochs only grow; signed distance keeps the comparison valid across a 32-bit wrap
-      while ((int32_t)(ld_acquire_sys(flags + q) - epoch) < 0) {
-        if (clock64() - t0 > kSpinLimit) {
-          *timeout_flag = 1;
-          break;
-        }
-        __nanosleep(64);
-      }
-    }
-  }
-  __syncthreads();
-}
-
+constexpr size_t kFlagBytes = 4096;  // flagA[world] at +0, flagB[world] at +1024, SNV block headers at kPeerHdrOff (ph_common.cuh)
+constexpr size_t kHdrOff = kPeerHdrOff;
+constexpr size_t kRecStride = kPeerRecStride;
 struct FinishArgs {
   const uint8_t* win;  // own window
   size_t off_cnt;
@@ -166,40 +141,6 @@ __global__ void __launch_bounds__(256) k_peer_collect(const uint8_t* win, size_t
   }
 }
 
-// SNV-sharded steps: waits for the step's flags, unpacks the records of every rank's SNV block (ph_pass.cu, PassArgs::
-// rec_dst: 8 label bytes, then 8 * C int32 counts from byte 16) into the caller's arrays; the last block advances the step
-__global__ void __launch_bounds__(256) k_peer_collect_rec(const uint8_t* win, size_t off_rec0, size_t off_rec1, int cap_recs,
-                                                         int world, uint32_t* epoch_ptr, unsigned* done, int C, int max_lines,
-                                                         uint8_t* label_out, int32_t* nobs_out, unsigned* timeout_flag) {
-  __shared__ int s_hdr[2 * PH_MAX_PEERS];
-  const uint32_t epoch = *epoch_ptr + 1u;
-  wait_flags(reinterpret_cast<const uint32_t*>(win), world, epoch, timeout_flag);
-  if (threadIdx.x < 2 * world) s_hdr[threadIdx.x] = (int)__ldcv(reinterpret_cast<const uint32_t*>(win + kHdrOff) + threadIdx.x);
-  __syncthreads();
-  const uint8_t* rec = win + ((epoch & 1u) ? off_rec1 : off_rec0);
-  const int cap_lines = cap_recs * 8;
-  const int rb = 64 * C;  // record bytes in use
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
-  for (int idx = tid; idx < world * cap_lines; idx += nt) {
-    const int r = idx / cap_lines, j = idx - r * cap_lines;
-    const int off = s_hdr[2 * r], cnt = s_hdr[2 * r + 1];
-    if (j >= cnt || off + j >= max_lines) continue;
-    const uint8_t* b = rec + ((size_t)r * cap_recs) * kRecStride + (size_t)(j >> 3) * rb;
-    const int s = j & 7;
-    label_out[off + j] = __ldcv(b + s);
-    const uint32_t* cn = reinterpret_cast<const uint32_t*>(b + 16) + s * C;
-    for (int c = 0; c < C; ++c) nobs_out[(size_t)(off + j) * C + c] = (int32_t)__ldcv(cn + c);
-  }
-  __syncthreads();  // every thread of the block has read the counter
-  if (threadIdx.x == 0) {
-    const unsigned prev = atomicAdd(done, 1u);
-    if (prev == gridDim.x - 1) {
-      *done = 0;
-      *epoch_ptr = epoch;
-    }
-  }
-}
-
 }  // namespace
 
 // implemented in ph_pass.cu: the COUNTS pass with its peer destinations
@@ -209,7 +150,7 @@ int ph_pass_counts(ph_handle* h, const uint8_t* cell_label, int C, const int32_t
 
 int ph_pass_assign_push(ph_handle* h, int mode, const uint8_t* cell_label, double lenA, uint8_t* const (*rec_dst)[PH_MAX_PEERS],
                         int32_t* const* hdr_dst, uint32_t* const* flag_dst, unsigned* done, int out_off, int world,
-                        const uint32_t* epoch_ptr, cudaStream_t st);
+                        uint32_t* epoch_ptr, const PhCollect& col, cudaStream_t st);
 
 extern "C" int ph_peer_handle_bytes(void) { return (int)sizeof(cudaIpcMemHandle_t); }
 
@@ -367,8 +308,9 @@ extern "C" int ph_peer_assign_branching(ph_peer* p, const uint8_t* cell_label, c
 
 // ---- SNV-sharded K1 + K1a: every rank holds ALL cells and the SNVs [snv_offset, snv_offset + n_snvs) of total_snvs.
 // Per-SNV tables are independent across SNVs, so the pass itself needs no exchange: the kernel epilogue stores each
-// batch's labels and counts as one 64/128-byte record into every rank's window (NVLink peer stores), the last CTA raises
-// the flag, and k_peer_collect_rec unpacks the assembled window once all ranks' flags are up.  Two launches per step.
+// batch's labels and counts as one record into every rank's window (NVLink peer stores) while it streams on, the last
+// CTA raises the flag, and every CTA of the SAME kernel then waits for the world's flags and unpacks its slice of the
+// assembled window into label_out / nobs_out.  ONE launch per step: pass, exchange and collect are one kernel.
 namespace {
 int peer_assign_snv(ph_peer* p, int mode, const uint8_t* cell_label, double lenA, int32_t snv_offset, uint8_t* label_out,
                     int32_t* nobs_out, void* stream) {
@@ -394,17 +336,23 @@ int peer_assign_snv(ph_peer* p, int mode, const uint8_t* cell_label, double lenA
   uint32_t* flag_dst[PH_MAX_PEERS] = {};
   for (int r = 0; r < p->world; ++r) {
     for (int q = 0; q < 2; ++q) rec_dst[q][r] = p->win[r] + p->off_rec[q] + (size_t)p->rank * p->cap_recs * kRecStride;
-    hdr_dst[r] = reinterpret_cast<int32_t*>(p->win[r] + kHdrOff) + 2 * p->rank;
+    hdr_dst[r] = reinterpret_cast<int32_t*>(p->win[r] + kHdrOff) + 4 * p->rank;
     flag_dst[r] = reinterpret_cast<uint32_t*>(p->win[r]) + p->rank;
   }
   uint32_t* epoch_ptr = reinterpret_cast<uint32_t*>(p->d_done + 4);
-  int rc = ph_pass_assign_push(h, mode, cell_label, lenA, rec_dst, hdr_dst, flag_dst, p->d_done, snv_offset, p->world, epoch_ptr, st);
+  PhCollect col;
+  col.win = p->win[p->rank];
+  col.off_rec[0] = p->off_rec[0];
+  col.off_rec[1] = p->off_rec[1];
+  col.cap_recs = p->cap_recs;
+  col.max_lines = p->max_lines;
+  col.C = C;
+  col.label_out = label_out;
+  col.nobs_out = nobs_out;
+  col.done = p->d_done + 3;
+  col.timeout_flag = p->d_done + 2;
+  int rc = ph_pass_assign_push(h, mode, cell_label, lenA, rec_dst, hdr_dst, flag_dst, p->d_done, snv_offset, p->world, epoch_ptr, col, st);
   if (rc != PH_OK) return rc;
-  const int total = p->world * p->cap_recs * 8;
-  const int cb = (total + 255) / 256 < h->sm_count * 2 ? (total + 255) / 256 : h->sm_count * 2;
-  k_peer_collect_rec<<<cb, 256, 0, st>>>(p->win[p->rank], p->off_rec[0], p->off_rec[1], p->cap_recs, p->world, epoch_ptr,
-                                         p->d_done + 3, C, p->max_lines, label_out, nobs_out, p->d_done + 2);
-  ph_count_launch();
   PH_CUDA(cudaGetLastError());
   return PH_OK;
 }

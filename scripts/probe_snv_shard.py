@@ -17,6 +17,7 @@ from phertilizer_b200.synth import CONFIGS, make_config
 name = sys.argv[1] if len(sys.argv) > 1 else "C3"
 parts = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 200
+groups = [int(x) for x in sys.argv[4].split(",")] if len(sys.argv) > 4 else [8]
 os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
 os.environ.setdefault("MASTER_PORT", "29547")
 dist.init_process_group("gloo", rank=0, world_size=1)
@@ -76,13 +77,15 @@ def bench(fn, graph, cold=False):
 
 plain = lambda i: st.assign_linear_dev(labs[i % 4], s.n / 2, lab_out, nobs_out, stream=torch.cuda.current_stream().cuda_stream)
 push = lambda i: sh.assign_linear_dev(labs[i % 4], s.n / 2, lab_out, nobs_out)
-out = {"config": name, "parts": parts, "cells": s.n, "snvs": s.m, "nnz": int(s.nnz), "stream_bytes": info["stream_bytes_by_snv"]}
-for label, fn in (("plain", plain), ("push+collect", push)):
-    for graph in (False, True):
-        us = bench(fn, graph)
-        out[f"{label}{'_graph' if graph else ''}_us"] = round(us, 2)
-    out[f"{label}_graph_cold_us"] = round(bench(fn, True, cold=True), 2)
-out["ideal_us_at_4TBps"] = round(info["stream_bytes_by_snv"] / 4.0e12 * 1e6, 2)
-print(json.dumps(out), flush=True)
+for grp in groups:
+    st.set_group(grp, grp)
+    out = {"config": name, "parts": parts, "group": grp, "cells": s.n, "snvs": s.m, "nnz": int(s.nnz), "stream_bytes": info["stream_bytes_by_snv"]}
+    for label, fn in (("plain", plain), ("push+collect", push)):
+        for graph in (False, True):
+            us = bench(fn, graph)
+            out[f"{label}{'_graph' if graph else ''}_us"] = round(us, 2)
+        out[f"{label}_graph_cold_us"] = round(bench(fn, True, cold=True), 2)
+    out["ideal_us_at_4TBps"] = round(info["stream_bytes_by_snv"] / 4.0e12 * 1e6, 2)
+    print(json.dumps(out), flush=True)
 sh.close()
 dist.destroy_process_group()

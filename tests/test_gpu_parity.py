@@ -309,11 +309,11 @@ def synth_env(request):
     st.close()
 
 
-@pytest.mark.parametrize("group", [8, 16, 32])
+@pytest.mark.parametrize("group", [4, 8, 16, 32, -1])
 def test_random_labels_all_group_sizes(synth_env, group):
     s, st, D = synth_env
     st.set_group(group, group)
-    rng = np.random.default_rng(100 + group)
+    rng = np.random.default_rng(100 + abs(group))
     for trial in range(3):
         C = int(rng.integers(1, 4))
         lab = np.zeros(s.n + 16, np.uint8)[: s.n]

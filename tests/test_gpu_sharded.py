@@ -45,6 +45,9 @@ def test_snv_sharded_records_one_rank():
             sh = SnvShardedStore.from_coo(s.n, s.m, cell, snv, var, total, 0, 1, 0)
             rng = np.random.default_rng(5)
             for trial in range(3):
+                group = (8, 4, -1)[trial]          # lines per batch = lines per pushed record
+                full.set_group(group, group)
+                sh.store.set_group(group, group)
                 lab = np.zeros(s.n + 16, np.uint8)[: s.n]
                 lab[:] = rng.integers(0, 3, s.n)
                 labA = np.zeros(s.n + 16, np.uint8)[: s.n]
