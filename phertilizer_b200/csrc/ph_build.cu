@@ -361,6 +361,8 @@ extern "C" int ph_create(int32_t n_cells, int32_t n_snvs, int64_t nnz, const int
     h->ctas_per_sm = e ? atoi(e) : 1;
     e = getenv("PH_ALIGNED_IMAGE");  // pass kernels: label image at a 2^16-aligned shared address when it fits (default on)
     h->aligned_image = e ? atoi(e) : 1;
+    e = getenv("PH_ZERO_COPY_OUT");  // host-pointer calls: kernels store results straight into page-locked host memory (default on)
+    h->zero_copy_out = e ? atoi(e) : 1;
   }
 
   int rc = PH_OK;

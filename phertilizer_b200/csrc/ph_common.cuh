@@ -78,7 +78,7 @@ struct ph_handle {
   double* d_L1;      // [n_codes]
   uint8_t* d_varpos; // [n_codes]
   int64_t device_bytes;
-  int chunk_bits, bank_order, ctas_per_sm, aligned_image;
+  int chunk_bits, bank_order, ctas_per_sm, aligned_image, zero_copy_out;
   double dense_min_avg, dense_min_share;  // a (var,total) code gets its own segment when it has >= this many entries per line on average
   // scratch (device)
   uint8_t* d_lab_minor;  // [max(n,m)] staged labels of the minor axis
