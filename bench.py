@@ -422,11 +422,12 @@ def run_ours(args):
             return st.assign_linear(labs_h[i % P].numpy()[:n_loc], lenA[i % P], out=(lab_out_np, nobs_out_np))
         labs_d[i % P].copy_(labs_h[i % P], non_blocking=True)
         if snv_store is not None:
-            snv_store.assign_linear_dev(labs_d[i % P], lenA[i % P], lab_out, nobs_out)
+            # the collect phase of the kernel unpacks straight into the page-locked host arrays (mapped memory): no D2H copy
+            snv_store.assign_linear_dev(labs_d[i % P], lenA[i % P], lab_out_h, nobs_out_h)
         else:
             sharded.assign_linear_dev(labs_d[i % P], lenA[i % P], packed, lab_out, nobs_out)
-        lab_out_h.copy_(lab_out, non_blocking=True)
-        nobs_out_h.copy_(nobs_out, non_blocking=True)
+            lab_out_h.copy_(lab_out, non_blocking=True)
+            nobs_out_h.copy_(nobs_out, non_blocking=True)
         torch.cuda.synchronize()
         return lab_out_h, nobs_out_h
 
@@ -506,8 +507,9 @@ def run_ours(args):
             "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n_loc) * world, "d2h_bytes_per_step": 5 * m * world,
                     "ms_per_step": 1e3 * e2e_s / args.steps,
-                    "path": "ph_assign_linear(on_device=0): host labels -> pinned -> H2D, kernel, D2H SNV labels + Nobs, sync"
-                            if world == 1 else ("pinned H2D labels, ph_peer_assign_linear(_snv), D2H labels + Nobs" if exchange in ("peer", "snv-peer") else
+                    "path": "ph_assign_linear(on_device=0): host labels -> pinned -> H2D, kernel storing SNV labels + Nobs into the page-locked host arrays, sync"
+                            if world == 1 else ("pinned H2D labels, ph_peer_assign_linear_snv unpacking straight into page-locked host arrays (labels + Nobs)" if exchange == "snv-peer" else
+                                                "pinned H2D labels, ph_peer_assign_linear, D2H labels + Nobs" if exchange == "peer" else
                                                 "pinned H2D labels, ph_snv_partial, NCCL all-reduce, ph_finish_linear, D2H labels + Nobs")},
             "gpu_launches": int(launches), "cuda_graphs": graphs is not None,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
