@@ -149,7 +149,7 @@ __device__ __forceinline__ void unpack_records(const PhCollect& c, int world, ui
   for (int idx = tid; idx < world * cap_lines; idx += nt) {
     const int r = idx / cap_lines, j = idx - r * cap_lines;
     const int off = s_hdr[4 * r], cnt = s_hdr[4 * r + 1], B = s_hdr[4 * r + 2], rb = s_hdr[4 * r + 3];
-    if (j >= cnt || off + j >= c.max_lines) continue;
+    if (B <= 0 || rb <= 0 || j >= cnt || off < 0 || off + j >= c.max_lines) continue;  // (a header that never arrived: timed-out wait)
     const int q = j / B, s = j - q * B;
     const uint8_t* b = rec + ((size_t)r * c.cap_recs) * kPeerRecStride + (size_t)q * rb;
     c.label_out[off + j] = __ldcv(b + s);

@@ -114,18 +114,13 @@ __global__ void __launch_bounds__(256) k_peer_finish(const FinishArgs a) {
   }
 }
 
-// waits for the step's flags, copies the output window (parity buffer of the step when `off_lab2` != 0) to the caller,
-// and the last block to finish advances the step counter
+// cell-sharded steps: waits for the owners' flags, copies the output window to the caller, and the last block to finish
+// advances the step counter
 __global__ void __launch_bounds__(256) k_peer_collect(const uint8_t* win, size_t off_flags, size_t off_lab, size_t off_nobs,
-                                                     size_t off_lab2, size_t off_nobs2, int world, uint32_t* epoch_ptr,
-                                                     unsigned* done, int n_list, int C, uint8_t* label_out,
-                                                     int32_t* nobs_out, unsigned* timeout_flag) {
+                                                     int world, uint32_t* epoch_ptr, unsigned* done, int n_list, int C,
+                                                     uint8_t* label_out, int32_t* nobs_out, unsigned* timeout_flag) {
   const uint32_t epoch = *epoch_ptr + 1u;
   wait_flags(reinterpret_cast<const uint32_t*>(win + off_flags), world, epoch, timeout_flag);
-  if (off_lab2 && (epoch & 1u)) {
-    off_lab = off_lab2;
-    off_nobs = off_nobs2;
-  }
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
   const uint32_t* src_n = reinterpret_cast<const uint32_t*>(win + off_nobs);
   for (int i = tid; i < n_list * C; i += nt) nobs_out[i] = (int32_t)__ldcv(src_n + i);
@@ -287,7 +282,7 @@ int peer_assign(ph_peer* p, int mode, const uint8_t* cell_label, double lenA, co
   else k_peer_finish<2><<<fb > 0 ? fb : 1, 256, 0, st>>>(f);
   ph_count_launch();
   const int cb = (n_list * C + 255) / 256 < h->sm_count * 2 ? (n_list * C + 255) / 256 : h->sm_count * 2;
-  k_peer_collect<<<cb, 256, 0, st>>>(p->win[p->rank], (size_t)1024, p->off_lab, p->off_nobs, (size_t)0, (size_t)0, p->world,
+  k_peer_collect<<<cb, 256, 0, st>>>(p->win[p->rank], (size_t)1024, p->off_lab, p->off_nobs, p->world,
                                      reinterpret_cast<uint32_t*>(p->d_done + 4), p->d_done + 3, n_list, C, label_out, nobs_out,
                                      p->d_done + 2);
   ph_count_launch();

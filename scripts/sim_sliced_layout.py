@@ -1,0 +1,110 @@
+"""CPU simulation of a candidate store layout (design aid for round 2, not product code).
+
+Today a warp streams 8 consecutive lines with lanes striding over the groups, so every lane crosses every sub-segment
+boundary.  Candidate: slices of 32 consecutive lines interleaved at 16-byte granularity, lane L streams line L, every
+(slice, sub-segment) padded to the slice's longest so that boundaries are warp-uniform.  Two unknowns are measured here
+on C3-shaped synthetic lines: (1) the padding that costs in HBM bytes, (2) shared-memory wavefronts per LDS.U8 request
+when 32 lanes gather labels of 32 different lines, with the round order rotated by the lane index.
+
+  python scripts/sim_sliced_layout.py [n_slices]
+"""
+import sys
+
+import numpy as np
+
+sys.path.insert(0, ".")
+from phertilizer_b200.like_lut import encode_pairs
+from phertilizer_b200.synth import CONFIGS, make_config
+
+n_slices = int(sys.argv[1]) if len(sys.argv) > 1 else 100
+CH, GE = 65520, 8
+cfg = CONFIGS["C3"]
+s = make_config("C3", with_embedding=False, m=32 * n_slices)
+cell, snv, var, total = (x.numpy() for x in (s.cell, s.snv, s.var, s.total))
+pv, pt, cnt, code = encode_pairs(var, total)
+D = 2                                   # dense codes of C3's by_snv orientation
+order = np.lexsort((cell, snv))
+cell, snv, code = cell[order], snv[order], code[order]
+starts = np.searchsorted(snv, np.arange(s.m + 1))
+NCH = (s.n + CH - 1) // CH
+
+
+def round_order(banks, rot):
+    """positions of a sub-segment's entries in round order: round k = k-th entry of every bank, banks visited from `rot`."""
+    key_bank = (banks - rot) % 32
+    o = np.argsort(key_bank, kind="stable")
+    kb = key_bank[o]
+    first = np.searchsorted(kb, kb)          # rank within the bank
+    rank = np.arange(len(kb)) - first
+    return o[np.lexsort((kb, rank))]
+
+
+def wavefronts(bank_matrix):
+    """bank_matrix [steps, 32] (-1 = padding entry, hits the shared 'excluded' word: broadcast) -> wavefronts per request."""
+    w = np.zeros(len(bank_matrix))
+    for i, row in enumerate(bank_matrix):
+        r = row[row >= 0]
+        w[i] = max(np.bincount(r, minlength=32).max() if len(r) else 0, 1)
+    return w
+
+
+# variant: lines permuted so that a slice holds lines of similar shape (sorted by their sub-segment sizes, the rarest
+# sub-segments most significant); the kernel's per-line results go back through the permutation
+sizes_all = np.zeros((s.m, D * NCH), int)
+for j in range(s.m):
+    c, k = cell[starts[j]:starts[j + 1]], code[starts[j]:starts[j + 1]]
+    for d in range(D):
+        for ch in range(NCH):
+            sizes_all[j, d * NCH + ch] = np.count_nonzero((k == d) & (c // CH == ch))
+g_all = (sizes_all + GE - 1) // GE
+perm = np.lexsort(tuple(g_all[:, q] for q in range(D * NCH)))   # last key (rarest sub-segment) most significant
+g_sorted = g_all[perm].reshape(n_slices, 32, D * NCH)
+groups_sorted = int((32 * g_sorted.max(axis=1)).sum())
+# variant 2: sort by the line's TOTAL groups only, sub-segment boundaries per lane (divergent), slice padded to its longest line
+tot = g_all.sum(axis=1)
+groups_total_sorted = int((32 * np.sort(tot).reshape(n_slices, 32).max(axis=1)).sum())
+groups_total_unsorted = int((32 * tot.reshape(n_slices, 32).max(axis=1)).sum())
+
+groups_now = groups_sliced = 0
+wf_now, wf_sliced, wf_sliced_norot = [], [], []
+for sl in range(n_slices):
+    per_line = []
+    for L in range(32):
+        j = sl * 32 + L
+        c, k = cell[starts[j]:starts[j + 1]], code[starts[j]:starts[j + 1]]
+        subs = []
+        for d in range(D):
+            for ch in range(NCH):
+                sel = c[(k == d) & (c // CH == ch)]
+                bank = ((16 + sel - ch * CH) // 4) % 32
+                subs.append(bank)
+        per_line.append(subs)
+    for q in range(D * NCH):
+        sizes = np.array([len(per_line[L][q]) for L in range(32)])
+        g_now = (sizes + GE - 1) // GE
+        groups_now += g_now.sum()
+        groups_sliced += 32 * g_now.max()
+        if sl < 12:  # bank behaviour: a few slices are enough
+            # today: one line, 32 consecutive entries of its round-ordered sequence per request
+            for L in range(0, 32, 8):
+                b = per_line[L][q]
+                seq = b[round_order(b, 0)]
+                pad = (-len(seq)) % 32
+                m_ = np.concatenate([seq, -np.ones(pad, int)]).reshape(-1, 32)
+                wf_now.append(wavefronts(m_))
+            # sliced: lane L is at the same position of ITS line
+            T = g_now.max() * GE
+            for rot, acc in ((True, wf_sliced), (False, wf_sliced_norot)):
+                M = -np.ones((T, 32), int)
+                for L in range(32):
+                    b = per_line[L][q]
+                    M[: len(b), L] = b[round_order(b, L if rot else 0)]
+                acc.append(wavefronts(M))
+print(f"lines {32 * n_slices}, observations {len(cell)}")
+print(f"groups today (8-entry padding)       : {groups_now}  ({groups_now * GE / len(cell):.4f} entries per dense+tail observation)")
+print(f"groups sliced (uniform sub-segments) : {groups_sliced}  (+{100 * (groups_sliced / groups_now - 1):.1f} % bytes)")
+print(f"  ... lines sorted by sub-segment sizes  : {groups_sorted}  (+{100 * (groups_sorted / groups_now - 1):.1f} % bytes)")
+print(f"  ... per-lane boundaries, slice padded to its longest line: unsorted +{100 * (groups_total_unsorted / groups_now - 1):.1f} %, "
+      f"lines sorted by length +{100 * (groups_total_sorted / groups_now - 1):.1f} %")
+print(f"LDS.U8 wavefronts per request  today: {np.concatenate(wf_now).mean():.2f}   sliced, rotated rounds: "
+      f"{np.concatenate(wf_sliced).mean():.2f}   sliced, unrotated: {np.concatenate(wf_sliced_norot).mean():.2f}")
