@@ -71,21 +71,28 @@ __device__ __forceinline__ double copy_at(const CopySrc& s, int ci, int cj) {
   return sqrt(acc);
 }
 
-// pass 1: max of d and of c over all pairs (their minima are the zero diagonals), NaN flag
-__global__ void k_aff_stats(const double* __restrict__ feat, int F, const CopySrc src,
-                            const int32_t* __restrict__ cells, int k, int use_copy, unsigned long long* red) {
+// pass 1: max of d and of c over all pairs (their minima are the zero diagonals), NaN flag.  d and c are symmetric bit
+// for bit ((a-b)^2 == (b-a)^2), so only tiles on or above the diagonal are evaluated.  32 x 32 tiles, 32 x 8 threads.
+__global__ void __launch_bounds__(256) k_aff_stats(const double* __restrict__ feat, int F, const CopySrc src,
+                                                   const int32_t* __restrict__ cells, int k, int use_copy,
+                                                   unsigned long long* red) {
+  if (blockIdx.y > blockIdx.x) return;  // tile row > tile column: the mirror image is evaluated instead
+  const int j = blockIdx.x * 32 + threadIdx.x;
   double md = 0.0, mc = 0.0;
   int nan = 0;
-  const size_t total = (size_t)k * k;
-  for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < total; p += (size_t)gridDim.x * blockDim.x) {
-    const int i = (int)(p / k), j = (int)(p - (size_t)i * k);
-    const double d = feat_dist(feat, F, i, j);
-    if (d != d) nan = 1;
-    md = fmax(md, d);
-    if (use_copy) {
-      const double c = copy_at(src, cells[i], cells[j]);
-      if (c != c) nan = 1;
-      mc = fmax(mc, c);
+  if (j < k) {
+    const int cj = use_copy ? cells[j] : 0;
+    for (int u = threadIdx.y; u < 32; u += 8) {
+      const int i = blockIdx.y * 32 + u;
+      if (i >= k) break;
+      const double d = feat_dist(feat, F, i, j);
+      if (d != d) nan = 1;
+      md = fmax(md, d);
+      if (use_copy) {
+        const double c = copy_at(src, cells[i], cj);
+        if (c != c) nan = 1;
+        mc = fmax(mc, c);
+      }
     }
   }
   // non-negative doubles order like their bit patterns
@@ -94,9 +101,9 @@ __global__ void k_aff_stats(const double* __restrict__ feat, int F, const CopySr
     mc = fmax(mc, __shfl_xor_sync(0xffffffffu, mc, o));
     nan |= __shfl_xor_sync(0xffffffffu, nan, o);
   }
-  if ((threadIdx.x & 31) == 0) {
-    atomicMax(red + 0, (unsigned long long)__double_as_longlong(md));
-    atomicMax(red + 1, (unsigned long long)__double_as_longlong(mc));
+  if (threadIdx.x == 0) {
+    if (md > 0.0) atomicMax(red + 0, (unsigned long long)__double_as_longlong(md));
+    if (mc > 0.0) atomicMax(red + 1, (unsigned long long)__double_as_longlong(mc));
     if (nan) atomicMax(red + 2, 1ull);
   }
 }
@@ -109,26 +116,44 @@ __global__ void k_aff_gather_c(const CopySrc src, const int32_t* __restrict__ ce
   }
 }
 
-// pass 2: W = exp(-1*d/kw) * copy_kernel
-__global__ void k_aff_build(const double* __restrict__ feat, int F, const CopySrc src,
-                            const int32_t* __restrict__ cells, int k, int use_copy, double kw, double kwc, double r,
-                            int strict, double* __restrict__ W, unsigned long long* red) {
-  const size_t total = (size_t)k * k;
+// pass 2: W = exp(-1*d/kw) * copy_kernel.  W is symmetric bit for bit (d and c are), so a 32 x 32 tile on or above the
+// diagonal is evaluated once and stored twice -- directly, and transposed through shared memory (both coalesced): half the
+// exp / sqrt / div work of the k^2 pairs.
+__global__ void __launch_bounds__(256) k_aff_build(const double* __restrict__ feat, int F, const CopySrc src,
+                                                   const int32_t* __restrict__ cells, int k, int use_copy, double kw,
+                                                   double kwc, double r, int strict, double* __restrict__ W,
+                                                   unsigned long long* red) {
+  if (blockIdx.y > blockIdx.x) return;
+  __shared__ double tile[32][33];
+  const int j = blockIdx.x * 32 + threadIdx.x;
+  const int cj = (use_copy && j < k) ? cells[j] : 0;
   int nan = 0;
-  for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < total; p += (size_t)gridDim.x * blockDim.x) {
-    const int i = (int)(p / k), j = (int)(p - (size_t)i * k);
-    const double d = feat_dist(feat, F, i, j);
-    double w = exp(__ddiv_rn(__dmul_rn(-1.0, d), kw));
-    if (use_copy) {
-      const double c = copy_at(src, cells[i], cells[j]);
-      double ck = exp(__ddiv_rn(__dmul_rn(-1.0, c), kwc));
-      if (strict ? (c >= r) : (c > r)) ck = 0.0;
-      w = __dmul_rn(w, ck);
+  for (int u = threadIdx.y; u < 32; u += 8) {
+    const int i = blockIdx.y * 32 + u;
+    double w = 0.0;
+    if (i < k && j < k) {
+      const double d = feat_dist(feat, F, i, j);
+      w = exp(__ddiv_rn(__dmul_rn(-1.0, d), kw));
+      if (use_copy) {
+        const double c = copy_at(src, cells[i], cj);
+        double ck = exp(__ddiv_rn(__dmul_rn(-1.0, c), kwc));
+        if (strict ? (c >= r) : (c > r)) ck = 0.0;
+        w = __dmul_rn(w, ck);
+      }
+      if (w != w) nan = 1;
+      W[(size_t)i * k + j] = w;
     }
-    if (w != w) nan = 1;
-    W[p] = w;
+    tile[u][threadIdx.x] = w;
   }
-  if (__any_sync(0xffffffffu, nan) && (threadIdx.x & 31) == 0) atomicMax(red + 2, 1ull);
+  if (blockIdx.y != blockIdx.x) {
+    __syncthreads();
+    const int jj = blockIdx.y * 32 + threadIdx.x;  // column of the mirrored tile = row of this one
+    for (int u = threadIdx.y; u < 32; u += 8) {
+      const int ii = blockIdx.x * 32 + u;          // row of the mirrored tile = column of this one
+      if (ii < k && jj < k) W[(size_t)ii * k + jj] = tile[threadIdx.x][u];
+    }
+  }
+  if (__any_sync(0xffffffffu, nan) && threadIdx.x == 0) atomicMax(red + 2, 1ull);
 }
 
 // w_j = sum_i W_ij with a zero diagonal, rows added in order (numpy's axis-0 reduction); dd = sqrt(w), 1 if isolated
@@ -136,16 +161,25 @@ __global__ void k_aff_degree(const double* __restrict__ W, int k, double* __rest
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= k) return;
   double s = 0.0;
-  for (int i = 0; i < k; ++i) s = __dadd_rn(s, i == j ? 0.0 : W[(size_t)i * k + j]);
+  int i = 0;
+  for (; i + 8 <= k; i += 8) {  // eight rows in flight, added in row order
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = W[(size_t)(i + u) * k + j];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s = __dadd_rn(s, (i + u) == j ? 0.0 : v[u]);
+  }
+  for (; i < k; ++i) s = __dadd_rn(s, i == j ? 0.0 : W[(size_t)i * k + j]);
   dd[j] = (s == 0.0) ? 1.0 : sqrt(s);
 }
 
-// L = -((W / dd[None, :]) / dd[:, None]), unit diagonal (csgraph_laplacian + _set_diag)
+// L = -((W / dd[None, :]) / dd[:, None]), unit diagonal (csgraph_laplacian + _set_diag); one row per block iteration
 __global__ void k_aff_laplacian(double* __restrict__ W, int k, const double* __restrict__ dd) {
-  const size_t total = (size_t)k * k;
-  for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < total; p += (size_t)gridDim.x * blockDim.x) {
-    const int i = (int)(p / k), j = (int)(p - (size_t)i * k);
-    W[p] = (i == j) ? 1.0 : __dmul_rn(__ddiv_rn(__ddiv_rn(W[p], dd[j]), dd[i]), -1.0);
+  for (int i = blockIdx.x; i < k; i += gridDim.x) {
+    const double di = dd[i];
+    double* row = W + (size_t)i * k;
+    for (int j = threadIdx.x; j < k; j += blockDim.x)
+      row[j] = (i == j) ? 1.0 : __dmul_rn(__ddiv_rn(__ddiv_rn(row[j], dd[j]), di), -1.0);
   }
 }
 
@@ -368,7 +402,8 @@ extern "C" int ph_affinity_build(ph_affinity* a, const int32_t* cells, int32_t k
   PH_CUDA(cudaMemsetAsync(a->d_red, 0, 4 * 8, st));
   const int blocks = 1184;
   const CopySrc src{a->d_copy, a->d_emb, a->n, a->D};
-  k_aff_stats<<<blocks, 256, 0, st>>>(a->d_feat, F, src, a->d_cells, k, use_copy_kernel, a->d_red);
+  const dim3 tgrid((k + 31) / 32, (k + 31) / 32), tblock(32, 8);  // tiles on or above the diagonal do the work
+  k_aff_stats<<<tgrid, tblock, 0, st>>>(a->d_feat, F, src, a->d_cells, k, use_copy_kernel, a->d_red);
   ph_count_launch();
   unsigned long long red[4];
   PH_CUDA(cudaMemcpyAsync(red, a->d_red, sizeof(red), cudaMemcpyDeviceToHost, st));
@@ -424,8 +459,8 @@ extern "C" int ph_affinity_build(ph_affinity* a, const int32_t* cells, int32_t k
     stats_out[3] = 1.0;
     return PH_OK;
   }
-  k_aff_build<<<blocks, 256, 0, st>>>(a->d_feat, F, src, a->d_cells, k, use_copy_kernel, kw, kwc, r, strict,
-                                      a->d_W, a->d_red);
+  k_aff_build<<<tgrid, tblock, 0, st>>>(a->d_feat, F, src, a->d_cells, k, use_copy_kernel, kw, kwc, r, strict,
+                                        a->d_W, a->d_red);
   ph_count_launch();
   PH_CUDA(cudaMemcpyAsync(red, a->d_red, sizeof(red), cudaMemcpyDeviceToHost, st));
   PH_CUDA(cudaStreamSynchronize(st));
