@@ -273,13 +273,33 @@ extern "C" int ph_gauss_node_ll(ph_handle* h, const double* X, int32_t D, const 
     d_pn = (double*)take((size_t)K * 8);
     d_pc = (double*)take((size_t)n * 8);
     if (need_x) dX = (double*)take((size_t)n * D * 8);
-    PH_CUDA(cudaMemcpyAsync(d_rows, rows.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
-    PH_CUDA(cudaMemcpyAsync(d_off, off.data(), (size_t)(K + 1) * 4, cudaMemcpyHostToDevice, st));
+    // the small host arrays travel through the handle's page-locked staging buffer (truly asynchronous copies; pageable
+    // sources are staged by the driver call by call, which costs milliseconds on some hosts and trees are scored by the hundred)
+    uint8_t* hp = h->h_stage;
+    const size_t hp_need = up((size_t)n * 4) + up((size_t)(K + 1) * 4) + up((size_t)n) + up((size_t)K * 8) + up((size_t)n * 8);
+    const bool staged = !on_device && hp && hp_need <= h->h_stage_bytes;
+    int32_t* p_rows = rows.data();
+    int32_t* p_off = off.data();
+    uint8_t* p_lab = lab.data();
+    double *p_pn = nullptr, *p_pc = nullptr;
+    if (staged) {
+      auto htake = [&](size_t b) { uint8_t* r = hp; hp += up(b); return r; };
+      p_rows = (int32_t*)htake((size_t)n * 4);
+      p_off = (int32_t*)htake((size_t)(K + 1) * 4);
+      p_lab = htake((size_t)n);
+      p_pn = (double*)htake((size_t)K * 8);
+      p_pc = (double*)htake((size_t)n * 8);
+      memcpy(p_rows, rows.data(), (size_t)n * 4);
+      memcpy(p_off, off.data(), (size_t)(K + 1) * 4);
+      memcpy(p_lab, lab.data(), (size_t)n);
+    }
+    PH_CUDA(cudaMemcpyAsync(d_rows, p_rows, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    PH_CUDA(cudaMemcpyAsync(d_off, p_off, (size_t)(K + 1) * 4, cudaMemcpyHostToDevice, st));
     const double* Xd = X;
     const uint8_t* labd = cell_node;
     if (!on_device) {
       if (!cached) PH_CUDA(cudaMemcpyAsync(dX, X, (size_t)n * D * 8, cudaMemcpyHostToDevice, st));
-      PH_CUDA(cudaMemcpyAsync(d_lab, lab.data(), n, cudaMemcpyHostToDevice, st));
+      PH_CUDA(cudaMemcpyAsync(d_lab, p_lab, n, cudaMemcpyHostToDevice, st));
       Xd = cached ? X : dX;
       labd = d_lab;
     }
@@ -300,10 +320,14 @@ extern "C" int ph_gauss_node_ll(ph_handle* h, const double* X, int32_t D, const 
     ph_count_launch(5);
     PH_CUDA(cudaGetLastError());
     if (!on_device) {
-      PH_CUDA(cudaMemcpyAsync(per_node, pn, (size_t)K * 8, cudaMemcpyDeviceToHost, st));
-      if (per_cell) PH_CUDA(cudaMemcpyAsync(per_cell, pc, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+      PH_CUDA(cudaMemcpyAsync(staged ? p_pn : per_node, pn, (size_t)K * 8, cudaMemcpyDeviceToHost, st));
+      if (per_cell) PH_CUDA(cudaMemcpyAsync(staged ? p_pc : per_cell, pc, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
     }
     PH_CUDA(cudaStreamSynchronize(st));  // host staging vectors go out of scope; the scratch is reused by the next call
+    if (staged) {
+      memcpy(per_node, p_pn, (size_t)K * 8);
+      if (per_cell) memcpy(per_cell, p_pc, (size_t)n * 8);
+    }
     return PH_OK;
   };
   rc = body();
