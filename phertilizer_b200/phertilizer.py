@@ -27,10 +27,14 @@ from .utils import check_obs, power_calc
 def _factorize(col):
     """(codes, uniques) with codes[i] the index of col[i] in uniques (any bijection: callers re-rank the uniques).
     Small non-negative integer ids -- the usual case -- take a counting pass instead of pandas' hash table."""
-    a = col.to_numpy()
-    if a.dtype.kind in "iu" and len(a) and int(a.min()) >= 0 and int(a.max()) < (1 << 27):
-        seen = np.bincount(a, minlength=int(a.max()) + 1) > 0
-        return (np.cumsum(seen) - 1)[a], np.nonzero(seen)[0].astype(a.dtype)
+    if getattr(col.dtype, "kind", "O") in "iu" and len(col):  # (string columns: no object-array detour, straight to pandas)
+        a = col.to_numpy()
+        lo, hi = int(a.min()), int(a.max())
+        if lo >= 0 and hi < (1 << 27):
+            seen = np.bincount(a, minlength=hi + 1) > 0
+            rank = np.cumsum(seen, dtype=np.int32)
+            rank -= 1
+            return rank[a], np.nonzero(seen)[0].astype(a.dtype)
     return pd.factorize(col, sort=False)
 
 
@@ -59,28 +63,38 @@ class Phertilizer:
         # Same labels and order as the reference; the per-observation string concatenation and label lookups (tens of
         # seconds at 2.4e7 observations) are done on the distinct (chr, mutation_id) pairs / cell ids only.
         vc = variant_count_data
+        # Every per-observation pass below is one streaming numpy operation on 32-bit indices (the store takes int32).
         cell_codes, cell_uniques = _factorize(vc["cell_id"])
         cell_labels = np.sort(np.asarray(cell_uniques))
         cell_rank = pd.Series(np.arange(len(cell_labels)), index=cell_labels)[np.asarray(cell_uniques)].to_numpy()
-        cell_idx = cell_rank[cell_codes]
+        cell_idx = cell_rank.astype(np.int32)[cell_codes]
+        del cell_codes
         chr_codes, chr_uniques = _factorize(vc["chr"])
         mid_codes, mid_uniques = _factorize(vc["mutation_id"])
-        pair = chr_codes.astype(np.int64) * max(len(mid_uniques), 1) + mid_codes.astype(np.int64)
-        n_pair_space = len(chr_uniques) * max(len(mid_uniques), 1)
-        if n_pair_space <= (1 << 27):
+        M = max(len(mid_uniques), 1)
+        n_pair_space = len(chr_uniques) * M
+        wide = np.int64 if n_pair_space >= (1 << 31) else np.int32
+        pair = chr_codes.astype(wide)
+        pair *= wide(M)
+        pair += mid_codes.astype(wide, copy=False)
+        del chr_codes, mid_codes
+        counting = n_pair_space <= (1 << 27)
+        if counting:
             # counting pass instead of sorting all observations
-            seen = np.bincount(pair, minlength=n_pair_space) > 0
-            pair_u = np.nonzero(seen)[0]
-            lut = np.zeros(n_pair_space, dtype=np.int64)
-            lut[pair_u] = np.arange(len(pair_u))
-            pair_inv = lut[pair]
+            pair_u = np.nonzero(np.bincount(pair, minlength=n_pair_space))[0]
         else:
             pair_u, pair_inv = np.unique(pair, return_inverse=True)
-        pair_str = (pd.Series(np.asarray(chr_uniques)[pair_u // max(len(mid_uniques), 1)]).astype("str") + "_"
-                    + pd.Series(np.asarray(mid_uniques)[pair_u % max(len(mid_uniques), 1)]).astype(str)).to_numpy()
+        pair_str = (pd.Series(np.asarray(chr_uniques)[pair_u // M]).astype("str") + "_"
+                    + pd.Series(np.asarray(mid_uniques)[pair_u % M]).astype(str)).to_numpy()
         mut_labels = np.sort(pd.unique(pair_str))
-        mut_rank = pd.Series(np.arange(len(mut_labels)), index=mut_labels)[pair_str].to_numpy()
-        mut_idx = mut_rank[pair_inv]
+        mut_rank = pd.Series(np.arange(len(mut_labels)), index=mut_labels)[pair_str].to_numpy().astype(np.int32)
+        if counting:
+            lut = np.zeros(n_pair_space, dtype=np.int32)   # pair -> index of its "chr_mutation" label, one gather
+            lut[pair_u] = mut_rank
+            mut_idx = lut[pair]
+        else:
+            mut_idx = mut_rank[pair_inv]
+        del pair
         self.cells = np.arange(cell_labels.shape[0], dtype="int")
         self.muts = np.arange(mut_labels.shape[0], dtype="int")
         cell_series = pd.Series(data=self.cells, index=cell_labels)
