@@ -492,7 +492,9 @@ def run_ours(args):
         # what the kernel really streams: 2 B per observation incl. 16-byte padding, tail words, sub-segment and tail
         # offsets, one label image per CTA, the outputs (labels + counts)
         nsub = info["dense_codes_by_snv"] * info["chunks_by_snv"]
-        phys = info["stream_bytes_by_snv"] + (m_loc * nsub + 1) * 4 + (m_loc + 1) * 8 + n_loc * info["sm_count"] + 5 * m_loc
+        # single GPU: whole-orientation passes read the batched-4 copy of the stream when the store keeps one
+        stream = info["stream4_bytes_by_snv"] if (world == 1 and info.get("stream4_bytes_by_snv", 0)) else info["stream_bytes_by_snv"]
+        phys = stream + (m_loc * nsub + 1) * 4 + (m_loc + 1) * 8 + n_loc * info["sm_count"] + 5 * m_loc
         achieved = ab / (kernel_ms * 1e-3) / 1e9
         traffic = None
         try:
@@ -523,7 +525,7 @@ def run_ours(args):
                          "peak_source": peak_src + ", of measured"},
             "cpu_baseline": cpu,
             "store": {k: info[k] for k in ("dense_codes_by_snv", "chunks_by_snv", "group_by_snv", "labels_in_smem_by_snv",
-                                           "stream_bytes_by_snv", "device_bytes")},
+                                           "stream_bytes_by_snv", "stream4_bytes_by_snv", "device_bytes")},
         }
         print(json.dumps(line), flush=True)
     peer = snv_store.peer if snv_store is not None else (sharded.peer if sharded is not None else None)

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PH_ABI_VERSION 3
+#define PH_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define PH_API __attribute__((visibility("default")))
@@ -62,6 +62,7 @@ typedef struct ph_info {
   int32_t labels_in_smem_by_snv, labels_in_smem_by_cell;
   int32_t chunks_by_snv, chunks_by_cell; /* 65520-index chunks of the minor axis (16-bit entries) */
   int64_t stream_bytes_by_snv, stream_bytes_by_cell; /* bytes one full pass reads from HBM (entries incl. padding + tail) */
+  int64_t stream4_bytes_by_snv, stream4_bytes_by_cell; /* same for the batched-4 copy whole-orientation passes use; 0 = not kept */
 } ph_info;
 
 PH_API const char* ph_last_error(void);

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libphertilizer_b200.so")
 
 PH_OK = 0
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class PhError(RuntimeError):
@@ -30,6 +30,7 @@ class PhInfo(C.Structure):
         ("labels_in_smem_by_snv", C.c_int32), ("labels_in_smem_by_cell", C.c_int32),
         ("chunks_by_snv", C.c_int32), ("chunks_by_cell", C.c_int32),
         ("stream_bytes_by_snv", C.c_int64), ("stream_bytes_by_cell", C.c_int64),
+        ("stream4_bytes_by_snv", C.c_int64), ("stream4_bytes_by_cell", C.c_int64),
     ]
 
 

@@ -111,8 +111,10 @@ __global__ void k_narrow(const int64_t* __restrict__ in, int64_t n, uint32_t* __
 // bank, so those LDS are conflict free wherever the sub-segment starts; only the ragged last rounds can collide.
 //
 // k_round_keys: keys sorted by (segment, bank, idx16) -> keys (segment, rank within bank, bank, idx16).
+// pos4 != null: the banks of line l are visited starting from bank (pos4[l] & 7), its slot in the batch of the
+// batched-4 copy (any rotation keeps a full round conflict free for the flat copy as well).
 __global__ void k_round_keys(const uint64_t* __restrict__ sorted, int64_t nnz, const int64_t* __restrict__ off, int NSUB,
-                             uint64_t* __restrict__ out, int* dup) {
+                             const int32_t* __restrict__ pos4, uint64_t* __restrict__ out, int* dup) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (; i < nnz; i += stride) {
@@ -130,7 +132,12 @@ __global__ void k_round_keys(const uint64_t* __restrict__ sorted, int64_t nnz, c
       if ((sorted[mid] >> 16) < kb) lo = mid + 1; else hi = mid;
     }
     const uint64_t r = (uint64_t)(i - lo);  // < 2048: a bank holds 2048 bytes of one chunk of the label image
-    out[i] = (k & 0xFFFFFFFF00000000ull) | (r << 21) | (k & 0x1FFFFFull);
+    uint64_t low = k & 0x1FFFFFull;         // bank << 16 | idx16
+    if (pos4) {
+      const uint64_t rot = (uint64_t)(pos4[seg / (NSUB + 1)] & 7);
+      low = (low & 0xFFFFull) | ((((low >> 16) - rot) & 31ull) << 16);
+    }
+    out[i] = (k & 0xFFFFFFFF00000000ull) | (r << 21) | low;
   }
 }
 
@@ -152,7 +159,8 @@ __device__ __forceinline__ int64_t place(int64_t r, int64_t cnt, int bank_order)
 
 __global__ void k_scatter(const uint64_t* __restrict__ keys, int64_t nnz, const int64_t* __restrict__ off, int NSUB,
                           const uint32_t* __restrict__ sub_off, const int64_t* __restrict__ tail_off, int bank_order,
-                          uint16_t* __restrict__ half, uint32_t* __restrict__ tail_words, int* dup) {
+                          uint16_t* __restrict__ half, uint32_t* __restrict__ tail_words, const int32_t* __restrict__ pos4,
+                          const uint32_t* __restrict__ bstep_off, uint16_t* __restrict__ half4, int* dup) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (; i < nnz; i += stride) {
@@ -165,10 +173,58 @@ __global__ void k_scatter(const uint64_t* __restrict__ keys, int64_t nnz, const 
     if (s < NSUB) {
       const int64_t cnt = off[seg + 1] - off[seg];
       half[(int64_t)sub_off[line * NSUB + s] * PH_GE + place(r, cnt, bank_order)] = (uint16_t)k;
+      if (half4) {
+        // batched-4 copy: the r-th entry in round order is entry r of the line's sub-segment; round r / 32 is one warp
+        // step (4 lanes x 8 slots), lane c = (r % 32) / 8 of line slot a, slot r % 8
+        const int p = pos4[line];
+        const int64_t b = p >> 3, a = p & 7;
+        const int64_t step = (int64_t)bstep_off[b * NSUB + s] + (r >> 5);
+        half4[((step << 5) + a * 4 + ((r >> 3) & 3)) * PH_GE + (r & 7)] = (uint16_t)k;
+      }
     } else {
       tail_words[tail_off[line] + r] = (uint32_t)k;
     }
   }
+}
+
+// ---- batched-4 copy: lines sorted by the shape (group counts) of their sub-segments
+__global__ void k_iota(int32_t* v, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = i;
+}
+__global__ void k_shape_key(const int64_t* __restrict__ groups, const int32_t* __restrict__ order, int n, int NSUB, int q,
+                            uint32_t* __restrict__ key) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) key[i] = (uint32_t)groups[(int64_t)order[i] * NSUB + q];
+}
+// perm4[i] = i-th line in shape order (-1 beyond n), pos4[line] = its rank
+__global__ void k_perm_pos(const int32_t* __restrict__ order, int n, int n_pad, int32_t* __restrict__ perm4,
+                           int32_t* __restrict__ pos4) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pad) return;
+  if (i < n) {
+    perm4[i] = order[i];
+    pos4[order[i]] = i;
+  } else {
+    perm4[i] = -1;
+  }
+}
+// warp steps of every (batch, sub-segment): the longest of the batch's 8 lines, 4 groups per step
+__global__ void k_batch_steps(const int64_t* __restrict__ groups, const int32_t* __restrict__ perm4, int n_batches, int NSUB,
+                              uint32_t* __restrict__ steps) {
+  const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k >= (int64_t)n_batches * NSUB) return;
+  const int64_t b = k / NSUB;
+  const int q = (int)(k - b * NSUB);
+  int64_t m = 0;
+  for (int a = 0; a < 8; ++a) {
+    const int line = perm4[b * 8 + a];
+    if (line >= 0) {
+      const int64_t g = groups[(int64_t)line * NSUB + q];
+      m = g > m ? g : m;
+    }
+  }
+  steps[k] = (uint32_t)((m + 3) >> 2);
 }
 
 int build_orient(ph_handle* h, PhOrient* o, const int32_t* d_major, const int32_t* d_minor, const uint16_t* d_code,
@@ -209,6 +265,7 @@ int build_orient(ph_handle* h, PhOrient* o, const int32_t* d_major, const int32_
   const int blocks = h->sm_count * 8;
   int64_t* d_off = nullptr;      // [nseg + 1] positions in the sorted order
   int64_t* d_sizes = nullptr;    // [n_major * NSUB + 1 | n_major + 1] sizes, then their exclusive sums
+  int32_t* d_pos4 = nullptr;     // [n_major] rank of every line in the shape order of the batched-4 copy
   int rc = PH_OK;
   auto body = [&]() -> int {
     const int64_t n_sub = (int64_t)n_major * NSUB;
@@ -234,10 +291,76 @@ int build_orient(ph_handle* h, PhOrient* o, const int32_t* d_major, const int32_
     }
     k_seg_offsets<<<(unsigned)((nseg + 1 + threads - 1) / threads), threads>>>(sorted, nnz, nseg, d_off);
     ph_count_launch();
+    if (nseg > 0) {
+      k_seg_sizes<<<(unsigned)((nseg + threads - 1) / threads), threads>>>(d_off, n_major, NSUB, d_groups, d_tails);
+      ph_count_launch();
+    }
+    // ---- batched-4 copy (see PhOrient): shape-sort the lines, fix every line's batch and slot, size the stream
+    // (only where the pass kernel can place the label image at a 64 KB-aligned shared address, which LAY = 3 builds on)
+    const bool want4 = h->batch4 && h->bank_order && h->aligned_image && nnz > 0 && NSUB > 0 && o->chunk_bits == 16 &&
+                       n_major >= 8 && (size_t)o->lab_bytes + 65536 + 16384 <= (size_t)h->max_smem;
+    if (want4) {
+      const int nb4 = (n_major + 7) / 8;
+      uint32_t *d_key = nullptr, *d_key2 = nullptr, *d_steps = nullptr;
+      int32_t *d_ord = nullptr, *d_ord2 = nullptr;
+      auto sub = [&]() -> int {
+        PH_CUDA(cudaMalloc(&d_key, (size_t)n_major * 4));
+        PH_CUDA(cudaMalloc(&d_key2, (size_t)n_major * 4));
+        PH_CUDA(cudaMalloc(&d_ord, (size_t)n_major * 4));
+        PH_CUDA(cudaMalloc(&d_ord2, (size_t)n_major * 4));
+        PH_CUDA(cudaMalloc(&o->perm4, (size_t)nb4 * 8 * 4));
+        PH_CUDA(cudaMalloc(&d_pos4, (size_t)n_major * 4));
+        const unsigned gb = (unsigned)((n_major + threads - 1) / threads);
+        k_iota<<<gb, threads>>>(d_ord, n_major);
+        // least significant key first; the radix sort is stable, so the last key (the rarest sub-segment) dominates
+        for (int q = 0; q < NSUB; ++q) {
+          k_shape_key<<<gb, threads>>>(d_groups, d_ord, n_major, NSUB, q, d_key);
+          cub::DoubleBuffer<uint32_t> kb(d_key, d_key2);
+          cub::DoubleBuffer<int32_t> vb(d_ord, d_ord2);
+          size_t need = 0;
+          PH_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need, kb, vb, n_major, 0, 32));
+          if (need > temp_bytes) PH_FAIL(PH_ERR_CUDA, "sort scratch too small");
+          PH_CUDA(cub::DeviceRadixSort::SortPairs(d_temp, need, kb, vb, n_major, 0, 32));
+          if (vb.Current() != d_ord) {  // keep the current order in d_ord
+            int32_t* t = d_ord; d_ord = d_ord2; d_ord2 = t;
+          }
+          if (kb.Current() != d_key) {
+            uint32_t* t = d_key; d_key = d_key2; d_key2 = t;
+          }
+        }
+        k_perm_pos<<<(unsigned)((nb4 * 8 + threads - 1) / threads), threads>>>(d_ord, n_major, nb4 * 8, o->perm4, d_pos4);
+        const int64_t nbs = (int64_t)nb4 * NSUB;
+        PH_CUDA(cudaMalloc(&d_steps, (size_t)(nbs + 1) * 4));
+        PH_CUDA(cudaMemset(d_steps, 0, (size_t)(nbs + 1) * 4));
+        k_batch_steps<<<(unsigned)((nbs + threads - 1) / threads), threads>>>(d_groups, o->perm4, nb4, NSUB, d_steps);
+        PH_CUDA(cudaMalloc(&o->bstep_off, (size_t)(nbs + 1) * 4));
+        size_t need = 0;
+        PH_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, need, d_steps, o->bstep_off, (int)(nbs + 1)));
+        if (need > temp_bytes) PH_FAIL(PH_ERR_CUDA, "scan scratch too small");
+        PH_CUDA(cub::DeviceScan::ExclusiveSum(d_temp, need, d_steps, o->bstep_off, (int)(nbs + 1)));
+        ph_count_launch(4 + 2 * NSUB);
+        uint32_t total = 0;
+        PH_CUDA(cudaMemcpy(&total, o->bstep_off + nbs, 4, cudaMemcpyDeviceToHost));
+        o->n_steps4 = total;
+        o->n_batches4 = nb4;
+        const size_t bytes4 = ((size_t)total + 8) * 32 * PH_GE * sizeof(uint16_t);  // zero = padding entries; slack for the load ring
+        PH_CUDA(cudaMalloc(&o->half4, bytes4));
+        PH_CUDA(cudaMemset(o->half4, 0, bytes4));
+        h->device_bytes += (int64_t)bytes4 + (nbs + 1) * 4 + (int64_t)nb4 * 32;
+        return PH_OK;
+      };
+      const int rc4 = sub();
+      cudaFree(d_key);
+      cudaFree(d_key2);
+      cudaFree(d_ord);
+      cudaFree(d_ord2);
+      cudaFree(d_steps);
+      if (rc4 != PH_OK) return rc4;
+    }
     if (nnz > 0 && h->bank_order && NSUB > 0) {
       // second sort: round order inside every sub-segment (segment sizes, hence d_off, do not change)
       uint64_t* other = (sorted == kbuf0) ? kbuf1 : kbuf0;
-      k_round_keys<<<blocks, threads>>>(sorted, nnz, d_off, NSUB, other, d_flag + 1);
+      k_round_keys<<<blocks, threads>>>(sorted, nnz, d_off, NSUB, o->half4 ? d_pos4 : nullptr, other, d_flag + 1);
       ph_count_launch();
       cub::DoubleBuffer<uint64_t> db(other, const_cast<uint64_t*>(sorted));
       int end_bit = 32 + ph_ceil_log2((uint64_t)nseg + 1);
@@ -245,10 +368,6 @@ int build_orient(ph_handle* h, PhOrient* o, const int32_t* d_major, const int32_
       PH_CUDA(cub::DeviceRadixSort::SortKeys(d_temp, temp_bytes, db, nnz, 0, end_bit));
       ph_count_launch(4);
       sorted = db.Current();
-    }
-    if (nseg > 0) {
-      k_seg_sizes<<<(unsigned)((nseg + threads - 1) / threads), threads>>>(d_off, n_major, NSUB, d_groups, d_tails);
-      ph_count_launch();
     }
     // exclusive sums in place (the extra trailing zero element receives the total)
     size_t need = 0, need2 = 0;
@@ -275,7 +394,7 @@ int build_orient(ph_handle* h, PhOrient* o, const int32_t* d_major, const int32_
     h->device_bytes += (int64_t)half_bytes + (o->n_tail + 8) * (int64_t)sizeof(uint32_t);
     if (nnz > 0) {
       k_scatter<<<blocks, threads>>>(sorted, nnz, d_off, NSUB, o->sub_off, o->tail_off, h->bank_order, o->half,
-                                     o->tail_words, d_flag + 1);
+                                     o->tail_words, o->half4 ? d_pos4 : nullptr, o->bstep_off, o->half4, d_flag + 1);
       ph_count_launch();
     }
     PH_CUDA(cudaGetLastError());
@@ -285,6 +404,7 @@ int build_orient(ph_handle* h, PhOrient* o, const int32_t* d_major, const int32_
   rc = body();
   cudaFree(d_off);
   cudaFree(d_sizes);
+  cudaFree(d_pos4);
   return rc;
 }
 
@@ -298,6 +418,9 @@ extern "C" void ph_destroy(ph_handle* h) {
     cudaFree(o->sub_off);
     cudaFree(o->tail_words);
     cudaFree(o->tail_off);
+    cudaFree(o->half4);
+    cudaFree(o->bstep_off);
+    cudaFree(o->perm4);
   }
   cudaFree(h->d_lab_img);
   cudaFree(h->d_emb);
@@ -363,6 +486,8 @@ extern "C" int ph_create(int32_t n_cells, int32_t n_snvs, int64_t nnz, const int
     h->aligned_image = e ? atoi(e) : 1;
     e = getenv("PH_ZERO_COPY_OUT");  // host-pointer calls: kernels store results straight into page-locked host memory (default on)
     h->zero_copy_out = e ? atoi(e) : 1;
+    e = getenv("PH_BATCH4");  // keep the batched-4 copy of the dense streams and use the 4-lanes-per-line pass (default on)
+    h->batch4 = e ? atoi(e) : 1;
   }
 
   int rc = PH_OK;
@@ -510,6 +635,8 @@ extern "C" int ph_get_info(const ph_handle* h, ph_info* out) {
   out->chunks_by_cell = h->by_cell.NCH;
   out->stream_bytes_by_snv = h->by_snv.n_groups * PH_GE * 2 + h->by_snv.n_tail * 4;
   out->stream_bytes_by_cell = h->by_cell.n_groups * PH_GE * 2 + h->by_cell.n_tail * 4;
+  out->stream4_bytes_by_snv = h->by_snv.half4 ? h->by_snv.n_steps4 * 32 * PH_GE * 2 + h->by_snv.n_tail * 4 : 0;
+  out->stream4_bytes_by_cell = h->by_cell.half4 ? h->by_cell.n_steps4 * 32 * PH_GE * 2 + h->by_cell.n_tail * 4 : 0;
   out->labels_in_smem_by_snv = h->by_snv.labels_in_smem;
   out->labels_in_smem_by_cell = h->by_cell.labels_in_smem;
   return PH_OK;

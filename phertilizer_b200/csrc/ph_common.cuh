@@ -60,6 +60,16 @@ struct PhOrient {
   int32_t lab_bytes;   // size of the label image
   int32_t batch;       // lines per warp batch (8 or 32)
   int32_t labels_in_smem;
+  // Second copy of the dense stream, "batched-4" (pass kernel LAY = 3): lines sorted by the shape of their sub-segments
+  // and taken 8 at a time; inside a batch every sub-segment is padded to the batch's longest in units of 4 groups, and
+  // a warp step is 32 consecutive groups = [line a = 0..7][lane c = 0..3] holding group 4 t + c of line a.  Four lanes
+  // stream one line, sub-segment boundaries fall on the same step for the whole warp, and with the round order of line a
+  // rotated by a banks the 32 gathers of a step hit 32 different banks.
+  uint16_t* half4;       // [n_steps4 * 32 * PH_GE] or null
+  uint32_t* bstep_off;   // [n_batches4 * NSUB + 1] first warp step of every (batch, sub-segment)
+  int32_t* perm4;        // [n_batches4 * 8] line of every batch slot, -1 = none
+  int64_t n_steps4;
+  int32_t n_batches4;
 };
 
 struct ph_handle {
@@ -78,7 +88,7 @@ struct ph_handle {
   double* d_L1;      // [n_codes]
   uint8_t* d_varpos; // [n_codes]
   int64_t device_bytes;
-  int chunk_bits, bank_order, ctas_per_sm, aligned_image, zero_copy_out;
+  int chunk_bits, bank_order, ctas_per_sm, aligned_image, zero_copy_out, batch4;
   double dense_min_avg, dense_min_share;  // a (var,total) code gets its own segment when it has >= this many entries per line on average
   // scratch (device)
   uint8_t* d_lab_minor;  // [max(n,m)] staged labels of the minor axis

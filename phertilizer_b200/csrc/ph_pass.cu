@@ -25,7 +25,9 @@ struct PassArgs {
   const uint32_t* __restrict__ tail_words;
   const int64_t* __restrict__ tail_off;
   int D, NCH, NSUB, chunk_bits, minor_bits, n_minor, lab_bytes;
-  int tab_bytes;  // LAY = 2: bytes of everything but the label image (they go below the image when they fit)
+  int tab_bytes;  // LAY >= 2: bytes of everything but the label image (they go below the image when they fit)
+  const uint16_t* __restrict__ half4;     // LAY = 3: the batched-4 copy of the stream (PhOrient)
+  const uint32_t* __restrict__ bstep_off;
   const uint8_t* __restrict__ minor_label;  // raw labels [n_minor] (SMEM_LAB) or the prepared label image (global)
   const int32_t* __restrict__ list;         // optional list of lines
   int n_work;
@@ -136,12 +138,14 @@ __host__ __device__ inline int warp_words(int B, int NSUB, int D, int NC) {
 // NC = counted classes.  LAY = 0: any chunk stride; 1: production layout (chunk stride 2^16: the label address is one
 // PRMT of the entry and the chunk base); 2: as 1 with the label image placed at a shared-memory address that is a
 // multiple of 2^16, so that the PRMT yields the complete shared-window address and the gather is a bare LDS.U8 [reg]
-// (no base add per observation).  The bytes below the image hold the per-warp tables.
+// (no base add per observation).  The bytes below the image hold the per-warp tables.  3: as 2, on the batched-4 copy of
+// the stream (PhOrient::half4): four lanes stream one line of the batch, sub-segment boundaries are warp-uniform.
 template <int B, int MODE, int NC, bool SMEM_LAB, int LAY>
 __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
   constexpr bool S16 = LAY >= 1;
-  constexpr bool AL = LAY == 2;
+  constexpr bool AL = LAY >= 2;
+  constexpr bool B4 = LAY == 3;
   const int nthreads = blockDim.x;
   const int D = a.D, NCH = a.NCH, NSUB = a.NSUB, NS1 = NSUB + 1, cb = a.chunk_bits;
   const int K2 = a.K + 2;
@@ -227,8 +231,9 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
     // ---- my line (lane % B): holder duties after the streaming phase
     const int myl = lane % B;
     const int myw = first + myl;
-    const bool have = myl < nl;
-    const int line = have ? (a.list ? __ldg(a.list + myw) : myw) : -1;
+    int line = -1;
+    if (myl < nl) line = a.list ? __ldg(a.list + myw) : myw;  // (batched-4: the list is the shape order, -1 = empty slot)
+    const bool have = line >= 0;
     uint32_t h_ml = 0;
     bool h_skip = !have;
     if (MODE == MODE_MAPPED) {
@@ -260,16 +265,93 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
     // s_e[k]: end (in groups) of sub-segment k = l * NSUB + s of the batch; s_start[l]: first group of line l
     uint32_t* s_e = s_b;
     uint32_t* s_start = s_b + B * NSUB;
-    for (int k = lane; k < B * NSUB; k += 32) {
+    if (B4) {
+      // batched-4 copy: s_e[q] = first warp step of sub-segment q of this batch, s_e[NSUB] = end of the batch
+      for (int k = lane; k <= NSUB; k += 32) s_e[k] = __ldg(a.bstep_off + (size_t)bidx * NSUB + k);
+    }
+    for (int k = lane; k < (B4 ? 0 : B * NSUB); k += 32) {
       const int l = k / NSUB, s = k - l * NSUB;
       const int ln = s_ln[l];
       s_e[k] = ln >= 0 ? __ldg(a.sub_off + (size_t)ln * NSUB + s + 1) : 0u;
     }
-    if (lane < B) s_start[lane] = (line >= 0 && NSUB > 0) ? __ldg(a.sub_off + (size_t)line * NSUB) : 0u;
+    if (!B4 && lane < B) s_start[lane] = (line >= 0 && NSUB > 0) ? __ldg(a.sub_off + (size_t)line * NSUB) : 0u;
     __syncwarp();
 
+    // ---- dense part, batched-4 copy: the batch is one contiguous run of warp steps; lane (a, c) = (lane / 4, lane % 4)
+    // reads group 4 t + c of line a at step t.  Everything about sub-segments is warp-uniform: q, the chunk base, the
+    // flush points.  A lane's packed counters are summed over the 4 lanes of its line and added to the line's
+    // (code, cluster) counter by one of them -- no MATCH / REDUX / atomics.
+    if (B4 && NSUB > 0) {
+      const int la = lane >> 2;  // my line of the batch
+      uint32_t st = s_e[0];
+      const uint32_t st_end = s_e[NSUB];
+      const uint4* gp = reinterpret_cast<const uint4*>(a.half4) + ((size_t)st << 5) + lane;
+      int q = 0, cur_d = 0;
+      uint32_t nb_eff = st, cbase = 0, acc = 0, st_flush = st;  // nb_eff = st: the first step enters the slow path
+      const uint8_t* maprow = s_map;
+      if (MODE == MODE_MAPPED) maprow = s_map + s_ml[la] * K2;
+      constexpr uint32_t kDeadline4 = PH_FLUSH_GROUPS;  // steps: one group per lane and step
+      auto flush4 = [&]() {  // warp-uniform call
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          uint32_t v = (acc >> (PH_FIELD_BITS * c)) & FM;
+          v += __shfl_xor_sync(FULL, v, 1);
+          v += __shfl_xor_sync(FULL, v, 2);
+          if ((lane & 3) == 0 && v) s_cnt[(la * D + cur_d) * NC + c] += v;
+        }
+        acc = 0;
+      };
+      auto slow4 = [&](uint32_t step) {  // warp-uniform: step and all bounds are
+        while (step >= s_e[q + 1]) ++q;
+        const int d = (int)(((uint32_t)q * magic_nch) >> 16);  // q / NCH
+        if (d != cur_d || step - st_flush >= kDeadline4) {
+          flush4();
+          cur_d = d;
+          st_flush = step;
+        }
+        cbase = (((uint32_t)q - (uint32_t)d * (uint32_t)NCH) << 16) + img_base;
+        nb_eff = min(s_e[q + 1], st_flush + kDeadline4);
+      };
+      auto one4 = [&](uint32_t addr) -> uint32_t {
+        uint32_t sh = label_dense(addr);
+        if (MODE == MODE_MAPPED) sh = maprow[sh];
+        return 1u << sh;
+      };
+      auto consume4 = [&](const uint4& w, uint32_t step) {
+        if (step >= nb_eff) slow4(step);
+        const uint32_t a0 = __byte_perm(w.x, cbase, 0x7610), a1 = __byte_perm(w.x, cbase, 0x7632);
+        const uint32_t a2 = __byte_perm(w.y, cbase, 0x7610), a3 = __byte_perm(w.y, cbase, 0x7632);
+        const uint32_t a4 = __byte_perm(w.z, cbase, 0x7610), a5 = __byte_perm(w.z, cbase, 0x7632);
+        const uint32_t a6 = __byte_perm(w.w, cbase, 0x7610), a7 = __byte_perm(w.w, cbase, 0x7632);
+        acc += ((one4(a0) + one4(a1)) + (one4(a2) + one4(a3))) + ((one4(a4) + one4(a5)) + (one4(a6) + one4(a7)));
+      };
+      uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0, r2 = r0, r3 = r0;
+      if (st < st_end) r0 = ld_stream(gp);
+      if (st + 1 < st_end) r1 = ld_stream(gp + 32);
+      if (st + 2 < st_end) r2 = ld_stream(gp + 64);
+      if (st + 3 < st_end) r3 = ld_stream(gp + 96);
+      while (st < st_end) {
+        consume4(r0, st);
+        if (st + 4 < st_end) r0 = ld_stream(gp + 128);
+        if (st + 1 < st_end) {
+          consume4(r1, st + 1);
+          if (st + 5 < st_end) r1 = ld_stream(gp + 160);
+        }
+        if (st + 2 < st_end) {
+          consume4(r2, st + 2);
+          if (st + 6 < st_end) r2 = ld_stream(gp + 192);
+        }
+        if (st + 3 < st_end) {
+          consume4(r3, st + 3);
+          if (st + 7 < st_end) r3 = ld_stream(gp + 224);
+        }
+        st += 4;
+        gp += 128;
+      }
+      flush4();
+    }
     // ---- dense part: maximal runs of lines that are contiguous in memory are streamed as one range of groups
-    if (NSUB > 0) {
+    if (!B4 && NSUB > 0) {
       int l0 = 0;
       while (l0 < nl) {
         int l1 = l0 + 1;
@@ -420,7 +502,7 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
         }
         if (cur != 0xffffffffu) fold();
       }
-      const int wi = myw;
+      const int wi = B4 ? line : myw;  // batched-4 walks the lines in shape order: results go to the line's own slot
       if (MODE == MODE_TABLE) {
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
@@ -695,13 +777,25 @@ int launch_pass(ph_handle* h, const PhOrient* o, PassArgs& a, cudaStream_t st) {
   size_t smem = 0;
   // first choice: the label image at a 2^16-aligned shared address (LAY = 2).  Costs up to 64 KB of address space below
   // the image (the tables live there), so it needs  64 KB + image + tables  to fit -- true for up to ~150 k minor indices.
+  // With it, whole-orientation passes (no line list, no peer push) run on the batched-4 copy of the stream (LAY = 3).
+  bool use4 = false;
   if (o->chunk_bits == 16 && h->aligned_image) {
-    const size_t full = pass_smem_bytes(h, o, MODE, NC, a.K, true, 1024, B, a.row_words, &lut);
+    const bool can4 = MODE != MODE_COUNTS && o->half4 && !a.list && !a.push && h->batch4;
+    const int Bt = can4 ? 8 : B;
+    const size_t full = pass_smem_bytes(h, o, MODE, NC, a.K, true, 1024, Bt, a.row_words, &lut);
     if (full && full + 65536 <= (size_t)h->max_smem) {
       smem = full + 65536;
       threads = 1024;
       aligned = true;
       a.tab_bytes = (int)(full - (size_t)o->lab_bytes);
+      if (can4) {
+        use4 = true;
+        B = 8;
+        a.list = o->perm4;              // the lines in shape order, 8 per batch, -1 = empty slot
+        a.n_work = o->n_batches4 * 8;
+        a.half4 = o->half4;
+        a.bstep_off = o->bstep_off;
+      }
     }
   }
   for (int pass = 0; pass < 2 && !smem; ++pass) {
@@ -750,7 +844,9 @@ int launch_pass(ph_handle* h, const PhOrient* o, PassArgs& a, cudaStream_t st) {
     else if (o->chunk_bits == 16) PH_LAUNCH(BB, true, 1);                      \
     else PH_LAUNCH(BB, true, 0);                                               \
   } while (0)
-  if (B == 32) PH_LAUNCH_B(32);
+  if (use4) {
+    if constexpr (MODE != MODE_COUNTS) PH_LAUNCH(8, true, 3);
+  } else if (B == 32) PH_LAUNCH_B(32);
   else if (B == 4) PH_LAUNCH_B(4);
   else PH_LAUNCH_B(8);
 #undef PH_LAUNCH_B
@@ -818,6 +914,40 @@ bool is_pinned(const void* p) {
     return false;
   }
   return at.type == cudaMemoryTypeHost;
+}
+
+// Results of a batched-4 pass land in device scratch in LINE order while the kernel walks the lines in shape order
+// (scattered 1- to 8-byte stores: fine in L2, slow as individual PCIe writes).  This kernel then streams the scratch
+// arrays into the page-locked host buffers with coalesced stores -- one launch instead of one D2H copy per array.
+struct CopySegs {
+  const uint8_t* src[4];
+  uint8_t* dst[4];
+  size_t bytes[4];
+  int n;
+};
+__global__ void k_copy_out(const CopySegs c) {
+  const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x, nt = (size_t)gridDim.x * blockDim.x;
+  for (int s = 0; s < c.n; ++s) {
+    const size_t words = c.bytes[s] >> 2;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(c.src[s]);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(c.dst[s]);
+    for (size_t i = tid; i < words; i += nt) dst[i] = src[i];
+    for (size_t i = (words << 2) + tid; i < c.bytes[s]; i += nt) c.dst[s][i] = c.src[s][i];  // last 0..3 bytes
+  }
+}
+int copy_out(const ph_handle* h, CopySegs& c, cudaStream_t st) {
+  size_t total = 0;
+  for (int s = 0; s < c.n; ++s) {
+    total += c.bytes[s];
+    if ((reinterpret_cast<uintptr_t>(c.src[s]) | reinterpret_cast<uintptr_t>(c.dst[s])) & 3) PH_FAIL(PH_ERR_ARG, "unaligned result buffer");
+  }
+  if (!total) return PH_OK;
+  const size_t want = (total / 4 + 255) / 256;
+  const int blocks = (int)(want < (size_t)h->sm_count * 4 ? (want ? want : 1) : (size_t)h->sm_count * 4);
+  k_copy_out<<<blocks, 256, 0, st>>>(c);
+  ph_count_launch();
+  PH_CUDA(cudaGetLastError());
+  return PH_OK;
 }
 
 // device-side alias of a page-locked host buffer (UVA: the same address when the allocation is mapped), else null
@@ -895,14 +1025,27 @@ int run_fast(ph_handle* h, PhOrient* o, int mode, const uint8_t* minor_label, in
     double *vS0 = device_view(pS0), *vS1 = device_view(pS1);
     int32_t *vNo = device_view(pNo), *vNv = device_view(pNv);
     const bool zc = h->zero_copy_out && (!pS0 || vS0) && (!pS1 || vS1) && (!pNo || vNo) && (!pNv || vNv);
-    if (zc) {
+    // a whole-orientation pass may run on the batched-4 copy, whose results come in shape order: scratch + k_copy_out
+    const bool b4 = !list && o->half4 && h->batch4;
+    const bool via_scratch = zc && b4;   // (the staging buffer carves are 256-byte aligned)
+    const bool zc_direct = zc && !b4;
+    if (zc_direct) {
       a.S0 = vS0; a.S1 = vS1; a.Nobs = vNo; a.Nvar = vNv;
     } else {
       a.S0 = S0 ? dS0 : nullptr; a.S1 = S1 ? dS1 : nullptr; a.Nobs = Nobs ? dNo : nullptr; a.Nvar = Nvar ? dNv : nullptr;
     }
     rc = launch_table<MODE_TABLE>(h, o, a, st);
     if (rc != PH_OK) return rc;
-    if (!zc) {
+    if (via_scratch) {
+      CopySegs c{};
+      auto add = [&](const void* src, void* dst, size_t bytes) {
+        if (!dst) return;
+        c.src[c.n] = (const uint8_t*)src; c.dst[c.n] = (uint8_t*)dst; c.bytes[c.n] = bytes; ++c.n;
+      };
+      add(dS0, vS0, nt * 8); add(dS1, vS1, nt * 8); add(dNo, vNo, nt * 4); add(dNv, vNv, nt * 4);
+      rc = copy_out(h, c, st);
+      if (rc != PH_OK) return rc;
+    } else if (!zc_direct) {
       if (pS0) PH_CUDA(cudaMemcpyAsync(pS0, dS0, nt * 8, cudaMemcpyDeviceToHost, st));
       if (pS1) PH_CUDA(cudaMemcpyAsync(pS1, dS1, nt * 8, cudaMemcpyDeviceToHost, st));
       if (pNo) PH_CUDA(cudaMemcpyAsync(pNo, dNo, nt * 4, cudaMemcpyDeviceToHost, st));
@@ -922,11 +1065,23 @@ int run_fast(ph_handle* h, PhOrient* o, int mode, const uint8_t* minor_label, in
   uint8_t* vL = device_view(pL);
   int32_t* vN = device_view(pN);
   const bool zc = h->zero_copy_out && vL && vN;
-  a.label_out = zc ? vL : h->d_u8;
-  a.nobs_out = zc ? vN : dNo;
+  // a whole-orientation pass may run on the batched-4 copy, whose results come in shape order (scattered stores):
+  // they go to device scratch, then k_copy_out streams them to the host buffers (or plain D2H copies if unaligned)
+  const bool b4 = !list && o->half4 && h->batch4;
+  const bool via_scratch = zc && b4 && (((reinterpret_cast<uintptr_t>(vL) | reinterpret_cast<uintptr_t>(vN)) & 3) == 0);
+  const bool zc_direct = zc && !b4;
+  a.label_out = zc_direct ? vL : h->d_u8;
+  a.nobs_out = zc_direct ? vN : dNo;
   rc = mode == MODE_LINEAR ? launch_pass<MODE_LINEAR, 1>(h, o, a, st) : launch_pass<MODE_BRANCHING, 2>(h, o, a, st);
   if (rc != PH_OK) return rc;
-  if (!zc) {
+  if (via_scratch) {
+    CopySegs c{};
+    c.n = 2;
+    c.src[0] = h->d_u8; c.dst[0] = vL; c.bytes[0] = (size_t)n_list;
+    c.src[1] = (const uint8_t*)dNo; c.dst[1] = (uint8_t*)vN; c.bytes[1] = (size_t)n_list * 4 * nobs_per;
+    rc = copy_out(h, c, st);
+    if (rc != PH_OK) return rc;
+  } else if (!zc_direct) {
     PH_CUDA(cudaMemcpyAsync(pL, h->d_u8, n_list, cudaMemcpyDeviceToHost, st));
     PH_CUDA(cudaMemcpyAsync(pN, dNo, (size_t)n_list * 4 * nobs_per, cudaMemcpyDeviceToHost, st));
   }

@@ -335,8 +335,20 @@ class SnvShardedStore:
         else:
             cell, snv, var, total = cell[keep].contiguous(), (snv[keep] - lo).contiguous(), var[keep].contiguous(), total[keep].contiguous()
         dev_index = device if isinstance(device, int) else device.index
-        st = ObservationStore.from_coo(n_cells, hi - lo, cell, snv, var, total, alpha=alpha, max_copies=max_copies,
-                                       device=dev_index, pairs=global_pairs(var, total, group))
+        import os
+
+        # the SNV-sharded step pushes its records batch by batch in line order: it runs on the flat copy of the stream,
+        # so the store need not keep the batched-4 copy (ph_create reads the knob)
+        saved = os.environ.get("PH_BATCH4")
+        os.environ["PH_BATCH4"] = "0"
+        try:
+            st = ObservationStore.from_coo(n_cells, hi - lo, cell, snv, var, total, alpha=alpha, max_copies=max_copies,
+                                           device=dev_index, pairs=global_pairs(var, total, group))
+        finally:
+            if saved is None:
+                os.environ.pop("PH_BATCH4", None)
+            else:
+                os.environ["PH_BATCH4"] = saved
         dev = torch.device("cuda", dev_index)
         try:
             return cls(st, n_cells, n_snvs, lo, hi, dev, group)

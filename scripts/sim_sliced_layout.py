@@ -108,3 +108,35 @@ print(f"  ... per-lane boundaries, slice padded to its longest line: unsorted +{
       f"lines sorted by length +{100 * (groups_total_sorted / groups_now - 1):.1f} %")
 print(f"LDS.U8 wavefronts per request  today: {np.concatenate(wf_now).mean():.2f}   sliced, rotated rounds: "
       f"{np.concatenate(wf_sliced).mean():.2f}   sliced, unrotated: {np.concatenate(wf_sliced_norot).mean():.2f}")
+
+# ---- variant B: batches of 8 shape-sorted lines, 4 lanes per line, every sub-segment padded to the batch's longest in
+# units of 4 groups (one warp step = 8 lines x 4 lanes); keeps today's task granularity (8 lines per warp batch)
+g_sorted8 = g_all[perm][: (s.m // 8) * 8].reshape(-1, 8, D * NCH)
+steps = (g_sorted8.max(axis=1) + 3) // 4                      # warp steps per (batch, sub-segment)
+groups_b = int(32 * steps.sum())
+g_unsorted8 = g_all[: (s.m // 8) * 8].reshape(-1, 8, D * NCH)
+groups_b_unsorted = int(32 * ((g_unsorted8.max(axis=1) + 3) // 4).sum())
+print(f"variant B (8 lines x 4 lanes, uniform sub-segments): sorted +{100 * (groups_b / groups_now - 1):.1f} % bytes, "
+      f"consecutive lines +{100 * (groups_b_unsorted / groups_now - 1):.1f} %")
+# bank behaviour of variant B: lane (a, c) reads entry (4 t + c) * 8 + e of line a, rounds rotated by a
+wf_b = []
+for b in range(min(24, len(g_sorted8))):
+    lines = perm[b * 8:(b + 1) * 8]
+    for q in range(D * NCH):
+        d, ch = divmod(q, NCH)
+        seqs = []
+        for a, j in enumerate(lines):
+            c, k = cell[starts[j]:starts[j + 1]], code[starts[j]:starts[j + 1]]
+            sel = c[(k == d) & (c // CH == ch)]
+            bank = ((16 + sel - ch * CH) // 4) % 32
+            seqs.append(bank[round_order(bank, a)])
+        T = int(steps[b, q])
+        M = -np.ones((T * 8, 32), int)                      # row = (t, e), column = lane a * 4 + c
+        for a in range(8):
+            sq = seqs[a]
+            idx = np.arange(len(sq))
+            grp, e = idx // 8, idx % 8
+            t, c4 = grp // 4, grp % 4
+            M[t * 8 + e, a * 4 + c4] = sq
+        wf_b.append(wavefronts(M))
+print(f"variant B LDS.U8 wavefronts per request: {np.concatenate(wf_b).mean():.2f}")

@@ -274,7 +274,7 @@ def test_pairwise_dist(env):
 
 
 # ------------------------------------------------------------------------------------------- seeded random inputs
-@pytest.fixture(scope="module", params=["default", "unaligned_image", "chunks512", "chunks64_nobank"])
+@pytest.fixture(scope="module", params=["default", "no_batch4", "unaligned_image", "chunks512", "chunks64_nobank"])
 def synth_env(request):
     """T1 (2000 x 3000).  The store is also built with tiny chunks of the minor axis (PH_CHUNK_BITS, a test knob of
     ph_create) so that the multi-chunk sub-segment logic runs on data the dense oracle can hold."""
@@ -283,7 +283,7 @@ def synth_env(request):
     from phertilizer_b200.store import ObservationStore
     from phertilizer_b200.synth import make_config
 
-    knobs = {"default": {}, "unaligned_image": {"PH_ALIGNED_IMAGE": "0"}, "chunks512": {"PH_CHUNK_BITS": "9", "PH_DENSE_MIN_AVG": "4", "PH_DENSE_MIN_SHARE": "0"},
+    knobs = {"default": {}, "no_batch4": {"PH_BATCH4": "0"}, "unaligned_image": {"PH_ALIGNED_IMAGE": "0"}, "chunks512": {"PH_CHUNK_BITS": "9", "PH_DENSE_MIN_AVG": "4", "PH_DENSE_MIN_SHARE": "0"},
              "chunks64_nobank": {"PH_CHUNK_BITS": "8", "PH_BANK_ORDER": "0", "PH_DENSE_MIN_AVG": "2", "PH_DENSE_MIN_SHARE": "0"}}[request.param]
     saved = {k: os.environ.get(k) for k in knobs}
     os.environ.update(knobs)
