@@ -5,9 +5,10 @@ A "step" is one pass of the hot path over all observations: the SNV reassignment
 (reference linear_split.py:203-237, `Linear_split.mut_assignment`) = K1 (per-SNV like0/like1 sums + observation
 counts over cellsA) fused with K1a (mean-likelihood decision), for a balanced random cellsA and all SNVs active.
 Workload (BASELINE.json configs[2], the one the north-star target is quoted on; it fits one GPU): synthetic
-100k cells x 200k SNVs at 0.02x coverage, 12 clones, ~396 M observations.  With --gpus N the cells are sharded
-across ranks (strong scaling: the total work is fixed) and the per-SNV partial tables are combined with one NCCL
-all-reduce per step.
+100k cells x 200k SNVs at 0.02x coverage, 12 clones, ~396 M observations.  With --gpus N the problem is fixed
+(strong scaling) and sharded by SNVs (default: per-SNV tables are independent, every rank runs ONE fused kernel per
+step that also pushes its results to all ranks over NVLink peer memory and unpacks the assembled window) or by cells
+(--shard cells: integer histograms over peer memory, or --exchange nccl: one all-reduce of the partial tables).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C3]
 
