@@ -325,28 +325,27 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
         const uint32_t a6 = __byte_perm(w.w, cbase, 0x7610), a7 = __byte_perm(w.w, cbase, 0x7632);
         acc += ((one4(a0) + one4(a1)) + (one4(a2) + one4(a3))) + ((one4(a4) + one4(a5)) + (one4(a6) + one4(a7)));
       };
-      uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0, r2 = r0, r3 = r0;
-      if (st < st_end) r0 = ld_stream(gp);
-      if (st + 1 < st_end) r1 = ld_stream(gp + 32);
-      if (st + 2 < st_end) r2 = ld_stream(gp + 64);
-      if (st + 3 < st_end) r3 = ld_stream(gp + 96);
+      // ring of RD 16-byte loads per lane in flight (RD * 512 B per warp)
+#ifndef PH_RING4
+#define PH_RING4 4
+#endif
+      constexpr int RD = PH_RING4;
+      uint4 ring[RD];
+#pragma unroll
+      for (int u = 0; u < RD; ++u) {
+        ring[u] = make_uint4(0, 0, 0, 0);
+        if (st + u < st_end) ring[u] = ld_stream(gp + 32 * u);
+      }
       while (st < st_end) {
-        consume4(r0, st);
-        if (st + 4 < st_end) r0 = ld_stream(gp + 128);
-        if (st + 1 < st_end) {
-          consume4(r1, st + 1);
-          if (st + 5 < st_end) r1 = ld_stream(gp + 160);
+#pragma unroll
+        for (int u = 0; u < RD; ++u) {
+          if (u == 0 || st + u < st_end) {
+            consume4(ring[u], st + u);
+            if (st + u + RD < st_end) ring[u] = ld_stream(gp + 32 * (u + RD));
+          }
         }
-        if (st + 2 < st_end) {
-          consume4(r2, st + 2);
-          if (st + 6 < st_end) r2 = ld_stream(gp + 192);
-        }
-        if (st + 3 < st_end) {
-          consume4(r3, st + 3);
-          if (st + 7 < st_end) r3 = ld_stream(gp + 224);
-        }
-        st += 4;
-        gp += 128;
+        st += RD;
+        gp += 32 * RD;
       }
       flush4();
     }
