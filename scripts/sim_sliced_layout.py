@@ -140,3 +140,51 @@ for b in range(min(24, len(g_sorted8))):
             M[t * 8 + e, a * 4 + c4] = sq
         wf_b.append(wavefronts(M))
 print(f"variant B LDS.U8 wavefronts per request: {np.concatenate(wf_b).mean():.2f}")
+
+# ---- variant B with "fuller rounds": a round in which at least `thr` of the 32 banks still have an entry is padded to all
+# 32 slots (missing banks get padding entries), so the entry index keeps its phase with the bank; later rounds stay ragged
+def padded_round_order(banks, rot, thr):
+    kb = (banks - rot) % 32
+    cnt = np.bincount(kb, minlength=32)
+    seq = []
+    k = 0
+    while True:
+        present = np.nonzero(cnt > k)[0]
+        if len(present) == 0:
+            break
+        if len(present) >= thr * 32:
+            row = np.full(32, -1)
+            row[present] = (present + rot) % 32
+            seq.extend(row.tolist())
+        else:
+            seq.extend(((present + rot) % 32).tolist())
+        k += 1
+    return np.array(seq, int)
+
+
+for thr in (1.01, 0.9, 0.75, 0.5):
+    tot_entries = 0
+    wf = []
+    for b in range(min(24, len(g_sorted8))):
+        lines = perm[b * 8:(b + 1) * 8]
+        for q in range(D * NCH):
+            d, ch = divmod(q, NCH)
+            seqs = []
+            for a, j in enumerate(lines):
+                c, k = cell[starts[j]:starts[j + 1]], code[starts[j]:starts[j + 1]]
+                sel = c[(k == d) & (c // CH == ch)]
+                bank = ((16 + sel - ch * CH) // 4) % 32
+                seqs.append(padded_round_order(bank, a, thr))
+            T = max((len(sq) + 31) // 32 for sq in seqs)
+            tot_entries += T * 32 * 8
+            M = -np.ones((T * 8, 32), int)
+            for a in range(8):
+                sq = seqs[a]
+                idx = np.arange(len(sq))
+                grp, e = idx // 8, idx % 8
+                t, c4 = grp // 4, grp % 4
+                M[t * 8 + e, a * 4 + c4] = sq
+            wf.append(wavefronts(M))
+    base = int(32 * steps[: min(24, len(g_sorted8))].sum()) * GE
+    print(f"variant B, rounds with >= {thr:.2f} occupancy padded: {np.concatenate(wf).mean():.2f} wavefronts per request, "
+          f"{100 * (tot_entries / base - 1):+.1f} % bytes vs unpadded variant B")
