@@ -133,6 +133,71 @@ def cpu_linear_passes(orc, labels, lenA, budget_s, max_passes):
     return t_tot, passes, out
 
 
+def extra_passes(st, w, info, peak, args):
+    """Device-timed (CUDA events, back to back, rotating label sets; every pass streams more than L2) numbers for the other
+    passes of the hot path on the same store: what `roofline` reports for the linear step, per pass."""
+    import torch
+
+    dev = torch.device("cuda", torch.cuda.current_device())
+    n, m, nnz = w["n"], w["m"], w["nnz_total"]
+    g = torch.Generator(device="cpu")
+    g.manual_seed(11)
+    P = 3
+    cl = [torch.randint(0, 3, (n + 16,), generator=g, dtype=torch.uint8).to(dev) for _ in range(P)]
+    sl = [torch.randint(0, 3, (m + 16,), generator=g, dtype=torch.uint8).to(dev) for _ in range(P)]
+    K = 12
+    cn = [torch.randint(0, K, (n + 16,), generator=g, dtype=torch.uint8).to(dev) for _ in range(P)]
+    sn = [torch.randint(0, K, (m + 16,), generator=g, dtype=torch.uint8).to(dev) for _ in range(P)]
+    present = torch.tril(torch.ones(K, K, dtype=torch.uint8)).contiguous().to(dev)
+    big = max(n, m)
+    lab_out = torch.empty(m + 16, dtype=torch.uint8, device=dev)
+    nobs_out = torch.empty(2 * m, dtype=torch.int32, device=dev)
+    S0 = torch.empty(big * 3, dtype=torch.float64, device=dev)
+    S1 = torch.empty_like(S0)
+    No = torch.empty(big * 3, dtype=torch.int32, device=dev)
+    Nv = torch.empty_like(No)
+    b0, b1 = torch.empty(16, dtype=torch.float64, device=dev), torch.empty(16, dtype=torch.float64, device=dev)
+    bn, bv = torch.empty(16, dtype=torch.int64, device=dev), torch.empty(16, dtype=torch.int64, device=dev)
+    per_node = torch.empty(K, dtype=torch.float64, device=dev)
+    per_cell = torch.empty(n, dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    by_snv = info["stream4_bytes_by_snv"] or info["stream_bytes_by_snv"]
+    by_cell = info["stream4_bytes_by_cell"] or info["stream_bytes_by_cell"]
+    nsub_s = info["dense_codes_by_snv"] * info["chunks_by_snv"]
+    nsub_c = info["dense_codes_by_cell"] * info["chunks_by_cell"]
+    ctas = info["sm_count"]
+    fixed_s = (m * nsub_s + 1) * 4 + (m + 1) * 8 + n * ctas
+    fixed_c = (n * nsub_c + 1) * 4 + (n + 1) * 8 + m * ctas
+    passes = {
+        "assign_branching": (lambda i: st.assign_branching_dev(cl[i % P], lab_out, nobs_out, stream=stream), by_snv + fixed_s + 9 * m,
+                             "ph_assign_branching: K1 + 3-way K1a, 2 cell clusters (branching_split.py:293-348)"),
+        "snv_table_c2": (lambda i: st.snv_table_dev(cl[i % P], 2, S0, S1, No, Nv, stream=stream), by_snv + fixed_s + 48 * m,
+                         "ph_snv_table: K1, S0/S1/Nobs/Nvar for 2 cell clusters"),
+        "cell_table_q2": (lambda i: st.cell_table_dev(sl[i % P], 2, S0, S1, No, Nv, stream=stream), by_cell + fixed_c + 48 * n,
+                          "ph_cell_table: K2, per-cell table over 2 SNV clusters (calc_tmb / check_metrics)"),
+        "block_sums_2x2": (lambda i: st.block_sums_dev(cl[i % P], 2, sl[i % P], 2, b0, b1, bn, bv, stream=stream), by_snv + fixed_s + 96 * m,
+                           "ph_block_sums: K3 = K1 table + fixed-order block reduction (compute_norm_likelihood / check_obs)"),
+        "tree_loglik_k12": (lambda i: st.tree_loglik_dev(cn[i % P], sn[i % P], present, K, per_node, per_cell, stream=stream), by_cell + fixed_c + 16 * n,
+                            "ph_tree_loglik: variant log-likelihood of a 12-node tree (clonal_tree.py:932-944)"),
+    }
+    out = {}
+    reps = max(5, min(args.steps, 20))
+    for name, (fn, phys, what) in passes.items():
+        for i in range(3):
+            fn(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(reps):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        out[name] = {"ms": ms, "nnz_per_s": nnz / (ms * 1e-3), "physical_bytes": int(phys), "physical_gbs": phys / (ms * 1e-3) / 1e9,
+                     "frac": phys / (ms * 1e-3) / 1e9 / peak, "what": what}
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ arms
 def run_reference(args):
     """CPU arm: the sparse oracle port of the reference path (OpenMP, all host cores) on the same workload."""
@@ -168,7 +233,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, w, 1, "host memory (no GPU on this arm)"),
+        "config": workload_config(args, w, args.gpus),
+        "notes": {"residency": "host memory (no GPU on this arm)", "l2_policy": "n/a (CPU arm; 0.8 GB of observations streamed per pass)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads(), "kind": "port",
                          "sample": f"all {w['nnz_total']} observations, {args.steps} timed passes; the dense reference "
                                    "cannot allocate this shape (4 x 160 GB), oracle/oracle_sparse.c restates its sums over CSC"},
@@ -178,19 +244,38 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, w, world, residency, exchange=None, l2_policy=None):
+def workload_config(args, w, world, exchange=None):
+    """Names the workload only (identical in both arms); how each arm handles L2 / residency is reported under `notes`."""
     c = w["cfg"]
     return {"workload": f"{args.workload}: synthetic {c['n']} cells x {c['m']} SNVs, coverage {c['cov']}, {c['K']} clones "
                         f"(BASELINE.json configs[2]); step = linear-split SNV reassignment pass (K1+K1a) over all observations",
             "nnz": w["nnz_total"], "cells": c["n"], "snvs": c["m"], "coverage": c["cov"], "clones": c["K"],
-            "sharding": ((f"SNVs sharded over {world} rank(s), all cells on every rank: per-SNV tables are independent, no partial-table "
-                          "exchange; each batch's labels + counts pushed as one record to every rank over NVLink peer memory while the kernel streams on, "
-                          "the same launch then waits for the world's flags and unpacks the window (one kernel per step, no NCCL)")
-                         if exchange == "snv-peer" else
-                         (f"cells sharded over {world} rank(s); " + ("per-SNV integer histograms pushed to the owning rank over NVLink peer memory, labels pushed back (no NCCL)"
-                                                                    if exchange == "peer" else "NCCL all-reduce of the [S0|S1|Nobs] table"))) if world > 1 else "single GPU",
-            "l2_policy": l2_policy or "inputs larger than L2 (0.8 GB of observations streamed per pass vs 126 MB L2); label vectors rotate every step",
-            "residency": residency}
+            "l2_policy": l2_policy_for(w["nnz_total"], world)}
+
+
+L2_NOMINAL = 134_217_728   # bytes; B200 reports 126-133 MB depending on the query: the rule below must not depend on it
+
+
+def needs_l2_flush(nnz_total, world):
+    """A rank streams ~2.1 B per observation per pass: below twice the L2 size part of it would stay cached between steps."""
+    return 2.1 * nnz_total / world < 2 * L2_NOMINAL
+
+
+def l2_policy_for(nnz_total, world):
+    return ("L2 flushed (write of a buffer of twice its size, untimed) before every timed step" if needs_l2_flush(nnz_total, world)
+            else "inputs larger than L2 (no flush)")
+
+
+def sharding_note(world, exchange):
+    if world == 1:
+        return "single GPU"
+    if exchange == "snv-peer":
+        return (f"SNVs sharded over {world} rank(s), all cells on every rank: per-SNV tables are independent, no partial-table exchange; every batch's "
+                "labels + counts leave the kernel as self-validating 8-byte words (step counter in the upper half) stored into every rank's window over "
+                "NVLink peer memory while the kernel streams on; the same launch then polls its own window and unpacks it (one kernel per step, no fence, "
+                "no flag, no NCCL)")
+    return f"cells sharded over {world} rank(s); " + ("per-SNV integer histograms pushed to the owning rank over NVLink peer memory, labels pushed back (no NCCL)"
+                                                      if exchange == "peer" else "NCCL all-reduce of the [S0|S1|Nobs] table")
 
 
 def run_ours(args):
@@ -228,7 +313,6 @@ def run_ours(args):
     else:
         w = make_workload(args.workload, dev, rank / world, (rank + 1) / world)
     n_loc, m, nnz_loc, nnz_tot = w["n_local"], w["m"], w["nnz_local"], w["nnz_total"]
-    pv, pt, code_t = encode_pairs_device(w["var"], w["total"]) if (rank == 0 and world == 1 and not args.no_cpu) else (None, None, None)
     pairs = None
     if world > 1:  # the ranks must agree on the (var,total) codes: the exchanged histograms are indexed by code
         from phertilizer_b200.sharded import global_pairs
@@ -260,7 +344,7 @@ def run_ours(args):
     # L2 policy: a pass streams the rank's observations once.  On one GPU that is 0.8 GB against 126 MB of L2; a rank of
     # a multi-GPU run may hold little enough for L2 to keep part of it between steps -> flush L2 before every timed step
     l2_bytes = int(torch.cuda.get_device_properties(dev).L2_cache_size)
-    flush_l2 = int(info["stream_bytes_by_snv"]) < 2 * l2_bytes
+    flush_l2 = needs_l2_flush(nnz_tot, world)
     flush_buf = torch.empty(2 * l2_bytes, dtype=torch.uint8, device=dev) if flush_l2 else None
     if flush_l2:
         l2_policy = (f"per-rank stream of {info['stream_bytes_by_snv'] / 1e6:.0f} MB is below 2 x L2 ({l2_bytes / 1e6:.0f} MB): L2 flushed (write of a "
@@ -273,9 +357,10 @@ def run_ours(args):
     P = 4
     g = torch.Generator(device="cpu")
     g.manual_seed(7)
-    labs_h, labs_d, lenA = [], [], []
+    labs_h, labs_d, lenA, full_labs_h = [], [], [], []
     for _ in range(P):
         full = (torch.rand(w["n"], generator=g) < 0.5).to(torch.uint8)
+        full_labs_h.append(full)
         lenA.append(float(full.sum()))
         loc = torch.zeros(n_loc + 16, dtype=torch.uint8)
         loc[:n_loc] = full[w["lo"]:w["hi"]]          # SNV-sharded: lo..hi = all cells
@@ -423,12 +508,12 @@ def run_ours(args):
             return st.assign_linear(labs_h[i % P].numpy()[:n_loc], lenA[i % P], out=(lab_out_np, nobs_out_np))
         labs_d[i % P].copy_(labs_h[i % P], non_blocking=True)
         if snv_store is not None:
-            # the collect phase of the kernel unpacks straight into the page-locked host arrays (mapped memory): no D2H copy
-            snv_store.assign_linear_dev(labs_d[i % P], lenA[i % P], lab_out_h, nobs_out_h)
+            # the collect phase unpacks in the peers' work order (scattered): into device arrays, then two D2H copies
+            snv_store.assign_linear_dev(labs_d[i % P], lenA[i % P], lab_out, nobs_out)
         else:
             sharded.assign_linear_dev(labs_d[i % P], lenA[i % P], packed, lab_out, nobs_out)
-            lab_out_h.copy_(lab_out, non_blocking=True)
-            nobs_out_h.copy_(nobs_out, non_blocking=True)
+        lab_out_h.copy_(lab_out, non_blocking=True)
+        nobs_out_h.copy_(nobs_out, non_blocking=True)
         torch.cuda.synchronize()
         return lab_out_h, nobs_out_h
 
@@ -456,29 +541,51 @@ def run_ours(args):
         e2e_s = float(t.item())
     e2e_value = args.steps * nnz_tot / e2e_s
 
-    # ---------------- CPU baseline (rank 0, N = 1): the oracle port on the host cores, and a parity spot check ----------------
+    # ---------------- CPU baseline + parity on EVERY line (rank 0): the oracle port on the host cores ----------------
+    # Every rank runs the N-rank step once per label set; rank 0 keeps the assembled outputs and compares each of them
+    # with oracle/oracle_sparse.c on ALL observations (N > 1: a wrong rank offset or a lost word cannot hide).
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        from oracle.oracle_sparse import SparseOracle, threads, use_all_cores
-        from phertilizer_b200.like_lut import like_tables
+    peer = snv_store.peer if snv_store is not None else (sharded.peer if sharded is not None else None)
+    if not args.no_cpu:
+        graphs = None
+        got = []
+        for j in range(P):
+            step_device(j)
+            torch.cuda.synchronize()
+            got.append((lab_out[:m].cpu().numpy().copy(), nobs_out.cpu().numpy().copy()))
+        timed_out = bool(peer.timed_out()) if peer is not None else False
+        verdict = torch.ones(1, dtype=torch.int32, device=dev)
+        if rank == 0:
+            from oracle.oracle_sparse import SparseOracle, threads, use_all_cores
+            from phertilizer_b200.store import encode_with_table
 
-        use_all_cores()
-        t0 = time.time()
-        L0, L1 = like_tables(pv, pt)
-        colptr, row, code = host_csc(w, code_t)
-        orc = SparseOracle.from_csc(w["n"], m, colptr, row, code, L0, L1, pv > 0)
-        log(f"[cpu] host CSC ready in {time.time() - t0:.1f}s")
-        hl = [l.numpy()[:n_loc] for l in labs_h]
-        t_tot, passes, (o_lab, o_nobs) = cpu_linear_passes(orc, hl, lenA, args.cpu_seconds, 40)
-        g_lab, g_nobs = st.assign_linear(hl[(passes - 1) % P], lenA[(passes - 1) % P])
-        same = bool(np.array_equal(g_lab, o_lab) and np.array_equal(g_nobs, o_nobs))
-        log(f"[cpu] {passes} passes in {t_tot:.2f}s on {threads()} threads; GPU labels == oracle labels: {same}")
-        if not same:
+            use_all_cores()
+            t0 = time.time()
+            wf = w if (world == 1 or snv_sharded) else make_workload(args.workload, dev)   # the oracle walks ALL observations
+            code_t = encode_with_table(wf["var"], wf["total"], st.pair_var, st.pair_total)
+            colptr, row, code = host_csc(wf, code_t)
+            orc = SparseOracle.from_csc(wf["n"], m, colptr, row, code, st.L0, st.L1, np.asarray(st.pair_var) > 0)
+            log(f"[cpu] host CSC ready in {time.time() - t0:.1f}s")
+            full_labs = [l.numpy() for l in full_labs_h]
+            t_tot, passes, _ = cpu_linear_passes(orc, full_labs, lenA, args.cpu_seconds if world == 1 else min(args.cpu_seconds, 3.0), 40)
+            same = not timed_out
+            for j in range(P):
+                o_lab, o_nobs = orc.assign_linear(full_labs[j], lenA[j])
+                same = same and bool(np.array_equal(got[j][0], o_lab) and np.array_equal(got[j][1], o_nobs))
+            log(f"[cpu] {passes} passes in {t_tot:.2f}s on {threads()} threads; {world}-rank GPU labels + Nobs == oracle on {P} label sets: {same}"
+                + (" (a peer wait TIMED OUT)" if timed_out else ""))
+            cpu = {"value": passes * nnz_tot / t_tot, "unit": UNIT, "cores": threads(), "kind": "port",
+                   "sample": f"all {nnz_tot} observations x {passes} passes of oracle/oracle_sparse.c orc_assign_linear (OpenMP); "
+                             "the dense numpy reference cannot allocate this shape (4 x 160 GB)",
+                   "gpu_matches_oracle": same, "label_sets_compared": P}
+            verdict[0] = 1 if same else 0
+        if world > 1:
+            dist.broadcast(verdict, 0)
+        if int(verdict.item()) == 0:
+            if rank == 0:
+                print(json.dumps({"metric": METRIC, "error": "GPU assignment differs from the CPU oracle on the benchmark workload",
+                                  "n_gpus": world, "cpu_baseline": cpu}), flush=True)
             raise SystemExit("bench: GPU assignment differs from the CPU oracle on the benchmark workload")
-        cpu = {"value": passes * nnz_tot / t_tot, "unit": UNIT, "cores": threads(), "kind": "port",
-               "sample": f"all {nnz_tot} observations x {passes} passes of oracle/oracle_sparse.c orc_assign_linear (OpenMP); "
-                         "the dense numpy reference cannot allocate this shape (4 x 160 GB)",
-               "gpu_matches_oracle": same}
 
     if rank == 0:
         peaks = {}
@@ -494,7 +601,7 @@ def run_ours(args):
         # offsets, one label image per CTA, the outputs (labels + counts)
         nsub = info["dense_codes_by_snv"] * info["chunks_by_snv"]
         # single GPU: whole-orientation passes read the batched-4 copy of the stream when the store keeps one
-        stream = info["stream4_bytes_by_snv"] if (world == 1 and info.get("stream4_bytes_by_snv", 0)) else info["stream_bytes_by_snv"]
+        stream = info["stream4_bytes_by_snv"] if (exchange in (None, "snv-peer") and info.get("stream4_bytes_by_snv", 0)) else info["stream_bytes_by_snv"]
         phys = stream + (m_loc * nsub + 1) * 4 + (m_loc + 1) * 8 + n_loc * info["sm_count"] + 5 * m_loc
         achieved = ab / (kernel_ms * 1e-3) / 1e9
         traffic = None
@@ -506,16 +613,22 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, w, world, "observations resident in HBM; `value` also has labels resident, `e2e` copies them every step", exchange, l2_policy),
+            "config": workload_config(args, w, world, exchange),
+            "notes": {"sharding": sharding_note(world, exchange), "l2_policy": l2_policy,
+                      "residency": "observations resident in HBM; `value` also has labels resident, `e2e` copies them every step"},
             "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n_loc) * world, "d2h_bytes_per_step": 5 * m * world,
                     "ms_per_step": 1e3 * e2e_s / args.steps,
                     "path": "ph_assign_linear(on_device=0): host labels -> pinned -> H2D, kernel storing SNV labels + Nobs into the page-locked host arrays, sync"
-                            if world == 1 else ("pinned H2D labels, ph_peer_assign_linear_snv unpacking straight into page-locked host arrays (labels + Nobs)" if exchange == "snv-peer" else
+                            if world == 1 else ("pinned H2D labels, ph_peer_assign_linear_snv, D2H labels + Nobs" if exchange == "snv-peer" else
                                                 "pinned H2D labels, ph_peer_assign_linear, D2H labels + Nobs" if exchange == "peer" else
                                                 "pinned H2D labels, ph_snv_partial, NCCL all-reduce, ph_finish_linear, D2H labels + Nobs")},
             "gpu_launches": int(launches), "cuda_graphs": graphs is not None,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            # `achieved` / `frac_alg6` follow SURVEY 8d (ALG-6 bytes: 4 B index + 2 B code per observation); the store
+            # moves a third of that (16-bit entries, code implied by the sub-segment), so ALG-6 bytes / time exceeds the
+            # HBM peak and is NOT a utilisation.  `frac` = bytes the kernel really moves / time / measured peak.
+            "roofline": {"bound": "hbm", "achieved": phys / (kernel_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": phys / (kernel_ms * 1e-3) / 1e9 / peak, "achieved_alg6": achieved, "frac_alg6": achieved / peak,
                          "traffic": traffic if world == 1 else None,
                          "kernel": "k_pass<MODE_LINEAR>" if world == 1 else ("k_pass<MODE_TABLE>" if exchange == "nccl" else
                                    ("k_pass<MODE_LINEAR, push + collect> (whole step = one launch)" if exchange == "snv-peer" else
@@ -525,11 +638,11 @@ def run_ours(args):
                          "physical_gbs": phys / (kernel_ms * 1e-3) / 1e9, "physical_frac": phys / (kernel_ms * 1e-3) / 1e9 / peak,
                          "peak_source": peak_src + ", of measured"},
             "cpu_baseline": cpu,
+            "extra": {"passes": extra_passes(st, w, info, peak, args) if world == 1 else None},
             "store": {k: info[k] for k in ("dense_codes_by_snv", "chunks_by_snv", "group_by_snv", "labels_in_smem_by_snv",
                                            "stream_bytes_by_snv", "stream4_bytes_by_snv", "device_bytes")},
         }
         print(json.dumps(line), flush=True)
-    peer = snv_store.peer if snv_store is not None else (sharded.peer if sharded is not None else None)
     if peer is not None:
         if peer.timed_out():
             log(f"[rank {rank}] WARNING: a peer wait timed out during the run")

@@ -45,6 +45,20 @@ __global__ void k_code_hist(const uint16_t* __restrict__ code, int64_t nnz, unsi
   if (threadIdx.x < 64 && threadIdx.x < n_codes && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
 }
 
+// duplicate check: one key per observation, (SNV, cell); equal neighbours after the sort = the pair is listed twice --
+// whatever the two entries' (var,total) codes are (the reference's `unstack` raises on such input, phertilizer.py:153-161)
+__global__ void k_pair_keys(const int32_t* __restrict__ snv, const int32_t* __restrict__ cell, int64_t nnz, uint64_t* __restrict__ keys) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < nnz; i += stride) keys[i] = ((uint64_t)(uint32_t)snv[i] << 32) | (uint32_t)cell[i];
+}
+__global__ void k_adjacent_equal(const uint64_t* __restrict__ keys, int64_t nnz, int* dup) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x + 1;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < nnz; i += stride)
+    if (keys[i] == keys[i - 1]) *dup = 1;
+}
+
 // key = segment id << 32 | payload.  Segment id = line * (NSUB + 1) + s; s = d * NCH + chunk for a dense code d,
 // s = NSUB for the tail.  Payload: idx16 (dense; optionally with the shared-memory bank of its label above it so that
 // the sort groups a sub-segment's entries by bank) or  minor | code << minor_bits  (tail).
@@ -63,7 +77,7 @@ __global__ void k_make_keys(const int32_t* __restrict__ major, const int32_t* __
     }
     uint32_t s, payload;
     const uint32_t ch = mn / (uint32_t)CH;
-    const uint32_t idx = 16u + (mn - ch * (uint32_t)CH);
+    const uint32_t idx = (uint32_t)PH_PAD + (mn - ch * (uint32_t)CH);
     if (c < (uint32_t)D) {
       s = c * (uint32_t)NCH + ch;
       payload = idx | (bank_order ? (((idx >> 2) & 31u) << 16) : 0u);
@@ -87,17 +101,66 @@ __global__ void k_seg_offsets(const uint64_t* __restrict__ keys, int64_t nnz, in
   off[s] = lo;
 }
 
-// per sub-segment: groups of PH_GE entries (rounded up); per line: tail entries
-__global__ void k_seg_sizes(const int64_t* __restrict__ off, int64_t n_major, int NSUB, int64_t* __restrict__ groups,
-                            int64_t* __restrict__ tails) {
+// Padded rounds.  In round order (k_round_keys) round k of a sub-segment holds the k-th entry of every bank that has one;
+// the first rounds are nearly full, the last ones ragged, and once a round is short the entry index loses its phase with
+// the bank, so the 32 lanes of a gather collide (2.17 wavefronts per LDS.U8 measured on C3).  The first K rounds -- those
+// in which at least `min_fill` of the 32 banks still hold an entry -- are therefore laid out on a fixed grid: entry of
+// (rotated) bank b of round k at position 32 k + b, the banks without an entry get a padding entry THAT SITS IN THE
+// SAME BANK (idx16 = 4 * bank: the excluded region of the label image has one word per bank).  Those gathers are
+// conflict free; the rest of the sub-segment follows compacted as before.
+//   plan[2 * sub]     = K, the padded rounds
+//   plan[2 * sub + 1] = R, the entries those rounds hold       (padded length = 32 K + cnt - R)
+// `sorted`: keys ordered by (segment, bank, idx16).
+__global__ void k_round_plan(const uint64_t* __restrict__ sorted, const int64_t* __restrict__ off, int64_t n_major, int NSUB,
+                             int min_fill, int32_t* __restrict__ plan) {
+  const int64_t sub = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (sub >= n_major * NSUB) return;
+  const int64_t line = sub / NSUB;
+  const int64_t seg = line * (NSUB + 1) + (sub - line * NSUB);
+  const int64_t b0 = off[seg], b1 = off[seg + 1];
+  int K = 0, R = 0;
+  if (min_fill <= 32 && b1 - b0 >= min_fill) {
+    int cnt[32];
+    int64_t lo = b0;
+    for (int b = 0; b < 32; ++b) {  // first position of bank b + 1 inside the sub-segment
+      const uint64_t want = ((uint64_t)seg << 16) | (uint64_t)(b + 1);
+      int64_t l = lo, h = b1;
+      while (l < h) {
+        const int64_t mid = (l + h) >> 1;
+        if ((sorted[mid] >> 16) < want) l = mid + 1; else h = mid;
+      }
+      cnt[b] = (int)(l - lo);
+      lo = l;
+    }
+    for (;;) {  // the occupancy of round K only falls with K
+      int nk = 0;
+#pragma unroll
+      for (int b = 0; b < 32; ++b) nk += cnt[b] > K ? 1 : 0;
+      if (nk < min_fill) break;
+      R += nk;
+      ++K;
+    }
+  }
+  plan[2 * sub] = K;
+  plan[2 * sub + 1] = R;
+}
+
+// per sub-segment: groups of PH_GE entries (rounded up, padded rounds included); per line: tail entries
+__global__ void k_seg_sizes(const int64_t* __restrict__ off, int64_t n_major, int NSUB, const int32_t* __restrict__ plan,
+                            int64_t* __restrict__ groups, int64_t* __restrict__ tails) {
   int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t nseg = n_major * (NSUB + 1);
   if (k >= nseg) return;
   const int64_t line = k / (NSUB + 1);
   const int s = (int)(k - line * (NSUB + 1));
-  const int64_t cnt = off[k + 1] - off[k];
-  if (s < NSUB) groups[line * NSUB + s] = (cnt + PH_GE - 1) / PH_GE;
-  else tails[line] = cnt;
+  int64_t cnt = off[k + 1] - off[k];
+  if (s < NSUB) {
+    const int64_t sub = line * NSUB + s;
+    if (plan) cnt += 32 * (int64_t)plan[2 * sub] - plan[2 * sub + 1];
+    groups[sub] = (cnt + PH_GE - 1) / PH_GE;
+  } else {
+    tails[line] = cnt;
+  }
 }
 
 __global__ void k_narrow(const int64_t* __restrict__ in, int64_t n, uint32_t* __restrict__ out) {
@@ -157,9 +220,47 @@ __device__ __forceinline__ int64_t place(int64_t r, int64_t cnt, int bank_order)
   return ((tf << 5) + ln) * PH_GE + e;
 }
 
+// where padded position r (of a sub-segment of cnt padded entries) lives in the two copies of the stream
+__device__ __forceinline__ void put_entry(uint16_t v, int64_t r, int64_t cnt, int64_t line, int s, int NSUB, int bank_order,
+                                          const uint32_t* __restrict__ sub_off, uint16_t* __restrict__ half,
+                                          const int32_t* __restrict__ pos4, const uint32_t* __restrict__ bstep_off,
+                                          uint16_t* __restrict__ half4) {
+  half[(int64_t)sub_off[line * NSUB + s] * PH_GE + place(r, cnt, bank_order)] = v;
+  if (half4) {
+    // batched-4 copy: position r of the line's sub-segment; 32 positions are one warp step (4 lanes x 8 slots),
+    // lane c = (r % 32) / 8 of line slot a, slot r % 8
+    const int p = pos4[line];
+    const int64_t b = p >> 3, a = p & 7;
+    const int64_t step = (int64_t)bstep_off[b * NSUB + s] + (r >> 5);
+    half4[((step << 5) + a * 4 + ((r >> 3) & 3)) * PH_GE + (r & 7)] = v;
+  }
+}
+
+// the padding entries of the padded rounds (k_round_plan): position 32 k + b holds idx16 = 4 * bank, i.e. the excluded
+// word of the very bank the position is reserved for; the real entries overwrite theirs afterwards (k_scatter).
+// One warp per sub-segment.
+__global__ void k_fill_rounds(const int64_t* __restrict__ off, int64_t n_major, int NSUB, const int32_t* __restrict__ plan,
+                              const uint32_t* __restrict__ sub_off, int bank_order, uint16_t* __restrict__ half,
+                              const int32_t* __restrict__ pos4, const uint32_t* __restrict__ bstep_off,
+                              uint16_t* __restrict__ half4) {
+  const int64_t sub = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int b = threadIdx.x & 31;
+  if (sub >= n_major * NSUB) return;
+  const int K = plan[2 * sub];
+  if (K == 0) return;
+  const int64_t line = sub / NSUB;
+  const int s = (int)(sub - line * NSUB);
+  const int64_t seg = line * (NSUB + 1) + s;
+  const int64_t cnt = off[seg + 1] - off[seg] + 32 * (int64_t)K - plan[2 * sub + 1];
+  const int rot = pos4 ? (pos4[line] & 7) : 0;
+  const uint16_t v = (uint16_t)(4 * ((b + rot) & 31));
+  for (int k = 0; k < K; ++k) put_entry(v, 32 * (int64_t)k + b, cnt, line, s, NSUB, bank_order, sub_off, half, pos4, bstep_off, half4);
+}
+
 __global__ void k_scatter(const uint64_t* __restrict__ keys, int64_t nnz, const int64_t* __restrict__ off, int NSUB,
-                          const uint32_t* __restrict__ sub_off, const int64_t* __restrict__ tail_off, int bank_order,
-                          uint16_t* __restrict__ half, uint32_t* __restrict__ tail_words, const int32_t* __restrict__ pos4,
+                          const int32_t* __restrict__ plan, const uint32_t* __restrict__ sub_off,
+                          const int64_t* __restrict__ tail_off, int bank_order, uint16_t* __restrict__ half,
+                          uint32_t* __restrict__ tail_words, const int32_t* __restrict__ pos4,
                           const uint32_t* __restrict__ bstep_off, uint16_t* __restrict__ half4, int* dup) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -169,18 +270,17 @@ __global__ void k_scatter(const uint64_t* __restrict__ keys, int64_t nnz, const 
     const int64_t seg = (int64_t)(k >> 32);
     const int64_t line = seg / (NSUB + 1);
     const int s = (int)(seg - line * (NSUB + 1));
-    const int64_t r = i - off[seg];
+    int64_t r = i - off[seg];  // rank in round order
     if (s < NSUB) {
-      const int64_t cnt = off[seg + 1] - off[seg];
-      half[(int64_t)sub_off[line * NSUB + s] * PH_GE + place(r, cnt, bank_order)] = (uint16_t)k;
-      if (half4) {
-        // batched-4 copy: the r-th entry in round order is entry r of the line's sub-segment; round r / 32 is one warp
-        // step (4 lanes x 8 slots), lane c = (r % 32) / 8 of line slot a, slot r % 8
-        const int p = pos4[line];
-        const int64_t b = p >> 3, a = p & 7;
-        const int64_t step = (int64_t)bstep_off[b * NSUB + s] + (r >> 5);
-        half4[((step << 5) + a * 4 + ((r >> 3) & 3)) * PH_GE + (r & 7)] = (uint16_t)k;
+      int64_t cnt = off[seg + 1] - off[seg];
+      if (plan) {
+        // keys in round order are (segment, round, rotated bank, idx16): padded rounds sit on the 32-wide grid
+        const int64_t K = plan[2 * (line * NSUB + s)], R = plan[2 * (line * NSUB + s) + 1];
+        const int64_t round = (int64_t)((k >> 21) & 0x7FFull), bank = (int64_t)((k >> 16) & 31ull);
+        cnt += 32 * K - R;
+        r = round < K ? 32 * round + bank : 32 * K + (r - R);
       }
+      put_entry((uint16_t)k, r, cnt, line, s, NSUB, bank_order, sub_off, half, pos4, bstep_off, half4);
     } else {
       tail_words[tail_off[line] + r] = (uint32_t)k;
     }
@@ -234,11 +334,11 @@ int build_orient(ph_handle* h, PhOrient* o, const int32_t* d_major, const int32_
   o->n_major = n_major;
   o->n_minor = n_minor;
   o->chunk_bits = h->chunk_bits;
-  const int CH = (1 << o->chunk_bits) - 16;
+  const int CH = (1 << o->chunk_bits) - PH_PAD;
   o->NCH = (n_minor + CH - 1) / CH;
   {
     const int last = n_minor - (o->NCH - 1) * CH;
-    o->lab_bytes = (((o->NCH - 1) << o->chunk_bits) + 16 + last + 15) & ~15;
+    o->lab_bytes = (((o->NCH - 1) << o->chunk_bits) + PH_PAD + last + 15) & ~15;
   }
   o->minor_bits = ph_ceil_log2((uint64_t)o->lab_bytes);  // a tail word = label-image address | code << minor_bits
   int D = 0;
@@ -266,6 +366,7 @@ int build_orient(ph_handle* h, PhOrient* o, const int32_t* d_major, const int32_
   int64_t* d_off = nullptr;      // [nseg + 1] positions in the sorted order
   int64_t* d_sizes = nullptr;    // [n_major * NSUB + 1 | n_major + 1] sizes, then their exclusive sums
   int32_t* d_pos4 = nullptr;     // [n_major] rank of every line in the shape order of the batched-4 copy
+  int32_t* d_plan = nullptr;     // [n_major * NSUB][2] padded rounds of every sub-segment (k_round_plan)
   int rc = PH_OK;
   auto body = [&]() -> int {
     const int64_t n_sub = (int64_t)n_major * NSUB;
@@ -291,14 +392,21 @@ int build_orient(ph_handle* h, PhOrient* o, const int32_t* d_major, const int32_
     }
     k_seg_offsets<<<(unsigned)((nseg + 1 + threads - 1) / threads), threads>>>(sorted, nnz, nseg, d_off);
     ph_count_launch();
+    if (nnz > 0 && h->bank_order && NSUB > 0 && h->round_fill <= 32) {
+      PH_CUDA(cudaMalloc(&d_plan, (size_t)n_sub * 2 * sizeof(int32_t)));
+      k_round_plan<<<(unsigned)((n_sub + threads - 1) / threads), threads>>>(sorted, d_off, n_major, NSUB, h->round_fill, d_plan);
+      ph_count_launch();
+    }
     if (nseg > 0) {
-      k_seg_sizes<<<(unsigned)((nseg + threads - 1) / threads), threads>>>(d_off, n_major, NSUB, d_groups, d_tails);
+      k_seg_sizes<<<(unsigned)((nseg + threads - 1) / threads), threads>>>(d_off, n_major, NSUB, d_plan, d_groups, d_tails);
       ph_count_launch();
     }
     // ---- batched-4 copy (see PhOrient): shape-sort the lines, fix every line's batch and slot, size the stream
-    // (only where the pass kernel can place the label image at a 64 KB-aligned shared address, which LAY = 3 builds on)
-    const bool want4 = h->batch4 && h->bank_order && h->aligned_image && nnz > 0 && NSUB > 0 && o->chunk_bits == 16 &&
-                       n_major >= 8 && (size_t)o->lab_bytes + 65536 + 16384 <= (size_t)h->max_smem;
+    // (only where the label image and the per-warp tables of a 1024-thread CTA fit in shared memory: LAY = 3 with the
+    // image at a 64 KB-aligned address when there is room for that, LAY = 4 otherwise)
+    const size_t tab4 = 32 * (size_t)(8 * (NSUB + 1) + 8 * D * PH_MAX_FAST_CLUSTERS + 2 * 8 + 3) * 4 + (size_t)h->n_codes * 17 + 256;
+    const bool want4 = h->batch4 && h->bank_order && nnz > 0 && NSUB > 0 && o->chunk_bits == 16 && n_major >= 8 &&
+                       (size_t)o->lab_bytes + tab4 <= (size_t)h->max_smem;
     if (want4) {
       const int nb4 = (n_major + 7) / 8;
       uint32_t *d_key = nullptr, *d_key2 = nullptr, *d_steps = nullptr;
@@ -393,7 +501,12 @@ int build_orient(ph_handle* h, PhOrient* o, const int32_t* d_major, const int32_
     PH_CUDA(cudaMemset(o->tail_words, 0, (size_t)(o->n_tail + 8) * sizeof(uint32_t)));
     h->device_bytes += (int64_t)half_bytes + (o->n_tail + 8) * (int64_t)sizeof(uint32_t);
     if (nnz > 0) {
-      k_scatter<<<blocks, threads>>>(sorted, nnz, d_off, NSUB, o->sub_off, o->tail_off, h->bank_order, o->half,
+      if (d_plan) {
+        k_fill_rounds<<<(unsigned)((n_sub * 32 + threads - 1) / threads), threads>>>(d_off, n_major, NSUB, d_plan, o->sub_off, h->bank_order,
+                                                                                    o->half, o->half4 ? d_pos4 : nullptr, o->bstep_off, o->half4);
+        ph_count_launch();
+      }
+      k_scatter<<<blocks, threads>>>(sorted, nnz, d_off, NSUB, d_plan, o->sub_off, o->tail_off, h->bank_order, o->half,
                                      o->tail_words, o->half4 ? d_pos4 : nullptr, o->bstep_off, o->half4, d_flag + 1);
       ph_count_launch();
     }
@@ -405,6 +518,7 @@ int build_orient(ph_handle* h, PhOrient* o, const int32_t* d_major, const int32_
   cudaFree(d_off);
   cudaFree(d_sizes);
   cudaFree(d_pos4);
+  cudaFree(d_plan);
   return rc;
 }
 
@@ -477,7 +591,7 @@ extern "C" int ph_create(int32_t n_cells, int32_t n_snvs, int64_t nnz, const int
     h->dense_min_share = e ? atof(e) : 0.02;
     e = getenv("PH_CHUNK_BITS");  // test knob: log2 of the label-image stride of one chunk of the minor axis
     h->chunk_bits = e ? atoi(e) : 16;
-    if (h->chunk_bits < 6 || h->chunk_bits > 16) h->chunk_bits = 16;
+    if (h->chunk_bits < 8 || h->chunk_bits > 16) h->chunk_bits = 16;
     e = getenv("PH_BANK_ORDER");  // order a sub-segment's entries by shared-memory bank (default on)
     h->bank_order = e ? atoi(e) : 1;
     e = getenv("PH_CTAS");  // pass kernels: CTAs per SM (1 x 1024 threads, or 2 x 512 when two label images fit)
@@ -486,6 +600,14 @@ extern "C" int ph_create(int32_t n_cells, int32_t n_snvs, int64_t nnz, const int
     h->aligned_image = e ? atoi(e) : 1;
     e = getenv("PH_ZERO_COPY_OUT");  // host-pointer calls: kernels store results straight into page-locked host memory (default on)
     h->zero_copy_out = e ? atoi(e) : 1;
+    // padded rounds (k_round_plan): rounds in which at least this share of the 32 banks hold an entry sit on a fixed
+    // grid with bank-matched padding entries; > 1 disables the padding (round order only)
+    e = getenv("PH_ROUND_FILL");
+    {
+      const double f = e ? atof(e) : 0.75;
+      h->round_fill = f > 1.0 ? 33 : (int)(f * 32.0 + 0.999);
+      if (h->round_fill < 1) h->round_fill = 1;
+    }
     e = getenv("PH_BATCH4");  // keep the batched-4 copy of the dense streams and use the 4-lanes-per-line pass (default on)
     h->batch4 = e ? atoi(e) : 1;
   }
@@ -559,6 +681,15 @@ extern "C" int ph_create(int32_t n_cells, int32_t n_snvs, int64_t nnz, const int
   }
   if (temp_bytes < (1u << 20)) temp_bytes = 1u << 20;  // also serves the offset scans
   PH_TRY(cudaMalloc(&d_temp, temp_bytes));
+  if (nnz > 1) {
+    k_pair_keys<<<h->sm_count * 8, 256>>>(d_snv, d_cell, nnz, kbuf0);
+    cub::DoubleBuffer<uint64_t> db(kbuf0, kbuf1);
+    int end_bit = 32 + ph_ceil_log2((uint64_t)n_snvs + 1);
+    if (end_bit > 64) end_bit = 64;
+    PH_TRY(cub::DeviceRadixSort::SortKeys(d_temp, temp_bytes, db, nnz, 0, end_bit));
+    k_adjacent_equal<<<h->sm_count * 8, 256>>>(db.Current(), nnz, d_flag + 1);
+    ph_count_launch(6);
+  }
   rc = build_orient(h, &h->by_snv, d_snv, d_cell, d_code, n_snvs, n_cells, h_hist, kbuf0, kbuf1, d_temp, temp_bytes, d_flag);
   if (rc != PH_OK) goto done;
   rc = build_orient(h, &h->by_cell, d_cell, d_snv, d_code, n_cells, n_snvs, h_hist, kbuf0, kbuf1, d_temp, temp_bytes, d_flag);

@@ -13,6 +13,9 @@
 #define PH_FIELD_BITS 10    // packed per-lane counter field width (3 labels x 10 bits, excluded label -> bit 30)
 #define PH_GE 8             // entries per group: a lane consumes one 16-byte group per step (32-byte groups were not faster)
 #define PH_FLUSH_GROUPS 127 // 8 increments per group -> a field gains <= 1016 < 1024 between flushes
+#define PH_PAD 128          // "excluded" bytes at the start of every chunk of the label image: one 4-byte word per shared-memory
+                            // bank, so that a padding entry can sit in ANY bank (idx16 = 4 * bank) without colliding with the
+                            // real entries of its warp step (ph_build.cu, padded rounds); idx16 = 0 is the plain padding entry
 
 extern thread_local char ph_err_msg[512];
 void ph_count_launch(int n = 1);
@@ -35,8 +38,8 @@ void ph_count_launch(int n = 1);
 
 // One orientation of the observation store: "lines" are SNVs (by_snv, CSC-like) or cells (by_cell, CSR-like).
 //
-// The minor axis is cut into chunks of CH = 2^chunk_bits - 16 indices, so that an entry is ONE 16-bit half-word
-//   idx16 = 16 + (minor - chunk * CH)            (values 0..15 never occur; 0 is the padding entry)
+// The minor axis is cut into chunks of CH = 2^chunk_bits - PH_PAD indices, so that an entry is ONE 16-bit half-word
+//   idx16 = PH_PAD + (minor - chunk * CH)        (values below PH_PAD are padding entries: they gather an "excluded" label)
 // A line's entries with one of the D most frequent ("dense") (var,total) codes are stored as D * NCH sub-segments
 // ordered by (code, chunk); every sub-segment is padded with idx16 = 0 to a whole number of 16-byte GROUPS (PH_GE = 8
 // entries), so a line -- and any run of consecutive lines -- is one contiguous, 16-byte aligned stream of groups.
@@ -45,7 +48,7 @@ void ph_count_launch(int n = 1);
 // Entries with rarer codes go to the "tail": tail_words = (label-image address) | code << minor_bits, sorted by
 // (code, address) inside a line; tail_off per line.
 // The kernels keep a label image of the minor axis in shared memory with the matching layout: chunk c at byte
-// c << chunk_bits, 16 "excluded" bytes (what the padding entries hit) followed by the labels of its indices.
+// c << chunk_bits, PH_PAD "excluded" bytes (what the padding entries hit) followed by the labels of its indices.
 struct PhOrient {
   uint16_t* half;
   uint32_t* sub_off;
@@ -88,7 +91,7 @@ struct ph_handle {
   double* d_L1;      // [n_codes]
   uint8_t* d_varpos; // [n_codes]
   int64_t device_bytes;
-  int chunk_bits, bank_order, ctas_per_sm, aligned_image, zero_copy_out, batch4;
+  int chunk_bits, bank_order, ctas_per_sm, aligned_image, zero_copy_out, batch4, round_fill;
   double dense_min_avg, dense_min_share;  // a (var,total) code gets its own segment when it has >= this many entries per line on average
   // scratch (device)
   uint8_t* d_lab_minor;  // [max(n,m)] staged labels of the minor axis
@@ -109,18 +112,29 @@ struct ph_handle {
 };
 
 // ---- peer-memory exchange helpers shared by ph_pass.cu and ph_peer.cu
-constexpr size_t kPeerHdrOff = 2048;   // window: flagA[world] at +0, flagB[world] at +1024, SNV block headers {offset, count, B, record bytes}[world] at +2048
-constexpr size_t kPeerRecStride = 128; // bytes reserved per 8 lines of a rank's record region (a record of B lines takes <= 16 B per line)
 constexpr long long kSpinLimit = 6000000000ll;  // ~3 s of SM clocks: a lost peer must not hang the GPU
 
-// what the collect phase of an SNV-sharded step needs (ph_peer.cu fills it, the pass kernel runs it)
-struct PhCollect {
-  const uint8_t* win;     // this rank's window
-  size_t off_rec[2];      // the two record regions (parity of the step)
-  int cap_recs, max_lines, C;
+// SNV-sharded steps (ph_peer.cu, ph_pass.cu): results travel as SELF-VALIDATING 8-byte words  epoch << 32 | payload
+// (the step counter rides in the upper half of every word, NCCL-LL style), so a receiver polls the data itself: no
+// system-scope fence, no flag round trip, no header.  Per line of a rank's work order (slot = batch * B + lane):
+//   word 0 = global SNV id << 8 | label      (id 0xFFFFFF = empty slot)
+//   word 1 = Nobs[A]        word 2 = Nobs[B] (branching only)
+// laid out  ll[parity][word][source rank][slot]  in every rank's window, so the B lanes of a batch store B consecutive
+// words per (peer, word): one coalesced 64-byte NVLink write.  hdr[parity][source rank] = epoch << 32 | slots used.
+// Steps alternate between the two parities: a fast rank may already push step e+1 while a peer still polls step e (it
+// cannot reach step e+2 before that peer has pushed step e+1, i.e. finished polling step e).
+constexpr int kLLWords = 3;
+struct PhLL {
+  uint8_t* dst[PH_MAX_PEERS];      // per peer window: &ll[0][0][this rank][0]
+  uint64_t* hdr_dst[PH_MAX_PEERS]; // per peer window: &hdr[0][this rank]
+  const uint8_t* own;              // own window: &ll[0][0][0][0]
+  const uint64_t* hdr_own;         // own window: &hdr[0][0]
+  size_t word_stride, par_stride;  // bytes between ll[.][w] and ll[.][w+1] / between the parities
+  int cap_slots;                   // slots reserved per source rank
+  int max_lines;                   // total SNVs (bounds the unpacked ids)
   uint8_t* label_out;
   int32_t* nobs_out;
-  unsigned* done;         // completion counter of the collect phase (self-resetting)
+  unsigned* done;                  // completion counter of the collect phase (self-resetting)
   unsigned* timeout_flag;
 };
 
@@ -129,6 +143,28 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
+}
+__device__ __forceinline__ uint64_t ld_relaxed_sys_u64(const void* p) {
+  uint64_t v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_sys_u64(void* p, uint64_t v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// spins until the word at p carries `epoch` in its upper half; returns the payload (0 and *ok = false on a timeout)
+__device__ __forceinline__ uint32_t ll_wait(const void* p, uint32_t epoch, long long t0, unsigned* timeout_flag, bool* ok) {
+  for (;;) {
+    const uint64_t w = ld_relaxed_sys_u64(p);
+    if ((uint32_t)(w >> 32) == epoch) return (uint32_t)w;
+    if (clock64() - t0 > kSpinLimit) {
+      *timeout_flag = 1;
+      *ok = false;
+      return 0u;
+    }
+    __nanosleep(32);
+  }
 }
 
 // thread 0 of the block polls `world` flags until each has reached `epoch`; ends with a block barrier
@@ -147,25 +183,6 @@ __device__ __forceinline__ void wait_flags(const uint32_t* flags, int world, uin
     }
   }
   __syncthreads();
-}
-
-// Unpacks the records of every rank's SNV block (ph_pass.cu, PassArgs::rec_dst: B label bytes, then B * C int32 counts
-// from byte 16; B and the record size come with the block's header) into the caller's arrays.  s_hdr: 4 * world ints.
-__device__ __forceinline__ void unpack_records(const PhCollect& c, int world, uint32_t epoch, int* s_hdr, int tid, int nt) {
-  if (threadIdx.x < 4 * world) s_hdr[threadIdx.x] = (int)__ldcv(reinterpret_cast<const uint32_t*>(c.win + kPeerHdrOff) + threadIdx.x);
-  __syncthreads();
-  const uint8_t* rec = c.win + c.off_rec[epoch & 1u];
-  const int cap_lines = c.cap_recs * 8;
-  for (int idx = tid; idx < world * cap_lines; idx += nt) {
-    const int r = idx / cap_lines, j = idx - r * cap_lines;
-    const int off = s_hdr[4 * r], cnt = s_hdr[4 * r + 1], B = s_hdr[4 * r + 2], rb = s_hdr[4 * r + 3];
-    if (B <= 0 || rb <= 0 || j >= cnt || off < 0 || off + j >= c.max_lines) continue;  // (a header that never arrived: timed-out wait)
-    const int q = j / B, s = j - q * B;
-    const uint8_t* b = rec + ((size_t)r * c.cap_recs) * kPeerRecStride + (size_t)q * rb;
-    c.label_out[off + j] = __ldcv(b + s);
-    const uint32_t* cn = reinterpret_cast<const uint32_t*>(b + 16) + s * c.C;
-    for (int k = 0; k < c.C; ++k) c.nobs_out[(size_t)(off + j) * c.C + k] = (int32_t)__ldcv(cn + k);
-  }
 }
 #endif
 

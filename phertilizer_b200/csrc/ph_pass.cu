@@ -51,15 +51,14 @@ struct PassArgs {
   uint32_t* flag_dst[PH_MAX_PEERS];  // per peer: where this rank's "partials landed" flag lives
   unsigned* done;                    // CTA completion counter (local, self-resetting)
   int blk, ncp, world, row_words;
-  // LINEAR / BRANCHING with push != 0 (SNV-sharded K1, ph_peer.cu): the outputs of a batch of B <= 8 lines form one
-  // RECORD of 16 + 4 * B * Cq bytes rounded up to 16 (Cq = counts per line: 1 linear, 2 branching) -- labels at bytes
-  // 0..B-1, the int32 counts from byte 16 -- which the warp stores into this rank's region of EVERY rank's window with
-  // one 16-byte store per lane (one contiguous NVLink write per peer and batch instead of 2 * B scattered 1- and 4-byte
-  // stores); then the flag, as for COUNTS
-  uint8_t* rec_dst[2][PH_MAX_PEERS];  // [parity of the step][rank]: records alternate between two regions
-  int32_t* hdr_dst[PH_MAX_PEERS];     // {out_off, n_work, B, record bytes} of this rank in every rank's window (for the collect kernel)
+  // LINEAR / BRANCHING with push != 0 (SNV-sharded K1, ph_peer.cu): the holders' results leave as self-validating
+  // 8-byte words (epoch << 32 | payload, ph_common.cuh PhLL) stored into this rank's region of EVERY rank's window --
+  // the B lanes of a batch write B consecutive words per (peer, word): coalesced NVLink stores that overlap the
+  // streaming of the following batches.  No fence, no flag: the SAME launch then polls the words of every rank in its
+  // own window and unpacks them into the caller's arrays.  Nothing in the pass phase waits for another CTA (batches come
+  // from the dispenser), so the kernel does not depend on all of its CTAs being co-resident.
+  PhLL ll;
   int push, out_off;
-  PhCollect col;              // push: the collect phase, run by every CTA of the same launch once all flags are up
   uint32_t* epoch_w;          // push: the step counter, advanced by the last CTA out of the collect phase
   const uint32_t* epoch_ptr;  // step counter in device memory (step = *epoch_ptr + 1): launches are CUDA-graph replayable
 };
@@ -95,12 +94,13 @@ __device__ __forceinline__ uint32_t clamp_nodes4(uint32_t w, uint32_t K) {
   return r;
 }
 
-// Label image of the minor axis (ph_common.cuh): chunk c at byte c << cb = 16 "excluded" bytes + the chunk's labels.
+// Label image of the minor axis (ph_common.cuh): chunk c at byte c << cb = PH_PAD "excluded" bytes + the chunk's labels.
 // NODES = false: labels 0..NC -> counter shifts.  NODES = true: node ids clamped to K, padding slots hold K + 1.
 template <bool NODES, int NC>
 __device__ __forceinline__ void fill_label_image(uint8_t* img, const uint8_t* __restrict__ raw, int n_minor, int NCH, int cb,
                                                  int K, int tid, int nthreads) {
-  const int CH = (1 << cb) - 16;
+  const int CH = (1 << cb) - PH_PAD;
+  constexpr int PW = PH_PAD / 4;  // words of the excluded region
   const uint32_t excl = NODES ? (uint32_t)(K + 1) : (uint32_t)(PH_FIELD_BITS * NC);
   for (int c = 0; c < NCH; ++c) {
     const int cnt = min(CH, n_minor - c * CH);
@@ -108,7 +108,7 @@ __device__ __forceinline__ void fill_label_image(uint8_t* img, const uint8_t* __
     const uint8_t* srcb = raw + (size_t)c * CH;
     const uint32_t* src = reinterpret_cast<const uint32_t*>(srcb);  // buffers are padded to 4 B
     uint32_t* dst = reinterpret_cast<uint32_t*>(img + ((size_t)c << cb));
-    if (tid < 4) dst[tid] = excl * 0x01010101u;
+    if (tid < PW) dst[tid] = excl * 0x01010101u;
     // whole 16-byte units of an aligned source go through 128-bit loads and stores (4x fewer round trips on the
     // start-up path of every CTA); the rest, and unaligned sources, word by word
     const int nv = (reinterpret_cast<uintptr_t>(srcb) & 15) == 0 ? (cnt >> 4) : 0;
@@ -119,11 +119,11 @@ __device__ __forceinline__ void fill_label_image(uint8_t* img, const uint8_t* __
       o.y = NODES ? clamp_nodes4(w.y, (uint32_t)K) : scale_labels4<NC>(w.y);
       o.z = NODES ? clamp_nodes4(w.z, (uint32_t)K) : scale_labels4<NC>(w.z);
       o.w = NODES ? clamp_nodes4(w.w, (uint32_t)K) : scale_labels4<NC>(w.w);
-      reinterpret_cast<uint4*>(dst + 4)[i] = o;
+      reinterpret_cast<uint4*>(dst + PW)[i] = o;
     }
     for (int i = 4 * nv + tid; i < nw; i += nthreads) {
       const uint32_t w = src[i];
-      dst[4 + i] = NODES ? clamp_nodes4(w, (uint32_t)K) : scale_labels4<NC>(w);
+      dst[PW + i] = NODES ? clamp_nodes4(w, (uint32_t)K) : scale_labels4<NC>(w);
     }
   }
 }
@@ -140,12 +140,15 @@ __host__ __device__ inline int warp_words(int B, int NSUB, int D, int NC) {
 // multiple of 2^16, so that the PRMT yields the complete shared-window address and the gather is a bare LDS.U8 [reg]
 // (no base add per observation).  The bytes below the image hold the per-warp tables.  3: as 2, on the batched-4 copy of
 // the stream (PhOrient::half4): four lanes stream one line of the batch, sub-segment boundaries are warp-uniform.
+// 4: the batched-4 copy with the image wherever it fits (as 1: one base add per observation) -- minor axes whose image
+// leaves no room for the 64 KB alignment (K2 on 200 k SNVs: a 200 KB image).
 template <int B, int MODE, int NC, bool SMEM_LAB, int LAY>
 __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
   constexpr bool S16 = LAY >= 1;
-  constexpr bool AL = LAY >= 2;
-  constexpr bool B4 = LAY == 3;
+  constexpr bool AL = LAY == 2 || LAY == 3;
+  constexpr bool B4 = LAY == 3 || LAY == 4;
+  constexpr bool PUSHABLE = MODE == MODE_LINEAR || MODE == MODE_BRANCHING;
   const int nthreads = blockDim.x;
   const int D = a.D, NCH = a.NCH, NSUB = a.NSUB, NS1 = NSUB + 1, cb = a.chunk_bits;
   const int K2 = a.K + 2;
@@ -224,6 +227,10 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
   // The dispenser round trip never sits on the critical path: the first batch is drawn before the staging above is
   // published (see `bidx0`), every following one while the holders finish the current batch.
   unsigned bidx = __shfl_sync(FULL, bidx0, 0);
+  if (PUSHABLE && a.push && bidx == 0 && lane < a.world) {
+    // the warp that drew the first batch announces how many slots this rank fills in this step
+    st_relaxed_sys_u64(a.ll.hdr_dst[lane] + par * PH_MAX_PEERS, ((uint64_t)epoch << 32) | (uint32_t)(n_batches * B));
+  }
   while (bidx < (unsigned)n_batches) {
     const int first = (int)bidx * B;
     const int nl = min(B, a.n_work - first);
@@ -309,7 +316,7 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
           cur_d = d;
           st_flush = step;
         }
-        cbase = (((uint32_t)q - (uint32_t)d * (uint32_t)NCH) << 16) + img_base;
+        cbase = (((uint32_t)q - (uint32_t)d * (uint32_t)NCH) << 16) + (AL ? img_base : 0u);
         nb_eff = min(s_e[q + 1], st_flush + kDeadline4);
       };
       auto one4 = [&](uint32_t addr) -> uint32_t {
@@ -449,6 +456,7 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
     // the dense codes from the batch counters, then the rare codes of the tail (words sorted by (code, address), so a
     // code is one run) -- i.e. a function of the integer (code, cluster) histogram only: the result does not depend on
     // how the observations were split over lanes, batches or GPUs.
+    uint32_t pay0 = 0xFFFFFF00u, pay1 = 0, pay2 = 0;  // push: this lane's line as LL payloads (empty slot by default)
     if (lane < B && have) {
       double s0[NC], s1[NC];
       unsigned nob[NC], nva[NC];
@@ -516,9 +524,9 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
         // linear_split.py:229-234  like0.mean(axis=0) >= like1.mean(axis=0) -> mutsB (ties -> mutsB)
         const double m0 = s0[0] / a.lenA, m1 = s1[0] / a.lenA;
         const uint8_t lb = (m0 >= m1) ? 2 : 1;
-        if (B <= 8 && a.push) {
-          reinterpret_cast<uint8_t*>(s_row32)[myl] = lb;
-          reinterpret_cast<int32_t*>(s_row32)[4 + myl] = (int32_t)nob[0];
+        if (a.push) {
+          pay0 = ((uint32_t)(a.out_off + line) << 8) | lb;
+          pay1 = nob[0];
         } else {
           a.label_out[wi] = lb;
           a.nobs_out[wi] = (int32_t)nob[0];
@@ -530,10 +538,10 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
         const double cC = s1[0] + s1[NC > 1 ? 1 : 0];
         const double mx = fmax(cA, fmax(cB, cC));
         const uint8_t lb = (cA == mx) ? 1 : ((cB == mx) ? 2 : 3);
-        if (B <= 8 && a.push) {
-          reinterpret_cast<uint8_t*>(s_row32)[myl] = lb;
-          reinterpret_cast<int32_t*>(s_row32)[4 + 2 * myl] = (int32_t)nob[0];
-          reinterpret_cast<int32_t*>(s_row32)[4 + 2 * myl + 1] = (int32_t)nob[NC > 1 ? 1 : 0];
+        if (a.push) {
+          pay0 = ((uint32_t)(a.out_off + line) << 8) | lb;
+          pay1 = nob[0];
+          pay2 = nob[NC > 1 ? 1 : 0];
         } else {
           a.label_out[wi] = lb;
           a.nobs_out[2 * (size_t)wi] = (int32_t)nob[0];
@@ -544,15 +552,20 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
       }
     }
     __syncwarp();
-    if (B <= 8 && (MODE == MODE_LINEAR || MODE == MODE_BRANCHING) && a.push) {
-      // the batch's record -> every rank's window: lane = (peer, 16-byte piece)
-      constexpr int PIECES = (16 + 4 * B * (MODE == MODE_LINEAR ? 1 : 2) + 15) / 16;
-      const uint4* src = reinterpret_cast<const uint4*>(s_row32);
-      for (int u = lane; u < a.world * PIECES; u += 32) {
-        const int p = u / PIECES, q = u - p * PIECES;
-        reinterpret_cast<uint4*>(a.rec_dst[par][p] + (size_t)bidx * (16 * PIECES))[q] = src[q];
+    if (PUSHABLE && a.push) {
+      // the batch's LL words -> every rank's window: lane = (peer * words + word, line); the B lanes of a (peer, word)
+      // store B consecutive 8-byte words
+      constexpr int NW = MODE == MODE_LINEAR ? 2 : 3;
+      constexpr int KPI = 32 / B;  // (peer, word) pairs per warp instruction
+      const int l = lane % B;
+      const uint32_t v0 = __shfl_sync(FULL, pay0, l), v1 = __shfl_sync(FULL, pay1, l);
+      const uint32_t v2 = NW == 3 ? __shfl_sync(FULL, pay2, l) : 0u;
+      const size_t slot_off = ((size_t)bidx * B + l) * 8 + (size_t)par * a.ll.par_stride;
+      for (int kk = lane / B; kk < a.world * NW; kk += KPI) {
+        const int p = kk / NW, wd = kk - p * NW;
+        const uint32_t v = wd == 0 ? v0 : (wd == 1 ? v1 : v2);
+        st_relaxed_sys_u64(a.ll.dst[p] + slot_off + (size_t)wd * a.ll.word_stride, ((uint64_t)epoch << 32) | v);
       }
-      __syncwarp();
     }
     if (MODE == MODE_COUNTS) {
       // the batch's rows are consecutive in the owner's slot: 16-byte stores straight into peer memory
@@ -571,7 +584,7 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
   // The last CTA to finish re-arms the batch dispenser for the next launch (no memset between launches).  Peer modes:
   // all partial rows (or pushed records) of this rank are on their way -- make them visible system-wide first; the last
   // CTA then raises this rank's flag in every peer's window.
-  const bool peer_mode = MODE == MODE_COUNTS || ((MODE == MODE_LINEAR || MODE == MODE_BRANCHING) && a.push);
+  const bool peer_mode = MODE == MODE_COUNTS;
   __syncthreads();
   if (threadIdx.x == 0) {
     // one system-scope fence per CTA: the barrier orders the other threads' peer stores before it (cumulativity)
@@ -581,30 +594,52 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
       *a.done = 0;
       *a.counter = 0;
       if (peer_mode) {
-        if (MODE != MODE_COUNTS)
-          for (int p = 0; p < a.world; ++p) {
-            a.hdr_dst[p][0] = a.out_off;
-            a.hdr_dst[p][1] = a.n_work;
-            a.hdr_dst[p][2] = B;
-            a.hdr_dst[p][3] = 16 * ((16 + 4 * B * (MODE == MODE_LINEAR ? 1 : 2) + 15) / 16);
-          }
         __threadfence_system();
         for (int p = 0; p < a.world; ++p)
           asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.flag_dst[p]), "r"(epoch) : "memory");
       }
     }
   }
-  if ((MODE == MODE_LINEAR || MODE == MODE_BRANCHING) && a.push) {
-    // ---- collect phase, same launch: every CTA (all are resident: one per SM) waits until every rank's block has
-    // landed in this rank's window, then unpacks its slice of the records into the caller's arrays
-    wait_flags(reinterpret_cast<const uint32_t*>(a.col.win), a.world, epoch, a.col.timeout_flag);
-    int* s_hdr = reinterpret_cast<int*>(s_tab0);  // the per-warp tables are free now (all warps passed the barrier above)
-    unpack_records(a.col, a.world, epoch, s_hdr, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+  if (PUSHABLE && a.push) {
+    // ---- collect phase, same launch: poll the LL words of every rank in this rank's own window (they carry the step
+    // counter, so the data validates itself) and unpack them into the caller's arrays.  A CTA only waits for words that
+    // resident CTAs of some rank push during their pass phase -- never for a CTA that has not started yet.
+    constexpr int NW = MODE == MODE_LINEAR ? 2 : 3;
+    int* s_cnt_r = reinterpret_cast<int*>(s_tab0);  // the per-warp tables are free now (all warps passed the barrier above)
+    const long long t0 = clock64();
+    bool ok = true;
+    if (threadIdx.x < a.world) {
+      const uint32_t c = ll_wait(a.ll.hdr_own + par * PH_MAX_PEERS + threadIdx.x, epoch, t0, a.ll.timeout_flag, &ok);
+      s_cnt_r[threadIdx.x] = ok ? min((int)c, a.ll.cap_slots) : 0;
+    }
+    __syncthreads();
+    const uint8_t* base = a.ll.own + (size_t)par * a.ll.par_stride;
+    const int cap = a.ll.cap_slots;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < a.world * cap; idx += gridDim.x * blockDim.x) {
+      const int r = idx / cap, j = idx - r * cap;
+      if (j >= s_cnt_r[r]) continue;
+      const uint8_t* w = base + ((size_t)r * cap + j) * 8;
+      ok = true;
+      const uint32_t p0 = ll_wait(w, epoch, t0, a.ll.timeout_flag, &ok);
+      const uint32_t g = p0 >> 8;
+      if (!ok || g >= (uint32_t)a.ll.max_lines) continue;  // empty slot (id 0xFFFFFF) or a word that never arrived
+      const uint32_t n0 = ll_wait(w + a.ll.word_stride, epoch, t0, a.ll.timeout_flag, &ok);
+      uint32_t n1 = 0;
+      if (NW == 3) n1 = ll_wait(w + 2 * a.ll.word_stride, epoch, t0, a.ll.timeout_flag, &ok);
+      if (!ok) continue;
+      a.ll.label_out[g] = (uint8_t)(p0 & 0xFFu);
+      if (NW == 2) {
+        a.ll.nobs_out[g] = (int32_t)n0;
+      } else {
+        a.ll.nobs_out[2 * (size_t)g] = (int32_t)n0;
+        a.ll.nobs_out[2 * (size_t)g + 1] = (int32_t)n1;
+      }
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
-      const unsigned prev = atomicAdd(a.col.done, 1u);
+      const unsigned prev = atomicAdd(a.ll.done, 1u);
       if (prev == gridDim.x - 1) {
-        *a.col.done = 0;
+        *a.ll.done = 0;
         *a.epoch_w = epoch;  // next step
       }
     }
@@ -706,7 +741,7 @@ __global__ void __launch_bounds__(kBlock, 1) k_node_table(const PassArgs a, cons
         const int64_t pb = (int64_t)so[d * NCH + ch] * PH_GE, pe = (int64_t)so[d * NCH + ch + 1] * PH_GE;
         for (int64_t p = pb + g; p < pe; p += G) {
           const uint32_t idx = a.half[p];
-          if (idx) atomicAdd(&cnt[node_at(((uint32_t)ch << cb) | idx)], 1u);  // idx 0 = padding
+          if (idx >= PH_PAD) atomicAdd(&cnt[node_at(((uint32_t)ch << cb) | idx)], 1u);  // idx < PH_PAD = padding
         }
       }
       __syncwarp(gmask);
@@ -770,31 +805,38 @@ int launch_pass(ph_handle* h, const PhOrient* o, PassArgs& a, cudaStream_t st) {
     B = (nb8 > warps && nb8 < 2 * warps) ? 4 : 8;
   }
   if (MODE == MODE_COUNTS) a.row_words = B * NC * a.ncp / 2;  // ncp is a multiple of 8: whole 16-byte units
-  if (a.push) a.row_words = 4 * ((16 + 4 * B * (MODE == MODE_LINEAR ? 1 : 2) + 15) / 16);  // one record
   int lut = 0, threads = 0;
   bool smem_lab = true, aligned = false;
   size_t smem = 0;
   // first choice: the label image at a 2^16-aligned shared address (LAY = 2).  Costs up to 64 KB of address space below
   // the image (the tables live there), so it needs  64 KB + image + tables  to fit -- true for up to ~150 k minor indices.
   // With it, whole-orientation passes (no line list, no peer push) run on the batched-4 copy of the stream (LAY = 3).
-  bool use4 = false;
-  if (o->chunk_bits == 16 && h->aligned_image) {
-    const bool can4 = MODE != MODE_COUNTS && o->half4 && !a.list && !a.push && h->batch4;
+  // Whole-orientation passes (no line list) run on the batched-4 copy of the stream when the store keeps one: LAY = 3
+  // with the aligned image, LAY = 4 (image wherever it fits) otherwise.
+  bool use4 = false, al4 = false;
+  const bool can4 = MODE != MODE_COUNTS && o->half4 && !a.list && h->batch4 && o->chunk_bits == 16;
+  if (o->chunk_bits == 16 && (h->aligned_image || can4)) {
     const int Bt = can4 ? 8 : B;
     const size_t full = pass_smem_bytes(h, o, MODE, NC, a.K, true, 1024, Bt, a.row_words, &lut);
-    if (full && full + 65536 <= (size_t)h->max_smem) {
+    const bool fits_al = h->aligned_image && full && full + 65536 <= (size_t)h->max_smem;
+    if (fits_al) {
       smem = full + 65536;
       threads = 1024;
       aligned = true;
       a.tab_bytes = (int)(full - (size_t)o->lab_bytes);
-      if (can4) {
-        use4 = true;
-        B = 8;
-        a.list = o->perm4;              // the lines in shape order, 8 per batch, -1 = empty slot
-        a.n_work = o->n_batches4 * 8;
-        a.half4 = o->half4;
-        a.bstep_off = o->bstep_off;
+    }
+    if (can4 && (fits_al || full)) {
+      if (!fits_al) {
+        smem = full;
+        threads = 1024;
       }
+      use4 = true;
+      al4 = fits_al;
+      B = 8;
+      a.list = o->perm4;              // the lines in shape order, 8 per batch, -1 = empty slot
+      a.n_work = o->n_batches4 * 8;
+      a.half4 = o->half4;
+      a.bstep_off = o->bstep_off;
     }
   }
   for (int pass = 0; pass < 2 && !smem; ++pass) {
@@ -814,7 +856,7 @@ int launch_pass(ph_handle* h, const PhOrient* o, PassArgs& a, cudaStream_t st) {
   }
   // one CTA of up to 32 warps per SM; PH_CTAS=2 halves the CTA instead when two copies of the image fit
   int ctas = 1;
-  if (h->ctas_per_sm == 2 && threads == 1024 && !aligned) {
+  if (h->ctas_per_sm == 2 && threads == 1024 && !aligned && !use4) {
     int lut2 = 0;
     const size_t smem2 = pass_smem_bytes(h, o, MODE, NC, a.K, smem_lab, 512, B, a.row_words, &lut2);
     if (smem2 && lut2 == lut && 2 * (smem2 + 1024) <= (size_t)h->smem_per_sm) {
@@ -843,8 +885,13 @@ int launch_pass(ph_handle* h, const PhOrient* o, PassArgs& a, cudaStream_t st) {
     else if (o->chunk_bits == 16) PH_LAUNCH(BB, true, 1);                      \
     else PH_LAUNCH(BB, true, 0);                                               \
   } while (0)
+  if (a.push && (int64_t)((a.n_work + B - 1) / B) * B > (int64_t)a.ll.cap_slots)
+    PH_FAIL(PH_ERR_UNSUPPORTED, "%d result slots exceed the %d reserved per rank in the peer window", ((a.n_work + B - 1) / B) * B, a.ll.cap_slots);
   if (use4) {
-    if constexpr (MODE != MODE_COUNTS) PH_LAUNCH(8, true, 3);
+    if constexpr (MODE != MODE_COUNTS) {
+      if (al4) PH_LAUNCH(8, true, 3);
+      else PH_LAUNCH(8, true, 4);
+    }
   } else if (B == 32) PH_LAUNCH_B(32);
   else if (B == 4) PH_LAUNCH_B(4);
   else PH_LAUNCH_B(8);
@@ -1420,10 +1467,10 @@ int ph_pass_counts(ph_handle* h, const uint8_t* cell_label, int C, const int32_t
   return C == 1 ? launch_pass<MODE_COUNTS, 1>(h, o, a, st) : launch_pass<MODE_COUNTS, 2>(h, o, a, st);
 }
 
-// SNV-sharded K1 + K1a (ph_peer.cu): this rank's SNVs, one record per batch of 8 lines pushed to every rank's window
-int ph_pass_assign_push(ph_handle* h, int mode, const uint8_t* cell_label, double lenA, uint8_t* const (*rec_dst)[PH_MAX_PEERS],
-                        int32_t* const* hdr_dst, uint32_t* const* flag_dst, unsigned* done, int out_off, int world,
-                        uint32_t* epoch_ptr, const PhCollect& col, cudaStream_t st) {
+// SNV-sharded K1 + K1a (ph_peer.cu): this rank's SNVs, results pushed as LL words to every rank's window and collected
+// by the same launch
+int ph_pass_assign_push(ph_handle* h, int mode, const uint8_t* cell_label, double lenA, const PhLL& ll, unsigned* done,
+                        int out_off, int world, uint32_t* epoch_ptr, cudaStream_t st) {
   PhOrient* o = &h->by_snv;
   PassArgs a;
   fill_common(h, o, a);
@@ -1431,16 +1478,11 @@ int ph_pass_assign_push(ph_handle* h, int mode, const uint8_t* cell_label, doubl
   a.lenA = lenA;
   a.n_work = o->n_major;
   a.minor_label = cell_label;
-  for (int r = 0; r < world; ++r) {
-    for (int q = 0; q < 2; ++q) a.rec_dst[q][r] = rec_dst[q][r];
-    a.hdr_dst[r] = hdr_dst[r];
-    a.flag_dst[r] = flag_dst[r];
-  }
+  a.ll = ll;
   a.done = done;
   a.world = world;
   a.epoch_ptr = epoch_ptr;
   a.epoch_w = epoch_ptr;
-  a.col = col;
   a.push = 1;
   a.out_off = out_off;
   return mode == MODE_LINEAR ? launch_pass<MODE_LINEAR, 1>(h, o, a, st) : launch_pass<MODE_BRANCHING, 2>(h, o, a, st);

@@ -9,6 +9,7 @@
 //      evaluates  sum_code fma(count, L[code])  exactly like the single-GPU holder does, applies the K1a decision rule
 //      and stores label + observation counts into EVERY rank's output window; then raises its second flag everywhere.
 //   C  k_peer_collect: waits for the owners' flags and copies the window to the caller's output buffers.
+// (The SNV-sharded steps further down need none of this: one kernel, self-validating words, no flags.)
 //
 // The exchanged quantity is an integer histogram, so the result is bit-identical to the single-GPU kernels for any
 // number of ranks.  Windows are plain cudaMalloc allocations shared through CUDA IPC handles (exchanged by the host
@@ -19,8 +20,8 @@ struct ph_peer {
   ph_handle* h;
   int rank, world;
   int32_t max_lines, blk_max, ncp;
-  size_t off_cnt, off_lab, off_nobs, off_rec[2], bytes;  // off_rec: the two record regions of the SNV-sharded steps
-  int32_t cap_recs;            // records (batches of 8 SNVs) one rank may push per step
+  size_t off_cnt, off_lab, off_nobs, off_ll, bytes;  // off_ll: the LL words of the SNV-sharded steps (ph_common.cuh, PhLL)
+  int32_t cap_slots;           // result slots (lines of the work order, padded to whole batches) one rank may push per step
   uint8_t* win[PH_MAX_PEERS];  // win[rank] = own allocation, others = IPC mappings
   bool opened[PH_MAX_PEERS];
   unsigned* d_done;            // [0],[1] CTA completion counters (pass, finish), [2] spin-timeout flag,
@@ -31,9 +32,8 @@ struct ph_peer {
 
 namespace {
 
-constexpr size_t kFlagBytes = 4096;  // flagA[world] at +0, flagB[world] at +1024, SNV block headers at kPeerHdrOff (ph_common.cuh)
-constexpr size_t kHdrOff = kPeerHdrOff;
-constexpr size_t kRecStride = kPeerRecStride;
+constexpr size_t kFlagBytes = 4096;  // flagA[world] at +0, flagB[world] at +1024, LL headers hdr[2][PH_MAX_PEERS] (8 B each) at +2048
+constexpr size_t kHdrOff = 2048;
 struct FinishArgs {
   const uint8_t* win;  // own window
   size_t off_cnt;
@@ -143,9 +143,8 @@ int ph_pass_counts(ph_handle* h, const uint8_t* cell_label, int C, const int32_t
                    uint16_t* const* cnt_dst, uint32_t* const* flag_dst, unsigned* done, int blk, int ncp, int world,
                    const uint32_t* epoch_ptr, cudaStream_t st);
 
-int ph_pass_assign_push(ph_handle* h, int mode, const uint8_t* cell_label, double lenA, uint8_t* const (*rec_dst)[PH_MAX_PEERS],
-                        int32_t* const* hdr_dst, uint32_t* const* flag_dst, unsigned* done, int out_off, int world,
-                        uint32_t* epoch_ptr, const PhCollect& col, cudaStream_t st);
+int ph_pass_assign_push(ph_handle* h, int mode, const uint8_t* cell_label, double lenA, const PhLL& ll, unsigned* done,
+                        int out_off, int world, uint32_t* epoch_ptr, cudaStream_t st);
 
 extern "C" int ph_peer_handle_bytes(void) { return (int)sizeof(cudaIpcMemHandle_t); }
 
@@ -167,7 +166,15 @@ extern "C" int ph_peer_create(ph_handle* h, int rank, int world, int32_t total_s
   // world = 1 is a degenerate but valid context (the window is local): the same kernels, no NVLink traffic
   if (world < 1 || world > PH_MAX_PEERS || rank < 0 || rank >= world)
     PH_FAIL(PH_ERR_ARG, "rank %d / world %d outside 1..%d", rank, world, PH_MAX_PEERS);
-  if (total_snvs <= 0) total_snvs = h->n_snvs;  // cell-sharded: every rank holds all SNVs
+  if (total_snvs <= 0) {
+    // cell-sharded (every rank holds all SNVs): the limits of the histogram exchange are checked HERE, so that set-up
+    // fails on every rank alike (the host language gathers the outcomes) instead of one rank refusing a later step
+    // while its peers have already launched and wait for it
+    if (h->n_cells > 65535)
+      PH_FAIL(PH_ERR_UNSUPPORTED, "%d local cells: the exchanged histogram rows are 16-bit (at most 65535 cells per rank)", h->n_cells);
+    if (h->n_codes > 64) PH_FAIL(PH_ERR_UNSUPPORTED, "%d (var,total) codes: histogram exchange supports up to 64", h->n_codes);
+    total_snvs = h->n_snvs;
+  }
   if (total_snvs < h->n_snvs) PH_FAIL(PH_ERR_ARG, "total_snvs=%d is less than the %d local SNVs", total_snvs, h->n_snvs);
   PH_CUDA(cudaSetDevice(h->device));
   ph_peer* p = new ph_peer();
@@ -178,17 +185,16 @@ extern "C" int ph_peer_create(ph_handle* h, int rank, int world, int32_t total_s
   p->max_lines = total_snvs;
   p->blk_max = (h->n_snvs + world - 1) / world;
   p->ncp = (h->n_codes + 7) & ~7;
-  if (p->ncp > 64) p->ncp = 64;  // histogram exchange (cell-sharded) is refused above 64 codes, see peer_assign
+  if (p->ncp > 64) p->ncp = 64;  // the histogram exchange (cell-sharded) is refused above 64 codes, see below
   p->off_cnt = kFlagBytes;
   const size_t cnt_bytes = (size_t)world * p->blk_max * 3 * p->ncp * sizeof(uint16_t);
   p->off_lab = (p->off_cnt + cnt_bytes + 255) & ~(size_t)255;
   p->off_nobs = (p->off_lab + (size_t)p->max_lines + 255) & ~(size_t)255;
-  // SNV-sharded steps: every rank pushes its block as records of 8 SNVs into its own region of each window; blocks are
-  // expected to be balanced (at most ceil(total / world) + 8 SNVs per rank)
-  p->cap_recs = ((total_snvs + world - 1) / world + 8 + 7) / 8;
-  p->off_rec[0] = (p->off_nobs + (size_t)p->max_lines * 3 * sizeof(int32_t) + 255) & ~(size_t)255;
-  p->off_rec[1] = p->off_rec[0] + (size_t)world * p->cap_recs * kRecStride;
-  p->bytes = p->off_rec[1] + (size_t)world * p->cap_recs * kRecStride + 256;
+  // SNV-sharded steps: every rank pushes the LL words of its block (work order, whole batches of 8) into its own region
+  // of each window; blocks are expected to be balanced (at most ceil(total / world) + 8 SNVs per rank)
+  p->cap_slots = (((total_snvs + world - 1) / world + 8 + 7) / 8) * 8 + 8;
+  p->off_ll = (p->off_nobs + (size_t)p->max_lines * 3 * sizeof(int32_t) + 255) & ~(size_t)255;
+  p->bytes = p->off_ll + (size_t)2 * kLLWords * world * p->cap_slots * 8 + 256;
   cudaError_t e = cudaMalloc(&p->win[rank], p->bytes);
   if (e == cudaSuccess) e = cudaMemset(p->win[rank], 0, p->bytes);
   if (e == cudaSuccess) e = cudaMalloc(&p->d_done, 64);
@@ -303,9 +309,10 @@ extern "C" int ph_peer_assign_branching(ph_peer* p, const uint8_t* cell_label, c
 
 // ---- SNV-sharded K1 + K1a: every rank holds ALL cells and the SNVs [snv_offset, snv_offset + n_snvs) of total_snvs.
 // Per-SNV tables are independent across SNVs, so the pass itself needs no exchange: the kernel epilogue stores each
-// batch's labels and counts as one record into every rank's window (NVLink peer stores) while it streams on, the last
-// CTA raises the flag, and every CTA of the SAME kernel then waits for the world's flags and unpacks its slice of the
-// assembled window into label_out / nobs_out.  ONE launch per step: pass, exchange and collect are one kernel.
+// batch's labels and counts as self-validating 8-byte words (step counter in the upper half) into every rank's window
+// (NVLink peer stores) while it streams on, and every CTA of the SAME kernel then polls its slice of the words in its own
+// window and unpacks them into label_out / nobs_out.  ONE launch per step, no fence, no flag, and no CTA ever waits for
+// a CTA that is not resident (the pass phase draws its batches from a dispenser).
 namespace {
 int peer_assign_snv(ph_peer* p, int mode, const uint8_t* cell_label, double lenA, int32_t snv_offset, uint8_t* label_out,
                     int32_t* nobs_out, void* stream) {
@@ -320,33 +327,31 @@ int peer_assign_snv(ph_peer* p, int mode, const uint8_t* cell_label, double lenA
   cudaStream_t st = (cudaStream_t)stream;
   const int C = mode == 1 ? 1 : 2;
   if (h->n_snvs <= 0) PH_FAIL(PH_ERR_ARG, "this rank holds no SNVs");
-  if (h->n_snvs > p->cap_recs * 8)
+  if (h->n_snvs > p->cap_slots - 8)
     PH_FAIL(PH_ERR_UNSUPPORTED, "%d local SNVs exceed the %d a balanced block may hold (ceil(total / world) + 8)", h->n_snvs,
-            p->cap_recs * 8);
-  // Records alternate between two regions (parity of the step counter): a fast rank may already push step e+1 into a
-  // peer whose collect kernel still unpacks step e (its own step e+2 cannot start before that peer has finished step e,
-  // see the flag order).
-  uint8_t* rec_dst[2][PH_MAX_PEERS] = {};
-  int32_t* hdr_dst[PH_MAX_PEERS] = {};
-  uint32_t* flag_dst[PH_MAX_PEERS] = {};
+            p->cap_slots - 8);
+  if (p->max_lines >= 0xFFFFFF) PH_FAIL(PH_ERR_UNSUPPORTED, "%d SNVs: the pushed words carry 24-bit SNV ids", p->max_lines);
+  // LL words alternate between two parities of the step counter: a fast rank may already push step e+1 into a peer that
+  // still polls step e (its own step e+2 cannot start before that peer has pushed step e+1, i.e. finished step e).
+  PhLL ll;
+  memset(&ll, 0, sizeof(ll));
+  const size_t word_stride = (size_t)p->world * p->cap_slots * 8;
   for (int r = 0; r < p->world; ++r) {
-    for (int q = 0; q < 2; ++q) rec_dst[q][r] = p->win[r] + p->off_rec[q] + (size_t)p->rank * p->cap_recs * kRecStride;
-    hdr_dst[r] = reinterpret_cast<int32_t*>(p->win[r] + kHdrOff) + 4 * p->rank;
-    flag_dst[r] = reinterpret_cast<uint32_t*>(p->win[r]) + p->rank;
+    ll.dst[r] = p->win[r] + p->off_ll + (size_t)p->rank * p->cap_slots * 8;
+    ll.hdr_dst[r] = reinterpret_cast<uint64_t*>(p->win[r] + kHdrOff) + p->rank;
   }
+  ll.own = p->win[p->rank] + p->off_ll;
+  ll.hdr_own = reinterpret_cast<const uint64_t*>(p->win[p->rank] + kHdrOff);
+  ll.word_stride = word_stride;
+  ll.par_stride = kLLWords * word_stride;
+  ll.cap_slots = p->cap_slots;
+  ll.max_lines = p->max_lines;
+  ll.label_out = label_out;
+  ll.nobs_out = nobs_out;
+  ll.done = p->d_done + 3;
+  ll.timeout_flag = p->d_done + 2;
   uint32_t* epoch_ptr = reinterpret_cast<uint32_t*>(p->d_done + 4);
-  PhCollect col;
-  col.win = p->win[p->rank];
-  col.off_rec[0] = p->off_rec[0];
-  col.off_rec[1] = p->off_rec[1];
-  col.cap_recs = p->cap_recs;
-  col.max_lines = p->max_lines;
-  col.C = C;
-  col.label_out = label_out;
-  col.nobs_out = nobs_out;
-  col.done = p->d_done + 3;
-  col.timeout_flag = p->d_done + 2;
-  int rc = ph_pass_assign_push(h, mode, cell_label, lenA, rec_dst, hdr_dst, flag_dst, p->d_done, snv_offset, p->world, epoch_ptr, col, st);
+  int rc = ph_pass_assign_push(h, mode, cell_label, lenA, ll, p->d_done, snv_offset, p->world, epoch_ptr, st);
   if (rc != PH_OK) return rc;
   PH_CUDA(cudaGetLastError());
   return PH_OK;

@@ -38,6 +38,61 @@ def _factorize(col):
     return pd.factorize(col, sort=False)
 
 
+def index_observations(variant_count_data):
+    """DataFrame[chr, mutation_id, cell_id, base, var, total] -> (cell labels, SNV labels, cell index, SNV index, var,
+    total) of the OBSERVED entries (phertilizer.py:235-253, 295-306).
+
+    The label sets come from ALL rows, as in the reference.  Rows with total == 0 are not observations there: its dense
+    matrices are `unstack(fill_value=0)` and "observed" is `count_nonzero(total)` everywhere (phertilizer.py:153-161,
+    linear_split.py:186-188), so such a row is indistinguishable from a missing one -- they are dropped here, after the
+    labels are fixed.  A (cell, mutation) pair listed twice makes the reference's `unstack` raise; so does this."""
+    # labels -> dense indices: sorted unique cell ids and "chr_mutation" strings (phertilizer.py:235-253).
+    # Same labels and order as the reference; the per-observation string concatenation and label lookups (tens of
+    # seconds at 2.4e7 observations) are done on the distinct (chr, mutation_id) pairs / cell ids only.
+    vc = variant_count_data
+    # Every per-observation pass below is one streaming numpy operation on 32-bit indices (the store takes int32).
+    cell_codes, cell_uniques = _factorize(vc["cell_id"])
+    cell_labels = np.sort(np.asarray(cell_uniques))
+    cell_rank = pd.Series(np.arange(len(cell_labels)), index=cell_labels)[np.asarray(cell_uniques)].to_numpy()
+    cell_idx = cell_rank.astype(np.int32)[cell_codes]
+    del cell_codes
+    chr_codes, chr_uniques = _factorize(vc["chr"])
+    mid_codes, mid_uniques = _factorize(vc["mutation_id"])
+    M = max(len(mid_uniques), 1)
+    n_pair_space = len(chr_uniques) * M
+    wide = np.int64 if n_pair_space >= (1 << 31) else np.int32
+    pair = chr_codes.astype(wide)
+    pair *= wide(M)
+    pair += mid_codes.astype(wide, copy=False)
+    del chr_codes, mid_codes
+    counting = n_pair_space <= (1 << 27)
+    if counting:
+        # counting pass instead of sorting all observations
+        pair_u = np.nonzero(np.bincount(pair, minlength=n_pair_space))[0]
+    else:
+        pair_u, pair_inv = np.unique(pair, return_inverse=True)
+    pair_str = (pd.Series(np.asarray(chr_uniques)[pair_u // M]).astype("str") + "_"
+                + pd.Series(np.asarray(mid_uniques)[pair_u % M]).astype(str)).to_numpy()
+    mut_labels = np.sort(pd.unique(pair_str))
+    mut_rank = pd.Series(np.arange(len(mut_labels)), index=mut_labels)[pair_str].to_numpy().astype(np.int32)
+    if counting:
+        lut = np.zeros(n_pair_space, dtype=np.int32)   # pair -> index of its "chr_mutation" label, one gather
+        lut[pair_u] = mut_rank
+        mut_idx = lut[pair]
+    else:
+        mut_idx = mut_rank[pair_inv]
+    del pair
+    var = vc["var"].to_numpy()
+    total = vc["total"].to_numpy()
+    if len(total) and bool((total <= 0).any()):
+        if bool(((total <= 0) & (var > 0)).any()):
+            raise ValueError("variant_count_data has rows with var > 0 and total == 0")
+        keep = total > 0
+        cell_idx, mut_idx, var, total = cell_idx[keep], mut_idx[keep], var[keep], total[keep]
+    # duplicates: the store rejects them on the device (ph_create sorts the (SNV, cell) keys anyway)
+    return cell_labels, mut_labels, cell_idx, mut_idx, var, total
+
+
 def _embed(bin_counts: np.ndarray, dim_reduce: bool) -> np.ndarray:
     """Row-normalise + UMAP (phertilizer.py:267-279) or the raw bins (284-285).  UMAP is third-party and stays so."""
     if not dim_reduce:
@@ -59,42 +114,7 @@ class Phertilizer:
         self.explored_seeds = None
         device = int(__import__("os").environ.get("PHERTILIZER_DEVICE", "0")) if device is None else device
 
-        # labels -> dense indices: sorted unique cell ids and "chr_mutation" strings (phertilizer.py:235-253).
-        # Same labels and order as the reference; the per-observation string concatenation and label lookups (tens of
-        # seconds at 2.4e7 observations) are done on the distinct (chr, mutation_id) pairs / cell ids only.
-        vc = variant_count_data
-        # Every per-observation pass below is one streaming numpy operation on 32-bit indices (the store takes int32).
-        cell_codes, cell_uniques = _factorize(vc["cell_id"])
-        cell_labels = np.sort(np.asarray(cell_uniques))
-        cell_rank = pd.Series(np.arange(len(cell_labels)), index=cell_labels)[np.asarray(cell_uniques)].to_numpy()
-        cell_idx = cell_rank.astype(np.int32)[cell_codes]
-        del cell_codes
-        chr_codes, chr_uniques = _factorize(vc["chr"])
-        mid_codes, mid_uniques = _factorize(vc["mutation_id"])
-        M = max(len(mid_uniques), 1)
-        n_pair_space = len(chr_uniques) * M
-        wide = np.int64 if n_pair_space >= (1 << 31) else np.int32
-        pair = chr_codes.astype(wide)
-        pair *= wide(M)
-        pair += mid_codes.astype(wide, copy=False)
-        del chr_codes, mid_codes
-        counting = n_pair_space <= (1 << 27)
-        if counting:
-            # counting pass instead of sorting all observations
-            pair_u = np.nonzero(np.bincount(pair, minlength=n_pair_space))[0]
-        else:
-            pair_u, pair_inv = np.unique(pair, return_inverse=True)
-        pair_str = (pd.Series(np.asarray(chr_uniques)[pair_u // M]).astype("str") + "_"
-                    + pd.Series(np.asarray(mid_uniques)[pair_u % M]).astype(str)).to_numpy()
-        mut_labels = np.sort(pd.unique(pair_str))
-        mut_rank = pd.Series(np.arange(len(mut_labels)), index=mut_labels)[pair_str].to_numpy().astype(np.int32)
-        if counting:
-            lut = np.zeros(n_pair_space, dtype=np.int32)   # pair -> index of its "chr_mutation" label, one gather
-            lut[pair_u] = mut_rank
-            mut_idx = lut[pair]
-        else:
-            mut_idx = mut_rank[pair_inv]
-        del pair
+        cell_labels, mut_labels, cell_idx, mut_idx, var, total = index_observations(variant_count_data)
         self.cells = np.arange(cell_labels.shape[0], dtype="int")
         self.muts = np.arange(mut_labels.shape[0], dtype="int")
         cell_series = pd.Series(data=self.cells, index=cell_labels)
@@ -109,8 +129,8 @@ class Phertilizer:
         copy_distance = CopyDistance(np.asarray(embedding, dtype=np.float64), device=device)
 
         # per-observation likelihoods become a (var,total) -> (like0, like1) table inside the store (295-306)
-        store = ObservationStore.from_coo(len(self.cells), len(self.muts), cell_idx, mut_idx, vc["var"].to_numpy(),
-                                          vc["total"].to_numpy(), alpha=alpha, max_copies=max_copies, device=device)
+        store = ObservationStore.from_coo(len(self.cells), len(self.muts), cell_idx, mut_idx, var, total, alpha=alpha,
+                                          max_copies=max_copies, device=device)
         if hasattr(store, "set_embedding"):
             store.set_embedding(embedding)       # tree scoring (K4) reads it hundreds of times
         self.data = Data(cell_lookup, mut_lookup, store, embedding, copy_distance, use_read_depth)

@@ -17,6 +17,8 @@ from __future__ import annotations
 
 import numpy as np
 
+from ._lib import PhError as _PhError
+
 
 def cell_block(n_cells: int, rank: int, world: int):
     """Contiguous block [lo, hi) of cells owned by `rank`."""
@@ -142,6 +144,8 @@ class PeerExchange:
                                                              _ptr(nobs_out_t), stream))
 
     def timed_out(self, stream=None) -> bool:
+        if self._p is None:
+            return True   # closed after a timeout
         return bool(self._L.ph_peer_timed_out(self._p, stream))
 
     def close(self):
@@ -207,9 +211,20 @@ class ShardedStore:
             self.dist.all_reduce(t, group=self.group)
         return t
 
+    def _check_peer(self):
+        """After the results have been copied back: a spin-wait that gave up (~3 s: a lost or stalled rank) means the
+        window held stale data when it was summed / unpacked.  The outputs must not be used and the step counters of the
+        ranks are no longer in step: the exchange is torn down.  Callers of the `*_dev` methods poll
+        `self.peer.timed_out()` themselves (bench.py does, once per run)."""
+        if self.peer is not None and self.peer.timed_out(self.b.stream()):
+            self.peer.close()
+            self.peer = None
+            raise _PhError("peer-memory exchange timed out waiting for a rank (about 3 s): results discarded, exchange closed")
+
     # ------------------------------------------------------------------ K1 family on device tensors
     def assign_linear_dev(self, label_t, lenA, packed_t, lab_out_t, nobs_out_t, list_t=None):
-        """label_t: this rank's local labels; lenA: GLOBAL |cellsA|; packed_t: float64 [3*k] scratch."""
+        """label_t: this rank's local labels; lenA: GLOBAL |cellsA|; packed_t: float64 [3*k] scratch.
+        Peer transport: the caller must poll `self.peer.timed_out()` before trusting the outputs (see _check_peer)."""
         k = self.n_snvs if list_t is None else int(list_t.numel())
         if self.peer is not None:
             return self.peer.assign_linear(label_t, lenA, lab_out_t, nobs_out_t, list_t, k, stream=self.b.stream())
@@ -239,7 +254,9 @@ class ShardedStore:
         lab = self.b.empty(k + 16, t.uint8)
         nobs = self.b.empty(k, t.int32)
         self.assign_linear_dev(self.local_labels(cell_label_global), lenA, packed, lab, nobs, lst)
-        return lab[:k].cpu().numpy(), nobs.cpu().numpy()
+        out = lab[:k].cpu().numpy(), nobs.cpu().numpy()
+        self._check_peer()
+        return out
 
     def assign_branching(self, cell_label_global, snv_list=None):
         t = self.torch
@@ -249,7 +266,9 @@ class ShardedStore:
         lab = self.b.empty(k + 16, t.uint8)
         nobs = self.b.empty(2 * k, t.int32)
         self.assign_branching_dev(self.local_labels(cell_label_global), packed, lab, nobs, lst)
-        return lab[:k].cpu().numpy(), nobs.cpu().numpy().reshape(k, 2)
+        out = lab[:k].cpu().numpy(), nobs.cpu().numpy().reshape(k, 2)
+        self._check_peer()
+        return out
 
     def snv_table(self, cell_label_global, C, snv_list=None):
         t = self.torch
@@ -280,7 +299,9 @@ class ShardedStore:
     def _sum(self, arr):
         if self.world == 1:
             return arr
-        t = self.torch.from_numpy(np.ascontiguousarray(arr)).to(self.b.device)
+        t = self.torch.from_numpy(np.ascontiguousarray(arr).copy())
+        if self.dist.get_backend(self.group) != "gloo":   # NCCL reduces device tensors
+            t = t.to(self.b.device)
         self.dist.all_reduce(t, group=self.group)
         return t.cpu().numpy()
 
@@ -335,20 +356,10 @@ class SnvShardedStore:
         else:
             cell, snv, var, total = cell[keep].contiguous(), (snv[keep] - lo).contiguous(), var[keep].contiguous(), total[keep].contiguous()
         dev_index = device if isinstance(device, int) else device.index
-        import os
-
-        # the SNV-sharded step pushes its records batch by batch in line order: it runs on the flat copy of the stream,
-        # so the store need not keep the batched-4 copy (ph_create reads the knob)
-        saved = os.environ.get("PH_BATCH4")
-        os.environ["PH_BATCH4"] = "0"
-        try:
-            st = ObservationStore.from_coo(n_cells, hi - lo, cell, snv, var, total, alpha=alpha, max_copies=max_copies,
-                                           device=dev_index, pairs=global_pairs(var, total, group))
-        finally:
-            if saved is None:
-                os.environ.pop("PH_BATCH4", None)
-            else:
-                os.environ["PH_BATCH4"] = saved
+        # the SNV-sharded step runs on the batched-4 copy of the stream like the single-GPU pass: its results travel as
+        # self-describing words (SNV id + label + counts), so the shape order of a rank's lines needs no set-up exchange
+        st = ObservationStore.from_coo(n_cells, hi - lo, cell, snv, var, total, alpha=alpha, max_copies=max_copies,
+                                       device=dev_index, pairs=global_pairs(var, total, group))
         dev = torch.device("cuda", dev_index)
         try:
             return cls(st, n_cells, n_snvs, lo, hi, dev, group)
@@ -376,14 +387,23 @@ class SnvShardedStore:
         lab = t.empty(self.n_snvs + 16, dtype=t.uint8, device=self.device)
         nobs = t.empty(self.n_snvs, dtype=t.int32, device=self.device)
         self.assign_linear_dev(self._labels_dev(cell_label), lenA, lab, nobs)
-        return lab[: self.n_snvs].cpu().numpy(), nobs.cpu().numpy()
+        out = lab[: self.n_snvs].cpu().numpy(), nobs.cpu().numpy()
+        self._check_peer()
+        return out
 
     def assign_branching(self, cell_label):
         t = self.torch
         lab = t.empty(self.n_snvs + 16, dtype=t.uint8, device=self.device)
         nobs = t.empty(2 * self.n_snvs, dtype=t.int32, device=self.device)
         self.assign_branching_dev(self._labels_dev(cell_label), lab, nobs)
-        return lab[: self.n_snvs].cpu().numpy(), nobs.cpu().numpy().reshape(self.n_snvs, 2)
+        out = lab[: self.n_snvs].cpu().numpy(), nobs.cpu().numpy().reshape(self.n_snvs, 2)
+        self._check_peer()
+        return out
+
+    def _check_peer(self):
+        """See ShardedStore._check_peer: a timed-out wait invalidates the step's outputs on this rank."""
+        if self.peer.timed_out(self._stream()):
+            raise _PhError("peer-memory exchange timed out waiting for a rank (about 3 s): results discarded")
 
     def close(self):
         self.peer.close()

@@ -1,4 +1,9 @@
-"""Real NCCL path: needs >= 2 GPUs on the box (skipped on the 1-GPU driver run; covered on CPU by test_sharded_gloo)."""
+"""Multi-rank K1 steps against the single-GPU call (scripts/check_sharded.py).
+
+The driver's box has ONE GPU: the 2- and 4-rank tests therefore run every rank as its own process on cuda:0 (gloo
+rendez-vous, CUDA IPC between processes of the same device, the GPU time-slices the ranks).  That exercises the real
+exchange code with world > 1 -- rank offsets, the words pushed into other processes' windows, the polling collect -- which a
+world = 1 run cannot.  With >= 2 GPUs the same script also runs over NCCL, one rank per GPU."""
 import os
 import subprocess
 import sys
@@ -9,24 +14,39 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def _run(nproc, port, *flags, timeout=900):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc), "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "scripts", "check_sharded.py"), *flags]
+    env = dict(os.environ)
+    env.pop("PH_BATCH4", None)
+    out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=timeout, env=env)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert f"sharded path == single GPU path on {nproc} ranks: True" in out.stdout, out.stdout[-3000:]
+    return out.stdout
+
+
+def test_two_ranks_on_one_gpu():
+    out = _run(2, 29533, "--one-gpu")
+    assert "snv-sharded peer" in out and "peer" in out
+
+
+def test_four_ranks_on_one_gpu():
+    _run(4, 29535, "--one-gpu", "--quick")
+
+
 def test_sharded_nccl_equals_single_gpu():
     import torch
 
-    n = torch.cuda.device_count()
-    if n < 2:
-        pytest.skip("needs >= 2 GPUs")
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29533", os.path.join(ROOT, "scripts", "check_sharded_nccl.py")]
-    out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
-    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
-    assert "== single GPU path on 2 ranks: True" in out.stdout
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (the one-GPU tests above cover the peer exchange with world > 1)")
+    out = _run(2, 29537)
+    assert "nccl" in out
 
 
-def test_snv_sharded_records_one_rank():
-    """The record push + unpack path of the SNV-sharded step on ONE GPU (world = 1: the window is local), so the driver's
-    single-GPU run exercises k_pass<push> and k_peer_collect_rec; must equal the plain single-GPU call bit for bit."""
+def test_snv_sharded_one_rank():
+    """The LL push + polling collect of the SNV-sharded step with world = 1 (the window is local); must equal the plain
+    single-GPU call bit for bit, on the batched-4 stream (default) and on the flat stream with 8 and 4 lines per batch."""
     import numpy as np
-    import torch
     import torch.distributed as dist
 
     from phertilizer_b200.sharded import SnvShardedStore
@@ -37,15 +57,17 @@ def test_snv_sharded_records_one_rank():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29541")
         dist.init_process_group("gloo", rank=0, world_size=1)
+    saved = os.environ.get("PH_BATCH4")
     try:
-        for name, over in (("T1", {}), ("T0", {}), ("C2", {"n": 3000, "m": 4099})):
+        for name, over, b4 in (("T1", {}, "1"), ("T0", {}, "0"), ("C2", {"n": 3000, "m": 4099}, "1"), ("C2", {"n": 3000, "m": 4099}, "0")):
+            os.environ["PH_BATCH4"] = b4
             s = make_config(name, with_embedding=False, **over)
             cell, snv, var, total = (x.numpy() for x in (s.cell, s.snv, s.var, s.total))
             full = ObservationStore.from_coo(s.n, s.m, cell, snv, var, total, device=0)
             sh = SnvShardedStore.from_coo(s.n, s.m, cell, snv, var, total, 0, 1, 0)
             rng = np.random.default_rng(5)
             for trial in range(3):
-                group = (8, 4, -1)[trial]          # lines per batch = lines per pushed record
+                group = (8, 4, -1)[trial]          # lines per batch of the flat stream
                 full.set_group(group, group)
                 sh.store.set_group(group, group)
                 lab = np.zeros(s.n + 16, np.uint8)[: s.n]
@@ -62,4 +84,8 @@ def test_snv_sharded_records_one_rank():
             sh.close()
             full.close()
     finally:
+        if saved is None:
+            os.environ.pop("PH_BATCH4", None)
+        else:
+            os.environ["PH_BATCH4"] = saved
         dist.destroy_process_group()
