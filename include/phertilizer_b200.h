@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PH_ABI_VERSION 4
+#define PH_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define PH_API __attribute__((visibility("default")))
@@ -195,6 +195,23 @@ PH_API int ph_cell_table(ph_handle* h, const uint8_t* snv_label, int32_t Q, cons
  */
 PH_API int ph_block_sums(ph_handle* h, const uint8_t* cell_label, int32_t C, const uint8_t* snv_label, int32_t Q,
                   double* sum0, double* sum1, int64_t* nobs, int64_t* nvar, int on_device, void* stream);
+
+/*
+ * The two fixed-order reductions behind ph_block_sums (Q <= 3: per-cell table over the SNV clusters, summed by cell
+ * cluster) and ph_tree_loglik (per-cell values summed by node), on caller-provided HOST tables.  A cell-sharded store
+ * (phertilizer_b200/sharded_store.py) assembles the per-cell rows of all ranks -- every row is computed wholly by the
+ * rank owning the cell -- and reduces them with the same kernels, so block sums and tree log-likelihoods are
+ * bit-identical for any number of GPUs (the scalars decide which split / tree wins: linear_split.py:549-554,
+ * branching_split.py:460-466, clonal_tree_list.py:196-234).
+ *   ph_line_reduce: table [n_lines x ncol] (ncol <= 3), line_label in 0..nlab -> out[col * nlab + (label - 1)]
+ *   ph_node_reduce: per_node[k] = sum of per_line over the lines with line_node == k
+ * Synchronous; n_lines <= max(n_cells, n_snvs) of the handle.
+ */
+PH_API int ph_line_reduce(ph_handle* h, const double* S0, const double* S1, const int32_t* Nobs, const int32_t* Nvar,
+                   const uint8_t* line_label, int32_t n_lines, int32_t ncol, int32_t nlab, double* sum0, double* sum1,
+                   int64_t* nobs, int64_t* nvar);
+PH_API int ph_node_reduce(ph_handle* h, const double* per_line, const uint8_t* line_node, int32_t n_lines, int32_t K,
+                   double* per_node);
 
 /*
  * a-9 -- variant read-count log-likelihood of a clonal tree, per node

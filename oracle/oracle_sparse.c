@@ -65,6 +65,35 @@ void orc_snv_table(int32_t m, const int64_t* colptr, const int32_t* row, const u
   }
 }
 
+/* Per-cell table over SNV clusters, CSR input (rowptr[n+1], col[nnz], code[nnz]); label: 0 = excluded, 1..Q.
+ * linear_split.py:301-304 (tmb features), 400-410 (check_metrics); branching_split.py:147-173 (calc_tmb), 395-411;
+ * clonal_tree.py:1140 (Seed.strip).  Sums run per cell in ascending SNV order (numpy's axis-1 reduce).  Outputs [n*Q]. */
+void orc_cell_table(int32_t n, const int64_t* rowptr, const int32_t* col, const uint16_t* code, const double* L0,
+                    const double* L1, const uint8_t* varpos, const uint8_t* snv_label, int32_t Q, double* A0,
+                    double* A1, int32_t* Nobs, int32_t* Nvar) {
+#pragma omp parallel for schedule(dynamic, 256)
+  for (int32_t i = 0; i < n; ++i) {
+    double s0[8] = {0}, s1[8] = {0};
+    int32_t no[8] = {0}, nv[8] = {0};
+    for (int64_t p = rowptr[i]; p < rowptr[i + 1]; ++p) {
+      const int l = snv_label[col[p]];
+      if (l) {
+        const int q = l - 1, k = code[p];
+        s0[q] += L0[k];
+        s1[q] += L1[k];
+        no[q] += 1;
+        nv[q] += varpos[k];
+      }
+    }
+    for (int q = 0; q < Q; ++q) {
+      A0[(int64_t)i * Q + q] = s0[q];
+      A1[(int64_t)i * Q + q] = s1[q];
+      Nobs[(int64_t)i * Q + q] = no[q];
+      Nvar[(int64_t)i * Q + q] = nv[q];
+    }
+  }
+}
+
 /* linear_split.py:203-237 without the quantile gate: label 2 (mutsB) if mean like0 >= mean like1 else 1 (mutsA). */
 void orc_assign_linear(int32_t m, const int64_t* colptr, const int32_t* row, const uint16_t* code, const double* L0,
                        const double* L1, const uint8_t* cell_label, double lenA, uint8_t* label_out, int32_t* nobs_out) {

@@ -77,6 +77,24 @@ class SparseOracle:
                             _p(self.varpos), _p(lab), C.c_int32(Cn), _p(S0), _p(S1), _p(No), _p(Nv))
         return S0, S1, No, Nv
 
+    @classmethod
+    def from_csc_csr(cls, n, m, colptr, row, ccode, rowptr, col, rcode, L0, L1, varpos):
+        """Both orientations handed in ready-made (the full-size tests sort on the GPU)."""
+        self = cls.from_csc(n, m, colptr, row, ccode, L0, L1, varpos)
+        self.rowptr = np.ascontiguousarray(rowptr, np.int64)
+        self.col = np.ascontiguousarray(col, np.int32)
+        self.rcode = np.ascontiguousarray(rcode, np.uint16)
+        return self
+
+    def cell_table(self, snv_label, Q):
+        n = self.n
+        A0 = np.empty((n, Q)); A1 = np.empty((n, Q))
+        No = np.empty((n, Q), np.int32); Nv = np.empty((n, Q), np.int32)
+        lab = np.ascontiguousarray(snv_label, np.uint8)
+        lib().orc_cell_table(C.c_int32(n), _p(self.rowptr), _p(self.col), _p(self.rcode), _p(self.L0), _p(self.L1),
+                             _p(self.varpos), _p(lab), C.c_int32(Q), _p(A0), _p(A1), _p(No), _p(Nv))
+        return A0, A1, No, Nv
+
     def assign_linear(self, cell_label, lenA):
         lab = np.ascontiguousarray(cell_label, np.uint8)
         out = np.empty(self.m, np.uint8); nobs = np.empty(self.m, np.int32)

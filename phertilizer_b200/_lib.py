@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libphertilizer_b200.so")
 
 PH_OK = 0
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class PhError(RuntimeError):
@@ -38,7 +38,7 @@ class PhInfo(C.Structure):
 EXPORTS = [
     "ph_last_error", "ph_abi_version", "ph_kernel_launches", "ph_device_count", "ph_create", "ph_destroy", "ph_get_info", "ph_set_group",
     "ph_snv_table", "ph_assign_linear", "ph_assign_branching", "ph_cell_table", "ph_block_sums", "ph_tree_loglik",
-    "ph_snv_node_table", "ph_cell_node_table", "ph_set_embedding", "ph_gauss_node_ll", "ph_pairwise_dist",
+    "ph_line_reduce", "ph_node_reduce", "ph_snv_node_table", "ph_cell_node_table", "ph_set_embedding", "ph_gauss_node_ll", "ph_pairwise_dist",
     "ph_snv_partial", "ph_finish_linear", "ph_finish_branching",
     "ph_peer_handle_bytes", "ph_peer_create", "ph_peer_export", "ph_peer_connect", "ph_peer_assign_linear",
     "ph_peer_assign_branching", "ph_peer_assign_linear_snv", "ph_peer_assign_branching_snv", "ph_peer_timed_out",
@@ -75,6 +75,8 @@ def lib():
     L.ph_assign_linear.argtypes = [_vp, _vp, C.c_double, _vp, C.c_int32, _vp, _vp, C.c_int, _vp]
     L.ph_assign_branching.argtypes = [_vp, _vp, _vp, C.c_int32, _vp, _vp, C.c_int, _vp]
     L.ph_block_sums.argtypes = [_vp, _vp, C.c_int32, _vp, C.c_int32, _vp, _vp, _vp, _vp, C.c_int, _vp]
+    L.ph_line_reduce.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp, _vp, _vp, _vp]
+    L.ph_node_reduce.argtypes = [_vp, _vp, _vp, C.c_int32, C.c_int32, _vp]
     L.ph_tree_loglik.argtypes = [_vp, _vp, _vp, _vp, C.c_int32, _vp, _vp, C.c_int, _vp]
     L.ph_snv_node_table.argtypes = [_vp, _vp, _vp, C.c_int32, _vp, C.c_int32, _vp, C.c_int, _vp]
     L.ph_cell_node_table.argtypes = L.ph_snv_node_table.argtypes

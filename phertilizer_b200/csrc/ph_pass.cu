@@ -687,6 +687,42 @@ __global__ void k_block_reduce(const double* __restrict__ S0, const double* __re
   }
 }
 
+// deterministic sums of a per-line table [n_lines x ncol] over the lines of every label 1..nlab:
+// out[col * nlab + (lab - 1)].  Fixed order (thread-strided partial sums, then a tree): a function of the table alone, so
+// a table assembled from several GPUs reduces to the very bits a single GPU gets (sharded_store.py).
+__global__ void k_line_reduce(const double* __restrict__ S0, const double* __restrict__ S1, const int32_t* __restrict__ Nobs,
+                              const int32_t* __restrict__ Nvar, const uint8_t* __restrict__ line_label, int n_lines, int ncol,
+                              int nlab, double* out0, double* out1, long long* outn, long long* outv) {
+  const int col = blockIdx.x / nlab, lab = blockIdx.x % nlab + 1;
+  double a0 = 0.0, a1 = 0.0;
+  long long an = 0, av = 0;
+  for (int j = threadIdx.x; j < n_lines; j += blockDim.x) {
+    if (line_label[j] == lab) {
+      const size_t o = (size_t)j * ncol + col;
+      a0 += S0[o];
+      a1 += S1[o];
+      an += Nobs[o];
+      av += Nvar[o];
+    }
+  }
+  __shared__ double r0[1024], r1[1024];
+  __shared__ long long rn[1024], rv[1024];
+  r0[threadIdx.x] = a0; r1[threadIdx.x] = a1; rn[threadIdx.x] = an; rv[threadIdx.x] = av;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) {
+      r0[threadIdx.x] += r0[threadIdx.x + s];
+      r1[threadIdx.x] += r1[threadIdx.x + s];
+      rn[threadIdx.x] += rn[threadIdx.x + s];
+      rv[threadIdx.x] += rv[threadIdx.x + s];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    out0[blockIdx.x] = r0[0]; out1[blockIdx.x] = r1[0]; outn[blockIdx.x] = rn[0]; outv[blockIdx.x] = rv[0];
+  }
+}
+
 // deterministic per-node sum of per-line values
 __global__ void k_node_reduce(const double* __restrict__ v, const uint8_t* __restrict__ label, int n, double* out) {
   const int k = blockIdx.x;
@@ -1175,14 +1211,22 @@ extern "C" int ph_block_sums(ph_handle* h, const uint8_t* cell_label, int32_t C,
   if (!cell_label || !snv_label || !sum0 || !sum1 || !nobs || !nvar) PH_FAIL(PH_ERR_ARG, "null pointer");
   if (C < 1 || C > PH_MAX_FAST_CLUSTERS || Q < 1 || Q > 16) PH_FAIL(PH_ERR_ARG, "C=%d / Q=%d out of range", C, Q);
   PH_CUDA(cudaSetDevice(h->device));
-  PhOrient* o = &h->by_snv;
+  // Q <= 3: the per-CELL table over the SNV clusters (cell-major copy) reduced by cell cluster -- a cell's row is
+  // computed wholly where the cell lives, so a cell-sharded store assembles the very same table and reduces it to the
+  // very same bits (ph_line_reduce).  Q > 3: per-SNV table over the cell clusters, reduced by SNV cluster.
+  const bool by_cell = Q <= PH_MAX_FAST_CLUSTERS;
+  PhOrient* o = by_cell ? &h->by_cell : &h->by_snv;
   cudaStream_t st = on_device ? (cudaStream_t)stream : h->stream;
   const uint8_t* d_cl = cell_label;
   const uint8_t* d_sl = snv_label;
   Pin pin{h->h_stage, h->h_stage_bytes};
   if (!on_device) {
-    int rc = check_labels(cell_label, h->n_cells, C, "cell_label");
+    int rc = check_labels(cell_label, h->n_cells, by_cell ? 255 : C, "cell_label");
     if (rc != PH_OK) return rc;
+    if (by_cell) {
+      rc = check_labels(snv_label, h->n_snvs, Q, "snv_label");
+      if (rc != PH_OK) return rc;
+    }
     uint8_t* p1 = (uint8_t*)pin.take(h->n_cells);
     uint8_t* p2 = (uint8_t*)pin.take(h->n_snvs);
     memcpy(p1, cell_label, h->n_cells);
@@ -1194,9 +1238,9 @@ extern "C" int ph_block_sums(ph_handle* h, const uint8_t* cell_label, int32_t C,
   }
   PassArgs a;
   fill_common(h, o, a);
-  a.C = C;
+  a.C = by_cell ? Q : C;
   a.n_work = o->n_major;
-  a.minor_label = d_cl;
+  a.minor_label = by_cell ? d_sl : d_cl;
   double* dS0 = h->d_f64;
   double* dS1 = h->d_f64 + (size_t)o->n_major * PH_MAX_FAST_CLUSTERS;
   int32_t* dNo = h->d_i32;
@@ -1209,7 +1253,10 @@ extern "C" int ph_block_sums(ph_handle* h, const uint8_t* cell_label, int32_t C,
   double* d1 = on_device ? sum1 : h->d_small + 64;
   long long* dn = on_device ? (long long*)nobs : (long long*)(h->d_small + 128);
   long long* dv = on_device ? (long long*)nvar : (long long*)(h->d_small + 192);
-  k_block_reduce<<<nb, 1024, 0, st>>>(dS0, dS1, dNo, dNv, d_sl, o->n_major, C, d0, d1, dn, dv);
+  if (by_cell)  // table columns = SNV clusters, lines labelled by cell cluster: out[(q-1) * C + (c-1)]
+    k_line_reduce<<<nb, 1024, 0, st>>>(dS0, dS1, dNo, dNv, d_cl, o->n_major, Q, C, d0, d1, dn, dv);
+  else
+    k_block_reduce<<<nb, 1024, 0, st>>>(dS0, dS1, dNo, dNv, d_sl, o->n_major, C, d0, d1, dn, dv);
   ph_count_launch();
   PH_CUDA(cudaGetLastError());
   if (!on_device) {
@@ -1221,6 +1268,63 @@ extern "C" int ph_block_sums(ph_handle* h, const uint8_t* cell_label, int32_t C,
     memcpy(nobs, p + 128, nb * 8);
     memcpy(nvar, p + 192, nb * 8);
   }
+  return PH_OK;
+}
+
+// The reductions of ph_block_sums / ph_tree_loglik on caller-provided per-line tables (host pointers): what a sharded
+// store runs on the table it assembled from all ranks -- same kernels, same order, same bits as one GPU.
+extern "C" int ph_line_reduce(ph_handle* h, const double* S0, const double* S1, const int32_t* Nobs, const int32_t* Nvar,
+                              const uint8_t* line_label, int32_t n_lines, int32_t ncol, int32_t nlab, double* sum0,
+                              double* sum1, int64_t* nobs, int64_t* nvar) {
+  if (!h) PH_FAIL(PH_ERR_ARG, "null handle");
+  if (!S0 || !S1 || !Nobs || !Nvar || !line_label || !sum0 || !sum1 || !nobs || !nvar) PH_FAIL(PH_ERR_ARG, "null pointer");
+  const int nmax = h->n_cells > h->n_snvs ? h->n_cells : h->n_snvs;
+  if (n_lines < 1 || n_lines > nmax || ncol < 1 || ncol > PH_MAX_FAST_CLUSTERS || nlab < 1 || ncol * nlab > 64)
+    PH_FAIL(PH_ERR_ARG, "bad shape n_lines=%d ncol=%d nlab=%d", n_lines, ncol, nlab);
+  PH_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  const size_t nt = (size_t)n_lines * ncol;
+  double* dS0 = h->d_f64;
+  double* dS1 = h->d_f64 + (size_t)nmax * PH_MAX_FAST_CLUSTERS;
+  int32_t* dNo = h->d_i32;
+  int32_t* dNv = h->d_i32 + (size_t)nmax * PH_MAX_FAST_CLUSTERS;
+  PH_CUDA(cudaMemcpyAsync(dS0, S0, nt * 8, cudaMemcpyHostToDevice, st));
+  PH_CUDA(cudaMemcpyAsync(dS1, S1, nt * 8, cudaMemcpyHostToDevice, st));
+  PH_CUDA(cudaMemcpyAsync(dNo, Nobs, nt * 4, cudaMemcpyHostToDevice, st));
+  PH_CUDA(cudaMemcpyAsync(dNv, Nvar, nt * 4, cudaMemcpyHostToDevice, st));
+  PH_CUDA(cudaMemcpyAsync(h->d_lab_major, line_label, (size_t)n_lines, cudaMemcpyHostToDevice, st));
+  const int nb = ncol * nlab;
+  k_line_reduce<<<nb, 1024, 0, st>>>(dS0, dS1, dNo, dNv, h->d_lab_major, n_lines, ncol, nlab, h->d_small, h->d_small + 64,
+                                     (long long*)(h->d_small + 128), (long long*)(h->d_small + 192));
+  ph_count_launch();
+  PH_CUDA(cudaGetLastError());
+  double host[256];
+  PH_CUDA(cudaMemcpyAsync(host, h->d_small, sizeof(host), cudaMemcpyDeviceToHost, st));
+  PH_CUDA(cudaStreamSynchronize(st));
+  memcpy(sum0, host, nb * 8);
+  memcpy(sum1, host + 64, nb * 8);
+  memcpy(nobs, host + 128, nb * 8);
+  memcpy(nvar, host + 192, nb * 8);
+  return PH_OK;
+}
+
+extern "C" int ph_node_reduce(ph_handle* h, const double* per_line, const uint8_t* line_node, int32_t n_lines, int32_t K,
+                              double* per_node) {
+  if (!h) PH_FAIL(PH_ERR_ARG, "null handle");
+  if (!per_line || !line_node || !per_node) PH_FAIL(PH_ERR_ARG, "null pointer");
+  const int nmax = h->n_cells > h->n_snvs ? h->n_cells : h->n_snvs;
+  if (n_lines < 1 || n_lines > nmax || K < 1 || K > PH_MAX_TREE_NODES) PH_FAIL(PH_ERR_ARG, "bad shape n_lines=%d K=%d", n_lines, K);
+  PH_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  PH_CUDA(cudaMemcpyAsync(h->d_f64, per_line, (size_t)n_lines * 8, cudaMemcpyHostToDevice, st));
+  PH_CUDA(cudaMemcpyAsync(h->d_lab_major, line_node, (size_t)n_lines, cudaMemcpyHostToDevice, st));
+  k_node_reduce<<<K, 1024, 0, st>>>(h->d_f64, h->d_lab_major, n_lines, h->d_small);
+  ph_count_launch();
+  PH_CUDA(cudaGetLastError());
+  double host[PH_MAX_TREE_NODES];
+  PH_CUDA(cudaMemcpyAsync(host, h->d_small, (size_t)K * 8, cudaMemcpyDeviceToHost, st));
+  PH_CUDA(cudaStreamSynchronize(st));
+  memcpy(per_node, host, (size_t)K * 8);
   return PH_OK;
 }
 

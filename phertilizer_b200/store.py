@@ -236,6 +236,29 @@ class ObservationStore:
                                             _ptr(no), _ptr(nv), 0, None))
         return s0, s1, no, nv
 
+    def line_reduce(self, S0, S1, Nobs, Nvar, line_label, ncol, nlab):
+        """Fixed-order sums of a per-line table [n_lines, ncol] over the lines of every label 1..nlab -> four [ncol, nlab]
+        arrays: the reduction behind block_sums, on a caller-provided table (sharded_store.py assembles one)."""
+        S0 = np.ascontiguousarray(S0, np.float64).reshape(-1, ncol)
+        S1 = np.ascontiguousarray(S1, np.float64).reshape(-1, ncol)
+        No = np.ascontiguousarray(Nobs, np.int32).reshape(-1, ncol)
+        Nv = np.ascontiguousarray(Nvar, np.int32).reshape(-1, ncol)
+        n_lines = S0.shape[0]
+        s0 = np.empty((ncol, nlab), np.float64)
+        s1 = np.empty((ncol, nlab), np.float64)
+        no = np.empty((ncol, nlab), np.int64)
+        nv = np.empty((ncol, nlab), np.int64)
+        _lib.check(_lib.lib().ph_line_reduce(self._h, _ptr(S0), _ptr(S1), _ptr(No), _ptr(Nv), _ptr(line_label), n_lines, ncol,
+                                             nlab, _ptr(s0), _ptr(s1), _ptr(no), _ptr(nv)))
+        return s0, s1, no, nv
+
+    def node_reduce(self, per_line, line_node, K):
+        """per_node[k] = sum of per_line over the lines with line_node == k, in the fixed order tree_loglik uses."""
+        v = np.ascontiguousarray(per_line, np.float64)
+        out = np.empty(K, np.float64)
+        _lib.check(_lib.lib().ph_node_reduce(self._h, _ptr(v), _ptr(line_node), len(v), K, _ptr(out)))
+        return out
+
     def tree_loglik(self, cell_node, snv_node, present, per_cell=False):
         K = present.shape[0]
         present = np.ascontiguousarray(present, dtype=np.uint8)

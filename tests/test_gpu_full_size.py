@@ -114,3 +114,117 @@ def test_assign_linear_equals_sparse_oracle_on_C2(big):
         g_lab, g_nobs = st.assign_linear(labA, lenA)
         o_lab, o_nobs = orc.assign_linear(labA, lenA)
         assert np.array_equal(g_lab, o_lab) and np.array_equal(g_nobs, o_nobs)
+
+
+# ------------------------------------------------------------------------------------------- against the sparse C oracle
+@pytest.fixture(scope="module")
+def big_oracle(big):
+    """oracle/oracle_sparse.c over both orientations of the same observations (host CSC + CSR; the sorts run on the GPU)."""
+    import torch
+
+    from oracle.oracle_sparse import SparseOracle, use_all_cores
+    from phertilizer_b200.store import encode_with_table
+
+    name, s, st = big
+    use_all_cores()
+    code_t = encode_with_table(s.var, s.total, st.pair_var, st.pair_total)
+
+    def orient(major, minor, n_major, n_minor):
+        order = torch.argsort(major.to(torch.int64) * n_minor + minor.to(torch.int64))
+        idx = minor[order].cpu().numpy()
+        code = code_t[order].cpu().numpy().astype(np.uint16)
+        del order
+        ptr = np.zeros(n_major + 1, np.int64)
+        np.cumsum(torch.bincount(major.to(torch.int64), minlength=n_major).cpu().numpy(), out=ptr[1:])
+        return ptr, idx, code
+
+    colptr, row, ccode = orient(s.snv, s.cell, s.m, s.n)
+    rowptr, col, rcode = orient(s.cell, s.snv, s.n, s.m)
+    torch.cuda.empty_cache()
+    return SparseOracle.from_csc_csr(s.n, s.m, colptr, row, ccode, rowptr, col, rcode, st.L0, st.L1, np.asarray(st.pair_var) > 0)
+
+
+def _clone_labels(s, K):
+    """Cell labels of a split along the ground-truth tree: the clade of clone 1 -> A, a sibling clade -> B, rest excluded."""
+    anc = s.ancestor_matrix()
+    clone = s.cell_clone.cpu().numpy()
+    a_clade = np.nonzero(anc[:, 1])[0]
+    rest = [k for k in range(len(s.parent)) if k not in set(a_clade.tolist()) and k != 0]
+    b_clade = np.nonzero(anc[:, rest[0]])[0] if rest else np.array([0])
+    lab = np.zeros(s.n + 16, np.uint8)[: s.n]
+    lab[np.isin(clone, a_clade)] = 1
+    lab[np.isin(clone, b_clade) & (lab == 0)] = 2
+    return lab
+
+
+def test_snv_and_cell_tables_equal_the_sparse_oracle(big, big_oracle):
+    name, s, st = big
+    rng = np.random.default_rng(6)
+    cl = np.zeros(s.n + 16, np.uint8)[: s.n]; cl[:] = rng.integers(0, 3, s.n)
+    t = st.snv_table(cl, 2)
+    S0, S1, No, Nv = big_oracle.snv_table(cl, 2)
+    assert np.array_equal(t["Nobs"], No) and np.array_equal(t["Nvar"], Nv)
+    assert np.allclose(t["S0"], S0, rtol=TOL, atol=0) and np.allclose(t["S1"], S1, rtol=TOL, atol=0)
+    sl = np.zeros(s.m + 16, np.uint8)[: s.m]; sl[:] = rng.integers(0, 3, s.m)
+    t = st.cell_table(sl, 2)
+    A0, A1, No, Nv = big_oracle.cell_table(sl, 2)
+    assert np.array_equal(t["Nobs"], No) and np.array_equal(t["Nvar"], Nv)
+    assert np.allclose(t["S0"], A0, rtol=TOL, atol=0) and np.allclose(t["S1"], A1, rtol=TOL, atol=0)
+
+
+def test_assign_branching_equals_the_sparse_oracle_up_to_exact_ties(big, big_oracle):
+    """Random labels and labels of a split along the ground-truth clone tree.  The oracle sums floats in cell order, the
+    CUDA path evaluates exact integer histograms: they may only disagree where the oracle's own candidates are equal to
+    rounding (<= 1e-12 relative) -- counted and reported (VERDICT r1, weak #13)."""
+    import json
+    import os
+
+    name, s, st = big
+    rng = np.random.default_rng(8)
+    report = {}
+    rnd = np.zeros(s.n + 16, np.uint8)[: s.n]; rnd[:] = rng.integers(0, 3, s.n)
+    for kind, lab in (("random", rnd), ("clone_split", _clone_labels(s, len(s.parent)))):
+        g_lab, g_nobs = st.assign_branching(lab)
+        o_lab, o_nobs = big_oracle.assign_branching(lab)
+        assert np.array_equal(np.asarray(g_nobs).reshape(-1, 2), o_nobs)
+        bad = np.nonzero(g_lab != o_lab)[0]
+        if len(bad):
+            S0, S1, _, _ = big_oracle.snv_table(lab, 2)
+            cand = np.stack([S1[:, 0] + S0[:, 1], S0[:, 0] + S1[:, 1], S1[:, 0] + S1[:, 1]])
+            a, b = cand[o_lab[bad] - 1, bad], cand[g_lab[bad] - 1, bad]
+            assert np.all(np.abs(a - b) <= 1e-12 * np.maximum(np.abs(a), np.abs(b))), (kind, len(bad))
+        report[kind] = {"snvs": int(s.m), "tie_divergences": int(len(bad))}
+    print(f"[{name}] branching labels differing from the float-order oracle (exact ties only): {report}")
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out):
+        json.dump(report, open(os.path.join(out, f"branching_ties_{name}.json"), "w"))
+
+
+def test_assign_linear_equals_the_sparse_oracle_on_clone_labels(big, big_oracle):
+    name, s, st = big
+    lab = (_clone_labels(s, len(s.parent)) == 1).astype(np.uint8)
+    lenA = float(max(int(lab.sum()), 1))
+    g_lab, g_nobs = st.assign_linear(lab, lenA)
+    o_lab, o_nobs = big_oracle.assign_linear(lab, lenA)
+    assert np.array_equal(g_nobs, o_nobs)
+    bad = np.nonzero(g_lab != o_lab)[0]
+    if len(bad):   # mean like0 vs mean like1: only exact ties may differ
+        S0, S1, _, _ = big_oracle.snv_table(lab, 1)
+        assert np.all(np.abs(S0[bad, 0] - S1[bad, 0]) <= 1e-12 * np.abs(S0[bad, 0]))
+
+
+def test_tree_loglik_equals_the_sparse_oracle(big, big_oracle):
+    """The ground-truth K-clone tree of the synthetic: per-node variant log-likelihood (clonal_tree.py:932-944)."""
+    name, s, st = big
+    K = len(s.parent)
+    cn = np.full(s.n + 16, 255, np.uint8)[: s.n]; cn[:] = s.cell_clone.cpu().numpy()
+    sn = np.full(s.m + 16, 255, np.uint8)[: s.m]; sn[:] = s.snv_node.cpu().numpy()
+    rng = np.random.default_rng(10)
+    cn[rng.random(s.n) < 0.03] = 255          # some cells / SNVs outside the tree
+    sn[rng.random(s.m) < 0.03] = 255
+    present = s.ancestor_matrix()
+    per_node, per_cell = st.tree_loglik(cn, sn, present, per_cell=True)
+    o_cell = big_oracle.tree_loglik(cn, sn, present)
+    assert np.allclose(per_cell, o_cell, rtol=TOL, atol=0)
+    for k in range(K):
+        assert abs(per_node[k] - o_cell[cn == k].sum()) <= TOL * abs(per_node[k])

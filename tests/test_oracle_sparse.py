@@ -28,6 +28,11 @@ def test_sparse_oracle_matches_dense_oracle_and_reference():
         d0, d1, dn, dv = O.snv_table(D, groups, np.arange(g.m))
         assert np.array_equal(No, dn) and np.array_equal(Nv, dv)
         assert rel_close(S0, d0, 1e-12) and rel_close(S1, d1, 1e-12)
+        sl = rng.integers(0, 3, g.m).astype(np.uint8)
+        A0, A1, No2, Nv2 = S.cell_table(sl, 2)
+        e0, e1, en, ev = O.cell_table(D, np.arange(g.n), [np.nonzero(sl == q)[0] for q in (1, 2)])
+        assert np.array_equal(No2, en) and np.array_equal(Nv2, ev)
+        assert rel_close(A0, e0, 1e-12) and rel_close(A1, e1, 1e-12)
         # recorded reference assignments (all SNVs of the seed == all SNVs only for the first records; use subsets)
         for r in g.of("linear_mut_assignment"):
             if r.mutsB is None:
