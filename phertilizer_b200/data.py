@@ -16,7 +16,7 @@ from .store import ObservationStore
 class Data:
     cell_lookup: pd.Series
     mut_lookup: pd.Series
-    store: ObservationStore
+    store: ObservationStore   # or sharded_store.CellShardedStore (same methods, cells sharded across GPUs)
     read_depth: np.ndarray
     copy_distance: object = None   # cluster.CopyDistance
     use_read_depth: bool = True

@@ -108,11 +108,26 @@ def _embed(bin_counts: np.ndarray, dim_reduce: bool) -> np.ndarray:
 
 class Phertilizer:
     def __init__(self, variant_count_data, bin_count_data, alpha=0.001, max_copies=5, mode="var", dim_reduce=True,
-                 device=None):
+                 device=None, device_group=None):
+        """`device_group`: a torch.distributed process group (or True for the default group) whose ranks each drive one
+        GPU.  The observations are then sharded by cells across the ranks (`sharded_store.CellShardedStore`)
+        and EVERY rank must construct the object and make the same calls: the tree-growing control flow runs redundantly
+        on all ranks, on identical data and RNG streams, and returns the same tree everywhere."""
         use_read_depth = mode != "var"
         self.mapping_list = None
         self.explored_seeds = None
-        device = int(__import__("os").environ.get("PHERTILIZER_DEVICE", "0")) if device is None else device
+        import os
+
+        self.device_group = None
+        world = 1
+        if device_group is not None:
+            import torch.distributed as dist
+
+            self.device_group = None if device_group is True else device_group
+            world = dist.get_world_size(self.device_group)
+            if device is None:
+                device = int(os.environ.get("PHERTILIZER_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+        device = int(os.environ.get("PHERTILIZER_DEVICE", "0")) if device is None else device
 
         cell_labels, mut_labels, cell_idx, mut_idx, var, total = index_observations(variant_count_data)
         self.cells = np.arange(cell_labels.shape[0], dtype="int")
@@ -129,8 +144,17 @@ class Phertilizer:
         copy_distance = CopyDistance(np.asarray(embedding, dtype=np.float64), device=device)
 
         # per-observation likelihoods become a (var,total) -> (like0, like1) table inside the store (295-306)
-        store = ObservationStore.from_coo(len(self.cells), len(self.muts), cell_idx, mut_idx, var, total, alpha=alpha,
-                                          max_copies=max_copies, device=device)
+        if world > 1:
+            import torch.distributed as dist
+
+            from .sharded_store import CellShardedStore
+
+            store = CellShardedStore.from_coo(len(self.cells), len(self.muts), cell_idx, mut_idx, var, total,
+                                              dist.get_rank(self.device_group), world, device, alpha=alpha,
+                                              max_copies=max_copies, group=self.device_group)
+        else:
+            store = ObservationStore.from_coo(len(self.cells), len(self.muts), cell_idx, mut_idx, var, total, alpha=alpha,
+                                              max_copies=max_copies, device=device)
         if hasattr(store, "set_embedding"):
             store.set_embedding(embedding)       # tree scoring (K4) reads it hundreds of times
         self.data = Data(cell_lookup, mut_lookup, store, embedding, copy_distance, use_read_depth)

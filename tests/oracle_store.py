@@ -68,13 +68,35 @@ class OracleStore:
     def tree_loglik(self, cell_node, snv_node, present, per_cell=False):
         K = present.shape[0]
         out = np.zeros(K)
+        pc = np.zeros(self.n_cells)
         for k in range(K):
             cells = np.nonzero(cell_node == k)[0]
             if len(cells) == 0:
                 continue
-            pm = np.nonzero((snv_node < K) & (present[k][np.minimum(snv_node, K - 1)] != 0))[0]
+            on = (snv_node < K) & (present[k][np.minimum(snv_node, K - 1)] != 0)
+            pm = np.nonzero(on)[0]
             out[k] = O.variant_likelihood_by_node(self.D, cells, pm)
-        return out
+            pc[cells] = self.D.like1[np.ix_(cells, pm)].sum(axis=1) + self.D.like0[np.ix_(cells, np.nonzero(~on)[0])].sum(axis=1)
+        return (out, pc) if per_cell else out
+
+    def line_reduce(self, S0, S1, Nobs, Nvar, line_label, ncol, nlab):
+        """CPU stand-in of ObservationStore.line_reduce (ph_line_reduce): [ncol, nlab] sums over the lines of every label."""
+        lab = np.asarray(line_label)
+        tabs = [np.asarray(t).reshape(-1, ncol) for t in (S0, S1, Nobs, Nvar)]
+        outs = [np.zeros((ncol, nlab), np.float64), np.zeros((ncol, nlab), np.float64), np.zeros((ncol, nlab), np.int64),
+                np.zeros((ncol, nlab), np.int64)]
+        for c in range(1, nlab + 1):
+            rows = lab[: tabs[0].shape[0]] == c
+            for t, o in zip(tabs, outs):
+                o[:, c - 1] = t[rows].sum(axis=0)
+        return tuple(outs)
+
+    def node_reduce(self, per_line, line_node, K):
+        v, lab = np.asarray(per_line, np.float64), np.asarray(line_node)[: len(per_line)]
+        return np.array([v[lab == k].sum() for k in range(K)])
+
+    def set_embedding(self, X):
+        pass
 
     def gauss_node_ll(self, X, cell_node, K, per_cell=False):
         out = np.zeros(K)

@@ -20,7 +20,11 @@ def _run(nproc, port, *flags, timeout=900):
     env = dict(os.environ)
     env.pop("PH_BATCH4", None)
     out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=timeout, env=env)
-    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    dump = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(dump):   # keep the ranks' own output next to the other run artefacts
+        open(os.path.join(dump, f"check_sharded_{nproc}{'_'.join(flags)}.log"), "w").write(out.stdout + "\n---- stderr ----\n" + out.stderr)
+    mine = "\n".join(l for l in (out.stdout + out.stderr).splitlines() if "rank" in l or "Error" in l or "error" in l)
+    assert out.returncode == 0, mine[-4000:] + out.stdout[-1500:]
     assert f"sharded path == single GPU path on {nproc} ranks: True" in out.stdout, out.stdout[-3000:]
     return out.stdout
 
