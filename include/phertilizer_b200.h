@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PH_ABI_VERSION 5
+#define PH_ABI_VERSION 6
 
 #if defined(__GNUC__)
 #define PH_API __attribute__((visibility("default")))
@@ -174,7 +174,10 @@ PH_API int ph_peer_assign_linear_snv(ph_peer* p, const uint8_t* cell_label, doub
                               uint8_t* label_out, int32_t* nobs_out, void* stream);
 PH_API int ph_peer_assign_branching_snv(ph_peer* p, const uint8_t* cell_label, int32_t snv_offset, uint8_t* label_out,
                                  int32_t* nobs_out, void* stream);
-PH_API int ph_peer_timed_out(ph_peer* p, void* stream); /* 1 if a wait for a peer ever gave up (~3 s) */
+PH_API int ph_peer_timed_out(ph_peer* p, void* stream); /* 1 if a wait for a peer ever gave up (~3 s; PH_PEER_TIMEOUT_MS) */
+/* Diagnostics of the first SNV-sharded wait that gave up: out[7] = {timed out, kind (1 header, 2 id/label word, 3/4 count
+ * words), source rank, slot, step wanted, step seen, payload seen}. */
+PH_API int ph_peer_debug(ph_peer* p, uint32_t* out);
 PH_API void ph_peer_destroy(ph_peer* p);
 
 /*

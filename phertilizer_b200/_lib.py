@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libphertilizer_b200.so")
 
 PH_OK = 0
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 class PhError(RuntimeError):
@@ -42,7 +42,7 @@ EXPORTS = [
     "ph_snv_partial", "ph_finish_linear", "ph_finish_branching",
     "ph_peer_handle_bytes", "ph_peer_create", "ph_peer_export", "ph_peer_connect", "ph_peer_assign_linear",
     "ph_peer_assign_branching", "ph_peer_assign_linear_snv", "ph_peer_assign_branching_snv", "ph_peer_timed_out",
-    "ph_peer_destroy",
+    "ph_peer_debug", "ph_peer_destroy",
     "ph_affinity_create", "ph_affinity_rows", "ph_affinity_nearest", "ph_affinity_build", "ph_affinity_matmat", "ph_affinity_matrix",
     "ph_affinity_destroy",
 ]
@@ -91,6 +91,7 @@ def lib():
     L.ph_peer_assign_linear.argtypes = [_vp, _vp, C.c_double, _vp, C.c_int32, _vp, _vp, _vp]
     L.ph_peer_assign_branching.argtypes = [_vp, _vp, _vp, C.c_int32, _vp, _vp, _vp]
     L.ph_peer_timed_out.argtypes = [_vp, _vp]
+    L.ph_peer_debug.argtypes = [_vp, _vp]
     L.ph_peer_destroy.argtypes = [_vp]
     L.ph_peer_destroy.restype = None
     L.ph_affinity_create.argtypes = [_vp, C.c_int32, C.c_int32, C.c_int, C.POINTER(_vp)]

@@ -402,11 +402,13 @@ int build_orient(ph_handle* h, PhOrient* o, const int32_t* d_major, const int32_
       ph_count_launch();
     }
     // ---- batched-4 copy (see PhOrient): shape-sort the lines, fix every line's batch and slot, size the stream
-    // (only where the label image and the per-warp tables of a 1024-thread CTA fit in shared memory: LAY = 3 with the
-    // image at a 64 KB-aligned address when there is room for that, LAY = 4 otherwise)
-    const size_t tab4 = 32 * (size_t)(8 * (NSUB + 1) + 8 * D * PH_MAX_FAST_CLUSTERS + 2 * 8 + 3) * 4 + (size_t)h->n_codes * 17 + 256;
+    // (where the per-warp tables of a 1024-thread CTA leave room for the label image -- at a 64 KB-aligned address
+    // (LAY = 3) or wherever it fits (LAY = 4) -- or at least for one 64 KB chunk of it: longer minor axes are walked in
+    // phases of a few chunks, ph_pass.cu launch_pass)
+    const size_t tab4 = 32 * (size_t)(8 * (NSUB + 1) + 8 * D * PH_MAX_FAST_CLUSTERS + 2 * 8 + 3) * 4 + (size_t)h->n_codes * 17 + 256 + 66 * 66;
+    const size_t img4 = (size_t)o->lab_bytes < 65536 ? (size_t)o->lab_bytes : 65536;
     const bool want4 = h->batch4 && h->bank_order && nnz > 0 && NSUB > 0 && o->chunk_bits == 16 && n_major >= 8 &&
-                       (size_t)o->lab_bytes + tab4 <= (size_t)h->max_smem;
+                       img4 + tab4 <= (size_t)h->max_smem;
     if (want4) {
       const int nb4 = (n_major + 7) / 8;
       uint32_t *d_key = nullptr, *d_key2 = nullptr, *d_steps = nullptr;
@@ -551,6 +553,7 @@ extern "C" void ph_destroy(ph_handle* h) {
   cudaFree(h->d_small);
   cudaFree(h->d_map);
   cudaFree(h->d_counter);
+  cudaFree(h->d_partial);
   if (h->h_stage) cudaFreeHost(h->h_stage);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -608,6 +611,8 @@ extern "C" int ph_create(int32_t n_cells, int32_t n_snvs, int64_t nnz, const int
       h->round_fill = f > 1.0 ? 33 : (int)(f * 32.0 + 0.999);
       if (h->round_fill < 1) h->round_fill = 1;
     }
+    e = getenv("PH_PHASE_CHUNKS");  // test knob: walk label images of more chunks than this in phases (ph_pass.cu launch_pass)
+    h->phase_chunks = e ? atoi(e) : 0;
     e = getenv("PH_BATCH4");  // keep the batched-4 copy of the dense streams and use the 4-lanes-per-line pass (default on)
     h->batch4 = e ? atoi(e) : 1;
   }

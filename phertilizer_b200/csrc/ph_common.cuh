@@ -91,7 +91,7 @@ struct ph_handle {
   double* d_L1;      // [n_codes]
   uint8_t* d_varpos; // [n_codes]
   int64_t device_bytes;
-  int chunk_bits, bank_order, ctas_per_sm, aligned_image, zero_copy_out, batch4, round_fill;
+  int chunk_bits, bank_order, ctas_per_sm, aligned_image, zero_copy_out, batch4, round_fill, phase_chunks;
   double dense_min_avg, dense_min_share;  // a (var,total) code gets its own segment when it has >= this many entries per line on average
   // scratch (device)
   uint8_t* d_lab_minor;  // [max(n,m)] staged labels of the minor axis
@@ -105,6 +105,8 @@ struct ph_handle {
   double* d_small;       // [4096] small outputs (block sums, per-node)
   uint8_t* d_map;        // [65*65] class / member maps
   unsigned* d_counter;   // batch dispenser of the pass kernels
+  uint32_t* d_partial;   // phased passes: per-line (code, cluster) counters handed from phase to phase (grown on demand)
+  size_t partial_bytes;
   // pinned host staging
   uint8_t* h_stage;
   size_t h_stage_bytes;
@@ -112,7 +114,7 @@ struct ph_handle {
 };
 
 // ---- peer-memory exchange helpers shared by ph_pass.cu and ph_peer.cu
-constexpr long long kSpinLimit = 6000000000ll;  // ~3 s of SM clocks: a lost peer must not hang the GPU
+constexpr long long kSpinLimit = 6000000000ll;  // ~3 s of SM clocks: a lost peer must not hang the GPU (PH_PEER_TIMEOUT_MS overrides)
 
 // SNV-sharded steps (ph_peer.cu, ph_pass.cu): results travel as SELF-VALIDATING 8-byte words  epoch << 32 | payload
 // (the step counter rides in the upper half of every word, NCCL-LL style), so a receiver polls the data itself: no
@@ -135,7 +137,8 @@ struct PhLL {
   uint8_t* label_out;
   int32_t* nobs_out;
   unsigned* done;                  // completion counter of the collect phase (self-resetting)
-  unsigned* timeout_flag;
+  unsigned* timeout_flag;          // [0] sticky flag; [1..7] what the first wait that gave up was waiting for (ph_peer_debug)
+  long long spin_limit;            // SM clocks a wait may take
 };
 
 #ifdef __CUDACC__
@@ -153,13 +156,18 @@ __device__ __forceinline__ void st_relaxed_sys_u64(void* p, uint64_t v) {
   asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// spins until the word at p carries `epoch` in its upper half; returns the payload (0 and *ok = false on a timeout)
-__device__ __forceinline__ uint32_t ll_wait(const void* p, uint32_t epoch, long long t0, unsigned* timeout_flag, bool* ok) {
+// spins until the word at p carries `epoch` in its upper half; returns the payload (0 and *ok = false on a timeout).
+// The first wait to give up records what it was waiting for: {kind, source rank, slot, epoch wanted, epoch seen, payload}.
+__device__ __forceinline__ uint32_t ll_wait(const void* p, uint32_t epoch, long long t0, long long limit, unsigned* timeout_flag,
+                                            bool* ok, unsigned kind, unsigned src, unsigned slot) {
   for (;;) {
     const uint64_t w = ld_relaxed_sys_u64(p);
     if ((uint32_t)(w >> 32) == epoch) return (uint32_t)w;
-    if (clock64() - t0 > kSpinLimit) {
-      *timeout_flag = 1;
+    if (clock64() - t0 > limit) {
+      if (atomicExch(timeout_flag, 1u) == 0u) {
+        timeout_flag[1] = kind; timeout_flag[2] = src; timeout_flag[3] = slot; timeout_flag[4] = epoch;
+        timeout_flag[5] = (unsigned)(w >> 32); timeout_flag[6] = (unsigned)w;
+      }
       *ok = false;
       return 0u;
     }

@@ -26,6 +26,12 @@ struct PassArgs {
   const int64_t* __restrict__ tail_off;
   int D, NCH, NSUB, chunk_bits, minor_bits, n_minor, lab_bytes;
   int tab_bytes;  // LAY >= 2: bytes of everything but the label image (they go below the image when they fit)
+  // Phased pass (batched-4 stream only): a minor axis whose label image exceeds shared memory (250 k cells, 500 k SNVs) is
+  // walked in phases of `ch_n` chunks from `ch_lo`; each phase stages the image of its chunks only and streams the
+  // sub-segments of those chunks; the integer (code, cluster) counters of every line travel from phase to phase through
+  // `partial` and the last phase finishes the lines (rare-code tail included, its labels gathered from global memory).
+  int ch_lo, ch_n, phased, phase_first, phase_last;
+  uint32_t* partial;  // [n_lines * D * NC]
   const uint16_t* __restrict__ half4;     // LAY = 3: the batched-4 copy of the stream (PhOrient)
   const uint32_t* __restrict__ bstep_off;
   const uint8_t* __restrict__ minor_label;  // raw labels [n_minor] (SMEM_LAB) or the prepared label image (global)
@@ -98,16 +104,16 @@ __device__ __forceinline__ uint32_t clamp_nodes4(uint32_t w, uint32_t K) {
 // NODES = false: labels 0..NC -> counter shifts.  NODES = true: node ids clamped to K, padding slots hold K + 1.
 template <bool NODES, int NC>
 __device__ __forceinline__ void fill_label_image(uint8_t* img, const uint8_t* __restrict__ raw, int n_minor, int NCH, int cb,
-                                                 int K, int tid, int nthreads) {
+                                                 int K, int tid, int nthreads, int ch_lo = 0) {
   const int CH = (1 << cb) - PH_PAD;
   constexpr int PW = PH_PAD / 4;  // words of the excluded region
   const uint32_t excl = NODES ? (uint32_t)(K + 1) : (uint32_t)(PH_FIELD_BITS * NC);
-  for (int c = 0; c < NCH; ++c) {
+  for (int c = ch_lo; c < ch_lo + NCH; ++c) {  // NCH chunks from ch_lo (a phase), image chunk c - ch_lo
     const int cnt = min(CH, n_minor - c * CH);
     const int nw = (cnt + 3) >> 2;
     const uint8_t* srcb = raw + (size_t)c * CH;
     const uint32_t* src = reinterpret_cast<const uint32_t*>(srcb);  // buffers are padded to 4 B
-    uint32_t* dst = reinterpret_cast<uint32_t*>(img + ((size_t)c << cb));
+    uint32_t* dst = reinterpret_cast<uint32_t*>(img + ((size_t)(c - ch_lo) << cb));
     if (tid < PW) dst[tid] = excl * 0x01010101u;
     // whole 16-byte units of an aligned source go through 128-bit loads and stores (4x fewer round trips on the
     // start-up path of every CTA); the rest, and unaligned sources, word by word
@@ -176,7 +182,9 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
 
   unsigned bidx0 = 0;
   if ((threadIdx.x & 31) == 0) bidx0 = atomicAdd(a.counter, 1u);  // first batch of this warp, consumed after the staging
-  if (SMEM_LAB) fill_label_image<MODE == MODE_MAPPED, NC>(s_lab, a.minor_label, a.n_minor, NCH, cb, a.K, threadIdx.x, nthreads);
+  if (SMEM_LAB)
+    fill_label_image<MODE == MODE_MAPPED, NC>(s_lab, a.minor_label, a.n_minor, (B4 && a.phased) ? a.ch_n : NCH, cb, a.K, threadIdx.x, nthreads,
+                                              (B4 && a.phased) ? a.ch_lo : 0);
   if (MODE == MODE_MAPPED) {
     // rows: node of the line (K, K+1: not in the tree -> nothing counts); columns: node of the minor index
     // (K: not in the tree -> absent, K+1: padding -> not counted)
@@ -290,11 +298,13 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
     // (code, cluster) counter by one of them -- no MATCH / REDUX / atomics.
     if (B4 && NSUB > 0) {
       const int la = lane >> 2;  // my line of the batch
-      uint32_t st = s_e[0];
-      const uint32_t st_end = s_e[NSUB];
-      const uint4* gp = reinterpret_cast<const uint4*>(a.half4) + ((size_t)st << 5) + lane;
+      // a full pass is ONE run of steps over all sub-segments; a phase walks, per dense code, the run of its chunks
+      const bool phased = a.phased != 0;
+      const int ch_lo = phased ? a.ch_lo : 0;
+      uint32_t st = 0, st_end = 0;
+      const uint4* gp = nullptr;
       int q = 0, cur_d = 0;
-      uint32_t nb_eff = st, cbase = 0, acc = 0, st_flush = st;  // nb_eff = st: the first step enters the slow path
+      uint32_t nb_eff = 0, cbase = 0, acc = 0, st_flush = 0;
       const uint8_t* maprow = s_map;
       if (MODE == MODE_MAPPED) maprow = s_map + s_ml[la] * K2;
       constexpr uint32_t kDeadline4 = PH_FLUSH_GROUPS;  // steps: one group per lane and step
@@ -316,7 +326,7 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
           cur_d = d;
           st_flush = step;
         }
-        cbase = (((uint32_t)q - (uint32_t)d * (uint32_t)NCH) << 16) + (AL ? img_base : 0u);
+        cbase = (((uint32_t)q - (uint32_t)d * (uint32_t)NCH - (uint32_t)ch_lo) << 16) + (AL ? img_base : 0u);
         nb_eff = min(s_e[q + 1], st_flush + kDeadline4);
       };
       auto one4 = [&](uint32_t addr) -> uint32_t {
@@ -338,23 +348,32 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
 #endif
       constexpr int RD = PH_RING4;
       uint4 ring[RD];
-#pragma unroll
-      for (int u = 0; u < RD; ++u) {
-        ring[u] = make_uint4(0, 0, 0, 0);
-        if (st + u < st_end) ring[u] = ld_stream(gp + 32 * u);
-      }
-      while (st < st_end) {
+      const int n_runs = phased ? D : 1;
+      for (int run = 0; run < n_runs; ++run) {
+        q = phased ? run * NCH + ch_lo : 0;
+        st = s_e[q];
+        st_end = phased ? s_e[run * NCH + ch_lo + a.ch_n] : s_e[NSUB];
+        gp = reinterpret_cast<const uint4*>(a.half4) + ((size_t)st << 5) + lane;
+        nb_eff = st;  // the first step of a run enters the slow path
+        st_flush = st;
 #pragma unroll
         for (int u = 0; u < RD; ++u) {
-          if (u == 0 || st + u < st_end) {
-            consume4(ring[u], st + u);
-            if (st + u + RD < st_end) ring[u] = ld_stream(gp + 32 * (u + RD));
-          }
+          ring[u] = make_uint4(0, 0, 0, 0);
+          if (st + u < st_end) ring[u] = ld_stream(gp + 32 * u);
         }
-        st += RD;
-        gp += 32 * RD;
+        while (st < st_end) {
+#pragma unroll
+          for (int u = 0; u < RD; ++u) {
+            if (u == 0 || st + u < st_end) {
+              consume4(ring[u], st + u);
+              if (st + u + RD < st_end) ring[u] = ld_stream(gp + 32 * (u + RD));
+            }
+          }
+          st += RD;
+          gp += 32 * RD;
+        }
+        flush4();
       }
-      flush4();
     }
     // ---- dense part: maximal runs of lines that are contiguous in memory are streamed as one range of groups
     if (!B4 && NSUB > 0) {
@@ -462,12 +481,18 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
       unsigned nob[NC], nva[NC];
 #pragma unroll
       for (int c = 0; c < NC; ++c) { s0[c] = 0.0; s1[c] = 0.0; nob[c] = 0; nva[c] = 0; }
+      const bool ph = B4 && a.phased;
       for (int d = 0; d < D; ++d) {
         const double l0 = L0[d], l1 = L1[d];
         const bool vp = VP[d] != 0;
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
-          const unsigned t = s_cnt[(myl * D + d) * NC + c];
+          unsigned t = s_cnt[(myl * D + d) * NC + c];
+          if (ph) {  // the line's counters of the earlier phases; not the last phase: hand them on
+            uint32_t* pp = a.partial + ((size_t)line * D + d) * NC + c;
+            if (!a.phase_first) t += *pp;
+            if (!a.phase_last) *pp = t;
+          }
           if (MODE == MODE_COUNTS) s_row[(myl * NC + c) * a.ncp + d] = (uint16_t)t;
           s0[c] = fma((double)t, l0, s0[c]);
           s1[c] = fma((double)t, l1, s1[c]);
@@ -495,10 +520,20 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
             rc[c] = 0;
           }
         };
-        for (int64_t r = tb; r < te; ++r) {
+        for (int64_t r = tb; r < ((ph && !a.phase_last) ? tb : te); ++r) {
           const uint32_t w = __ldg(a.tail_words + r);
           const uint32_t code = w >> a.minor_bits;
-          uint32_t sh = label_at(w & mmask);
+          uint32_t sh;
+          if (ph) {
+            // the shared image holds this phase's chunks only: the rare entries (about 1 %) gather their raw label from
+            // global memory -- address in the full image -> minor index -> label -> counter shift / clamped node
+            const uint32_t ad = w & mmask, ch = ad >> cb, ix = ad & ((1u << cb) - 1u);
+            const uint32_t raw = __ldg(a.minor_label + (size_t)ch * ((1u << cb) - PH_PAD) + (ix - PH_PAD));
+            if (MODE == MODE_MAPPED) sh = raw < (uint32_t)a.K ? raw : (uint32_t)a.K;
+            else sh = (raw >= 1u && raw <= (uint32_t)NC) ? PH_FIELD_BITS * (raw - 1u) : (uint32_t)(PH_FIELD_BITS * NC);
+          } else {
+            sh = label_at(w & mmask);
+          }
           if (MODE == MODE_MAPPED) sh = h_maprow[sh];
           if (code != cur) {
             if (cur != 0xffffffffu) fold();
@@ -510,7 +545,9 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
         if (cur != 0xffffffffu) fold();
       }
       const int wi = B4 ? line : myw;  // batched-4 walks the lines in shape order: results go to the line's own slot
-      if (MODE == MODE_TABLE) {
+      if (ph && !a.phase_last) {
+        // an earlier phase: the counters went to `partial`, the line is finished by the last phase
+      } else if (MODE == MODE_TABLE) {
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
           const size_t o = (size_t)wi * NC + c;
@@ -609,7 +646,8 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
     const long long t0 = clock64();
     bool ok = true;
     if (threadIdx.x < a.world) {
-      const uint32_t c = ll_wait(a.ll.hdr_own + par * PH_MAX_PEERS + threadIdx.x, epoch, t0, a.ll.timeout_flag, &ok);
+      const uint32_t c = ll_wait(a.ll.hdr_own + par * PH_MAX_PEERS + threadIdx.x, epoch, t0, a.ll.spin_limit, a.ll.timeout_flag, &ok, 1u,
+                                 threadIdx.x, 0u);
       s_cnt_r[threadIdx.x] = ok ? min((int)c, a.ll.cap_slots) : 0;
     }
     __syncthreads();
@@ -620,12 +658,12 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
       if (j >= s_cnt_r[r]) continue;
       const uint8_t* w = base + ((size_t)r * cap + j) * 8;
       ok = true;
-      const uint32_t p0 = ll_wait(w, epoch, t0, a.ll.timeout_flag, &ok);
+      const uint32_t p0 = ll_wait(w, epoch, t0, a.ll.spin_limit, a.ll.timeout_flag, &ok, 2u, (unsigned)r, (unsigned)j);
       const uint32_t g = p0 >> 8;
       if (!ok || g >= (uint32_t)a.ll.max_lines) continue;  // empty slot (id 0xFFFFFF) or a word that never arrived
-      const uint32_t n0 = ll_wait(w + a.ll.word_stride, epoch, t0, a.ll.timeout_flag, &ok);
+      const uint32_t n0 = ll_wait(w + a.ll.word_stride, epoch, t0, a.ll.spin_limit, a.ll.timeout_flag, &ok, 3u, (unsigned)r, (unsigned)j);
       uint32_t n1 = 0;
-      if (NW == 3) n1 = ll_wait(w + 2 * a.ll.word_stride, epoch, t0, a.ll.timeout_flag, &ok);
+      if (NW == 3) n1 = ll_wait(w + 2 * a.ll.word_stride, epoch, t0, a.ll.spin_limit, a.ll.timeout_flag, &ok, 4u, (unsigned)r, (unsigned)j);
       if (!ok) continue;
       a.ll.label_out[g] = (uint8_t)(p0 & 0xFFu);
       if (NW == 2) {
@@ -816,9 +854,9 @@ __global__ void __launch_bounds__(kBlock, 1) k_node_table(const PassArgs a, cons
 
 // shared memory of one k_pass CTA with `threads` threads; 0 = does not fit
 size_t pass_smem_bytes(const ph_handle* h, const PhOrient* o, int mode, int NC, int K, bool smem_lab, int threads, int B,
-                       int row_words, int* lut_in_smem) {
+                       int row_words, int* lut_in_smem, long long image_bytes = -1) {
   size_t b = 0;
-  if (smem_lab) b += (size_t)o->lab_bytes;
+  if (smem_lab) b += image_bytes >= 0 ? (size_t)image_bytes : (size_t)o->lab_bytes;
   if (mode == MODE_MAPPED) b += (((size_t)(K + 2) * (K + 2)) + 15) & ~(size_t)15;
   const size_t warps = (size_t)(threads / 32) * (warp_words(B, o->NSUB, o->D, NC) + row_words) * 4 + 16;
   const size_t lut = ((size_t)h->n_codes * 17 + 15) & ~(size_t)15;
@@ -851,6 +889,8 @@ int launch_pass(ph_handle* h, const PhOrient* o, PassArgs& a, cudaStream_t st) {
   // with the aligned image, LAY = 4 (image wherever it fits) otherwise.
   bool use4 = false, al4 = false;
   const bool can4 = MODE != MODE_COUNTS && o->half4 && !a.list && h->batch4 && o->chunk_bits == 16;
+  int n_phases = 1, cpp = o->NCH;   // phased pass: chunks per phase (see PassArgs)
+  size_t tab4 = 0;
   if (o->chunk_bits == 16 && (h->aligned_image || can4)) {
     const int Bt = can4 ? 8 : B;
     const size_t full = pass_smem_bytes(h, o, MODE, NC, a.K, true, 1024, Bt, a.row_words, &lut);
@@ -861,18 +901,39 @@ int launch_pass(ph_handle* h, const PhOrient* o, PassArgs& a, cudaStream_t st) {
       aligned = true;
       a.tab_bytes = (int)(full - (size_t)o->lab_bytes);
     }
-    if (can4 && (fits_al || full)) {
-      if (!fits_al) {
-        smem = full;
-        threads = 1024;
+    const int force_cpp = h->phase_chunks > 0 && h->phase_chunks < o->NCH ? h->phase_chunks : 0;  // test knob PH_PHASE_CHUNKS
+    if (can4 && ((!full && !fits_al) || force_cpp)) {
+      // the image of the whole minor axis does not fit: walk it in phases of `cpp` chunks.  Aligned image (2 chunks of
+      // 64 KB above a 64 KB boundary) when that takes no more phases than the 3 chunks an unaligned image holds.
+      int lut0 = 0;
+      tab4 = pass_smem_bytes(h, o, MODE, NC, a.K, true, 1024, 8, a.row_words, &lut0, 0);
+      if (tab4 && tab4 + 65536 <= (size_t)h->max_smem) {
+        const int cpp_u = (int)(((size_t)h->max_smem - tab4) >> 16);
+        const int cpp_a = h->aligned_image && (size_t)h->max_smem >= tab4 + 65536 + 65536 ? (int)(((size_t)h->max_smem - 65536 - tab4) >> 16) : 0;
+        const int ph_u = (o->NCH + cpp_u - 1) / cpp_u;
+        const int ph_a = cpp_a > 0 ? (o->NCH + cpp_a - 1) / cpp_a : 1 << 30;
+        al4 = ph_a <= ph_u;
+        cpp = al4 ? cpp_a : cpp_u;
+        if (force_cpp && force_cpp <= cpp) cpp = force_cpp;
+        n_phases = (o->NCH + cpp - 1) / cpp;
+        lut = lut0;
+        if (al4) a.tab_bytes = (int)tab4;
       }
+    }
+    if (can4 && (fits_al || full || n_phases > 1)) {
+      if (n_phases == 1) {
+        if (!fits_al) smem = full;
+        al4 = fits_al;
+      }
+      threads = 1024;
       use4 = true;
-      al4 = fits_al;
+      aligned = al4;
       B = 8;
       a.list = o->perm4;              // the lines in shape order, 8 per batch, -1 = empty slot
       a.n_work = o->n_batches4 * 8;
       a.half4 = o->half4;
       a.bstep_off = o->bstep_off;
+      if (n_phases > 1) smem = 1;     // set per phase below
     }
   }
   for (int pass = 0; pass < 2 && !smem; ++pass) {
@@ -925,8 +986,38 @@ int launch_pass(ph_handle* h, const PhOrient* o, PassArgs& a, cudaStream_t st) {
     PH_FAIL(PH_ERR_UNSUPPORTED, "%d result slots exceed the %d reserved per rank in the peer window", ((a.n_work + B - 1) / B) * B, a.ll.cap_slots);
   if (use4) {
     if constexpr (MODE != MODE_COUNTS) {
-      if (al4) PH_LAUNCH(8, true, 3);
-      else PH_LAUNCH(8, true, 4);
+      if (n_phases > 1) {
+        const size_t need = (size_t)o->n_major * o->D * PH_MAX_FAST_CLUSTERS * sizeof(uint32_t);
+        if (need > h->partial_bytes) {
+          cudaFree(h->d_partial);
+          h->d_partial = nullptr;
+          h->partial_bytes = 0;
+          PH_CUDA(cudaMalloc(&h->d_partial, need));
+          h->partial_bytes = need;
+        }
+        a.partial = h->d_partial;
+        a.phased = 1;
+      }
+      const int push = a.push;
+      for (int p = 0; p < n_phases; ++p) {
+        if (n_phases > 1) {
+          a.ch_lo = p * cpp;
+          a.ch_n = o->NCH - a.ch_lo < cpp ? o->NCH - a.ch_lo : cpp;
+          a.phase_first = p == 0;
+          a.phase_last = p == n_phases - 1;
+          a.push = a.phase_last ? push : 0;   // results leave with the last phase only
+          // image of this phase's chunks: whole 64 KB chunks, the last chunk of the axis as long as its labels
+          const int CH = (1 << o->chunk_bits) - PH_PAD;
+          const int last = o->n_minor - (o->NCH - 1) * CH;
+          const size_t tail_b = (a.ch_lo + a.ch_n == o->NCH) ? (size_t)((PH_PAD + last + 15) & ~15) : (size_t)65536;
+          a.lab_bytes = (int)(((size_t)(a.ch_n - 1) << 16) + tail_b);
+          smem = tab4 + (size_t)a.lab_bytes + (al4 ? 65536 : 0);
+        }
+        if (al4) PH_LAUNCH(8, true, 3);
+        else PH_LAUNCH(8, true, 4);
+        if (p + 1 < n_phases) ph_count_launch();
+      }
+      a.push = push;
     }
   } else if (B == 32) PH_LAUNCH_B(32);
   else if (B == 4) PH_LAUNCH_B(4);

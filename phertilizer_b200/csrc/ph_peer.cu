@@ -14,6 +14,8 @@
 // The exchanged quantity is an integer histogram, so the result is bit-identical to the single-GPU kernels for any
 // number of ranks.  Windows are plain cudaMalloc allocations shared through CUDA IPC handles (exchanged by the host
 // language -- torch.distributed in this repository -- as opaque 64-byte blobs).
+#include <stdlib.h>
+
 #include "ph_common.cuh"
 
 struct ph_peer {
@@ -24,6 +26,7 @@ struct ph_peer {
   int32_t cap_slots;           // result slots (lines of the work order, padded to whole batches) one rank may push per step
   uint8_t* win[PH_MAX_PEERS];  // win[rank] = own allocation, others = IPC mappings
   bool opened[PH_MAX_PEERS];
+  long long spin_limit;        // SM clocks a wait of the SNV-sharded collect may take (PH_PEER_TIMEOUT_MS, default ~3 s)
   unsigned* d_done;            // [0],[1] CTA completion counters (pass, finish), [2] spin-timeout flag,
                                // [3] collect completion counter, [4] step counter ("epoch"), advanced by the last
                                // block of every collect kernel: no launch parameter changes from step to step, so a
@@ -184,6 +187,11 @@ extern "C" int ph_peer_create(ph_handle* h, int rank, int world, int32_t total_s
   p->world = world;
   p->max_lines = total_snvs;
   p->blk_max = (h->n_snvs + world - 1) / world;
+  p->spin_limit = kSpinLimit;
+  if (const char* e = getenv("PH_PEER_TIMEOUT_MS")) {
+    const long long ms = atoll(e);
+    if (ms > 0) p->spin_limit = ms * 2000000ll;  // ~2 GHz SM clock
+  }
   p->ncp = (h->n_codes + 7) & ~7;
   if (p->ncp > 64) p->ncp = 64;  // the histogram exchange (cell-sharded) is refused above 64 codes, see below
   p->off_cnt = kFlagBytes;
@@ -197,8 +205,12 @@ extern "C" int ph_peer_create(ph_handle* h, int rank, int world, int32_t total_s
   p->bytes = p->off_ll + (size_t)2 * kLLWords * world * p->cap_slots * 8 + 256;
   cudaError_t e = cudaMalloc(&p->win[rank], p->bytes);
   if (e == cudaSuccess) e = cudaMemset(p->win[rank], 0, p->bytes);
-  if (e == cudaSuccess) e = cudaMalloc(&p->d_done, 64);
-  if (e == cudaSuccess) e = cudaMemset(p->d_done, 0, 64);
+  if (e == cudaSuccess) e = cudaMalloc(&p->d_done, 256);
+  if (e == cudaSuccess) e = cudaMemset(p->d_done, 0, 256);
+  // the window must BE zero before its handle leaves this call: a peer stores into it as soon as the host-side set-up
+  // barrier lets it go, and a memset still queued on this device (another process holding the GPU's time slice, a busy
+  // stream) would wipe those words afterwards -- every rank would then wait for data that had already arrived
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
     snprintf(ph_err_msg, sizeof(ph_err_msg), "peer window allocation failed: %s", cudaGetErrorString(e));
     ph_peer_destroy(p);
@@ -349,7 +361,8 @@ int peer_assign_snv(ph_peer* p, int mode, const uint8_t* cell_label, double lenA
   ll.label_out = label_out;
   ll.nobs_out = nobs_out;
   ll.done = p->d_done + 3;
-  ll.timeout_flag = p->d_done + 2;
+  ll.timeout_flag = p->d_done + 16;   // [16] flag, [17..22] what the first failed wait was waiting for
+  ll.spin_limit = p->spin_limit;
   uint32_t* epoch_ptr = reinterpret_cast<uint32_t*>(p->d_done + 4);
   int rc = ph_pass_assign_push(h, mode, cell_label, lenA, ll, p->d_done, snv_offset, p->world, epoch_ptr, st);
   if (rc != PH_OK) return rc;
@@ -375,5 +388,17 @@ extern "C" int ph_peer_timed_out(ph_peer* p, void* stream) {
   cudaSetDevice(p->h->device);
   cudaStreamSynchronize((cudaStream_t)stream);
   cudaMemcpy(&v, p->d_done + 2, sizeof(v), cudaMemcpyDeviceToHost);
-  return v ? 1 : 0;
+  unsigned v2 = 0;
+  cudaMemcpy(&v2, p->d_done + 16, sizeof(v2), cudaMemcpyDeviceToHost);
+  return (v | v2) ? 1 : 0;
+}
+
+// what the first wait of an SNV-sharded step that gave up was waiting for:
+// out[0..6] = {timed out, kind (1 header, 2 id/label word, 3 / 4 count words), source rank, slot, epoch wanted, epoch seen, payload seen}
+extern "C" int ph_peer_debug(ph_peer* p, uint32_t* out) {
+  if (!p || !out) PH_FAIL(PH_ERR_ARG, "null argument");
+  PH_CUDA(cudaSetDevice(p->h->device));
+  PH_CUDA(cudaDeviceSynchronize());
+  PH_CUDA(cudaMemcpy(out, p->d_done + 16, 7 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  return PH_OK;
 }

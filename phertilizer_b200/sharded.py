@@ -148,6 +148,17 @@ class PeerExchange:
             return True   # closed after a timeout
         return bool(self._L.ph_peer_timed_out(self._p, stream))
 
+    def debug(self) -> dict:
+        """What the first wait of an SNV-sharded step that gave up was waiting for (ph_peer_debug)."""
+        import ctypes as C
+
+        buf = (C.c_uint32 * 8)()
+        if self._p is None:
+            return {}
+        self._lib.check(self._L.ph_peer_debug(self._p, buf))
+        names = ("timed_out", "kind", "source_rank", "slot", "step_wanted", "step_seen", "payload_seen")
+        return dict(zip(names, [int(x) for x in buf][:7]))
+
     def close(self):
         if self._p is not None:
             self._L.ph_peer_destroy(self._p)
@@ -403,7 +414,7 @@ class SnvShardedStore:
     def _check_peer(self):
         """See ShardedStore._check_peer: a timed-out wait invalidates the step's outputs on this rank."""
         if self.peer.timed_out(self._stream()):
-            raise _PhError("peer-memory exchange timed out waiting for a rank (about 3 s): results discarded")
+            raise _PhError(f"peer-memory exchange timed out waiting for a rank: results discarded ({self.peer.debug()})")
 
     def close(self):
         self.peer.close()
