@@ -235,6 +235,16 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
   // The dispenser round trip never sits on the critical path: the first batch is drawn before the staging above is
   // published (see `bidx0`), every following one while the holders finish the current batch.
   unsigned bidx = __shfl_sync(FULL, bidx0, 0);
+  // batched-4 stream: ring of RD 16-byte loads per lane in flight (RD * 512 B per warp).  The ring of the NEXT batch is
+  // primed before the holders finish the current one (`primed`), so the tail / fp64 / store phase of a batch overlaps the
+  // first loads of its successor instead of leaving the warp without a byte in flight.
+#ifndef PH_RING4
+#define PH_RING4 4
+#endif
+  constexpr int RD = PH_RING4;
+  uint4 ring[B4 ? RD : 1];
+  bool primed = false;
+  int ebuf = 0;  // which of the two sub-segment bound tables (s_b) belongs to the current batch
   if (PUSHABLE && a.push && bidx == 0 && lane < a.world) {
     // the warp that drew the first batch announces how many slots this rank fills in this step
     st_relaxed_sys_u64(a.ll.hdr_dst[lane] + par * PH_MAX_PEERS, ((uint64_t)epoch << 32) | (uint32_t)(n_batches * B));
@@ -278,9 +288,9 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
       for (int k = lane; k < a.row_words; k += 32) s_row32[k] = 0;
     __syncwarp();
     // s_e[k]: end (in groups) of sub-segment k = l * NSUB + s of the batch; s_start[l]: first group of line l
-    uint32_t* s_e = s_b;
+    uint32_t* s_e = s_b + (B4 ? ebuf * NS1 : 0);
     uint32_t* s_start = s_b + B * NSUB;
-    if (B4) {
+    if (B4 && !primed) {
       // batched-4 copy: s_e[q] = first warp step of sub-segment q of this batch, s_e[NSUB] = end of the batch
       for (int k = lane; k <= NSUB; k += 32) s_e[k] = __ldg(a.bstep_off + (size_t)bidx * NSUB + k);
     }
@@ -292,6 +302,8 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
     if (!B4 && lane < B) s_start[lane] = (line >= 0 && NSUB > 0) ? __ldg(a.sub_off + (size_t)line * NSUB) : 0u;
     __syncwarp();
 
+    unsigned bnext = 0;
+    bool drawn = false;
     // ---- dense part, batched-4 copy: the batch is one contiguous run of warp steps; lane (a, c) = (lane / 4, lane % 4)
     // reads group 4 t + c of line a at step t.  Everything about sub-segments is warp-uniform: q, the chunk base, the
     // flush points.  A lane's packed counters are summed over the 4 lanes of its line and added to the line's
@@ -342,12 +354,6 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
         const uint32_t a6 = __byte_perm(w.w, cbase, 0x7610), a7 = __byte_perm(w.w, cbase, 0x7632);
         acc += ((one4(a0) + one4(a1)) + (one4(a2) + one4(a3))) + ((one4(a4) + one4(a5)) + (one4(a6) + one4(a7)));
       };
-      // ring of RD 16-byte loads per lane in flight (RD * 512 B per warp)
-#ifndef PH_RING4
-#define PH_RING4 4
-#endif
-      constexpr int RD = PH_RING4;
-      uint4 ring[RD];
       const int n_runs = phased ? D : 1;
       for (int run = 0; run < n_runs; ++run) {
         q = phased ? run * NCH + ch_lo : 0;
@@ -356,12 +362,20 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
         gp = reinterpret_cast<const uint4*>(a.half4) + ((size_t)st << 5) + lane;
         nb_eff = st;  // the first step of a run enters the slow path
         st_flush = st;
+        if (!primed) {
 #pragma unroll
-        for (int u = 0; u < RD; ++u) {
-          ring[u] = make_uint4(0, 0, 0, 0);
-          if (st + u < st_end) ring[u] = ld_stream(gp + 32 * u);
+          for (int u = 0; u < RD; ++u) {
+            ring[u] = make_uint4(0, 0, 0, 0);
+            if (st + u < st_end) ring[u] = ld_stream(gp + 32 * u);
+          }
         }
+        primed = false;
         while (st < st_end) {
+          // the next batch is drawn shortly before this one ends: the dispenser's round trip hides behind the last steps
+          if (!drawn && run == n_runs - 1 && st + 16 >= st_end) {
+            if (lane == 0) bnext = atomicAdd(a.counter, 1u);
+            drawn = true;
+          }
 #pragma unroll
           for (int u = 0; u < RD; ++u) {
             if (u == 0 || st + u < st_end) {
@@ -468,8 +482,25 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
       }
     }
     __syncwarp();
-    unsigned bnext = 0;
-    if (lane == 0) bnext = atomicAdd(a.counter, 1u);  // next batch: the round trip overlaps the holders' work
+    if (!drawn && lane == 0) bnext = atomicAdd(a.counter, 1u);  // next batch: the round trip overlaps the holders' work
+    if (B4 && NSUB > 0 && !a.phased) {
+      // prime the ring of the next batch now: its first loads fly while the holders below finish this one
+      const unsigned bn = __shfl_sync(FULL, bnext, 0);
+      if (bn < (unsigned)n_batches) {
+        uint32_t* s_n = s_b + (ebuf ^ 1) * NS1;
+        for (int k = lane; k <= NSUB; k += 32) s_n[k] = __ldg(a.bstep_off + (size_t)bn * NSUB + k);
+        __syncwarp();
+        const uint32_t st_n = s_n[0], end_n = s_n[NSUB];
+        const uint4* gp_n = reinterpret_cast<const uint4*>(a.half4) + ((size_t)st_n << 5) + lane;
+#pragma unroll
+        for (int u = 0; u < RD; ++u) {
+          ring[u] = make_uint4(0, 0, 0, 0);
+          if (st_n + u < end_n) ring[u] = ld_stream(gp_n + 32 * u);
+        }
+        primed = true;
+        ebuf ^= 1;
+      }
+    }
 
     // ---- holders: lane l finishes line l.  Every sum is  sum_code fma(count, L[code])  in ascending code order --
     // the dense codes from the batch counters, then the rare codes of the tail (words sorted by (code, address), so a
@@ -520,8 +551,7 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
             rc[c] = 0;
           }
         };
-        for (int64_t r = tb; r < ((ph && !a.phase_last) ? tb : te); ++r) {
-          const uint32_t w = __ldg(a.tail_words + r);
+        auto tail_one = [&](uint32_t w) {
           const uint32_t code = w >> a.minor_bits;
           uint32_t sh;
           if (ph) {
@@ -541,6 +571,16 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
           }
 #pragma unroll
           for (int c = 0; c < NC; ++c) rc[c] += (sh == (uint32_t)(PH_FIELD_BITS * c)) ? 1u : 0u;
+        };
+        // four words per round trip (they sit in L2: prefetched when the batch started); the array has 8 words of slack
+        const int64_t te_eff = (ph && !a.phase_last) ? tb : te;
+        for (int64_t r0 = tb; r0 < te_eff; r0 += 4) {
+          uint32_t w4[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) w4[u] = __ldg(a.tail_words + r0 + u);
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (r0 + u < te_eff) tail_one(w4[u]);
         }
         if (cur != 0xffffffffu) fold();
       }

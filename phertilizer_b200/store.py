@@ -116,13 +116,27 @@ class ObservationStore:
 
     # ------------------------------------------------------------------ construction
     @classmethod
-    def from_coo(cls, n_cells, n_snvs, cell, snv, var, total, alpha=0.001, max_copies=5, device=0, pairs=None):
+    def from_coo(cls, n_cells, n_snvs, cell, snv, var, total, alpha=0.001, max_copies=5, device=0, pairs=None, codes=None):
         """cell/snv/var/total: numpy arrays (host) or torch CUDA tensors (stay on the device).
         pairs=(pair_var, pair_total): use this (var,total) table and code order instead of deriving it from the data
-        (the ranks of a cell-sharded store must agree on the codes)."""
+        (the ranks of a cell-sharded store must agree on the codes).
+        codes: the observations' indices into `pairs`, already computed (int16 / uint16; var and total are then ignored)."""
         L = _lib.lib()
         on_dev = not isinstance(cell, np.ndarray)
-        if on_dev:
+        if codes is not None:
+            if pairs is None:
+                raise _lib.PhError("codes= needs the (var,total) table they index (pairs=)")
+            pv, pt = (np.asarray(x, np.int64) for x in pairs)
+            code = codes.contiguous() if on_dev else np.ascontiguousarray(codes, dtype=np.uint16)
+            if on_dev:
+                cell = cell.to(torch_int32()).contiguous()
+                snv = snv.to(torch_int32()).contiguous()
+                nnz = int(cell.numel())
+            else:
+                cell = np.ascontiguousarray(cell, dtype=np.int32)
+                snv = np.ascontiguousarray(snv, dtype=np.int32)
+                nnz = int(cell.shape[0])
+        elif on_dev:
             if pairs is None:
                 pv, pt, code = encode_pairs_device(var, total)
             else:
@@ -300,6 +314,11 @@ class ObservationStore:
             _lib.check(_lib.lib().ph_gauss_node_ll(self._h, _ptr(X), X.shape[1], _ptr(cell_node), K, _ptr(out), _ptr(pc), 0,
                                                    None))
         return (out, pc) if per_cell else out
+
+    def gauss_node_ll_dev(self, X_t, D, cell_node_t, K, per_node_t, per_cell_t=None, stream=None):
+        """K4 on device tensors (X_t: float64 [n_cells, D] row-major); enqueued on `stream`."""
+        _lib.check(_lib.lib().ph_gauss_node_ll(self._h, _ptr(X_t), int(D), _ptr(cell_node_t), int(K), _ptr(per_node_t),
+                                               _ptr(per_cell_t), 1, stream))
 
     # ------------------------------------------------------------------ device-pointer calls (torch tensors, async)
     def snv_table_dev(self, cell_label_t, C_, S0=None, S1=None, Nobs=None, Nvar=None, snv_list_t=None, stream=None):

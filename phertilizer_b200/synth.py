@@ -68,24 +68,8 @@ def _partition_sizes(total: int, K: int, rng: np.random.Generator, floor_frac: f
     return sizes
 
 
-def make_synthetic(n: int, m: int, cov: float, K: int, seed: int, D: int = 2, alpha: float = 0.001,
-                   device: str | torch.device = "cpu", with_embedding: bool = True,
-                   chunk: int = 1 << 26) -> Synthetic:
-    rng = np.random.default_rng(seed)
-    parent = np.full(K, -1, dtype=np.int64)
-    for k in range(1, K):
-        parent[k] = rng.integers(0, k)
-    cell_sizes = _partition_sizes(n, K, rng)
-    snv_sizes = _partition_sizes(m, K, rng)
-    cell_clone_np = rng.permutation(np.repeat(np.arange(K, dtype=np.uint8), cell_sizes))
-    snv_node_np = rng.permutation(np.repeat(np.arange(K, dtype=np.uint8), snv_sizes))
-
-    dev = torch.device(device)
-    g = torch.Generator(device=dev)
-    g.manual_seed(seed)
-    cell_clone = torch.from_numpy(cell_clone_np).to(dev)
-    snv_node = torch.from_numpy(snv_node_np).to(dev)
-
+def _sample_observations(n, m, cov, cell_clone, snv_node, anc, alpha, dev, g, chunk):
+    """COO observations of n cells x m SNVs (cells = rows of `cell_clone`): positions, totals, variant counts."""
     # positions: Bernoulli(p) process over the flattened n*m grid, via geometric gaps
     p = 1.0 - math.exp(-cov)
     grid = n * m
@@ -115,13 +99,6 @@ def make_synthetic(n: int, m: int, cov: float, K: int, seed: int, D: int = 2, al
     total = (torch.bucketize(u, cdf, right=True) + 1).clamp_(max=kmax).to(torch.int32)
     del u
 
-    anc = torch.zeros((K, K), dtype=torch.bool)
-    for k in range(K):
-        q = k
-        while q >= 0:
-            anc[k, q] = True
-            q = int(parent[q])
-    anc = anc.to(dev)
     present = anc[cell_clone[cell.long()].long(), snv_node[snv.long()].long()]
     p1 = 0.5 * (1 - alpha) + 0.5 * alpha / 3
     pv = torch.where(present, torch.tensor(p1, device=dev, dtype=torch.float32),
@@ -132,6 +109,35 @@ def make_synthetic(n: int, m: int, cov: float, K: int, seed: int, D: int = 2, al
         hit = (torch.rand(nnz, device=dev, generator=g) < pv) & (total > k)
         var += hit.to(torch.int32)
     del pv
+    return cell, snv, var, total
+
+
+def make_synthetic(n: int, m: int, cov: float, K: int, seed: int, D: int = 2, alpha: float = 0.001,
+                   device: str | torch.device = "cpu", with_embedding: bool = True,
+                   chunk: int = 1 << 26) -> Synthetic:
+    rng = np.random.default_rng(seed)
+    parent = np.full(K, -1, dtype=np.int64)
+    for k in range(1, K):
+        parent[k] = rng.integers(0, k)
+    cell_sizes = _partition_sizes(n, K, rng)
+    snv_sizes = _partition_sizes(m, K, rng)
+    cell_clone_np = rng.permutation(np.repeat(np.arange(K, dtype=np.uint8), cell_sizes))
+    snv_node_np = rng.permutation(np.repeat(np.arange(K, dtype=np.uint8), snv_sizes))
+
+    dev = torch.device(device)
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    cell_clone = torch.from_numpy(cell_clone_np).to(dev)
+    snv_node = torch.from_numpy(snv_node_np).to(dev)
+
+    anc = torch.zeros((K, K), dtype=torch.bool)
+    for k in range(K):
+        q = k
+        while q >= 0:
+            anc[k, q] = True
+            q = int(parent[q])
+    anc = anc.to(dev)
+    cell, snv, var, total = _sample_observations(n, m, cov, cell_clone, snv_node, anc, alpha, dev, g, chunk)
 
     emb = None
     if with_embedding:
@@ -150,6 +156,69 @@ def make_synthetic(n: int, m: int, cov: float, K: int, seed: int, D: int = 2, al
             prof = 333.0 * (1 + 0.5 * np.repeat(cna, 50, axis=1)[:, :D])
             prof_t = torch.from_numpy(prof).to(dev)
             emb = torch.poisson(prof_t[cell_clone.long()], generator=g)
+    return Synthetic(n, m, cell, snv, var, total, parent, cell_clone, snv_node, emb)
+
+
+def make_blocked(name: str, device="cuda", blocks: int = 8, with_embedding: bool = False, **over):
+    """A config generated in `blocks` independent blocks of cells that share one clone tree (config 5: 2.48 G
+    observations -- the one-shot generator above would need > 100 GB of scratch).  Same model, another random stream, so
+    NOT the data set `make_config` yields.  Returns a Synthetic whose var / total are uint8 (totals are capped at 24)."""
+    cfg = dict(CONFIGS[name])
+    cfg.update(over)
+    n, m, cov, K, seed, D = cfg["n"], cfg["m"], cfg["cov"], cfg["K"], cfg["seed"], cfg["D"]
+    alpha = 0.001
+    rng = np.random.default_rng(seed)
+    parent = np.full(K, -1, dtype=np.int64)
+    for k in range(1, K):
+        parent[k] = rng.integers(0, k)
+    cell_sizes = _partition_sizes(n, K, rng)
+    snv_sizes = _partition_sizes(m, K, rng)
+    cell_clone_np = rng.permutation(np.repeat(np.arange(K, dtype=np.uint8), cell_sizes))
+    snv_node_np = rng.permutation(np.repeat(np.arange(K, dtype=np.uint8), snv_sizes))
+    dev = torch.device(device)
+    cell_clone = torch.from_numpy(cell_clone_np).to(dev)
+    snv_node = torch.from_numpy(snv_node_np).to(dev)
+    anc = torch.zeros((K, K), dtype=torch.bool)
+    for k in range(K):
+        q = k
+        while q >= 0:
+            anc[k, q] = True
+            q = int(parent[q])
+    anc = anc.to(dev)
+    parts = []
+    for b in range(blocks):
+        lo, hi = (n * b) // blocks, (n * (b + 1)) // blocks
+        g = torch.Generator(device=dev)
+        g.manual_seed(seed * 1000 + b)
+        c, s_, v, t = _sample_observations(hi - lo, m, cov, cell_clone[lo:hi], snv_node, anc, alpha, dev, g, 1 << 26)
+        parts.append((c + lo, s_, v.to(torch.uint8), t.to(torch.uint8)))
+        del c, s_, v, t
+    if parts:
+        cell, snv, var, total = (torch.cat([p[i] for p in parts]) for i in range(4))
+    else:   # blocks = 0: the clone structure / embedding only
+        cell = snv = torch.zeros(0, dtype=torch.int32, device=dev)
+        var = total = torch.zeros(0, dtype=torch.uint8, device=dev)
+    del parts
+    emb = None
+    if with_embedding:
+        g = torch.Generator(device=dev)
+        g.manual_seed(seed * 1000 + 999)
+        if D <= 8:
+            ang = 2 * math.pi * np.arange(K) / K
+            centres = np.zeros((K, D))
+            centres[:, 0] = 3 * np.cos(ang)
+            if D > 1:
+                centres[:, 1] = 3 * np.sin(ang)
+            emb = torch.from_numpy(centres).to(dev)[cell_clone.long()] + 0.3 * torch.randn(n, D, dtype=torch.float64, device=dev, generator=g)
+        else:
+            nseg = (D + 49) // 50
+            cna = rng.integers(-1, 2, size=(K, nseg))
+            cna[0] = 0
+            prof = torch.from_numpy(333.0 * (1 + 0.5 * np.repeat(cna, 50, axis=1)[:, :D])).to(dev)
+            emb = torch.empty(n, D, dtype=torch.float64, device=dev)
+            for lo in range(0, n, 16384):   # row blocks: torch.poisson needs the rate tensor materialised
+                hi = min(n, lo + 16384)
+                emb[lo:hi] = torch.poisson(prof[cell_clone[lo:hi].long()], generator=g)
     return Synthetic(n, m, cell, snv, var, total, parent, cell_clone, snv_node, emb)
 
 

@@ -4,6 +4,9 @@
 import os, sys, time
 import torch
 sys.path.insert(0, ".")
+if os.environ.get("PH_LIB"):   # development aid: time an alternative build of the library (e.g. another ring depth)
+    from phertilizer_b200 import _lib as _l
+    _l.LIB_PATH = os.path.abspath(os.environ["PH_LIB"])
 from phertilizer_b200.synth import make_config
 from phertilizer_b200.store import ObservationStore
 

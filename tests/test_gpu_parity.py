@@ -402,10 +402,13 @@ def test_determinism(synth_env):
 
 
 # ------------------------------------------------------------------------------------------- wide matrices
+@pytest.mark.parametrize("phase_chunks", [0, 1, 2])
 @pytest.mark.parametrize("shape", ["many_cells", "many_snvs"])
-def test_wide_matrix_multi_chunk(shape):
-    """More than 65520 indices on the minor axis (three 16-bit chunks, the production layout) and lines long enough
-    (thousands of entries) for the bank-ordered sub-segments; the other orientation has ~2 entries per line (tail only)."""
+def test_wide_matrix_multi_chunk(shape, phase_chunks, monkeypatch):
+    """More than 65408 indices on the minor axis (three 16-bit chunks, the production layout) and lines long enough
+    (thousands of entries) for the bank-ordered sub-segments; the other orientation has ~2 entries per line (tail only).
+    phase_chunks > 0 (PH_PHASE_CHUNKS): the whole-orientation passes walk the label image in phases of that many chunks,
+    as they do when the image of the minor axis exceeds shared memory (250 k cells, 500 k SNVs: config 5)."""
     from phertilizer_b200.store import ObservationStore
     from phertilizer_b200.synth import make_synthetic
 
@@ -413,6 +416,8 @@ def test_wide_matrix_multi_chunk(shape):
     n, m = (big, small) if shape == "many_cells" else (small, big)
     s = make_synthetic(n, m, 0.05, 4, seed=23, with_embedding=False)
     cell, snv, var, total = (x.numpy() for x in (s.cell, s.snv, s.var, s.total))
+    if phase_chunks:
+        monkeypatch.setenv("PH_PHASE_CHUNKS", str(phase_chunks))
     st = ObservationStore.from_coo(n, m, cell, snv, var, total)
     info = st.info()
     assert max(info["chunks_by_snv"], info["chunks_by_cell"]) == 3
@@ -434,6 +439,9 @@ def test_wide_matrix_multi_chunk(shape):
         A0, A1, No2, Nv2 = O.cell_table(D, cells, mg)
         assert np.array_equal(t2["Nobs"], No2) and np.array_equal(t2["Nvar"], Nv2)
         assert rel_close(t2["S0"], A0, TOL) and rel_close(t2["S1"], A1, TOL)
+        t3 = st.cell_table(sl, C)                     # whole orientation: the batched-4 stream (phased when asked to)
+        assert np.array_equal(t3["Nobs"][cells], No2) and np.array_equal(t3["Nvar"][cells], Nv2)
+        assert rel_close(t3["S0"][cells], A0, TOL) and rel_close(t3["S1"][cells], A1, TOL)
     labA = st.cell_labels(np.nonzero(rng.random(n) < 0.5)[0])
     lab2, nobs = st.assign_linear(labA, float(labA.sum()))
     a, b = O.linear_mut_assignment(D, np.nonzero(labA)[0], np.arange(m), nobs_per_cluster=-1)
