@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PH_ABI_VERSION 6
+#define PH_ABI_VERSION 7
 
 #if defined(__GNUC__)
 #define PH_API __attribute__((visibility("default")))
@@ -175,8 +175,9 @@ PH_API int ph_peer_assign_linear_snv(ph_peer* p, const uint8_t* cell_label, doub
 PH_API int ph_peer_assign_branching_snv(ph_peer* p, const uint8_t* cell_label, int32_t snv_offset, uint8_t* label_out,
                                  int32_t* nobs_out, void* stream);
 PH_API int ph_peer_timed_out(ph_peer* p, void* stream); /* 1 if a wait for a peer ever gave up (~3 s; PH_PEER_TIMEOUT_MS) */
-/* Diagnostics of the first SNV-sharded wait that gave up: out[7] = {timed out, kind (1 header, 2 id/label word, 3/4 count
- * words), source rank, slot, step wanted, step seen, payload seen}. */
+/* Diagnostics of the first SNV-sharded wait that gave up: out[24] = {timed out, kind (1 header, 2 id/label word, 3/4 count
+ * words), source rank, slot, step wanted, step seen, payload seen, this rank's step counter, then per source rank r:
+ * slots its header announced for that step (0xFFFFFFFF = no header), id/label words of that step present in the window}. */
 PH_API int ph_peer_debug(ph_peer* p, uint32_t* out);
 PH_API void ph_peer_destroy(ph_peer* p);
 
@@ -276,6 +277,25 @@ PH_API int ph_affinity_build(ph_affinity* a, const int32_t* cells, int32_t k, co
                       int use_copy_kernel, double radius, int strict, double* stats_out, double* dd_out);
 PH_API int ph_affinity_matmat(ph_affinity* a, const double* X, int32_t c, double* Y);
 PH_API int ph_affinity_matrix(ph_affinity* a, double* out); /* the k x k Laplacian (tests) */
+/*
+ * The same clustering step with the k x k matrices sharded by ROWS across the GPUs of a node (one process per GPU,
+ * SURVEY.md section 8e / 8f): a context created with ph_affinity_create_rows holds at most max_rows rows.  Per cell set:
+ *   ph_affinity_stats_rows     max of d_mat / c_mat over this rank's rows [row_lo, row_hi) (out3 = max d, max c, has_nan);
+ *                              the host language takes the maximum over the ranks -> kw, kwc = 0.2 * max, r = max c
+ *   ph_affinity_build_rows     this rank's rows of W and their sqrt-degrees (dd_block); the ranks' blocks concatenated are dd
+ *   ph_affinity_laplacian_rows W rows -> Laplacian rows, given the whole dd
+ *   ph_affinity_matmat_rows    Y[row_lo:row_hi, :] = L[row_lo:row_hi, :] @ X
+ * Every entry, degree and product row is computed by one rank with the arithmetic of the single-GPU kernels (W is symmetric
+ * bit for bit, so a row sum in column order IS the column sum in row order): the assembled results are bit-identical to
+ * ph_affinity_build / ph_affinity_matmat.  radius must be 1 (the reference CLI's value: r = max c_mat).
+ */
+PH_API int ph_affinity_create_rows(const double* embedding, int32_t n, int32_t D, int device, int32_t max_rows, ph_affinity** out);
+PH_API int ph_affinity_stats_rows(ph_affinity* a, const int32_t* cells, int32_t k, const double* feats, int32_t F,
+                           int use_copy_kernel, int32_t row_lo, int32_t row_hi, double* out3);
+PH_API int ph_affinity_build_rows(ph_affinity* a, int32_t F, double kw, double kwc, double r, int strict, double* dd_block,
+                           int* has_nan);
+PH_API int ph_affinity_laplacian_rows(ph_affinity* a, const double* dd_full);
+PH_API int ph_affinity_matmat_rows(ph_affinity* a, const double* X, int32_t c, double* Y_block);
 PH_API void ph_affinity_destroy(ph_affinity* a);
 
 /*

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libphertilizer_b200.so")
 
 PH_OK = 0
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 
 class PhError(RuntimeError):
@@ -44,7 +44,8 @@ EXPORTS = [
     "ph_peer_assign_branching", "ph_peer_assign_linear_snv", "ph_peer_assign_branching_snv", "ph_peer_timed_out",
     "ph_peer_debug", "ph_peer_destroy",
     "ph_affinity_create", "ph_affinity_rows", "ph_affinity_nearest", "ph_affinity_build", "ph_affinity_matmat", "ph_affinity_matrix",
-    "ph_affinity_destroy",
+    "ph_affinity_destroy", "ph_affinity_create_rows", "ph_affinity_stats_rows", "ph_affinity_build_rows", "ph_affinity_laplacian_rows",
+    "ph_affinity_matmat_rows",
 ]
 
 _lib = None
@@ -100,6 +101,11 @@ def lib():
     L.ph_affinity_build.argtypes = [_vp, _vp, C.c_int32, _vp, C.c_int32, C.c_int, C.c_double, C.c_int, _vp, _vp]
     L.ph_affinity_matmat.argtypes = [_vp, _vp, C.c_int32, _vp]
     L.ph_affinity_matrix.argtypes = [_vp, _vp]
+    L.ph_affinity_create_rows.argtypes = [_vp, C.c_int32, C.c_int32, C.c_int, C.c_int32, C.POINTER(_vp)]
+    L.ph_affinity_stats_rows.argtypes = [_vp, _vp, C.c_int32, _vp, C.c_int32, C.c_int, C.c_int32, C.c_int32, _vp]
+    L.ph_affinity_build_rows.argtypes = [_vp, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_int, _vp, C.POINTER(C.c_int)]
+    L.ph_affinity_laplacian_rows.argtypes = [_vp, _vp]
+    L.ph_affinity_matmat_rows.argtypes = [_vp, _vp, C.c_int32, _vp]
     L.ph_affinity_destroy.argtypes = [_vp]
     L.ph_affinity_destroy.restype = None
     L.ph_set_embedding.argtypes = [_vp, _vp, C.c_int32]

@@ -38,6 +38,9 @@ struct ph_affinity {
   size_t sort_tmp_bytes;
   double* h_pin;     // [cap*16] pinned staging
   int32_t cap, k;    // capacity (= n), current cell-set size
+  int32_t cap_rows;  // rows of the k x k matrices this context can hold (= cap, or the row block of a sharded context)
+  int32_t row_lo, row_hi, use_copy, rows_mode;  // row block held after ph_affinity_build_rows (cells sharded across GPUs)
+  double* d_ddf;     // [cap] full sqrt-degree vector (row-block mode)
   cudaStream_t st;
 };
 
@@ -185,9 +188,9 @@ __global__ void k_aff_laplacian(double* __restrict__ W, int k, const double* __r
 
 // Y[i, :] = L[i, :] @ X  (X: k x c row-major, c <= 8); one warp per row, lanes stride the row, fixed reduction order
 template <int C>
-__global__ void k_aff_matmat(const double* __restrict__ L, int k, const double* __restrict__ X, double* __restrict__ Y) {
+__global__ void k_aff_matmat(const double* __restrict__ L, int k, const double* __restrict__ X, double* __restrict__ Y, int nrows) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= k) return;
+  if (warp >= nrows) return;
   const double* row = L + (size_t)warp * k;
   double acc[C];
 #pragma unroll
@@ -201,6 +204,97 @@ __global__ void k_aff_matmat(const double* __restrict__ L, int k, const double* 
   for (int c = 0; c < C; ++c) {
     for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
     if (lane == 0) Y[(size_t)warp * C + c] = acc[c];
+  }
+}
+
+// ---- row-block variants: the rank of a multi-GPU run holds rows [row_lo, row_hi) of the k x k matrices (all columns).
+// Every entry is evaluated directly (no mirrored tiles); d, c and hence W are symmetric bit for bit, so the entries -- and
+// the row sums below -- are the bits the single-GPU kernels produce.
+__global__ void __launch_bounds__(256) k_aff_stats_rect(const double* __restrict__ feat, int F, const CopySrc src,
+                                                        const int32_t* __restrict__ cells, int k, int use_copy, int row_lo,
+                                                        int row_hi, unsigned long long* red) {
+  const int j = blockIdx.x * 32 + threadIdx.x;
+  double md = 0.0, mc = 0.0;
+  int nan = 0;
+  if (j < k) {
+    const int cj = use_copy ? cells[j] : 0;
+    for (int u = threadIdx.y; u < 32; u += 8) {
+      const int i = row_lo + blockIdx.y * 32 + u;
+      if (i >= row_hi) break;
+      const double d = feat_dist(feat, F, i, j);
+      if (d != d) nan = 1;
+      md = fmax(md, d);
+      if (use_copy) {
+        const double c = copy_at(src, cells[i], cj);
+        if (c != c) nan = 1;
+        mc = fmax(mc, c);
+      }
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    md = fmax(md, __shfl_xor_sync(0xffffffffu, md, o));
+    mc = fmax(mc, __shfl_xor_sync(0xffffffffu, mc, o));
+    nan |= __shfl_xor_sync(0xffffffffu, nan, o);
+  }
+  if (threadIdx.x == 0) {
+    if (md > 0.0) atomicMax(red + 0, (unsigned long long)__double_as_longlong(md));
+    if (mc > 0.0) atomicMax(red + 1, (unsigned long long)__double_as_longlong(mc));
+    if (nan) atomicMax(red + 2, 1ull);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_aff_build_rect(const double* __restrict__ feat, int F, const CopySrc src,
+                                                        const int32_t* __restrict__ cells, int k, int use_copy, double kw,
+                                                        double kwc, double r, int strict, int row_lo, int row_hi,
+                                                        double* __restrict__ W, unsigned long long* red) {
+  const int j = blockIdx.x * 32 + threadIdx.x;
+  const int cj = (use_copy && j < k) ? cells[j] : 0;
+  int nan = 0;
+  for (int u = threadIdx.y; u < 32; u += 8) {
+    const int i = row_lo + blockIdx.y * 32 + u;
+    if (i < row_hi && j < k) {
+      const double d = feat_dist(feat, F, i, j);
+      double w = exp(__ddiv_rn(__dmul_rn(-1.0, d), kw));
+      if (use_copy) {
+        const double c = copy_at(src, cells[i], cj);
+        double ck = exp(__ddiv_rn(__dmul_rn(-1.0, c), kwc));
+        if (strict ? (c >= r) : (c > r)) ck = 0.0;
+        w = __dmul_rn(w, ck);
+      }
+      if (w != w) nan = 1;
+      W[(size_t)(i - row_lo) * k + j] = w;
+    }
+  }
+  if (__any_sync(0xffffffffu, nan) && threadIdx.x == 0) atomicMax(red + 2, 1ull);
+}
+
+// w_i = sum_j W_ij with a zero diagonal, columns added in order: W is symmetric, so this is the sequence of additions
+// k_aff_degree performs down column i.  One thread per row, eight loads in flight.
+__global__ void k_aff_rowsum(const double* __restrict__ W, int nr, int k, int row_lo, double* __restrict__ dd) {
+  const int rr = blockIdx.x * blockDim.x + threadIdx.x;
+  if (rr >= nr) return;
+  const int i = row_lo + rr;
+  const double* row = W + (size_t)rr * k;
+  double s = 0.0;
+  int j = 0;
+  for (; j + 8 <= k; j += 8) {
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = row[j + u];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s = __dadd_rn(s, (j + u) == i ? 0.0 : v[u]);
+  }
+  for (; j < k; ++j) s = __dadd_rn(s, j == i ? 0.0 : row[j]);
+  dd[rr] = (s == 0.0) ? 1.0 : sqrt(s);
+}
+
+__global__ void k_aff_laplacian_rect(double* __restrict__ W, int nr, int k, int row_lo, const double* __restrict__ dd) {
+  for (int rr = blockIdx.x; rr < nr; rr += gridDim.x) {
+    const int i = row_lo + rr;
+    const double di = dd[i];
+    double* row = W + (size_t)rr * k;
+    for (int j = threadIdx.x; j < k; j += blockDim.x)
+      row[j] = (i == j) ? 1.0 : __dmul_rn(__ddiv_rn(__ddiv_rn(row[j], dd[j]), di), -1.0);
   }
 }
 
@@ -292,16 +386,17 @@ extern "C" void ph_affinity_destroy(ph_affinity* a) {
   if (!a) return;
   cudaSetDevice(a->device);
   cudaFree(a->d_copy); cudaFree(a->d_emb); cudaFree(a->d_W); cudaFree(a->d_tmp); cudaFree(a->d_feat); cudaFree(a->d_dd); cudaFree(a->d_x);
-  cudaFree(a->d_y); cudaFree(a->d_cells); cudaFree(a->d_red); cudaFree(a->d_sort_tmp);
+  cudaFree(a->d_y); cudaFree(a->d_cells); cudaFree(a->d_red); cudaFree(a->d_sort_tmp); cudaFree(a->d_ddf);
   if (a->h_pin) cudaFreeHost(a->h_pin);
   if (a->st) cudaStreamDestroy(a->st);
   delete a;
 }
 
-extern "C" int ph_affinity_create(const double* embedding, int32_t n, int32_t D, int device, ph_affinity** out) {
+namespace {
+int affinity_create(const double* embedding, int32_t n, int32_t D, int device, int32_t max_rows, ph_affinity** out) {
   if (!embedding || !out) PH_FAIL(PH_ERR_ARG, "null pointer");
   *out = nullptr;
-  if (n < 1 || D < 1) PH_FAIL(PH_ERR_ARG, "bad shape n=%d D=%d", n, D);
+  if (n < 1 || D < 1 || max_rows < 1 || max_rows > n) PH_FAIL(PH_ERR_ARG, "bad shape n=%d D=%d rows=%d", n, D, max_rows);
   int ndev = 0;
   PH_CUDA(cudaGetDeviceCount(&ndev));
   if (device < 0 || device >= ndev) PH_FAIL(PH_ERR_CUDA, "device %d not available (%d CUDA devices)", device, ndev);
@@ -309,15 +404,17 @@ extern "C" int ph_affinity_create(const double* embedding, int32_t n, int32_t D,
   size_t free_b = 0, total_b = 0;
   PH_CUDA(cudaMemGetInfo(&free_b, &total_b));
   const size_t nn = (size_t)n * n * sizeof(double);
+  const size_t wn = (size_t)max_rows * n * sizeof(double);  // the affinity / Laplacian rows this context holds
   const size_t margin = (size_t)1 << 30;
+  const bool full = max_rows == n;
   // the distance matrix is kept next to the affinity when both fit (and a third n x n block remains for the quantile
   // sort); otherwise a low-dimensional embedding is re-evaluated entry by entry
-  bool store = 3 * nn + margin <= free_b;
+  bool store = (full ? 3 * nn : nn + 2 * wn) + margin <= free_b;
   if (const char* e = getenv("PH_AFFINITY_STORE")) store = atoi(e) != 0;
-  if (!store && D > 16 && 2 * nn + margin <= free_b) store = true;
-  if ((store ? 2 : 1) * nn + margin > free_b)
+  if (!store && D > 16 && nn + wn + margin <= free_b) store = true;
+  if ((store ? nn : 0) + wn + margin > free_b)
     PH_FAIL(PH_ERR_UNSUPPORTED, "%d cells need %.1f GB for the dense affinity matrix (%.1f GB free)", n,
-            (store ? 2.0 : 1.0) * nn / 1e9, free_b / 1e9);
+            ((store ? nn : 0) + wn) / 1e9, free_b / 1e9);
   if (!store && D > 16)
     PH_FAIL(PH_ERR_UNSUPPORTED, "%d cells x %d embedding dimensions: the distance matrix neither fits nor can be recomputed cheaply", n, D);
   ph_affinity* a = new (std::nothrow) ph_affinity();
@@ -327,12 +424,14 @@ extern "C" int ph_affinity_create(const double* embedding, int32_t n, int32_t D,
   a->n = n;
   a->D = D;
   a->cap = n;
+  a->cap_rows = max_rows;
   auto body = [&]() -> int {
     PH_CUDA(cudaStreamCreateWithFlags(&a->st, cudaStreamNonBlocking));
     if (store) PH_CUDA(cudaMalloc(&a->d_copy, nn));
-    PH_CUDA(cudaMalloc(&a->d_W, nn));
+    PH_CUDA(cudaMalloc(&a->d_W, wn));
     PH_CUDA(cudaMalloc(&a->d_feat, (size_t)n * kMaxF * 8));
     PH_CUDA(cudaMalloc(&a->d_dd, (size_t)n * 8));
+    PH_CUDA(cudaMalloc(&a->d_ddf, (size_t)n * 8));
     PH_CUDA(cudaMalloc(&a->d_x, (size_t)n * kMaxCols * 8));
     PH_CUDA(cudaMalloc(&a->d_y, (size_t)n * kMaxCols * 8));
     PH_CUDA(cudaMalloc(&a->d_cells, (size_t)n * 4));
@@ -355,6 +454,18 @@ extern "C" int ph_affinity_create(const double* embedding, int32_t n, int32_t D,
   *out = a;
   return PH_OK;
 }
+}  // namespace
+
+extern "C" int ph_affinity_create(const double* embedding, int32_t n, int32_t D, int device, ph_affinity** out) {
+  return affinity_create(embedding, n, D, device, n, out);
+}
+
+// a context that holds at most `max_rows` rows of the k x k matrices: the row block of one rank when the clustering is
+// sharded across GPUs (ph_affinity_*_rows).  Cell sets small enough for k * k entries still go through ph_affinity_build.
+extern "C" int ph_affinity_create_rows(const double* embedding, int32_t n, int32_t D, int device, int32_t max_rows,
+                                       ph_affinity** out) {
+  return affinity_create(embedding, n, D, device, max_rows, out);
+}
 
 // rows of the copy-distance matrix (impute_mut_features reads a few rows; `copy_distance` itself is an output only for
 // small inputs / tests)
@@ -369,7 +480,7 @@ extern "C" int ph_affinity_rows(ph_affinity* a, const int32_t* rows, int32_t n_r
   // staged through the W buffer in slabs of at most n rows
   int done = 0;
   while (done < n_rows) {
-    const int nr = n_rows - done < a->n ? n_rows - done : a->n;
+    const int nr = n_rows - done < a->cap_rows ? n_rows - done : a->cap_rows;
     if (rows) PH_CUDA(cudaMemcpyAsync(a->d_cells, rows + done, (size_t)nr * 4, cudaMemcpyHostToDevice, a->st));
     k_gather_rows<<<1184, 256, 0, a->st>>>(src, rows ? a->d_cells : nullptr, done, nr, a->d_W);
     ph_count_launch();
@@ -378,6 +489,7 @@ extern "C" int ph_affinity_rows(ph_affinity* a, const int32_t* rows, int32_t n_r
     done += nr;
   }
   a->k = 0;  // the W buffer no longer holds a Laplacian
+  a->rows_mode = 0;
   return PH_OK;
 }
 
@@ -390,11 +502,15 @@ extern "C" int ph_affinity_build(ph_affinity* a, const int32_t* cells, int32_t k
                                  int use_copy_kernel, double radius, int strict, double* stats_out, double* dd_out) {
   if (!a || !cells || !feats || !stats_out) PH_FAIL(PH_ERR_ARG, "null pointer");
   if (k < 1 || k > a->cap || F < 1 || F > kMaxF) PH_FAIL(PH_ERR_ARG, "bad shape k=%d F=%d", k, F);
+  if ((size_t)k * k > (size_t)a->cap_rows * a->n)
+    PH_FAIL(PH_ERR_UNSUPPORTED, "%d x %d affinity exceeds this context's %d rows: use the row-block calls", k, k, a->cap_rows);
   for (int i = 0; i < k; ++i)
     if (cells[i] < 0 || cells[i] >= a->n) PH_FAIL(PH_ERR_ARG, "cells[%d]=%d out of range", i, cells[i]);
   PH_CUDA(cudaSetDevice(a->device));
   cudaStream_t st = a->st;
   a->k = 0;
+  a->row_lo = a->row_hi = 0;
+  a->rows_mode = 0;
   memcpy(a->h_pin, feats, (size_t)k * F * 8);
   memcpy(a->h_pin + (size_t)k * F, cells, (size_t)k * 4);
   PH_CUDA(cudaMemcpyAsync(a->d_feat, a->h_pin, (size_t)k * F * 8, cudaMemcpyHostToDevice, st));
@@ -418,7 +534,7 @@ extern "C" int ph_affinity_build(ph_affinity* a, const int32_t* cells, int32_t k
     // np.quantile(c_mat, radius), method "linear": sort the k*k distances, interpolate between two order statistics
     const size_t N = (size_t)k * k;
     if (N >= ((size_t)1 << 31)) PH_FAIL(PH_ERR_UNSUPPORTED, "quantile over %zu distances", N);
-    if (!a->d_tmp) PH_CUDA(cudaMalloc(&a->d_tmp, (size_t)a->cap * a->cap * 8));
+    if (!a->d_tmp) PH_CUDA(cudaMalloc(&a->d_tmp, (size_t)a->cap_rows * a->cap * 8));
     size_t need = 0;
     cub::DoubleBuffer<double> db(a->d_W, a->d_tmp);
     PH_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, need, db, (int)N, 0, 64, st));
@@ -487,18 +603,20 @@ extern "C" int ph_affinity_matmat(ph_affinity* a, const double* X, int32_t c, do
   PH_CUDA(cudaSetDevice(a->device));
   cudaStream_t st = a->st;
   const int k = a->k;
+  if (a->rows_mode) PH_FAIL(PH_ERR_ARG, "the context holds a row block: use ph_affinity_matmat_rows");
+  const int nrows = k;
   memcpy(a->h_pin, X, (size_t)k * c * 8);
   PH_CUDA(cudaMemcpyAsync(a->d_x, a->h_pin, (size_t)k * c * 8, cudaMemcpyHostToDevice, st));
   const int threads = 256, blocks = (k * 32 + threads - 1) / threads;
   switch (c) {
-    case 1: k_aff_matmat<1><<<blocks, threads, 0, st>>>(a->d_W, k, a->d_x, a->d_y); break;
-    case 2: k_aff_matmat<2><<<blocks, threads, 0, st>>>(a->d_W, k, a->d_x, a->d_y); break;
-    case 3: k_aff_matmat<3><<<blocks, threads, 0, st>>>(a->d_W, k, a->d_x, a->d_y); break;
-    case 4: k_aff_matmat<4><<<blocks, threads, 0, st>>>(a->d_W, k, a->d_x, a->d_y); break;
-    case 5: k_aff_matmat<5><<<blocks, threads, 0, st>>>(a->d_W, k, a->d_x, a->d_y); break;
-    case 6: k_aff_matmat<6><<<blocks, threads, 0, st>>>(a->d_W, k, a->d_x, a->d_y); break;
-    case 7: k_aff_matmat<7><<<blocks, threads, 0, st>>>(a->d_W, k, a->d_x, a->d_y); break;
-    default: k_aff_matmat<8><<<blocks, threads, 0, st>>>(a->d_W, k, a->d_x, a->d_y); break;
+    case 1: k_aff_matmat<1><<<blocks, threads, 0, st>>>(a->d_W, k, a->d_x, a->d_y, nrows); break;
+    case 2: k_aff_matmat<2><<<blocks, threads, 0, st>>>(a->d_W, k, a->d_x, a->d_y, nrows); break;
+    case 3: k_aff_matmat<3><<<blocks, threads, 0, st>>>(a->d_W, k, a->d_x, a->d_y, nrows); break;
+    case 4: k_aff_matmat<4><<<blocks, threads, 0, st>>>(a->d_W, k, a->d_x, a->d_y, nrows); break;
+    case 5: k_aff_matmat<5><<<blocks, threads, 0, st>>>(a->d_W, k, a->d_x, a->d_y, nrows); break;
+    case 6: k_aff_matmat<6><<<blocks, threads, 0, st>>>(a->d_W, k, a->d_x, a->d_y, nrows); break;
+    case 7: k_aff_matmat<7><<<blocks, threads, 0, st>>>(a->d_W, k, a->d_x, a->d_y, nrows); break;
+    default: k_aff_matmat<8><<<blocks, threads, 0, st>>>(a->d_W, k, a->d_x, a->d_y, nrows); break;
   }
   ph_count_launch();
   PH_CUDA(cudaGetLastError());
@@ -511,8 +629,129 @@ extern "C" int ph_affinity_matmat(ph_affinity* a, const double* X, int32_t c, do
 // the k x k matrix currently held (affinity-derived Laplacian) -- tests and small inputs only
 extern "C" int ph_affinity_matrix(ph_affinity* a, double* out) {
   if (!a || !out) PH_FAIL(PH_ERR_ARG, "null pointer");
-  if (a->k < 1) PH_FAIL(PH_ERR_ARG, "no Laplacian: call ph_affinity_build first");
+  if (a->k < 1 || a->rows_mode) PH_FAIL(PH_ERR_ARG, "no (whole) Laplacian: call ph_affinity_build first");
   PH_CUDA(cudaSetDevice(a->device));
   PH_CUDA(cudaMemcpy(out, a->d_W, (size_t)a->k * a->k * 8, cudaMemcpyDeviceToHost));
+  return PH_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row-block calls: the clustering of one cell set sharded across GPUs.  Rank r holds rows [row_lo, row_hi) of the
+// affinity / Laplacian; the host language combines the ranks between the steps (max of the statistics, concatenation of
+// the degree vector and of the product's row blocks) -- see phertilizer_b200/cluster.py ShardedCopyDistance.  Every
+// number is computed by exactly one rank with the arithmetic of the single-GPU kernels, so the assembled results are
+// bit-identical to ph_affinity_build / ph_affinity_matmat.  radius < 1 (a quantile of all k^2 distances) is not
+// sharded: use the single-GPU call.
+// ------------------------------------------------------------------------------------------------
+extern "C" int ph_affinity_stats_rows(ph_affinity* a, const int32_t* cells, int32_t k, const double* feats, int32_t F,
+                                      int use_copy_kernel, int32_t row_lo, int32_t row_hi, double* out3) {
+  if (!a || !cells || !feats || !out3) PH_FAIL(PH_ERR_ARG, "null pointer");
+  if (k < 1 || k > a->cap || F < 1 || F > kMaxF) PH_FAIL(PH_ERR_ARG, "bad shape k=%d F=%d", k, F);
+  if (row_lo < 0 || row_hi > k || row_lo > row_hi || row_hi - row_lo > a->cap_rows)
+    PH_FAIL(PH_ERR_ARG, "row block [%d, %d) outside 0..%d or larger than the context's %d rows", row_lo, row_hi, k, a->cap_rows);
+  for (int i = 0; i < k; ++i)
+    if (cells[i] < 0 || cells[i] >= a->n) PH_FAIL(PH_ERR_ARG, "cells[%d]=%d out of range", i, cells[i]);
+  PH_CUDA(cudaSetDevice(a->device));
+  cudaStream_t st = a->st;
+  a->k = 0;
+  a->row_lo = row_lo;
+  a->row_hi = row_hi;
+  a->use_copy = use_copy_kernel;
+  a->rows_mode = 1;
+  memcpy(a->h_pin, feats, (size_t)k * F * 8);
+  memcpy(a->h_pin + (size_t)k * F, cells, (size_t)k * 4);
+  PH_CUDA(cudaMemcpyAsync(a->d_feat, a->h_pin, (size_t)k * F * 8, cudaMemcpyHostToDevice, st));
+  PH_CUDA(cudaMemcpyAsync(a->d_cells, a->h_pin + (size_t)k * F, (size_t)k * 4, cudaMemcpyHostToDevice, st));
+  PH_CUDA(cudaMemsetAsync(a->d_red, 0, 4 * 8, st));
+  a->k = -k;  // features / cells staged, no matrix yet (F kept in d_red[3] would be overkill: the caller passes it again)
+  const int nr = row_hi - row_lo;
+  if (nr > 0) {
+    const CopySrc src{a->d_copy, a->d_emb, a->n, a->D};
+    const dim3 grid((k + 31) / 32, (nr + 31) / 32), block(32, 8);
+    k_aff_stats_rect<<<grid, block, 0, st>>>(a->d_feat, F, src, a->d_cells, k, use_copy_kernel, row_lo, row_hi, a->d_red);
+    ph_count_launch();
+  }
+  unsigned long long red[4];
+  PH_CUDA(cudaMemcpyAsync(red, a->d_red, sizeof(red), cudaMemcpyDeviceToHost, st));
+  PH_CUDA(cudaStreamSynchronize(st));
+  memcpy(&out3[0], &red[0], 8);
+  memcpy(&out3[1], &red[1], 8);
+  out3[2] = red[2] ? 1.0 : 0.0;
+  return PH_OK;
+}
+
+extern "C" int ph_affinity_build_rows(ph_affinity* a, int32_t F, double kw, double kwc, double r, int strict, double* dd_block,
+                                      int* has_nan) {
+  if (!a || !dd_block || !has_nan) PH_FAIL(PH_ERR_ARG, "null pointer");
+  if (a->k >= 0) PH_FAIL(PH_ERR_ARG, "call ph_affinity_stats_rows first");
+  PH_CUDA(cudaSetDevice(a->device));
+  cudaStream_t st = a->st;
+  const int k = -a->k, nr = a->row_hi - a->row_lo;
+  *has_nan = 0;
+  if (nr > 0) {
+    const CopySrc src{a->d_copy, a->d_emb, a->n, a->D};
+    const dim3 grid((k + 31) / 32, (nr + 31) / 32), block(32, 8);
+    PH_CUDA(cudaMemsetAsync(a->d_red, 0, 4 * 8, st));
+    k_aff_build_rect<<<grid, block, 0, st>>>(a->d_feat, F, src, a->d_cells, k, a->use_copy, kw, kwc, r, strict, a->row_lo, a->row_hi,
+                                             a->d_W, a->d_red);
+    k_aff_rowsum<<<(nr + 63) / 64, 64, 0, st>>>(a->d_W, nr, k, a->row_lo, a->d_dd);
+    ph_count_launch(2);
+    PH_CUDA(cudaGetLastError());
+    unsigned long long red[4];
+    PH_CUDA(cudaMemcpyAsync(red, a->d_red, sizeof(red), cudaMemcpyDeviceToHost, st));
+    PH_CUDA(cudaMemcpyAsync(a->h_pin, a->d_dd, (size_t)nr * 8, cudaMemcpyDeviceToHost, st));
+    PH_CUDA(cudaStreamSynchronize(st));
+    memcpy(dd_block, a->h_pin, (size_t)nr * 8);
+    *has_nan = red[2] ? 1 : 0;
+  }
+  return PH_OK;
+}
+
+extern "C" int ph_affinity_laplacian_rows(ph_affinity* a, const double* dd_full) {
+  if (!a || !dd_full) PH_FAIL(PH_ERR_ARG, "null pointer");
+  if (a->k >= 0) PH_FAIL(PH_ERR_ARG, "call ph_affinity_stats_rows / ph_affinity_build_rows first");
+  PH_CUDA(cudaSetDevice(a->device));
+  cudaStream_t st = a->st;
+  const int k = -a->k, nr = a->row_hi - a->row_lo;
+  memcpy(a->h_pin, dd_full, (size_t)k * 8);
+  PH_CUDA(cudaMemcpyAsync(a->d_ddf, a->h_pin, (size_t)k * 8, cudaMemcpyHostToDevice, st));
+  if (nr > 0) {
+    k_aff_laplacian_rect<<<1184, 256, 0, st>>>(a->d_W, nr, k, a->row_lo, a->d_ddf);
+    ph_count_launch();
+    PH_CUDA(cudaGetLastError());
+  }
+  PH_CUDA(cudaStreamSynchronize(st));
+  a->k = k;  // the block of the Laplacian is in place
+  return PH_OK;
+}
+
+// Y_block = L[row_lo:row_hi, :] @ X   (X: k x c host array, Y_block: (row_hi - row_lo) x c)
+extern "C" int ph_affinity_matmat_rows(ph_affinity* a, const double* X, int32_t c, double* Y_block) {
+  if (!a || !X || !Y_block) PH_FAIL(PH_ERR_ARG, "null pointer");
+  if (a->k < 1 || !a->rows_mode) PH_FAIL(PH_ERR_ARG, "no Laplacian rows: call ph_affinity_laplacian_rows first");
+  if (c < 1 || c > kMaxCols) PH_FAIL(PH_ERR_ARG, "c=%d outside 1..%d", c, kMaxCols);
+  PH_CUDA(cudaSetDevice(a->device));
+  cudaStream_t st = a->st;
+  const int k = a->k, nrows = a->row_hi - a->row_lo;
+  memcpy(a->h_pin, X, (size_t)k * c * 8);
+  PH_CUDA(cudaMemcpyAsync(a->d_x, a->h_pin, (size_t)k * c * 8, cudaMemcpyHostToDevice, st));
+  if (nrows > 0) {
+    const int threads = 256, blocks = (nrows * 32 + threads - 1) / threads;
+    switch (c) {
+      case 1: k_aff_matmat<1><<<blocks, threads, 0, st>>>(a->d_W, k, a->d_x, a->d_y, nrows); break;
+      case 2: k_aff_matmat<2><<<blocks, threads, 0, st>>>(a->d_W, k, a->d_x, a->d_y, nrows); break;
+      case 3: k_aff_matmat<3><<<blocks, threads, 0, st>>>(a->d_W, k, a->d_x, a->d_y, nrows); break;
+      case 4: k_aff_matmat<4><<<blocks, threads, 0, st>>>(a->d_W, k, a->d_x, a->d_y, nrows); break;
+      case 5: k_aff_matmat<5><<<blocks, threads, 0, st>>>(a->d_W, k, a->d_x, a->d_y, nrows); break;
+      case 6: k_aff_matmat<6><<<blocks, threads, 0, st>>>(a->d_W, k, a->d_x, a->d_y, nrows); break;
+      case 7: k_aff_matmat<7><<<blocks, threads, 0, st>>>(a->d_W, k, a->d_x, a->d_y, nrows); break;
+      default: k_aff_matmat<8><<<blocks, threads, 0, st>>>(a->d_W, k, a->d_x, a->d_y, nrows); break;
+    }
+    ph_count_launch();
+    PH_CUDA(cudaGetLastError());
+    PH_CUDA(cudaMemcpyAsync(a->h_pin + (size_t)k * kMaxCols, a->d_y, (size_t)nrows * c * 8, cudaMemcpyDeviceToHost, st));
+  }
+  PH_CUDA(cudaStreamSynchronize(st));
+  if (nrows > 0) memcpy(Y_block, a->h_pin + (size_t)k * kMaxCols, (size_t)nrows * c * 8);
   return PH_OK;
 }

@@ -241,6 +241,12 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
 #ifndef PH_RING4
 #define PH_RING4 4
 #endif
+#ifndef PH_PIPE
+#define PH_PIPE 1   // prime the next batch's ring before the holders of the current one (0: the plain order)
+#endif
+#ifndef PH_TAIL4
+#define PH_TAIL4 1  // rare-code tail: four words per round trip (0: one by one)
+#endif
   constexpr int RD = PH_RING4;
   uint4 ring[B4 ? RD : 1];
   bool primed = false;
@@ -372,7 +378,7 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
         primed = false;
         while (st < st_end) {
           // the next batch is drawn shortly before this one ends: the dispenser's round trip hides behind the last steps
-          if (!drawn && run == n_runs - 1 && st + 16 >= st_end) {
+          if (PH_PIPE && !drawn && run == n_runs - 1 && st + 16 >= st_end) {
             if (lane == 0) bnext = atomicAdd(a.counter, 1u);
             drawn = true;
           }
@@ -483,7 +489,7 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
     }
     __syncwarp();
     if (!drawn && lane == 0) bnext = atomicAdd(a.counter, 1u);  // next batch: the round trip overlaps the holders' work
-    if (B4 && NSUB > 0 && !a.phased) {
+    if (PH_PIPE && B4 && NSUB > 0 && !a.phased) {
       // prime the ring of the next batch now: its first loads fly while the holders below finish this one
       const unsigned bn = __shfl_sync(FULL, bnext, 0);
       if (bn < (unsigned)n_batches) {
@@ -574,6 +580,7 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
         };
         // four words per round trip (they sit in L2: prefetched when the batch started); the array has 8 words of slack
         const int64_t te_eff = (ph && !a.phase_last) ? tb : te;
+#if PH_TAIL4
         for (int64_t r0 = tb; r0 < te_eff; r0 += 4) {
           uint32_t w4[4];
 #pragma unroll
@@ -582,6 +589,9 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
           for (int u = 0; u < 4; ++u)
             if (r0 + u < te_eff) tail_one(w4[u]);
         }
+#else
+        for (int64_t r = tb; r < te_eff; ++r) tail_one(__ldg(a.tail_words + r));
+#endif
         if (cur != 0xffffffffu) fold();
       }
       const int wi = B4 ? line : myw;  // batched-4 walks the lines in shape order: results go to the line's own slot

@@ -186,7 +186,9 @@ extern "C" int ph_peer_create(ph_handle* h, int rank, int world, int32_t total_s
   p->rank = rank;
   p->world = world;
   p->max_lines = total_snvs;
-  p->blk_max = (h->n_snvs + world - 1) / world;
+  // (every offset below must be the same on all ranks: a rank computes where ITS words go in a PEER's window from its own
+  // copy of this layout.  SNV-sharded ranks hold blocks of different sizes -- only global quantities may enter.)
+  p->blk_max = (total_snvs + world - 1) / world;
   p->spin_limit = kSpinLimit;
   if (const char* e = getenv("PH_PEER_TIMEOUT_MS")) {
     const long long ms = atoll(e);
@@ -395,10 +397,48 @@ extern "C" int ph_peer_timed_out(ph_peer* p, void* stream) {
 
 // what the first wait of an SNV-sharded step that gave up was waiting for:
 // out[0..6] = {timed out, kind (1 header, 2 id/label word, 3 / 4 count words), source rank, slot, epoch wanted, epoch seen, payload seen}
+// out[7] = this rank's step counter; out[8 + 2 r], out[9 + 2 r] = for source rank r: slots announced by its header of the
+// wanted step (0xFFFFFFFF: header absent) and id/label words of that step present in this rank's window
+namespace {
+__global__ void k_peer_scan(const uint8_t* own_ll, const uint64_t* hdr_own, size_t par_stride, int cap, int world, uint32_t epoch,
+                            uint32_t* out) {
+  const int r = blockIdx.x;
+  if (r >= world) return;
+  const int par = (int)(epoch & 1u);
+  __shared__ unsigned cnt;
+  if (threadIdx.x == 0) cnt = 0;
+  __syncthreads();
+  const uint8_t* base = own_ll + (size_t)par * par_stride + (size_t)r * cap * 8;
+  unsigned c = 0;
+  for (int j = threadIdx.x; j < cap; j += blockDim.x)
+    if ((uint32_t)(ld_relaxed_sys_u64(base + (size_t)j * 8) >> 32) == epoch) ++c;
+  atomicAdd(&cnt, c);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint64_t h = ld_relaxed_sys_u64(hdr_own + par * PH_MAX_PEERS + r);
+    out[8 + 2 * r] = (uint32_t)(h >> 32) == epoch ? (uint32_t)h : 0xFFFFFFFFu;
+    out[9 + 2 * r] = cnt;
+  }
+}
+}  // namespace
+
 extern "C" int ph_peer_debug(ph_peer* p, uint32_t* out) {
   if (!p || !out) PH_FAIL(PH_ERR_ARG, "null argument");
   PH_CUDA(cudaSetDevice(p->h->device));
   PH_CUDA(cudaDeviceSynchronize());
+  memset(out, 0, 24 * sizeof(uint32_t));
   PH_CUDA(cudaMemcpy(out, p->d_done + 16, 7 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  PH_CUDA(cudaMemcpy(out + 7, p->d_done + 4, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  if (out[0]) {
+    uint32_t* d_out = reinterpret_cast<uint32_t*>(p->d_done + 32);   // [32..56) of the 64-word block
+    PH_CUDA(cudaMemset(d_out, 0, 24 * sizeof(uint32_t)));
+    const size_t word_stride = (size_t)p->world * p->cap_slots * 8;
+    k_peer_scan<<<p->world, 256>>>(p->win[p->rank] + p->off_ll, reinterpret_cast<const uint64_t*>(p->win[p->rank] + kHdrOff),
+                                   kLLWords * word_stride, p->cap_slots, p->world, out[4], d_out);
+    PH_CUDA(cudaDeviceSynchronize());
+    uint32_t tmp[24];
+    PH_CUDA(cudaMemcpy(tmp, d_out, sizeof(tmp), cudaMemcpyDeviceToHost));
+    for (int i = 8; i < 8 + 2 * p->world; ++i) out[i] = tmp[i];
+  }
   return PH_OK;
 }

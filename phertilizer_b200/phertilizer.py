@@ -141,7 +141,13 @@ class Phertilizer:
         bc["cell_index"] = cell_series[bc["cell"]].values
         bc = bc.sort_values(by=["cell_index"]).drop(["cell", "cell_index"], axis=1).to_numpy()
         embedding = _embed(bc, dim_reduce)
-        copy_distance = CopyDistance(np.asarray(embedding, dtype=np.float64), device=device)
+        if world > 1:
+            from .cluster import ShardedCopyDistance
+
+            copy_distance = ShardedCopyDistance(np.asarray(embedding, dtype=np.float64), device=device, group=self.device_group,
+                                                min_rows=int(os.environ.get("PH_SHARD_MIN_ROWS", "4096")))
+        else:
+            copy_distance = CopyDistance(np.asarray(embedding, dtype=np.float64), device=device)
 
         # per-observation likelihoods become a (var,total) -> (like0, like1) table inside the store (295-306)
         if world > 1:

@@ -152,12 +152,15 @@ class PeerExchange:
         """What the first wait of an SNV-sharded step that gave up was waiting for (ph_peer_debug)."""
         import ctypes as C
 
-        buf = (C.c_uint32 * 8)()
+        buf = (C.c_uint32 * 24)()
         if self._p is None:
             return {}
         self._lib.check(self._L.ph_peer_debug(self._p, buf))
-        names = ("timed_out", "kind", "source_rank", "slot", "step_wanted", "step_seen", "payload_seen")
-        return dict(zip(names, [int(x) for x in buf][:7]))
+        v = [int(x) for x in buf]
+        names = ("timed_out", "kind", "source_rank", "slot", "step_wanted", "step_seen", "payload_seen", "own_step_counter")
+        out = dict(zip(names, v[:8]))
+        out["per_source(announced, arrived)"] = [(v[8 + 2 * r], v[9 + 2 * r]) for r in range(8)]
+        return out
 
     def close(self):
         if self._p is not None:

@@ -27,6 +27,8 @@ ap.add_argument("--one-gpu", action="store_true")
 ap.add_argument("--quick", action="store_true", help="fewer datasets / trials (the time-sliced one-GPU mode is slow)")
 args = ap.parse_args()
 
+if args.one_gpu:   # the ranks time-slice ONE GPU: a rank may wait several scheduler slices for its peer's kernel to run
+    os.environ.setdefault("PH_PEER_TIMEOUT_MS", "20000")
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 local = 0 if args.one_gpu else int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
@@ -133,6 +135,35 @@ for stem, n, m, cell, snv, var, total in datasets():
     ok &= not ss.peer.timed_out()
     ss.close()
     full.close()
+# ---- the cell clustering sharded by rows (cluster.ShardedCopyDistance) against the single-GPU context: bit-identical
+from phertilizer_b200.cluster import CopyDistance, ShardedCopyDistance
+
+s = make_config("T1")
+emb = s.embedding.numpy()
+one = CopyDistance(emb, device=local)
+shd = ShardedCopyDistance(emb, device=local, min_rows=64)
+rng = np.random.default_rng(21)
+for trial, (k, F, use_copy, strict) in enumerate(((s.n, 1, True, False), (777, 2, True, True), (1200, 1, False, False), (50, 1, True, False))):
+    cells = np.sort(rng.choice(s.n, k, replace=False)).astype(np.int32)
+    feats = rng.random((k, F))
+    st1, dd1 = one.build(cells, feats, use_copy, 1.0, strict)
+    st2, dd2 = shd.build(cells, feats, use_copy, 1.0, strict)
+    good = all(st1[q] == st2[q] for q in ("kw", "kwc", "r", "has_nan")) and np.array_equal(dd1, dd2)
+    X = rng.standard_normal((k, 3))
+    good = good and np.array_equal(one.matmat(X), shd.matmat(X))
+    l1 = one.min_cut(cells, feats, use_copy, 1.0, strict, np.random.RandomState(5))
+    l2 = shd.min_cut(cells, feats, use_copy, 1.0, strict, np.random.RandomState(5))
+    good = good and np.array_equal(l1, l2)
+    if not good: print(f"[rank {rank}] sharded clustering mismatch, trial {trial}")
+    ok &= bool(good)
+mask = (rng.random(s.n) < 0.6).astype(np.uint8)
+rows = np.sort(rng.choice(s.n, 300, replace=False)).astype(np.int32)
+i1, t1 = one.nearest(rows, mask)
+i2, t2 = shd.nearest(rows, mask)
+ok &= bool(np.array_equal(i1, i2) and np.array_equal(t1, t2))
+used.add("row-sharded clustering")
+one.close(); shd.close()
+
 t = torch.tensor([1 if ok else 0])
 if nccl:
     t = t.cuda()
