@@ -147,13 +147,15 @@ __host__ __device__ inline int warp_words(int B, int NSUB, int D, int NC) {
 // (no base add per observation).  The bytes below the image hold the per-warp tables.  3: as 2, on the batched-4 copy of
 // the stream (PhOrient::half4): four lanes stream one line of the batch, sub-segment boundaries are warp-uniform.
 // 4: the batched-4 copy with the image wherever it fits (as 1: one base add per observation) -- minor axes whose image
-// leaves no room for the 64 KB alignment (K2 on 200 k SNVs: a 200 KB image).
+// leaves no room for the 64 KB alignment (K2 on 200 k SNVs: a 200 KB image).  5 / 6: as 3 / 4, in phases (PassArgs).
 template <int B, int MODE, int NC, bool SMEM_LAB, int LAY>
 __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
   constexpr bool S16 = LAY >= 1;
-  constexpr bool AL = LAY == 2 || LAY == 3;
-  constexpr bool B4 = LAY == 3 || LAY == 4;
+  constexpr bool AL = LAY == 2 || LAY == 3 || LAY == 5;
+  constexpr bool B4 = LAY >= 3;
+  constexpr bool PHASED = LAY >= 5;   // 5 / 6 = 3 / 4 walking the label image in phases (a compile-time switch: the
+                                      // plain pass is at the 64-register cap and pays for every extra live value)
   constexpr bool PUSHABLE = MODE == MODE_LINEAR || MODE == MODE_BRANCHING;
   const int nthreads = blockDim.x;
   const int D = a.D, NCH = a.NCH, NSUB = a.NSUB, NS1 = NSUB + 1, cb = a.chunk_bits;
@@ -183,8 +185,8 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
   unsigned bidx0 = 0;
   if ((threadIdx.x & 31) == 0) bidx0 = atomicAdd(a.counter, 1u);  // first batch of this warp, consumed after the staging
   if (SMEM_LAB)
-    fill_label_image<MODE == MODE_MAPPED, NC>(s_lab, a.minor_label, a.n_minor, (B4 && a.phased) ? a.ch_n : NCH, cb, a.K, threadIdx.x, nthreads,
-                                              (B4 && a.phased) ? a.ch_lo : 0);
+    fill_label_image<MODE == MODE_MAPPED, NC>(s_lab, a.minor_label, a.n_minor, PHASED ? a.ch_n : NCH, cb, a.K, threadIdx.x, nthreads,
+                                              PHASED ? a.ch_lo : 0);
   if (MODE == MODE_MAPPED) {
     // rows: node of the line (K, K+1: not in the tree -> nothing counts); columns: node of the minor index
     // (K: not in the tree -> absent, K+1: padding -> not counted)
@@ -242,10 +244,12 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
 #define PH_RING4 4
 #endif
 #ifndef PH_PIPE
-#define PH_PIPE 1   // prime the next batch's ring before the holders of the current one (0: the plain order)
+#define PH_PIPE 0   // 1: prime the next batch's ring before the holders of the current one.  Measured on C3 (same box,
+                    // scripts/probe_r2.py): 168.7 us against 166.7 us for the plain order -- the ring's registers stay live
+                    // across the holders and the compiler gives that back in the streaming loop.  Kept as a switch.
 #endif
 #ifndef PH_TAIL4
-#define PH_TAIL4 1  // rare-code tail: four words per round trip (0: one by one)
+#define PH_TAIL4 0  // 1: rare-code tail four words per round trip.  Measured: 172.7 us against 166.7 us (same reason).
 #endif
   constexpr int RD = PH_RING4;
   uint4 ring[B4 ? RD : 1];
@@ -317,7 +321,7 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
     if (B4 && NSUB > 0) {
       const int la = lane >> 2;  // my line of the batch
       // a full pass is ONE run of steps over all sub-segments; a phase walks, per dense code, the run of its chunks
-      const bool phased = a.phased != 0;
+      constexpr bool phased = PHASED;
       const int ch_lo = phased ? a.ch_lo : 0;
       uint32_t st = 0, st_end = 0;
       const uint4* gp = nullptr;
@@ -489,7 +493,7 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
     }
     __syncwarp();
     if (!drawn && lane == 0) bnext = atomicAdd(a.counter, 1u);  // next batch: the round trip overlaps the holders' work
-    if (PH_PIPE && B4 && NSUB > 0 && !a.phased) {
+    if (PH_PIPE && B4 && NSUB > 0 && !PHASED) {
       // prime the ring of the next batch now: its first loads fly while the holders below finish this one
       const unsigned bn = __shfl_sync(FULL, bnext, 0);
       if (bn < (unsigned)n_batches) {
@@ -518,7 +522,7 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
       unsigned nob[NC], nva[NC];
 #pragma unroll
       for (int c = 0; c < NC; ++c) { s0[c] = 0.0; s1[c] = 0.0; nob[c] = 0; nva[c] = 0; }
-      const bool ph = B4 && a.phased;
+      constexpr bool ph = PHASED;
       for (int d = 0; d < D; ++d) {
         const double l0 = L0[d], l1 = L1[d];
         const bool vp = VP[d] != 0;
@@ -1063,7 +1067,10 @@ int launch_pass(ph_handle* h, const PhOrient* o, PassArgs& a, cudaStream_t st) {
           a.lab_bytes = (int)(((size_t)(a.ch_n - 1) << 16) + tail_b);
           smem = tab4 + (size_t)a.lab_bytes + (al4 ? 65536 : 0);
         }
-        if (al4) PH_LAUNCH(8, true, 3);
+        if (n_phases > 1) {
+          if (al4) PH_LAUNCH(8, true, 5);
+          else PH_LAUNCH(8, true, 6);
+        } else if (al4) PH_LAUNCH(8, true, 3);
         else PH_LAUNCH(8, true, 4);
         if (p + 1 < n_phases) ph_count_launch();
       }

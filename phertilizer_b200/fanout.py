@@ -34,12 +34,24 @@ def visible_devices():
     return list(range(device_count()))
 
 
-def _init(queue, variant_data, bin_count_data, ctor_kwargs):
+_NAMES = ("cell_labels", "mut_labels", "cell_idx", "mut_idx", "var", "total", "bins")
+
+
+def _init(queue, shared_dir, ctor_kwargs):
     global _PH
+    import numpy as np
+
     from .phertilizer import Phertilizer
 
     device = queue.get()
-    _PH = Phertilizer(variant_data, bin_count_data, device=device, **ctor_kwargs)
+    # the parent indexed the observations once (phertilizer.prepare_inputs) and left the arrays in shared memory: the workers
+    # map them instead of unpickling two DataFrames and repeating the label pass each
+    arrays = []
+    for name in _NAMES:
+        path = os.path.join(shared_dir, name + ".npy")
+        labels = name.endswith("_labels")
+        arrays.append(np.load(path, allow_pickle=labels, mmap_mode=None if labels else "r"))
+    _PH = Phertilizer(None, None, device=device, _indexed=tuple(arrays), **ctor_kwargs)
 
 
 def _one(args):
@@ -59,18 +71,32 @@ def run_many(variant_data, bin_count_data, ctor_kwargs, run_kwargs, devices=None
     devices = visible_devices() if devices is None else list(devices)
     if not devices:
         raise RuntimeError("no CUDA device: phertilizer_b200 has no CPU fallback")
+    import shutil
+    import tempfile
+
+    import numpy as np
+
+    from .phertilizer import prepare_inputs
+
     ctx = mp.get_context("spawn")
     queue = ctx.Queue()
     for d in devices:
         queue.put(d)
     results = [None] * len(run_kwargs)
     lookups = None
-    with ProcessPoolExecutor(max_workers=min(len(devices), len(run_kwargs)), mp_context=ctx, initializer=_init,
-                             initargs=(queue, variant_data, bin_count_data, ctor_kwargs)) as pool:
-        for i, out, text, lk in pool.map(_one, [(i, kw, quiet) for i, kw in enumerate(run_kwargs)]):
-            results[i] = (*out, text)
-            if lk is not None:
-                lookups = lk
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+    shared_dir = tempfile.mkdtemp(prefix="phertilizer_b200_", dir=base)
+    try:
+        for name, arr in zip(_NAMES, prepare_inputs(variant_data, bin_count_data)):
+            np.save(os.path.join(shared_dir, name + ".npy"), np.asarray(arr), allow_pickle=name.endswith("_labels"))
+        with ProcessPoolExecutor(max_workers=min(len(devices), len(run_kwargs)), mp_context=ctx, initializer=_init,
+                                 initargs=(queue, shared_dir, ctor_kwargs)) as pool:
+            for i, out, text, lk in pool.map(_one, [(i, kw, quiet) for i, kw in enumerate(run_kwargs)]):
+                results[i] = (*out, text)
+                if lk is not None:
+                    lookups = lk
+    finally:
+        shutil.rmtree(shared_dir, ignore_errors=True)
     return results, lookups
 
 

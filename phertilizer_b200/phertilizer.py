@@ -93,6 +93,17 @@ def index_observations(variant_count_data):
     return cell_labels, mut_labels, cell_idx, mut_idx, var, total
 
 
+def prepare_inputs(variant_count_data, bin_count_data):
+    """Everything `Phertilizer.__init__` derives from the two input frames on the host: index_observations() plus the binned
+    read counts in cell-index order (phertilizer.py:259-263)."""
+    cell_labels, mut_labels, cell_idx, mut_idx, var, total = index_observations(variant_count_data)
+    cell_series = pd.Series(data=np.arange(cell_labels.shape[0], dtype="int"), index=cell_labels)
+    bc = bin_count_data.copy()
+    bc["cell_index"] = cell_series[bc["cell"]].values
+    bc = bc.sort_values(by=["cell_index"]).drop(["cell", "cell_index"], axis=1).to_numpy()
+    return cell_labels, mut_labels, cell_idx, mut_idx, var, total, bc
+
+
 def _embed(bin_counts: np.ndarray, dim_reduce: bool) -> np.ndarray:
     """Row-normalise + UMAP (phertilizer.py:267-279) or the raw bins (284-285).  UMAP is third-party and stays so."""
     if not dim_reduce:
@@ -108,7 +119,7 @@ def _embed(bin_counts: np.ndarray, dim_reduce: bool) -> np.ndarray:
 
 class Phertilizer:
     def __init__(self, variant_count_data, bin_count_data, alpha=0.001, max_copies=5, mode="var", dim_reduce=True,
-                 device=None, device_group=None):
+                 device=None, device_group=None, _indexed=None):
         """`device_group`: a torch.distributed process group (or True for the default group) whose ranks each drive one
         GPU.  The observations are then sharded by cells across the ranks (`sharded_store.CellShardedStore`)
         and EVERY rank must construct the object and make the same calls: the tree-growing control flow runs redundantly
@@ -129,17 +140,16 @@ class Phertilizer:
                 device = int(os.environ.get("PHERTILIZER_DEVICE", os.environ.get("LOCAL_RANK", "0")))
         device = int(os.environ.get("PHERTILIZER_DEVICE", "0")) if device is None else device
 
-        cell_labels, mut_labels, cell_idx, mut_idx, var, total = index_observations(variant_count_data)
+        # `_indexed` (fanout.py): the label -> index pass and the cell-ordered bin matrix were done once by the parent of
+        # the `--runs` workers and arrive as plain arrays (memory-mapped), instead of every worker repeating them
+        if _indexed is not None:
+            cell_labels, mut_labels, cell_idx, mut_idx, var, total, bc = _indexed
+        else:
+            cell_labels, mut_labels, cell_idx, mut_idx, var, total, bc = prepare_inputs(variant_count_data, bin_count_data)
         self.cells = np.arange(cell_labels.shape[0], dtype="int")
         self.muts = np.arange(mut_labels.shape[0], dtype="int")
-        cell_series = pd.Series(data=self.cells, index=cell_labels)
         cell_lookup = pd.Series(data=cell_labels, index=self.cells)
         mut_lookup = pd.Series(data=mut_labels, index=self.muts)
-
-        # binned read counts in cell-index order (259-263), embedding, pairwise copy distance on the GPU (286)
-        bc = bin_count_data.copy()
-        bc["cell_index"] = cell_series[bc["cell"]].values
-        bc = bc.sort_values(by=["cell_index"]).drop(["cell", "cell_index"], axis=1).to_numpy()
         embedding = _embed(bc, dim_reduce)
         if world > 1:
             from .cluster import ShardedCopyDistance
