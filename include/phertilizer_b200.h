@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PH_ABI_VERSION 7
+#define PH_ABI_VERSION 8
 
 #if defined(__GNUC__)
 #define PH_API __attribute__((visibility("default")))
@@ -306,6 +306,16 @@ PH_API void ph_affinity_destroy(ph_affinity* a);
  */
 PH_API int ph_pairwise_dist(const double* X, int32_t n, int32_t D, int32_t row_begin, int32_t row_end, double* out,
                      int device, int on_device, void* stream);
+
+/*
+ * K5 on the FP64 tensor cores: d^2 = |x_i|^2 + |x_j|^2 - 2 x_i.x_j with the inner products from DMMA (mma.sync m8n8k4
+ * f64 -- tcgen05 has no fp64 type), pairs whose squared distance is below 1e-4 of |x_i|^2 + |x_j|^2 re-evaluated by
+ * direct differences.  Every distance within 1e-9 relative of ph_pairwise_dist, NOT bit-identical to it: opt-in, for
+ * high-dimensional embeddings (--no-umap with thousands of bins) where the direct kernel is bound by the fp64 pipe.
+ * Device pointers only, enqueued on `stream`; sq_scratch: n doubles of device scratch.
+ */
+PH_API int ph_pairwise_dist_gram(const double* X, int32_t n, int32_t D, int32_t row_begin, int32_t row_end, double* out,
+                          double* sq_scratch, int device, void* stream);
 
 #ifdef __cplusplus
 }

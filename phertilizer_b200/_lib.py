@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libphertilizer_b200.so")
 
 PH_OK = 0
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 
 class PhError(RuntimeError):
@@ -38,7 +38,7 @@ class PhInfo(C.Structure):
 EXPORTS = [
     "ph_last_error", "ph_abi_version", "ph_kernel_launches", "ph_device_count", "ph_create", "ph_destroy", "ph_get_info", "ph_set_group",
     "ph_snv_table", "ph_assign_linear", "ph_assign_branching", "ph_cell_table", "ph_block_sums", "ph_tree_loglik",
-    "ph_line_reduce", "ph_node_reduce", "ph_snv_node_table", "ph_cell_node_table", "ph_set_embedding", "ph_gauss_node_ll", "ph_pairwise_dist",
+    "ph_line_reduce", "ph_node_reduce", "ph_snv_node_table", "ph_cell_node_table", "ph_set_embedding", "ph_gauss_node_ll", "ph_pairwise_dist", "ph_pairwise_dist_gram",
     "ph_snv_partial", "ph_finish_linear", "ph_finish_branching",
     "ph_peer_handle_bytes", "ph_peer_create", "ph_peer_export", "ph_peer_connect", "ph_peer_assign_linear",
     "ph_peer_assign_branching", "ph_peer_assign_linear_snv", "ph_peer_assign_branching_snv", "ph_peer_timed_out",
@@ -111,6 +111,7 @@ def lib():
     L.ph_set_embedding.argtypes = [_vp, _vp, C.c_int32]
     L.ph_gauss_node_ll.argtypes = [_vp, _vp, C.c_int32, _vp, C.c_int32, _vp, _vp, C.c_int, _vp]
     L.ph_pairwise_dist.argtypes = [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, C.c_int, C.c_int, _vp]
+    L.ph_pairwise_dist_gram.argtypes = [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, _vp, C.c_int, _vp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("ph_last_error", "ph_kernel_launches", "ph_destroy", "ph_peer_destroy", "ph_affinity_destroy"):

@@ -208,6 +208,110 @@ __global__ void __launch_bounds__(256) k_pdist(const double* __restrict__ X, int
   }
 }
 
+// ---------------------------------------------------------------- K5, Gram form on the FP64 tensor cores
+// d(i,j)^2 = |x_i|^2 + |x_j|^2 - 2 x_i . x_j with the inner products from DMMA (mma.sync m8n8k4 f64: tcgen05 has no fp64
+// type, the fp64 tensor path of sm_100 is the legacy warp-level instruction).  One multiply-add per pair and dimension
+// instead of subtract, multiply, add: a third of the direct kernel's instructions, on the tensor pipe.  The cancellation
+// of the Gram form costs relative accuracy (|x_i|^2 + |x_j|^2) / d^2 * eps: pairs whose squared distance falls below
+// kGramFix * (|x_i|^2 + |x_j|^2) are re-evaluated by direct differences (the epilogue's fix-up), which bounds the
+// relative error of every distance by ~ sqrt(D) * eps / kGramFix < 1e-9 -- NOT bit-identical to scipy's loop, hence
+// opt-in (ph_pairwise_dist_gram); the direct kernel stays the default because the clustering compares distances exactly.
+//
+// CTA: 128 rows x 64 columns, 8 warps as 4 x 2, warp tile 32 x 32 = 4 x 4 MMA tiles; slabs of 32 dimensions staged in
+// shared memory as [row][32] with the position of dimension c rotated by 4 * (row % 8): the 32 lanes of a fragment load
+// (4 consecutive dimensions x 8 consecutive rows) and of a staging store (32 dimensions of one row) both touch every
+// 8-byte bank pair exactly twice -- the minimum for 256 bytes.
+constexpr double kGramFix = 1e-4;
+constexpr int GM = 128, GN = 64, GK = 32;
+
+__global__ void k_row_sqnorm(const double* __restrict__ X, int n, int D, double* __restrict__ sq) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n) return;
+  const double* x = X + (size_t)warp * D;
+  double acc = 0.0;
+  for (int d = lane; d < D; d += 32) acc = fma(x[d], x[d], acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) sq[warp] = acc;
+}
+
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(256) k_pdist_gram(const double* __restrict__ X, const double* __restrict__ sq, int n, int D,
+                                                    int row_begin, int row_end, double* __restrict__ out) {
+  __shared__ double sa[GM * GK];
+  __shared__ double sb[GN * GK];
+  const int i0 = row_begin + blockIdx.y * GM;
+  const int j0 = blockIdx.x * GN;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wm = warp >> 1, wn = warp & 1;   // warp tile origin: rows wm * 32, columns wn * 32
+  const int g = lane >> 2, t = lane & 3;     // fragment coordinates
+  double acc[4][4][2];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+  for (int d0 = 0; d0 < D; d0 += GK) {
+    // stage: one row of 32 dimensions per warp instruction (256 contiguous bytes of X), zero beyond the matrix
+    for (int r = warp; r < GM; r += 8) {
+      const int gi = i0 + r, d = d0 + lane;
+      sa[r * GK + ((lane + 4 * (r & 7)) & 31)] = (gi < row_end && d < D) ? X[(size_t)gi * D + d] : 0.0;
+    }
+    for (int r = warp; r < GN; r += 8) {
+      const int gj = j0 + r, d = d0 + lane;
+      sb[r * GK + ((lane + 4 * (r & 7)) & 31)] = (gj < n && d < D) ? X[(size_t)gj * D + d] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k0 = 0; k0 < GK; k0 += 4) {
+      const int p = (k0 + t + 4 * g) & 31;   // rows of a fragment are r0 + g with r0 a multiple of 8: (r & 7) = g
+      double fa[4], fb[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) fa[a] = sa[(wm * 32 + a * 8 + g) * GK + p];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) fb[b] = sb[(wn * 32 + b * 8 + g) * GK + p];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], fa[a], fb[b]);
+    }
+    __syncthreads();
+  }
+  // epilogue: thread holds C[row = g][columns 2 t, 2 t + 1] of every 8 x 8 tile
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int gi = i0 + wm * 32 + a * 8 + g;
+    if (gi >= row_end) continue;
+    const double si = sq[gi];
+    const double* xi = X + (size_t)gi * D;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int gj = j0 + wn * 32 + b * 8 + 2 * t + e;
+        if (gj >= n) continue;
+        const double sj = sq[gj];
+        double d2 = (si + sj) - 2.0 * acc[a][b][e];
+        if (gi == gj) {
+          d2 = 0.0;
+        } else if (!(d2 > kGramFix * (si + sj))) {
+          // near pair (or a rounding-negative value): direct differences, the reference's own arithmetic
+          const double* xj = X + (size_t)gj * D;
+          double s = 0.0;
+          for (int d = 0; d < D; ++d) {
+            const double df = __dsub_rn(xi[d], xj[d]);
+            s = __dadd_rn(s, __dmul_rn(df, df));
+          }
+          d2 = s;
+        }
+        out[(size_t)(gi - row_begin) * n + gj] = sqrt(d2);
+      }
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" int ph_gauss_node_ll(ph_handle* h, const double* X, int32_t D, const uint8_t* cell_node, int32_t K,
@@ -386,4 +490,27 @@ extern "C" int ph_pairwise_dist(const double* X, int32_t n, int32_t D, int32_t r
   cudaFree(dX);
   cudaFree(dO);
   return rc;
+}
+
+// K5 on the FP64 tensor cores (Gram form + direct fix-up of near pairs, see k_pdist_gram): every distance within 1e-9
+// relative of the direct kernel, not bit-identical to it.  Device pointers only (the n x n result of a large embedding
+// never fits a host transfer budget anyway); `sq_scratch` [n] doubles of device scratch for the squared row norms.
+extern "C" int ph_pairwise_dist_gram(const double* X, int32_t n, int32_t D, int32_t row_begin, int32_t row_end, double* out,
+                                     double* sq_scratch, int device, void* stream) {
+  if (!X || !out || !sq_scratch) PH_FAIL(PH_ERR_ARG, "null pointer");
+  if (n < 1 || D < 1 || row_begin < 0 || row_end > n || row_begin > row_end)
+    PH_FAIL(PH_ERR_ARG, "bad shape n=%d D=%d rows=[%d,%d)", n, D, row_begin, row_end);
+  int ndev = 0;
+  PH_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) PH_FAIL(PH_ERR_CUDA, "device %d not available (%d CUDA devices)", device, ndev);
+  PH_CUDA(cudaSetDevice(device));
+  const int nr = row_end - row_begin;
+  if (nr == 0) return PH_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  k_row_sqnorm<<<(n * 32 + 255) / 256, 256, 0, st>>>(X, n, D, sq_scratch);
+  dim3 grid((n + GN - 1) / GN, (nr + GM - 1) / GM);
+  k_pdist_gram<<<grid, 256, 0, st>>>(X, sq_scratch, n, D, row_begin, row_end, out);
+  ph_count_launch(2);
+  PH_CUDA(cudaGetLastError());
+  return PH_OK;
 }

@@ -371,3 +371,21 @@ def pairwise_dist(X, row_begin=0, row_end=None, device=0):
     out = np.empty((row_end - row_begin, n), np.float64)
     _lib.check(_lib.lib().ph_pairwise_dist(_ptr(X), n, D, row_begin, row_end, _ptr(out), device, 0, None))
     return out
+
+
+def pairwise_dist_gram(X, row_begin=0, row_end=None, device=0):
+    """K5 on the FP64 tensor cores (ph_pairwise_dist_gram): rows [row_begin, row_end) of squareform(pdist(X)), every entry
+    within 1e-9 relative of `pairwise_dist` (not bit-identical).  torch only holds the device buffers."""
+    import torch
+
+    dev = torch.device("cuda", device)
+    Xd = torch.from_numpy(np.ascontiguousarray(X, dtype=np.float64)).to(dev)
+    n, D = Xd.shape
+    row_end = n if row_end is None else row_end
+    out = torch.empty((row_end - row_begin, n), dtype=torch.float64, device=dev)
+    sq = torch.empty(n, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().ph_pairwise_dist_gram(_ptr(Xd), n, D, row_begin, row_end, _ptr(out), _ptr(sq), device,
+                                                    torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+    return out.cpu().numpy()

@@ -466,3 +466,32 @@ def test_wide_matrix_multi_chunk(shape, phase_chunks, monkeypatch):
         sc = O.snv_node_scores(D, j, {k: member[k][cell_node.astype(np.int64)] for k in range(4)})
         assert rel_close(row, np.array([sc[k] for k in range(4)]), TOL)
     st.close()
+
+
+def test_pairwise_dist_gram_tensor_core_path():
+    """K5 in Gram form on the FP64 tensor cores (DMMA) with the direct fix-up of near pairs: within 1e-9 relative of scipy
+    (north_star tolerance), exact zeros on the diagonal, near-duplicate rows resolved by the direct arithmetic."""
+    from scipy.spatial.distance import pdist, squareform
+
+    from phertilizer_b200.store import pairwise_dist, pairwise_dist_gram
+
+    g = load_golden("example")
+    X = g.inputs["read_depth"].astype(np.float64)          # 1427 cells x 577 bins (--no-umap embedding)
+    ref = squareform(pdist(X))
+    got = pairwise_dist_gram(X)
+    assert got.shape == ref.shape and np.all(np.diag(got) == 0.0)
+    off = ~np.eye(len(X), dtype=bool)
+    assert np.max(np.abs(got[off] - ref[off]) / ref[off]) < 1e-9
+    rng = np.random.default_rng(2)
+    for n, D in ((333, 70), (129, 33), (64, 5000), (200, 1)):
+        Y = rng.poisson(300.0, size=(n, D)).astype(np.float64)
+        Y[1] = Y[0]                                         # identical rows: distance exactly 0
+        Y[3] = Y[2]; Y[3, 0] += 1.0                          # near pair: far below the Gram form's resolution threshold
+        ref = squareform(pdist(Y))
+        got = pairwise_dist_gram(Y, 5, n - 3) if n > 100 else pairwise_dist_gram(Y)
+        sub = ref[5:n - 3] if n > 100 else ref
+        nz = sub > 0
+        assert np.all(got[~nz] == 0.0)
+        assert np.max(np.abs(got[nz] - sub[nz]) / sub[nz]) < 1e-9, (n, D)
+        if n <= 100:
+            assert got[0, 1] == 0.0 and got[2, 3] == pairwise_dist(Y)[2, 3]
