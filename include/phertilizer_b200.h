@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PH_ABI_VERSION 8
+#define PH_ABI_VERSION 9
 
 #if defined(__GNUC__)
 #define PH_API __attribute__((visibility("default")))
@@ -306,6 +306,23 @@ PH_API void ph_affinity_destroy(ph_affinity* a);
  */
 PH_API int ph_pairwise_dist(const double* X, int32_t n, int32_t D, int32_t row_begin, int32_t row_end, double* out,
                      int device, int on_device, void* stream);
+
+/*
+ * Device-resident block vectors for the eigensolver of the cut (sklearn spectral_embedding -> scipy LOBPCG, utils.py:131-150):
+ * ten slots of k x 3 row-major doubles next to the Laplacian of the last ph_affinity_build / ph_affinity_laplacian_rows.
+ *   ph_affinity_bv_set / _get   host <-> slot
+ *   ph_affinity_bv_apply        slot dst = L @ slot src (whole Laplacian); row-block contexts return this rank's rows of the
+ *                               product in host_block instead (the caller assembles the ranks' blocks and sets dst)
+ *   ph_affinity_bv_gram         out[(a,i),(b,j)] = <left_a[:, i], right_b[:, j]>, row-major (3 nl) x (3 nr), fixed-order reduction
+ *   ph_affinity_bv_combine      slot dst = sum_t slot_t @ C_t  (C_t 3 x 3 row-major, 1..4 terms; products and sums rounded
+ *                               separately, in term order; coefficient 1 copies, 0 skips)
+ * The LOBPCG recurrence then moves 3 x 3 ... 9 x 18 Gram matrices over PCIe per iteration instead of k x 3 operands.
+ */
+PH_API int ph_affinity_bv_set(ph_affinity* a, int slot, const double* host_k_by_3);
+PH_API int ph_affinity_bv_get(ph_affinity* a, int slot, double* host_k_by_3);
+PH_API int ph_affinity_bv_apply(ph_affinity* a, int src, int dst, double* host_block_or_null);
+PH_API int ph_affinity_bv_gram(ph_affinity* a, const int32_t* left, int32_t nl, const int32_t* right, int32_t nr, double* out);
+PH_API int ph_affinity_bv_combine(ph_affinity* a, int dst, const int32_t* slots, const double* coeffs, int32_t n_terms);
 
 /*
  * K5 on the FP64 tensor cores: d^2 = |x_i|^2 + |x_j|^2 - 2 x_i.x_j with the inner products from DMMA (mma.sync m8n8k4

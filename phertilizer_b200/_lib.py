@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libphertilizer_b200.so")
 
 PH_OK = 0
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 
 class PhError(RuntimeError):
@@ -45,7 +45,8 @@ EXPORTS = [
     "ph_peer_debug", "ph_peer_destroy",
     "ph_affinity_create", "ph_affinity_rows", "ph_affinity_nearest", "ph_affinity_build", "ph_affinity_matmat", "ph_affinity_matrix",
     "ph_affinity_destroy", "ph_affinity_create_rows", "ph_affinity_stats_rows", "ph_affinity_build_rows", "ph_affinity_laplacian_rows",
-    "ph_affinity_matmat_rows",
+    "ph_affinity_matmat_rows", "ph_affinity_bv_set", "ph_affinity_bv_get", "ph_affinity_bv_apply", "ph_affinity_bv_gram",
+    "ph_affinity_bv_combine",
 ]
 
 _lib = None
@@ -106,6 +107,11 @@ def lib():
     L.ph_affinity_build_rows.argtypes = [_vp, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_int, _vp, C.POINTER(C.c_int)]
     L.ph_affinity_laplacian_rows.argtypes = [_vp, _vp]
     L.ph_affinity_matmat_rows.argtypes = [_vp, _vp, C.c_int32, _vp]
+    L.ph_affinity_bv_set.argtypes = [_vp, C.c_int, _vp]
+    L.ph_affinity_bv_get.argtypes = [_vp, C.c_int, _vp]
+    L.ph_affinity_bv_apply.argtypes = [_vp, C.c_int, C.c_int, _vp]
+    L.ph_affinity_bv_gram.argtypes = [_vp, _vp, C.c_int32, _vp, C.c_int32, _vp]
+    L.ph_affinity_bv_combine.argtypes = [_vp, C.c_int, _vp, _vp, C.c_int32]
     L.ph_affinity_destroy.argtypes = [_vp]
     L.ph_affinity_destroy.restype = None
     L.ph_set_embedding.argtypes = [_vp, _vp, C.c_int32]

@@ -20,6 +20,9 @@ import numpy as np
 from . import _lib
 
 SMALL = 64
+# the LOBPCG iteration of the cut with its block vectors resident on the GPU (device_lobpcg below); PH_DEVICE_LOBPCG=0 keeps
+# scipy's host iteration and only serves it `L @ X` products
+DEVICE_LOBPCG = __import__("os").environ.get("PH_DEVICE_LOBPCG", "1") != "0"
 
 
 def _dptr(a):
@@ -106,6 +109,34 @@ class CopyDistance:
         _lib.check(self._L.ph_affinity_matrix(self._h, _dptr(out)))
         return out
 
+    # ------------------------------------------------------------------ device-resident block vectors (k x 3 slots)
+    def bv_set(self, slot, X):
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        _lib.check(self._L.ph_affinity_bv_set(self._h, int(slot), _dptr(X)))
+
+    def bv_get(self, slot) -> np.ndarray:
+        out = np.empty((self._k, 3), np.float64)
+        _lib.check(self._L.ph_affinity_bv_get(self._h, int(slot), _dptr(out)))
+        return out
+
+    def bv_apply(self, src, dst):
+        """slot dst = L @ slot src, on the device."""
+        _lib.check(self._L.ph_affinity_bv_apply(self._h, int(src), int(dst), None))
+
+    def bv_gram(self, left, right) -> np.ndarray:
+        """[3 len(left), 3 len(right)] matrix of inner products of the slots' columns (fixed-order reduction)."""
+        l = np.ascontiguousarray(left, dtype=np.int32)
+        r = np.ascontiguousarray(right, dtype=np.int32)
+        out = np.empty((3 * len(l), 3 * len(r)), np.float64)
+        _lib.check(self._L.ph_affinity_bv_gram(self._h, _dptr(l), len(l), _dptr(r), len(r), _dptr(out)))
+        return out
+
+    def bv_combine(self, dst, terms):
+        """slot dst = sum over (slot, C) in terms of slot @ C, C 3 x 3 (dst may be one of the sources)."""
+        slots = np.ascontiguousarray([t[0] for t in terms], dtype=np.int32)
+        coeffs = np.ascontiguousarray(np.stack([np.asarray(t[1], np.float64).reshape(3, 3) for t in terms]))
+        _lib.check(self._L.ph_affinity_bv_combine(self._h, int(dst), _dptr(slots), _dptr(coeffs), len(terms)))
+
     def min_cut(self, cells, feats, use_copy_kernel, radius, strict, random_state):
         """Two-way normalised cut of `cells` -> labels (0/1 per cell), or None when the affinity contains NaN (the
         reference then terminates the clustering).  Mirrors sklearn.cluster.spectral_clustering(n_clusters=2,
@@ -126,12 +157,185 @@ class CopyDistance:
         else:
             X = random_state.standard_normal(size=(k, n_components + 1))
             X[:, 0] = dd.ravel()
-            A = self.laplacian() if k < SMALL else (lambda V: self.matmat(V))
-            _, diffusion_map = lobpcg(A, X, tol=None, largest=False, maxiter=2000)
+            if k < SMALL:
+                _, diffusion_map = lobpcg(self.laplacian(), X, tol=None, largest=False, maxiter=2000)
+            elif DEVICE_LOBPCG:
+                _, diffusion_map = device_lobpcg(self, X, maxiter=2000)
+            else:
+                _, diffusion_map = lobpcg(lambda V: self.matmat(V), X, tol=None, largest=False, maxiter=2000)
         embedding = diffusion_map.T[:n_components]
         embedding = embedding / dd          # recover u = D^-1/2 x
         embedding = _deterministic_vector_sign_flip(embedding)
         return cluster_qr(embedding[:n_components].T)
+
+
+def device_lobpcg(ctx, X0, maxiter=2000, restart_control=20):
+    """scipy.sparse.linalg.lobpcg(A, X0, tol=None, largest=False, maxiter=maxiter) for the Laplacian held by `ctx`, with the
+    block vectors on the device.
+
+    sklearn's spectral_embedding (the reference's normalizedMinCut, utils.py:131-150) hands the normalised Laplacian and a
+    k x 3 start block to scipy's LOBPCG.  The method itself is a short recurrence on six k x 3 blocks (X, AX, residuals R, AR,
+    directions P, AP) driven by 3 x 3 ... 9 x 9 Gram matrices: here the blocks never leave the GPU (`ctx.bv_*`: product,
+    Gram, linear combination), the small dense algebra (Cholesky, inverse, symmetric eigenproblem) stays with the same scipy
+    routines on the host, and the control flow -- active mask, restarts, implicit / explicit Gram matrices, the final
+    Rayleigh-Ritz on the best iterate -- follows scipy's (no constraints, no preconditioner, standard problem).  Only the
+    summation order of the k-long inner products differs from BLAS, as the order of the GPU product `L @ X` already did."""
+    from scipy.linalg import LinAlgError, cholesky, eigh, inv
+
+    k, m = X0.shape
+    assert m == 3
+    X, AX, R, AR, P, AP, BEST, T1, T2 = range(9)
+    I3 = np.eye(3)
+    tol = np.sqrt(np.finfo(np.float64).eps) * k
+
+    def pad(M):
+        out = np.zeros((3, 3))
+        out[: M.shape[0], : M.shape[1]] = M
+        return out
+
+    def orthonormalize(slot, ca):
+        """In-place (B = I) orthonormalisation of the first ca columns by Cholesky; returns inv(chol) or None."""
+        G = ctx.bv_gram([slot], [slot])[:ca, :ca]
+        try:
+            U = inv(cholesky(G, overwrite_a=True), overwrite_a=True)
+        except LinAlgError:
+            return None
+        ctx.bv_combine(slot, [(slot, pad(U))])
+        return U
+
+    ctx.bv_set(X, X0)
+    if orthonormalize(X, 3) is None:
+        raise ValueError("Linearly dependent initial approximations")
+    ctx.bv_apply(X, AX)
+    lam, V = eigh(ctx.bv_gram([X], [AX]), check_finite=False)
+    ii = np.argsort(lam)[:m]
+    lam, V = lam[ii], np.asarray(V[:, ii])
+    ctx.bv_combine(X, [(X, V)])
+    ctx.bv_combine(AX, [(AX, V)])
+
+    active = np.ones(m, dtype=bool)
+    smallest = np.abs(np.finfo(np.float64).max)
+    best_is_current = False
+    it = -1
+    restart, forced_restart, explicit = True, False, False
+    have_p = False
+    myeps = np.sqrt(np.finfo(np.float64).eps)
+    while it < maxiter:
+        it += 1
+        ctx.bv_combine(R, [(AX, I3), (X, -np.diag(lam))])          # R = AX - X * lambda
+        rn = np.sqrt(np.abs(np.diag(ctx.bv_gram([R], [R]))))
+        rnorm = np.sum(np.abs(rn)) / m
+        if rnorm < smallest:
+            smallest = rnorm
+            ctx.bv_combine(BEST, [(X, I3)])
+        elif rnorm > 2 ** restart_control * smallest:
+            forced_restart = True
+            ctx.bv_apply(X, AX)
+        active = active & (rn > tol)
+        ca = int(active.sum())
+        if ca == 0:
+            break
+        S = np.zeros((3, 3))
+        S[np.nonzero(active)[0], np.arange(ca)] = 1.0                  # active columns first, zero columns behind
+        ctx.bv_combine(R, [(R, S)])
+        if it > 0:
+            ctx.bv_combine(P, [(P, S)])
+            ctx.bv_combine(AP, [(AP, S)])
+        XR = ctx.bv_gram([X], [R])
+        ctx.bv_combine(R, [(R, I3), (X, -XR)])                        # orthogonal to X
+        if orthonormalize(R, ca) is None:
+            break
+        ctx.bv_apply(R, AR)
+        if it > 0:
+            invR = orthonormalize(P, ca)
+            if invR is not None:
+                ctx.bv_combine(AP, [(AP, pad(invR))])
+                restart = forced_restart
+            else:
+                restart = True
+        if not (rn.max() > myeps and not explicit):
+            explicit = True
+        left = [X, R] if restart else [X, R, P]
+        right = ([X, R, AX, AR] if restart else [X, R, P, AX, AR, AP])
+        G = ctx.bv_gram(left, right)
+        nl = len(left)
+
+        def blk(a, b, rows, cols):
+            return G[3 * a: 3 * a + rows, 3 * b: 3 * b + cols]
+
+        iX, iR, iP = 0, 1, 2
+        jAX, jAR, jAP = (2, 3, None) if restart else (3, 4, 5)
+        gXAR = blk(iX, jAR, m, ca)
+        gRAR = blk(iR, jAR, ca, ca)
+        if explicit:
+            gRAR = (gRAR + gRAR.T) / 2
+            gXAX = blk(iX, jAX, m, m)
+            gXAX = (gXAX + gXAX.T) / 2
+            gXBX = blk(iX, iX, m, m)
+            gRBR = blk(iR, iR, ca, ca)
+            gXBR = blk(iX, iR, m, ca)
+        else:
+            gXAX = np.diag(lam)
+            gXBX = np.eye(m)
+            gRBR = np.eye(ca)
+            gXBR = np.zeros((m, ca))
+        lam_all = Vall = None
+        if not restart:
+            gXAP = blk(iX, jAP, m, ca)
+            gRAP = blk(iR, jAP, ca, ca)
+            gPAP = blk(iP, jAP, ca, ca)
+            gXBP = blk(iX, iP, m, ca)
+            gRBP = blk(iR, iP, ca, ca)
+            if explicit:
+                gPAP = (gPAP + gPAP.T) / 2
+                gPBP = blk(iP, iP, ca, ca)
+            else:
+                gPBP = np.eye(ca)
+            gramA = np.block([[gXAX, gXAR, gXAP], [gXAR.T, gRAR, gRAP], [gXAP.T, gRAP.T, gPAP]])
+            gramB = np.block([[gXBX, gXBR, gXBP], [gXBR.T, gRBR, gRBP], [gXBP.T, gRBP.T, gPBP]])
+            try:
+                lam_all, Vall = eigh(gramA, gramB, check_finite=False)
+            except LinAlgError:
+                restart = True
+        if restart:
+            gramA = np.block([[gXAX, gXAR], [gXAR.T, gRAR]])
+            gramB = np.block([[gXBX, gXBR], [gXBR.T, gRBR]])
+            try:
+                lam_all, Vall = eigh(gramA, gramB, check_finite=False)
+            except LinAlgError:
+                break
+        ii = np.argsort(lam_all)[:m]
+        lam = lam_all[ii]
+        Vall = Vall[:, ii]
+        eX, eR = Vall[:m], Vall[m: m + ca]
+        if not restart:
+            eP = Vall[m + ca:]
+            ctx.bv_combine(T1, [(R, pad(eR)), (P, pad(eP))])
+            ctx.bv_combine(T2, [(AR, pad(eR)), (AP, pad(eP))])
+        else:
+            ctx.bv_combine(T1, [(R, pad(eR))])
+            ctx.bv_combine(T2, [(AR, pad(eR))])
+        ctx.bv_combine(X, [(X, eX), (T1, I3)])
+        ctx.bv_combine(AX, [(AX, eX), (T2, I3)])
+        P, T1 = T1, P                                                   # the new directions; their old slots become scratch
+        AP, T2 = T2, AP
+        have_p = True
+
+    ctx.bv_combine(R, [(AX, I3), (X, -np.diag(lam))])
+    rn = np.sqrt(np.abs(np.diag(ctx.bv_gram([R], [R]))))
+    if np.sum(np.abs(rn)) / m < smallest:
+        ctx.bv_combine(BEST, [(X, I3)])
+    # final "exact" Rayleigh-Ritz on the best iterate
+    ctx.bv_apply(BEST, AX)
+    G = ctx.bv_gram([BEST], [BEST, AX])
+    gXBX, gXAX = G[:, :3], G[:, 3:]
+    gXAX = (gXAX + gXAX.T) / 2
+    gXBX = (gXBX + gXBX.T) / 2
+    lam, V = eigh(gXAX, gXBX, check_finite=False)
+    ii = np.argsort(lam)[:m]
+    lam, V = lam[ii], np.asarray(V[:, ii])
+    ctx.bv_combine(BEST, [(BEST, V)])
+    return lam, ctx.bv_get(BEST)
 
 
 class ShardedCopyDistance(CopyDistance):
@@ -236,6 +440,14 @@ class ShardedCopyDistance(CopyDistance):
         if self._rows is not None:
             raise _lib.PhError("the Laplacian is sharded by rows: no host copy")
         return super().laplacian()
+
+    def bv_apply(self, src, dst):
+        if self._rows is None:
+            return super().bv_apply(src, dst)
+        lo, hi = self._rows
+        Yb = np.empty((max(hi - lo, 1), 3), np.float64)
+        _lib.check(self._L.ph_affinity_bv_apply(self._h, int(src), int(dst), _dptr(Yb)))
+        self.bv_set(dst, self._assemble(Yb[: hi - lo], self._k, lo, hi))
 
     def nearest(self, rows, donor_mask):
         """Rows are independent: every rank takes a slice of the list, the slices are assembled."""

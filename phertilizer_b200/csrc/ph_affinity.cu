@@ -41,12 +41,16 @@ struct ph_affinity {
   int32_t cap_rows;  // rows of the k x k matrices this context can hold (= cap, or the row block of a sharded context)
   int32_t row_lo, row_hi, use_copy, rows_mode;  // row block held after ph_affinity_build_rows (cells sharded across GPUs)
   double* d_ddf;     // [cap] full sqrt-degree vector (row-block mode)
+  double* d_bv;      // [kSlots][cap * kBW] block vectors of the device-resident eigensolver (ph_affinity_bv_*)
+  double* d_gram;    // [kGramChunks + 1][kGramMax] partial / final Gram entries
   cudaStream_t st;
 };
 
 namespace {
 
 constexpr int kMaxF = 8, kMaxCols = 8;
+constexpr int kSlots = 10, kBW = 3;              // block-vector slots of kBW columns each (LOBPCG block size 3)
+constexpr int kGramChunks = 256, kGramMax = 9 * 18;  // Gram: up to 3 x 6 slots, reduced in 256 row chunks
 
 // d(i,j) = sqrt(sum_f (x_if - x_jf)^2), multiply and add rounded separately like scipy's C loop
 __device__ __forceinline__ double feat_dist(const double* __restrict__ f, int F, int i, int j) {
@@ -298,6 +302,74 @@ __global__ void k_aff_laplacian_rect(double* __restrict__ W, int nr, int k, int 
   }
 }
 
+// ---- block-vector kernels of the device-resident eigensolver.  A slot is a k x 3 row-major array.
+struct BvList {
+  const double* p[6];
+  int n;
+};
+// G[(a, i), (b, j)] = sum_r L_a[r, i] * R_b[r, j]: per chunk of rows a fixed-order partial, then the chunks in order
+__global__ void __launch_bounds__(256) k_bv_gram_part(const BvList L, const BvList R, int k, double* __restrict__ part) {
+  const int nl = L.n * kBW, nr = R.n * kBW;
+  const int rows_per = (k + gridDim.x - 1) / gridDim.x;
+  const int r0 = blockIdx.x * rows_per, r1 = min(k, r0 + rows_per);
+  __shared__ double sh[8][kGramMax];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // every warp walks rows warp, warp + 8, ... of the chunk; lane = pair index (i, j) strided over the nl * nr entries
+  for (int e = lane; e < nl * nr; e += 32) {
+    const int i = e / nr, j = e - i * nr;
+    const double* lp = L.p[i / kBW] + (i % kBW);
+    const double* rp = R.p[j / kBW] + (j % kBW);
+    double acc = 0.0;
+    for (int r = r0 + warp; r < r1; r += 8) acc = fma(lp[(size_t)r * kBW], rp[(size_t)r * kBW], acc);
+    sh[warp][e] = acc;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < nl * nr; e += blockDim.x) {
+    double t = sh[0][e];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) t += sh[w][e];
+    part[(size_t)blockIdx.x * kGramMax + e] = t;
+  }
+}
+__global__ void k_bv_gram_final(const double* __restrict__ part, int chunks, int ne, double* __restrict__ out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= ne) return;
+  double t = 0.0;
+  for (int c = 0; c < chunks; ++c) t += part[(size_t)c * kGramMax + e];
+  out[e] = t;
+}
+// dst[r, :] = sum_t U_t[r, :] @ C_t   (C_t: 3 x 3 row-major, up to 4 terms; products and sums rounded separately, terms in
+// order: R = AX * I + X * (-diag(lambda)) is then the reference's  AX - X * lambda  bit for bit).  dst may alias a source.
+struct BvTerms {
+  const double* u[4];
+  double c[4][kBW * kBW];
+  int n;
+};
+__global__ void k_bv_combine(const BvTerms T, int k, double* __restrict__ dst) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= k) return;
+  double o[kBW] = {0.0, 0.0, 0.0};
+  bool first[kBW] = {true, true, true};
+  for (int t = 0; t < T.n; ++t) {
+    double x[kBW];
+#pragma unroll
+    for (int i = 0; i < kBW; ++i) x[i] = T.u[t][(size_t)r * kBW + i];
+#pragma unroll
+    for (int i = 0; i < kBW; ++i)
+#pragma unroll
+      for (int j = 0; j < kBW; ++j) {
+        const double c = T.c[t][i * kBW + j];
+        if (c != 0.0) {   // (selection / padding coefficients: an exact copy, and nothing added for the zeros)
+          const double pr = c == 1.0 ? x[i] : __dmul_rn(x[i], c);
+          o[j] = first[j] ? pr : __dadd_rn(o[j], pr);
+          first[j] = false;
+        }
+      }
+  }
+#pragma unroll
+  for (int j = 0; j < kBW; ++j) dst[(size_t)r * kBW + j] = o[j];
+}
+
 // rows == NULL: rows row0, row0+1, ...
 __global__ void k_gather_rows(const CopySrc src, const int32_t* __restrict__ rows, int row0, int nr,
                               double* __restrict__ out) {
@@ -386,7 +458,7 @@ extern "C" void ph_affinity_destroy(ph_affinity* a) {
   if (!a) return;
   cudaSetDevice(a->device);
   cudaFree(a->d_copy); cudaFree(a->d_emb); cudaFree(a->d_W); cudaFree(a->d_tmp); cudaFree(a->d_feat); cudaFree(a->d_dd); cudaFree(a->d_x);
-  cudaFree(a->d_y); cudaFree(a->d_cells); cudaFree(a->d_red); cudaFree(a->d_sort_tmp); cudaFree(a->d_ddf);
+  cudaFree(a->d_y); cudaFree(a->d_cells); cudaFree(a->d_red); cudaFree(a->d_sort_tmp); cudaFree(a->d_ddf); cudaFree(a->d_bv); cudaFree(a->d_gram);
   if (a->h_pin) cudaFreeHost(a->h_pin);
   if (a->st) cudaStreamDestroy(a->st);
   delete a;
@@ -432,6 +504,8 @@ int affinity_create(const double* embedding, int32_t n, int32_t D, int device, i
     PH_CUDA(cudaMalloc(&a->d_feat, (size_t)n * kMaxF * 8));
     PH_CUDA(cudaMalloc(&a->d_dd, (size_t)n * 8));
     PH_CUDA(cudaMalloc(&a->d_ddf, (size_t)n * 8));
+    PH_CUDA(cudaMalloc(&a->d_bv, (size_t)kSlots * n * kBW * 8));
+    PH_CUDA(cudaMalloc(&a->d_gram, (size_t)(kGramChunks + 1) * kGramMax * 8));
     PH_CUDA(cudaMalloc(&a->d_x, (size_t)n * kMaxCols * 8));
     PH_CUDA(cudaMalloc(&a->d_y, (size_t)n * kMaxCols * 8));
     PH_CUDA(cudaMalloc(&a->d_cells, (size_t)n * 4));
@@ -753,5 +827,117 @@ extern "C" int ph_affinity_matmat_rows(ph_affinity* a, const double* X, int32_t 
   }
   PH_CUDA(cudaStreamSynchronize(st));
   if (nrows > 0) memcpy(Y_block, a->h_pin + (size_t)k * kMaxCols, (size_t)nrows * c * 8);
+  return PH_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Device-resident block vectors for the eigensolver of the cut (phertilizer_b200/cluster.py device_lobpcg): the LOBPCG
+// iteration of sklearn's spectral_embedding (utils.py:131-150 -> scipy.sparse.linalg.lobpcg) works on a handful of k x 3
+// blocks (X, AX, R, AR, P, AP); keeping them here leaves only 3 x 3 ... 9 x 9 Gram matrices to cross the PCIe bus per
+// iteration instead of k x 3 operands and results of every product.  Slots 0 .. 9, each k x 3 row-major.
+// ------------------------------------------------------------------------------------------------
+namespace {
+int bv_check(ph_affinity* a, int slot) {
+  if (!a) PH_FAIL(PH_ERR_ARG, "null context");
+  if (a->k < 1) PH_FAIL(PH_ERR_ARG, "no Laplacian: build one first");
+  if (slot < 0 || slot >= kSlots) PH_FAIL(PH_ERR_ARG, "slot %d outside 0..%d", slot, kSlots - 1);
+  return PH_OK;
+}
+double* bv_ptr(ph_affinity* a, int slot) { return a->d_bv + (size_t)slot * a->cap * kBW; }
+}  // namespace
+
+extern "C" int ph_affinity_bv_set(ph_affinity* a, int slot, const double* host_k_by_3) {
+  int rc = bv_check(a, slot);
+  if (rc != PH_OK) return rc;
+  if (!host_k_by_3) PH_FAIL(PH_ERR_ARG, "null pointer");
+  PH_CUDA(cudaSetDevice(a->device));
+  memcpy(a->h_pin, host_k_by_3, (size_t)a->k * kBW * 8);
+  PH_CUDA(cudaMemcpyAsync(bv_ptr(a, slot), a->h_pin, (size_t)a->k * kBW * 8, cudaMemcpyHostToDevice, a->st));
+  PH_CUDA(cudaStreamSynchronize(a->st));
+  return PH_OK;
+}
+
+extern "C" int ph_affinity_bv_get(ph_affinity* a, int slot, double* host_k_by_3) {
+  int rc = bv_check(a, slot);
+  if (rc != PH_OK) return rc;
+  if (!host_k_by_3) PH_FAIL(PH_ERR_ARG, "null pointer");
+  PH_CUDA(cudaSetDevice(a->device));
+  PH_CUDA(cudaMemcpyAsync(a->h_pin, bv_ptr(a, slot), (size_t)a->k * kBW * 8, cudaMemcpyDeviceToHost, a->st));
+  PH_CUDA(cudaStreamSynchronize(a->st));
+  memcpy(host_k_by_3, a->h_pin, (size_t)a->k * kBW * 8);
+  return PH_OK;
+}
+
+// dst = L @ src on the device (whole Laplacian), or -- row-block contexts -- Y_block = L[row_lo:row_hi, :] @ src to the host
+// (the caller assembles the ranks' blocks and puts the result back with ph_affinity_bv_set)
+extern "C" int ph_affinity_bv_apply(ph_affinity* a, int src, int dst, double* host_block_or_null) {
+  int rc = bv_check(a, src);
+  if (rc == PH_OK && !a->rows_mode) rc = bv_check(a, dst);
+  if (rc != PH_OK) return rc;
+  PH_CUDA(cudaSetDevice(a->device));
+  cudaStream_t st = a->st;
+  const int k = a->k, nrows = a->rows_mode ? a->row_hi - a->row_lo : k;
+  if (a->rows_mode && !host_block_or_null) PH_FAIL(PH_ERR_ARG, "row-block context: pass the host buffer of the block");
+  double* out = a->rows_mode ? a->d_y : bv_ptr(a, dst);
+  if (nrows > 0) {
+    const int threads = 256, blocks = (nrows * 32 + threads - 1) / threads;
+    k_aff_matmat<kBW><<<blocks, threads, 0, st>>>(a->d_W, k, bv_ptr(a, src), out, nrows);
+    ph_count_launch();
+    PH_CUDA(cudaGetLastError());
+  }
+  if (a->rows_mode) {
+    if (nrows > 0) PH_CUDA(cudaMemcpyAsync(a->h_pin, out, (size_t)nrows * kBW * 8, cudaMemcpyDeviceToHost, st));
+    PH_CUDA(cudaStreamSynchronize(st));
+    if (nrows > 0) memcpy(host_block_or_null, a->h_pin, (size_t)nrows * kBW * 8);
+  }
+  return PH_OK;
+}
+
+// out[(a, i), (b, j)] = sum_r left_a[r, i] * right_b[r, j], row-major (3 nl) x (3 nr); nl <= 3, nr <= 6 slots
+extern "C" int ph_affinity_bv_gram(ph_affinity* a, const int32_t* left, int32_t nl, const int32_t* right, int32_t nr, double* out) {
+  if (!a || !left || !right || !out) PH_FAIL(PH_ERR_ARG, "null pointer");
+  if (a->k < 1) PH_FAIL(PH_ERR_ARG, "no Laplacian: build one first");
+  if (nl < 1 || nl > 3 || nr < 1 || nr > 6) PH_FAIL(PH_ERR_ARG, "nl=%d / nr=%d out of range", nl, nr);
+  BvList L, R;
+  L.n = nl;
+  R.n = nr;
+  for (int i = 0; i < nl; ++i) {
+    if (left[i] < 0 || left[i] >= kSlots) PH_FAIL(PH_ERR_ARG, "slot %d out of range", left[i]);
+    L.p[i] = bv_ptr(a, left[i]);
+  }
+  for (int i = 0; i < nr; ++i) {
+    if (right[i] < 0 || right[i] >= kSlots) PH_FAIL(PH_ERR_ARG, "slot %d out of range", right[i]);
+    R.p[i] = bv_ptr(a, right[i]);
+  }
+  PH_CUDA(cudaSetDevice(a->device));
+  cudaStream_t st = a->st;
+  const int ne = nl * kBW * nr * kBW;
+  const int chunks = a->k < 64 * kGramChunks ? (a->k + 63) / 64 : kGramChunks;   // a function of k only: fixed order
+  k_bv_gram_part<<<chunks, 256, 0, st>>>(L, R, a->k, a->d_gram + kGramMax);
+  k_bv_gram_final<<<1, 192, 0, st>>>(a->d_gram + kGramMax, chunks, ne, a->d_gram);
+  ph_count_launch(2);
+  PH_CUDA(cudaGetLastError());
+  PH_CUDA(cudaMemcpyAsync(a->h_pin, a->d_gram, (size_t)ne * 8, cudaMemcpyDeviceToHost, st));
+  PH_CUDA(cudaStreamSynchronize(st));
+  memcpy(out, a->h_pin, (size_t)ne * 8);
+  return PH_OK;
+}
+
+// dst = sum_t slot_t @ C_t  (C_t 3 x 3 row-major in coeffs[t * 9 ...]; 1 <= n_terms <= 4); dst may be one of the sources
+extern "C" int ph_affinity_bv_combine(ph_affinity* a, int dst, const int32_t* slots, const double* coeffs, int32_t n_terms) {
+  int rc = bv_check(a, dst);
+  if (rc != PH_OK) return rc;
+  if (!slots || !coeffs || n_terms < 1 || n_terms > 4) PH_FAIL(PH_ERR_ARG, "bad terms");
+  BvTerms T;
+  T.n = n_terms;
+  for (int t = 0; t < n_terms; ++t) {
+    if (slots[t] < 0 || slots[t] >= kSlots) PH_FAIL(PH_ERR_ARG, "slot %d out of range", slots[t]);
+    T.u[t] = bv_ptr(a, slots[t]);
+    for (int i = 0; i < kBW * kBW; ++i) T.c[t][i] = coeffs[t * kBW * kBW + i];
+  }
+  PH_CUDA(cudaSetDevice(a->device));
+  k_bv_combine<<<(a->k + 255) / 256, 256, 0, a->st>>>(T, a->k, bv_ptr(a, dst));
+  ph_count_launch();
+  PH_CUDA(cudaGetLastError());
   return PH_OK;
 }

@@ -45,6 +45,14 @@ dist_out = torch.empty(R * n, dtype=torch.float64, device=dev)
 ms = timeit(lambda: _lib.check(_lib.lib().ph_pairwise_dist(_ptr(e), n, D, 0, R, _ptr(dist_out), 0, 1, stream)), reps=5)
 out["K5"] = {"rows": R, "ms": ms, "write_gbs": R * n * 8 / (ms * 1e-3) / 1e9, "write_frac": R * n * 8 / (ms * 1e-3) / 1e9 / peak,
              "fp64_flops": 3.0 * R * n * D / (ms * 1e-3)}
+if D >= 32:   # the Gram form on the FP64 tensor cores (opt-in path) beside the direct kernel
+    sq = torch.empty(n, dtype=torch.float64, device=dev)
+    ref = dist_out[: R * n].clone()
+    ms = timeit(lambda: _lib.check(_lib.lib().ph_pairwise_dist_gram(_ptr(e), n, D, 0, R, _ptr(dist_out), _ptr(sq), 0, stream)), reps=5)
+    got = dist_out[: R * n]
+    nz = ref > 0
+    out["K5_gram_dmma"] = {"rows": R, "ms": ms, "pair_dims_per_s": R * n * D / (ms * 1e-3), "speedup_vs_direct": out["K5"]["ms"] / ms,
+                           "max_rel_diff_vs_direct": float(((got[nz] - ref[nz]).abs() / ref[nz]).max().item())}
 dense.close()
 if D <= 16:
     k = min(n, 60000)

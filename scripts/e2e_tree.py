@@ -76,9 +76,14 @@ for name in ("snv_table", "cell_table", "assign_linear", "assign_branching", "bl
 from phertilizer_b200.cluster import CopyDistance
 for mod in (LS, BS):
     timed(mod, "impute_mut_features", "host:impute_mut_features")
-timed(CopyDistance, "min_cut", "cluster:min_cut(total: GPU affinity + Laplacian, LOBPCG with GPU matmat)")
-timed(CopyDistance, "build", "gpu:affinity_build")
-timed(CopyDistance, "matmat", "gpu:laplacian_matmat")
+from phertilizer_b200.cluster import ShardedCopyDistance
+cd_cls = ShardedCopyDistance if world > 1 else CopyDistance
+timed(CopyDistance, "min_cut", "cluster:min_cut(total: GPU affinity + Laplacian, LOBPCG)")
+timed(cd_cls, "build", "gpu:affinity_build")
+timed(cd_cls, "matmat", "gpu:laplacian_matmat(host operands)")
+timed(cd_cls, "bv_apply", "gpu:laplacian_product(device-resident block)")
+timed(CopyDistance, "bv_gram", "gpu:lobpcg_gram")
+timed(CopyDistance, "bv_combine", "gpu:lobpcg_combine")
 timed(LS.Linear_split, "cluster_cells", "split:cluster_cells(total)")
 timed(BS.Branching_split, "cluster_cells", "split:cluster_cells(total)")
 timed(ClonalTree, "compute_likelihood", "tree:compute_likelihood(total)")
