@@ -133,9 +133,16 @@ class CopyDistance:
 
     def bv_combine(self, dst, terms):
         """slot dst = sum over (slot, C) in terms of slot @ C, C 3 x 3 (dst may be one of the sources)."""
-        slots = np.ascontiguousarray([t[0] for t in terms], dtype=np.int32)
-        coeffs = np.ascontiguousarray(np.stack([np.asarray(t[1], np.float64).reshape(3, 3) for t in terms]))
-        _lib.check(self._L.ph_affinity_bv_combine(self._h, int(dst), _dptr(slots), _dptr(coeffs), len(terms)))
+        buf = getattr(self, "_bv_buf", None)
+        if buf is None:   # reused marshalling buffers: this is called a dozen times per LOBPCG iteration
+            buf = self._bv_buf = (np.zeros(4, np.int32), np.zeros((4, 3, 3), np.float64))
+            self._bv_ptr = (_dptr(buf[0]), _dptr(buf[1]))
+        for t, (slot, Cm) in enumerate(terms):
+            buf[0][t] = slot
+            buf[1][t] = Cm
+        rc = self._L.ph_affinity_bv_combine(self._h, int(dst), self._bv_ptr[0], self._bv_ptr[1], len(terms))
+        if rc:
+            _lib.check(rc)
 
     def min_cut(self, cells, feats, use_copy_kernel, radius, strict, random_state):
         """Two-way normalised cut of `cells` -> labels (0/1 per cell), or None when the affinity contains NaN (the
@@ -223,7 +230,8 @@ def device_lobpcg(ctx, X0, maxiter=2000, restart_control=20):
     while it < maxiter:
         it += 1
         ctx.bv_combine(R, [(AX, I3), (X, -np.diag(lam))])          # R = AX - X * lambda
-        rn = np.sqrt(np.abs(np.diag(ctx.bv_gram([R], [R]))))
+        G0 = ctx.bv_gram([X, R], [R])                               # X^T R (used below) and R^T R in one reduction
+        rn = np.sqrt(np.abs(np.diag(G0[3:])))
         rnorm = np.sum(np.abs(rn)) / m
         if rnorm < smallest:
             smallest = rnorm
@@ -241,7 +249,7 @@ def device_lobpcg(ctx, X0, maxiter=2000, restart_control=20):
         if it > 0:
             ctx.bv_combine(P, [(P, S)])
             ctx.bv_combine(AP, [(AP, S)])
-        XR = ctx.bv_gram([X], [R])
+        XR = G0[:3] @ S                                                # X^T (R S): the selection only permutes / drops columns
         ctx.bv_combine(R, [(R, I3), (X, -XR)])                        # orthogonal to X
         if orthonormalize(R, ca) is None:
             break

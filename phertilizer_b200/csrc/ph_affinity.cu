@@ -50,7 +50,7 @@ namespace {
 
 constexpr int kMaxF = 8, kMaxCols = 8;
 constexpr int kSlots = 10, kBW = 3;              // block-vector slots of kBW columns each (LOBPCG block size 3)
-constexpr int kGramChunks = 256, kGramMax = 9 * 18;  // Gram: up to 3 x 6 slots, reduced in 256 row chunks
+constexpr int kGramChunks = 148, kGramMax = 9 * 18;  // Gram: up to 3 x 6 slots, reduced in up to 148 row chunks (one wave)
 
 // d(i,j) = sqrt(sum_f (x_if - x_jf)^2), multiply and add rounded separately like scipy's C loop
 __device__ __forceinline__ double feat_dist(const double* __restrict__ f, int F, int i, int j) {
@@ -307,15 +307,19 @@ struct BvList {
   const double* p[6];
   int n;
 };
-// G[(a, i), (b, j)] = sum_r L_a[r, i] * R_b[r, j]: per chunk of rows a fixed-order partial, then the chunks in order
-__global__ void __launch_bounds__(256) k_bv_gram_part(const BvList L, const BvList R, int k, double* __restrict__ part) {
-  const int nl = L.n * kBW, nr = R.n * kBW;
+// G[(a, i), (b, j)] = sum_r L_a[r, i] * R_b[r, j]: per chunk of rows a fixed-order partial; the CTA that finishes last
+// adds the chunks in order (a function of k only: deterministic) and stores the result straight into page-locked host
+// memory, so one launch and one stream synchronisation serve a Gram matrix.
+__global__ void __launch_bounds__(256) k_bv_gram(const BvList L, const BvList R, int k, double* __restrict__ part,
+                                                 unsigned* __restrict__ ticket, double* __restrict__ out_host) {
+  const int nl = L.n * kBW, nr = R.n * kBW, ne = nl * nr;
   const int rows_per = (k + gridDim.x - 1) / gridDim.x;
   const int r0 = blockIdx.x * rows_per, r1 = min(k, r0 + rows_per);
   __shared__ double sh[8][kGramMax];
+  __shared__ bool last;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // every warp walks rows warp, warp + 8, ... of the chunk; lane = pair index (i, j) strided over the nl * nr entries
-  for (int e = lane; e < nl * nr; e += 32) {
+  // every warp walks rows warp, warp + 8, ... of the chunk; lane = entry (i, j) strided over the nl * nr entries
+  for (int e = lane; e < ne; e += 32) {
     const int i = e / nr, j = e - i * nr;
     const double* lp = L.p[i / kBW] + (i % kBW);
     const double* rp = R.p[j / kBW] + (j % kBW);
@@ -324,19 +328,32 @@ __global__ void __launch_bounds__(256) k_bv_gram_part(const BvList L, const BvLi
     sh[warp][e] = acc;
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < nl * nr; e += blockDim.x) {
+  for (int e = threadIdx.x; e < ne; e += blockDim.x) {
     double t = sh[0][e];
 #pragma unroll
     for (int w = 1; w < 8; ++w) t += sh[w][e];
     part[(size_t)blockIdx.x * kGramMax + e] = t;
   }
-}
-__global__ void k_bv_gram_final(const double* __restrict__ part, int chunks, int ne, double* __restrict__ out) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= ne) return;
-  double t = 0.0;
-  for (int c = 0; c < chunks; ++c) t += part[(size_t)c * kGramMax + e];
-  out[e] = t;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  for (int e = threadIdx.x; e < ne; e += blockDim.x) {
+    double t = 0.0;
+    int c = 0;
+    for (; c + 8 <= (int)gridDim.x; c += 8) {   // eight independent loads in flight, added in chunk order
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldcg(part + (size_t)(c + u) * kGramMax + e);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) t += v[u];
+    }
+    for (; c < (int)gridDim.x; ++c) t += __ldcg(part + (size_t)c * kGramMax + e);
+    out_host[e] = t;
+  }
+  if (threadIdx.x == 0) *ticket = 0;
 }
 // dst[r, :] = sum_t U_t[r, :] @ C_t   (C_t: 3 x 3 row-major, up to 4 terms; products and sums rounded separately, terms in
 // order: R = AX * I + X * (-diag(lambda)) is then the reference's  AX - X * lambda  bit for bit).  dst may alias a source.
@@ -506,6 +523,7 @@ int affinity_create(const double* embedding, int32_t n, int32_t D, int device, i
     PH_CUDA(cudaMalloc(&a->d_ddf, (size_t)n * 8));
     PH_CUDA(cudaMalloc(&a->d_bv, (size_t)kSlots * n * kBW * 8));
     PH_CUDA(cudaMalloc(&a->d_gram, (size_t)(kGramChunks + 1) * kGramMax * 8));
+    PH_CUDA(cudaMemsetAsync(a->d_gram, 0, (size_t)kGramMax * 8, a->st));   // [0]: the completion ticket of k_bv_gram
     PH_CUDA(cudaMalloc(&a->d_x, (size_t)n * kMaxCols * 8));
     PH_CUDA(cudaMalloc(&a->d_y, (size_t)n * kMaxCols * 8));
     PH_CUDA(cudaMalloc(&a->d_cells, (size_t)n * 4));
@@ -912,13 +930,11 @@ extern "C" int ph_affinity_bv_gram(ph_affinity* a, const int32_t* left, int32_t 
   PH_CUDA(cudaSetDevice(a->device));
   cudaStream_t st = a->st;
   const int ne = nl * kBW * nr * kBW;
-  const int chunks = a->k < 64 * kGramChunks ? (a->k + 63) / 64 : kGramChunks;   // a function of k only: fixed order
-  k_bv_gram_part<<<chunks, 256, 0, st>>>(L, R, a->k, a->d_gram + kGramMax);
-  k_bv_gram_final<<<1, 192, 0, st>>>(a->d_gram + kGramMax, chunks, ne, a->d_gram);
-  ph_count_launch(2);
+  const int chunks = a->k < 128 * kGramChunks ? (a->k + 127) / 128 : kGramChunks;   // a function of k only: fixed order
+  k_bv_gram<<<chunks, 256, 0, st>>>(L, R, a->k, a->d_gram + kGramMax, reinterpret_cast<unsigned*>(a->d_gram), a->h_pin);
+  ph_count_launch();
   PH_CUDA(cudaGetLastError());
-  PH_CUDA(cudaMemcpyAsync(a->h_pin, a->d_gram, (size_t)ne * 8, cudaMemcpyDeviceToHost, st));
-  PH_CUDA(cudaStreamSynchronize(st));
+  PH_CUDA(cudaStreamSynchronize(st));   // the last CTA stored the matrix into the page-locked buffer itself
   memcpy(out, a->h_pin, (size_t)ne * 8);
   return PH_OK;
 }
