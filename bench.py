@@ -198,6 +198,39 @@ def extra_passes(st, w, info, peak, args):
     return out
 
 
+def e2e_tree_small():
+    """BASELINE.json's metric names a second quantity: end-to-end `phertilize()` wall time.  A live measurement that fits a
+    bench run: config 2 (10k cells x 50k SNVs, ~24 M observations), 3 starts x 10 iterations with post-processing, through the
+    public `Phertilizer` class.  The north-star shape C3 at 1 / 2 / 4 / 8 GPUs is measured by scripts/e2e_tree.py (minutes) and
+    committed under profiles/ (r2_e2e_tree.md)."""
+    import io
+    from contextlib import redirect_stdout
+
+    import torch
+
+    from phertilizer_b200.phertilizer import Phertilizer
+    from phertilizer_b200.synth import make_config, to_dataframes
+
+    try:
+        s = make_config("C2", device="cuda")
+        vc, bc = to_dataframes(s)
+        t0 = time.time()
+        ph = Phertilizer(vc, bc, mode="rd", dim_reduce=False)
+        torch.cuda.synchronize()
+        t_init = time.time() - t0
+        t0 = time.time()
+        with redirect_stdout(io.StringIO()):
+            tree, trees, _ = ph.phertilize(max_iterations=10, starts=3, seed=9905900, radius=1, gamma=0.95, d=10,
+                                           use_copy_kernel=True, post_process=True)
+        t_run = time.time() - t0
+        return {"config": "C2: 10000 cells x 50000 SNVs, coverage 0.05, 5 clones; -s 3 -j 10 --post_process --no-umap", "nnz": int(s.nnz),
+                "init_s": round(t_init, 2), "phertilize_s": round(t_run, 2), "tree_nodes": int(tree.tree.number_of_nodes()),
+                "candidate_trees": int(trees.size()), "norm_loglikelihood": float(tree.norm_loglikelihood),
+                "larger_shapes": "profiles/r2_e2e_tree.md (C3 at 1 / 2 / 4 / 8 GPUs, C4 at the CLI defaults)"}
+    except Exception as e:  # the tree is an extra: never take the bench line down with it
+        return {"error": str(e)[:300]}
+
+
 # ------------------------------------------------------------------------------------------------ arms
 def run_reference(args):
     """CPU arm: the sparse oracle port of the reference path (OpenMP, all host cores) on the same workload."""
@@ -638,7 +671,8 @@ def run_ours(args):
                          "physical_gbs": phys / (kernel_ms * 1e-3) / 1e9, "physical_frac": phys / (kernel_ms * 1e-3) / 1e9 / peak,
                          "peak_source": peak_src + ", of measured"},
             "cpu_baseline": cpu,
-            "extra": {"passes": extra_passes(st, w, info, peak, args) if world == 1 else None},
+            "extra": {"passes": extra_passes(st, w, info, peak, args) if world == 1 else None,
+                      "e2e_tree": e2e_tree_small() if (world == 1 and not args.no_tree) else None},
             "store": {k: info[k] for k in ("dense_codes_by_snv", "chunks_by_snv", "group_by_snv", "labels_in_smem_by_snv",
                                            "stream_bytes_by_snv", "stream4_bytes_by_snv", "device_bytes")},
         }
@@ -661,6 +695,7 @@ def main():
     ap.add_argument("--workload", default="C3")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU baseline budget (N=1 only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-tree", action="store_true", help="skip the small end-to-end tree (extra.e2e_tree)")
     ap.add_argument("--clock-seconds", type=float, default=1.0, help="untimed load stretch sampled for SM clocks")
     ap.add_argument("--no-cuda-graphs", dest="cuda_graphs", action="store_false",
                     help="launch every step eagerly instead of replaying a captured CUDA graph")

@@ -10,7 +10,7 @@ mkdir -p gpurun_out
 (timeout 900 python scripts/e2e_tree.py C3 --starts 3 --iterations 10 --quiet --out gpurun_out/r2f_e2e_C3_n1.json) > gpurun_out/r2f_e2e_C3_n1.log 2>&1
 (timeout 900 python scripts/e2e_tree.py C4 --starts 16 --iterations 50 --quiet --out gpurun_out/r2f_e2e_C4_defaults_n1.json) > gpurun_out/r2f_e2e_C4_n1.log 2>&1
 # ncu: launch list of the bench command, full capture of the K1 and K2 pass kernels and of the dense kernels
-(timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2f_launches.csv python bench.py --steps 5 --warmup 3 --no-cpu --clock-seconds 0 --no-cuda-graphs) > gpurun_out/r2f_ncu_l.log 2>&1
-(timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_pass -s 4 -c 2 -o gpurun_out/r2f_prof_k1 -f python bench.py --steps 5 --warmup 3 --no-cpu --clock-seconds 0 --no-cuda-graphs) > gpurun_out/r2f_ncu_k1.log 2>&1
+(timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2f_launches.csv python bench.py --steps 5 --warmup 3 --no-cpu --no-tree --clock-seconds 0 --no-cuda-graphs) > gpurun_out/r2f_ncu_l.log 2>&1
+(timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_pass -s 4 -c 2 -o gpurun_out/r2f_prof_k1 -f python bench.py --steps 5 --warmup 3 --no-cpu --no-tree --clock-seconds 0 --no-cuda-graphs) > gpurun_out/r2f_ncu_k1.log 2>&1
 (timeout 900 ncu --set full --clock-control none -k regex:"k_gauss|k_pdist|k_aff" -c 12 -o gpurun_out/r2f_prof_dense -f python scripts/dense_probe.py 20000 577) > gpurun_out/r2f_ncu_dense.log 2>&1
 for f in gpurun_out/r2f_*.log; do echo "== $f"; tail -n 3 $f | cut -c1-500; done
