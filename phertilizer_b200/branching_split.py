@@ -15,7 +15,7 @@ import pandas as pd
 
 from .clonal_tree import BranchingTree
 from .clonal_tree_list import ClonalTreeList
-from .utils import impute_mut_features, split_by_labels
+from .utils import impute_mut_features, setdiff1d, split_by_labels
 
 np.seterr(invalid="ignore", divide="ignore")
 
@@ -42,7 +42,7 @@ class Branching_split:
         draws = self.rng.random(arr.shape[0])
         arrA = arr[draws < 1 / 3]
         arrB = arr[draws > 2 / 3]
-        return arrA, arrB, np.setdiff1d(arr, np.concatenate([arrA, arrB]))
+        return arrA, arrB, setdiff1d(arr, np.concatenate([arrA, arrB]))
 
     def calc_tmb(self, cells, muts):
         t = self.store.cell_table(self.store.snv_labels(muts), 1, cells, want=("Nobs", "Nvar"))
@@ -83,8 +83,9 @@ class Branching_split:
         if np.quantile(nobs[:, 0], 0.75) < lim or np.quantile(nobs[:, 1], 0.75) < lim:
             return np.empty(shape=0, dtype=int), np.empty(shape=0, dtype=int), self.muts
         muts = np.asarray(self.muts)
-        # the reference appends to python lists and wraps them in np.array (dtype float64 when empty)
-        return tuple(np.array(list(muts[label == k])) for k in (1, 2, 3))
+        # the reference appends to python lists and wraps them in np.array: dtype float64 when a list stays empty
+        parts = (muts[label == k] for k in (1, 2, 3))
+        return tuple(part if len(part) else np.array([]) for part in parts)
 
     def check_metrics(self, ca, cb, ma, mb, mc):
         st = self.store
@@ -107,7 +108,7 @@ class Branching_split:
     def compute_norm_likelihood(self, cellsA, cellsB, mutsA, mutsB, mutsC):
         st = self.store
         mutsC = np.asarray(mutsC).astype(int)
-        rest = np.setdiff1d(self.cells, np.concatenate([cellsA, cellsB]))
+        rest = setdiff1d(self.cells, np.concatenate([cellsA, cellsB]))
         s0, s1, nobs, _ = st.block_sums(st.cell_labels(cellsA, cellsB, rest), 3, st.snv_labels(mutsA, mutsB, mutsC), 3)
         total_like = ((s1[2, 0] + s1[2, 1]) + s1[2, 2]) + s0[1, 0] + s0[0, 1]
         total = ((nobs[2, 0] + nobs[2, 1]) + nobs[2, 2]) + nobs[1, 0] + nobs[0, 1]

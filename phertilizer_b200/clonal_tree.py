@@ -13,7 +13,7 @@ from dataclasses import dataclass, field
 import networkx as nx
 import numpy as np
 
-from .utils import (dict_to_dataframe, generate_cell_dataframe, generate_mut_dataframe, get_next_label, pickle_save)
+from .utils import (setdiff1d, dict_to_dataframe, generate_cell_dataframe, generate_mut_dataframe, get_next_label, pickle_save)
 
 _NOT_IN_TREE = 255
 
@@ -522,14 +522,14 @@ class Seed:
         cells = np.asarray(self.cells)
         if len(muts) and len(cells):
             nv = store.snv_table(store.cell_labels(cells), 1, muts, want=("Nvar",))["Nvar"][:, 0]
-            self.muts = np.setdiff1d(muts, muts[nv == 0])
+            self.muts = setdiff1d(muts, muts[nv == 0])
         else:
-            self.muts = np.setdiff1d(muts, muts)
+            self.muts = setdiff1d(muts, muts)
         if len(self.muts) and len(cells):
             nc = store.cell_table(store.snv_labels(self.muts), 1, cells, want=("Nvar",))["Nvar"][:, 0]
-            self.cells = np.setdiff1d(cells, cells[nc == 0])
+            self.cells = setdiff1d(cells, cells[nc == 0])
         else:
-            self.cells = np.setdiff1d(cells, cells)
+            self.cells = setdiff1d(cells, cells)
 
     def count_obs(self, store):
         from .utils import check_obs

@@ -21,7 +21,7 @@ import pandas as pd
 
 from .clonal_tree import LinearTree
 from .clonal_tree_list import ClonalTreeList
-from .utils import check_obs, impute_mut_features, split_by_labels
+from .utils import check_obs, impute_mut_features, setdiff1d, split_by_labels
 
 np.seterr(invalid="ignore", divide="ignore")
 
@@ -54,7 +54,7 @@ class Linear_split:
         num_mutsA = int(np.floor(p * muts.shape[0]))
         if num_mutsA < np.count_nonzero(vaf_prob) and not np.any(np.isnan(vaf_prob)):
             mutsA = self.rng.choice(muts, size=num_mutsA, p=vaf_prob, replace=False)
-            return mutsA, np.setdiff1d(muts, mutsA)
+            return mutsA, setdiff1d(muts, mutsA)
         return self.random_init_array(muts, p)
 
     # ------------------------------------------------------------------ SNV step
@@ -63,7 +63,7 @@ class Linear_split:
         if np.quantile(nobs, 0.75) < self.params.nobs_per_cluster:
             return muts, None
         mutsB = muts[label == 2]
-        return np.setdiff1d(muts, mutsB), mutsB
+        return setdiff1d(muts, mutsB), mutsB
 
     # ------------------------------------------------------------------ cell step
     def create_affinity(self, cells, mutsB=None):
@@ -132,7 +132,7 @@ class Linear_split:
     def compute_norm_likelihood(self, cellsA, cellsB, mutsA, mutsB):
         """[sum like0(cellsA x mutsB) + sum like1(seed cells x mutsA)] / observed entries of the same blocks."""
         st = self.store
-        rest = np.setdiff1d(self.cells, cellsA)
+        rest = setdiff1d(self.cells, cellsA)
         s0, s1, nobs, _ = st.block_sums(st.cell_labels(cellsA, rest), 2, st.snv_labels(mutsA, mutsB), 2)
         total_like = s0[1, 0] + (s1[0, 0] + s1[0, 1])
         total = nobs[1, 0] + (nobs[0, 0] + nobs[0, 1])
@@ -161,8 +161,8 @@ class Linear_split:
                 oldA = cellsA
                 mutsA, mutsB = self.mut_assignment(cellsA, muts)
             if len(cellsA) > 0 and len(cellsB) > 0:
-                cellsB_tree = np.setdiff1d(self.cells, cellsA)
-                mutsB_tree = np.setdiff1d(self.muts, mutsA)
+                cellsB_tree = setdiff1d(self.cells, cellsA)
+                mutsB_tree = setdiff1d(self.muts, mutsA)
                 f1, f2, f3 = self.check_metrics(cellsA, cellsB_tree, mutsA, mutsB_tree)
                 if f1 <= self.params.low_cmb and f2 >= self.params.high_cmb and f3:
                     candidates.insert(LinearTree(cellsA, cellsB_tree, mutsA, mutsB_tree))

@@ -21,7 +21,7 @@ from .data import Data
 from .params import Params
 from .cluster import CopyDistance
 from .store import ObservationStore
-from .utils import check_obs, power_calc
+from .utils import check_obs, power_calc, setdiff1d
 
 
 def _factorize(col):
@@ -306,8 +306,8 @@ class Phertilizer:
             while idx >= 0:
                 nxt = tree_list.index_tree(idx)
                 cA, mA = nxt.get_tip_cells(0), nxt.get_tip_muts(0)
-                nxt.cell_mapping[0] = {0: np.setdiff1d(cA, ca_cells)}
-                nxt.mut_mapping[0] = np.setdiff1d(mA, ma_muts)
+                nxt.cell_mapping[0] = {0: setdiff1d(cA, ca_cells)}
+                nxt.mut_mapping[0] = setdiff1d(mA, ma_muts)
                 curr_seed.set_linear(nxt)
                 ca_cells, ma_muts = cA, mA
                 next_seeds = nxt.get_seeds()

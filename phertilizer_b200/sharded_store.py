@@ -113,10 +113,34 @@ class CellShardedStore:
         full[self.lo:self.hi] = block
         return self._sum(full)
 
+    def _combine_tables(self, tables, rows_local):
+        """ONE collective for a dict of per-line tables: they travel side by side in a float64 buffer (the integer counts
+        are far below 2^53: exact) and come back with their own dtypes.  rows_local: the tables are this rank's block of
+        cells (assembled by position) -- else per-SNV partial tables of all ranks (summed)."""
+        if self.world == 1 or not tables:
+            return tables
+        keys = list(tables)
+        cols = [np.asarray(tables[k]).reshape(len(tables[k]), -1) for k in keys]
+        width = [c.shape[1] for c in cols]
+        n_rows = self.n_cells if rows_local else cols[0].shape[0]
+        buf = np.zeros((n_rows, sum(width)), np.float64)
+        view = buf[self.lo:self.hi] if rows_local else buf
+        at = 0
+        for c, w in zip(cols, width):
+            view[:, at:at + w] = c
+            at += w
+        buf = self._sum(buf)
+        out, at = {}, 0
+        for k, c, w in zip(keys, cols, width):
+            part = buf[:, at:at + w]
+            out[k] = part.astype(c.dtype) if c.dtype.kind in "iu" else np.ascontiguousarray(part)
+            at += w
+        return out
+
     # ------------------------------------------------------------------ K1 family (per SNV, over cell clusters)
     def snv_table(self, cell_label, C_, snv_list=None, want=("S0", "S1", "Nobs", "Nvar")):
         t = self.local.snv_table(self._loc(cell_label), C_, snv_list, want=want)
-        return {k: self._sum(v) for k, v in t.items()}
+        return self._combine_tables(t, rows_local=False)
 
     def assign_linear(self, cell_label, lenA, snv_list=None):
         if self.k1 is None or self.world == 1:
@@ -131,7 +155,7 @@ class CellShardedStore:
     # ------------------------------------------------------------------ K2 family (per cell: owned by one rank)
     def cell_table(self, snv_label, Q, cell_list=None, want=("S0", "S1", "Nobs", "Nvar")):
         t = self.local.cell_table(snv_label, Q, None, want=want)
-        out = {k: self._assemble(v) for k, v in t.items()}
+        out = self._combine_tables(t, rows_local=True)
         if cell_list is not None:
             idx = np.asarray(cell_list, np.int64)
             out = {k: v[idx] for k, v in out.items()}
@@ -155,7 +179,7 @@ class CellShardedStore:
             s0, s1, no, nv = self.local.block_sums(self._loc(cl), C_, snv_label, Q)
             return self._sum(s0), self._sum(s1), self._sum(no), self._sum(nv)
         t = self.local.cell_table(snv_label, Q, None)
-        full = {k: self._assemble(v) for k, v in t.items()}
+        full = self._combine_tables(t, rows_local=True)
         return self.local.line_reduce(full["S0"], full["S1"], full["Nobs"], full["Nvar"], _padded(cl, self.n_cells), Q, C_)
 
     def tree_loglik(self, cell_node, snv_node, present, per_cell=False):

@@ -147,3 +147,22 @@ def dict_to_dataframe(event_mapping):
     df.columns = [f"node_{n}" for n in list(event_mapping.keys())]
     df.index.rename("bin", inplace=True)
     return df
+
+
+def setdiff1d(ar1, ar2):
+    """`np.setdiff1d(ar1, ar2)` -- sorted unique values of ar1 that are not in ar2 -- for the tree's index arrays.
+
+    numpy sorts / hashes both arguments (3 ms per call on 1e5 indices, 9 s of a C3 tree); cell and SNV index sets are
+    non-negative integers drawn from a dense range, so a mark array gives the same result in one linear pass.  Anything else
+    (floats, negative values, sparse ranges) goes to numpy."""
+    a, b = np.asarray(ar1), np.asarray(ar2)
+    if a.dtype.kind in "iu" and a.size and (b.size == 0 or b.dtype.kind in "iu"):
+        lo = int(a.min()) if b.size == 0 else min(int(a.min()), int(b.min()))
+        hi = int(a.max()) if b.size == 0 else max(int(a.max()), int(b.max()))
+        if lo >= 0 and hi < 4 * (a.size + b.size) + 4096:
+            mark = np.zeros(hi + 1, dtype=bool)
+            mark[a] = True
+            if b.size:
+                mark[b] = False
+            return np.flatnonzero(mark).astype(a.dtype, copy=False)
+    return np.setdiff1d(ar1, ar2)
