@@ -309,6 +309,28 @@ __global__ void k_perm_pos(const int32_t* __restrict__ order, int n, int n_pad, 
     perm4[i] = -1;
   }
 }
+// Batches in the order the pass hands them out: longest first.  The dispenser of k_pass counts up, so the last batches
+// drawn -- the ones whose length decides how long the other warps of the grid wait at the end -- are the shortest
+// (longest-processing-time-first scheduling).  key[b] = ~(warp steps of batch b): an ascending sort puts the longest first.
+__global__ void k_batch_len_key(const uint32_t* __restrict__ steps, int n_batches, int NSUB, uint32_t* __restrict__ key,
+                                int32_t* __restrict__ id) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n_batches) return;
+  uint32_t t = 0;
+  for (int q = 0; q < NSUB; ++q) t += steps[(int64_t)b * NSUB + q];
+  key[b] = ~t;
+  id[b] = b;
+}
+// perm4 / pos4 with whole batches (blocks of 8 consecutive lines of `order`) permuted by `border`
+__global__ void k_perm_blocks(const int32_t* __restrict__ order, int n, const int32_t* __restrict__ border, int n_batches,
+                              int32_t* __restrict__ perm4, int32_t* __restrict__ pos4) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_batches * 8) return;
+  const int src = border[i >> 3] * 8 + (i & 7);
+  const int line = src < n ? order[src] : -1;
+  perm4[i] = line;
+  if (line >= 0) pos4[line] = i;
+}
 // warp steps of every (batch, sub-segment): the longest of the batch's 8 lines, 4 groups per step
 __global__ void k_batch_steps(const int64_t* __restrict__ groups, const int32_t* __restrict__ perm4, int n_batches, int NSUB,
                               uint32_t* __restrict__ steps) {
@@ -443,6 +465,35 @@ int build_orient(ph_handle* h, PhOrient* o, const int32_t* d_major, const int32_
         PH_CUDA(cudaMalloc(&d_steps, (size_t)(nbs + 1) * 4));
         PH_CUDA(cudaMemset(d_steps, 0, (size_t)(nbs + 1) * 4));
         k_batch_steps<<<(unsigned)((nbs + threads - 1) / threads), threads>>>(d_groups, o->perm4, nb4, NSUB, d_steps);
+        if (h->lpt_order && nb4 > 1) {
+          // hand the batches out longest first: sort them by their step count, permute whole batches, recount
+          uint32_t *d_bk = nullptr, *d_bk2 = nullptr;
+          int32_t *d_bi = nullptr, *d_bi2 = nullptr;
+          auto lpt = [&]() -> int {
+            PH_CUDA(cudaMalloc(&d_bk, (size_t)nb4 * 4));
+            PH_CUDA(cudaMalloc(&d_bk2, (size_t)nb4 * 4));
+            PH_CUDA(cudaMalloc(&d_bi, (size_t)nb4 * 4));
+            PH_CUDA(cudaMalloc(&d_bi2, (size_t)nb4 * 4));
+            k_batch_len_key<<<(unsigned)((nb4 + threads - 1) / threads), threads>>>(d_steps, nb4, NSUB, d_bk, d_bi);
+            cub::DoubleBuffer<uint32_t> kb(d_bk, d_bk2);
+            cub::DoubleBuffer<int32_t> vb(d_bi, d_bi2);
+            size_t need = 0;
+            PH_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need, kb, vb, nb4, 0, 32));
+            if (need > temp_bytes) PH_FAIL(PH_ERR_CUDA, "sort scratch too small");
+            PH_CUDA(cub::DeviceRadixSort::SortPairs(d_temp, need, kb, vb, nb4, 0, 32));  // stable: ties keep the shape order
+            k_perm_blocks<<<(unsigned)((nb4 * 8 + threads - 1) / threads), threads>>>(d_ord, n_major, vb.Current(), nb4, o->perm4, d_pos4);
+            PH_CUDA(cudaMemset(d_steps, 0, (size_t)(nbs + 1) * 4));
+            k_batch_steps<<<(unsigned)((nbs + threads - 1) / threads), threads>>>(d_groups, o->perm4, nb4, NSUB, d_steps);
+            ph_count_launch(4);
+            return PH_OK;
+          };
+          const int rcl = lpt();
+          cudaFree(d_bk);
+          cudaFree(d_bk2);
+          cudaFree(d_bi);
+          cudaFree(d_bi2);
+          if (rcl != PH_OK) return rcl;
+        }
         PH_CUDA(cudaMalloc(&o->bstep_off, (size_t)(nbs + 1) * 4));
         size_t need = 0;
         PH_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, need, d_steps, o->bstep_off, (int)(nbs + 1)));
@@ -457,6 +508,12 @@ int build_orient(ph_handle* h, PhOrient* o, const int32_t* d_major, const int32_
         PH_CUDA(cudaMalloc(&o->half4, bytes4));
         PH_CUDA(cudaMemset(o->half4, 0, bytes4));
         h->device_bytes += (int64_t)bytes4 + (nbs + 1) * 4 + (int64_t)nb4 * 32;
+        const size_t acc_bytes = (size_t)nb4 * 8 * D * PH_MAX_FAST_CLUSTERS * 4;
+        PH_CUDA(cudaMalloc(&o->part_acc, acc_bytes));
+        PH_CUDA(cudaMemset(o->part_acc, 0, acc_bytes));
+        PH_CUDA(cudaMalloc(&o->part_tick, (size_t)nb4 * 4));
+        PH_CUDA(cudaMemset(o->part_tick, 0, (size_t)nb4 * 4));
+        h->device_bytes += (int64_t)acc_bytes + (int64_t)nb4 * 4;
         return PH_OK;
       };
       const int rc4 = sub();
@@ -537,6 +594,8 @@ extern "C" void ph_destroy(ph_handle* h) {
     cudaFree(o->half4);
     cudaFree(o->bstep_off);
     cudaFree(o->perm4);
+    cudaFree(o->part_acc);
+    cudaFree(o->part_tick);
   }
   cudaFree(h->d_lab_img);
   cudaFree(h->d_emb);
@@ -613,6 +672,18 @@ extern "C" int ph_create(int32_t n_cells, int32_t n_snvs, int64_t nnz, const int
     }
     e = getenv("PH_PHASE_CHUNKS");  // test knob: walk label images of more chunks than this in phases (ph_pass.cu launch_pass)
     h->phase_chunks = e ? atoi(e) : 0;
+    e = getenv("PH_LPT_ORDER");  // batched-4 copy: batches laid out (= handed out) longest first (default on)
+    h->lpt_order = e ? atoi(e) : 1;
+    // split tail of the batched-4 pass (ph_pass.cu PassArgs): parts per batch = 2^PH_SPLIT_SH (0 = off), over the last
+    // PH_SPLIT_TAIL percent of (warps of the grid) batches
+    e = getenv("PH_SPLIT_SH");
+    h->split_sh = e ? atoi(e) : 0;  // off: measured slower wherever it was tried -- the fence + ticket
+                                     // round trips of a part cost more than the shorter end of the pass returns
+    if (h->split_sh < 0 || h->split_sh > 4) h->split_sh = 0;
+    e = getenv("PH_SPLIT_TAIL");
+    h->split_tail = e ? atoi(e) : 150;
+    e = getenv("PH_ITEM_BATCHES");  // batched-4 pass: 8-line batches per item -- 0 = automatic, 1 / 2 / 4 = forced
+    h->item_batches = e ? atoi(e) : 0;
     e = getenv("PH_BATCH4");  // keep the batched-4 copy of the dense streams and use the 4-lanes-per-line pass (default on)
     h->batch4 = e ? atoi(e) : 1;
   }

@@ -71,6 +71,8 @@ struct PhOrient {
   uint16_t* half4;       // [n_steps4 * 32 * PH_GE] or null
   uint32_t* bstep_off;   // [n_batches4 * NSUB + 1] first warp step of every (batch, sub-segment)
   int32_t* perm4;        // [n_batches4 * 8] line of every batch slot, -1 = none
+  uint32_t* part_acc;    // [n_batches4 * 8 * D * PH_MAX_FAST_CLUSTERS] split-tail counters (ph_pass.cu PassArgs), zero at rest
+  unsigned* part_tick;   // [n_batches4] split-tail tickets, zero at rest
   int64_t n_steps4;
   int32_t n_batches4;
 };
@@ -91,7 +93,7 @@ struct ph_handle {
   double* d_L1;      // [n_codes]
   uint8_t* d_varpos; // [n_codes]
   int64_t device_bytes;
-  int chunk_bits, bank_order, ctas_per_sm, aligned_image, zero_copy_out, batch4, round_fill, phase_chunks;
+  int chunk_bits, bank_order, ctas_per_sm, aligned_image, zero_copy_out, batch4, round_fill, phase_chunks, lpt_order, split_sh, split_tail, item_batches;
   double dense_min_avg, dense_min_share;  // a (var,total) code gets its own segment when it has >= this many entries per line on average
   // scratch (device)
   uint8_t* d_lab_minor;  // [max(n,m)] staged labels of the minor axis

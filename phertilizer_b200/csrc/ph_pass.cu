@@ -32,6 +32,15 @@ struct PassArgs {
   // `partial` and the last phase finishes the lines (rare-code tail included, its labels gathered from global memory).
   int ch_lo, ch_n, phased, phase_first, phase_last;
   uint32_t* partial;  // [n_lines * D * NC]
+  // Split tail (batched-4 stream, one phase): the dispenser hands out batches [0, split_from) whole and every later batch
+  // in 2^split_sh parts (equal ranges of its warp steps), each part to whichever warp draws it.  A part adds its integer
+  // (line, code, cluster) counters to the batch's row of `part_acc` (integer atomics: exact, order-free) and takes a
+  // ticket; the warp holding the last ticket reads the row back (re-arming it) and finishes the batch's lines.  Nobody
+  // waits.  It shortens the end of the pass, where warps run out of work one whole batch apart: the last items are
+  // a quarter of a batch long.
+  int n_items, split_from, split_sh;
+  uint32_t* part_acc;   // [(n_batches - split_from) * 8 * D * NC], zero between launches
+  unsigned* part_tick;  // [n_batches - split_from], zero between launches
   const uint16_t* __restrict__ half4;     // LAY = 3: the batched-4 copy of the stream (PhOrient)
   const uint32_t* __restrict__ bstep_off;
   const uint8_t* __restrict__ minor_label;  // raw labels [n_minor] (SMEM_LAB) or the prepared label image (global)
@@ -118,14 +127,25 @@ __device__ __forceinline__ void fill_label_image(uint8_t* img, const uint8_t* __
     // whole 16-byte units of an aligned source go through 128-bit loads and stores (4x fewer round trips on the
     // start-up path of every CTA); the rest, and unaligned sources, word by word
     const int nv = (reinterpret_cast<uintptr_t>(srcb) & 15) == 0 ? (cnt >> 4) : 0;
-    for (int i = tid; i < nv; i += nthreads) {
-      const uint4 w = __ldg(reinterpret_cast<const uint4*>(srcb) + i);
-      uint4 o;
-      o.x = NODES ? clamp_nodes4(w.x, (uint32_t)K) : scale_labels4<NC>(w.x);
-      o.y = NODES ? clamp_nodes4(w.y, (uint32_t)K) : scale_labels4<NC>(w.y);
-      o.z = NODES ? clamp_nodes4(w.z, (uint32_t)K) : scale_labels4<NC>(w.z);
-      o.w = NODES ? clamp_nodes4(w.w, (uint32_t)K) : scale_labels4<NC>(w.w);
-      reinterpret_cast<uint4*>(dst + PW)[i] = o;
+#ifndef PH_STAGE_UNROLL
+#define PH_STAGE_UNROLL 4   // 16-byte loads of the staging loop in flight per thread (one L2 round trip for 4 units)
+#endif
+    constexpr int SU = PH_STAGE_UNROLL;
+    for (int i0 = tid; i0 < nv; i0 += SU * nthreads) {
+      uint4 w[SU];
+#pragma unroll
+      for (int u = 0; u < SU; ++u)
+        if (i0 + u * nthreads < nv) w[u] = __ldg(reinterpret_cast<const uint4*>(srcb) + i0 + u * nthreads);
+#pragma unroll
+      for (int u = 0; u < SU; ++u) {
+        if (i0 + u * nthreads >= nv) break;
+        uint4 o;
+        o.x = NODES ? clamp_nodes4(w[u].x, (uint32_t)K) : scale_labels4<NC>(w[u].x);
+        o.y = NODES ? clamp_nodes4(w[u].y, (uint32_t)K) : scale_labels4<NC>(w[u].y);
+        o.z = NODES ? clamp_nodes4(w[u].z, (uint32_t)K) : scale_labels4<NC>(w[u].z);
+        o.w = NODES ? clamp_nodes4(w[u].w, (uint32_t)K) : scale_labels4<NC>(w[u].w);
+        reinterpret_cast<uint4*>(dst + PW)[i0 + u * nthreads] = o;
+      }
     }
     for (int i = 4 * nv + tid; i < nw; i += nthreads) {
       const uint32_t w = src[i];
@@ -134,10 +154,46 @@ __device__ __forceinline__ void fill_label_image(uint8_t* img, const uint8_t* __
   }
 }
 
-// per-warp shared-memory words: sub-segment bounds [B][NSUB+1], counters [B][D][NC], line ids [B], line labels [B]
-__host__ __device__ inline int warp_words(int B, int NSUB, int D, int NC) {
-  return (B * (NSUB + 1) + B * D * NC + 2 * B + 3) & ~3;
+// per-warp shared-memory words: sub-segment bounds [B][NSUB+1], counters [B][D][NC], line ids [B], line labels [B].
+// b4 (batched-4 stream): the bounds are the step offsets of the item's B / 8 batches, (B / 8) NSUB + 1 words (two tables
+// of NSUB + 1 for the PH_PIPE build) -- what lets 16-line items fit next to a 200 KB label image.
+__host__ __device__ inline int warp_words(int B, int NSUB, int D, int NC, bool b4 = false) {
+  int bounds = B * (NSUB + 1);
+  if (b4) {
+    bounds = (B >= 8 ? B / 8 : 1) * NSUB + 1;
+    if (bounds < 2 * (NSUB + 1)) bounds = 2 * (NSUB + 1);
+  }
+  return (bounds + B * D * NC + 2 * B + 3) & ~3;
 }
+
+#ifdef PH_STAMPS
+// Timeline probe (variant builds only, scripts/probe_stamps.py): per CTA [entry, image staged, last warp left the
+// streaming loop, last warp left the kernel] in globaltimer nanoseconds, plus the batches its warps drew.
+__device__ unsigned long long g_stamps[256 * 8];
+__device__ __forceinline__ unsigned long long stamp_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define PH_STAMP_SET(i) do { if (threadIdx.x == 0 && blockIdx.x < 256) g_stamps[blockIdx.x * 8 + (i)] = stamp_now(); } while (0)
+#define PH_STAMP_MAX(i) do { if ((threadIdx.x & 31) == 0 && blockIdx.x < 256) atomicMax(&g_stamps[blockIdx.x * 8 + (i)], stamp_now()); } while (0)
+#define PH_STAMP_ADD(i, v) do { if ((threadIdx.x & 31) == 0 && blockIdx.x < 256) atomicAdd(&g_stamps[blockIdx.x * 8 + (i)], (unsigned long long)(v)); } while (0)
+#define PH_STAMP_T(var) const unsigned long long var = stamp_now()
+extern "C" __attribute__((visibility("default"))) int ph_debug_stamps(unsigned long long* out, int clear) {
+  cudaDeviceSynchronize();
+  if (out && cudaMemcpyFromSymbol(out, g_stamps, sizeof(g_stamps)) != cudaSuccess) return 1;
+  if (clear) {
+    static unsigned long long zeros[256 * 8];
+    if (cudaMemcpyToSymbol(g_stamps, zeros, sizeof(zeros)) != cudaSuccess) return 1;
+  }
+  return 0;
+}
+#else
+#define PH_STAMP_SET(i) do { } while (0)
+#define PH_STAMP_MAX(i) do { } while (0)
+#define PH_STAMP_ADD(i, v) do { } while (0)
+#define PH_STAMP_T(var) do { } while (0)
+#endif
 
 // One warp walks a batch of B lines handed out by an atomic counter.  After the streaming phase lane (l % B) finishes
 // line l alone ("holder"): rare-code tail, fp64 sums, epilogue, store.
@@ -148,6 +204,17 @@ __host__ __device__ inline int warp_words(int B, int NSUB, int D, int NC) {
 // the stream (PhOrient::half4): four lanes stream one line of the batch, sub-segment boundaries are warp-uniform.
 // 4: the batched-4 copy with the image wherever it fits (as 1: one base add per observation) -- minor axes whose image
 // leaves no room for the 64 KB alignment (K2 on 200 k SNVs: a 200 KB image).  5 / 6: as 3 / 4, in phases (PassArgs).
+#ifndef PH_RING4
+#define PH_RING4 4
+#endif
+#ifndef PH_PIPE
+#define PH_PIPE 0   // 1: prime the next batch's ring before the holders of the current one.  Measured on C3 (same box,
+                    // scripts/probe_r2.py): 168.7 us against 166.7 us for the plain order -- the ring's registers stay live
+                    // across the holders and the compiler gives that back in the streaming loop.  Kept as a switch.
+#endif
+#ifndef PH_TAIL4
+#define PH_TAIL4 0  // 1: rare-code tail four words per round trip.  Measured: 172.7 us against 166.7 us (same reason).
+#endif
 template <int B, int MODE, int NC, bool SMEM_LAB, int LAY>
 __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -157,6 +224,13 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
   constexpr bool PHASED = LAY >= 5;   // 5 / 6 = 3 / 4 walking the label image in phases (a compile-time switch: the
                                       // plain pass is at the 64-register cap and pays for every extra live value)
   constexpr bool PUSHABLE = MODE == MODE_LINEAR || MODE == MODE_BRANCHING;
+  constexpr bool SPLIT = B4 && !PHASED && MODE != MODE_COUNTS && !(PH_PIPE) && B == 8;  // split tail (PassArgs)
+  // batched-4 stream: an item is NB8 consecutive 8-line batches of the stream -- ONE run of warp steps over NB8 * NSUB
+  // sub-segments -- and the B = 8 * NB8 holder lanes finish its lines together.  The per-item code outside the streaming
+  // loop (about 900 SASS instructions: list / offset loads, rare-code tails, fp64 folds and divisions, stores) is issued
+  // once per item whatever B is, and a warp streams nothing meanwhile: 5.8 of 26.8 us per 8-line batch on C3.
+  constexpr int NB8 = B4 ? (B >= 8 ? B / 8 : 1) : 1;
+  static_assert(!B4 || B == 8 || (B % 8 == 0 && !PHASED && !(PH_PIPE)), "batched-4 items are whole 8-line batches");
   const int nthreads = blockDim.x;
   const int D = a.D, NCH = a.NCH, NSUB = a.NSUB, NS1 = NSUB + 1, cb = a.chunk_bits;
   const int K2 = a.K + 2;
@@ -173,15 +247,17 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
   double* s_L1 = s_L0 + (a.lut_in_smem ? a.n_codes : 0);
   uint8_t* s_vp = reinterpret_cast<uint8_t*>(s_L1 + (a.lut_in_smem ? a.n_codes : 0));
   if (a.lut_in_smem) off += ((size_t)a.n_codes * 17 + 15) & ~(size_t)15;
-  const int wsz = warp_words(B, NSUB, D, NC) + a.row_words;  // both terms are multiples of 4 words
+  const int wsz = warp_words(B, NSUB, D, NC, B4) + a.row_words;  // both terms are multiples of 4 words
   uint32_t* s_tab0 = reinterpret_cast<uint32_t*>(smem + off);  // start of the per-warp tables
   uint32_t* s_row32 = s_tab0 + (threadIdx.x >> 5) * wsz;
   uint16_t* s_row = reinterpret_cast<uint16_t*>(s_row32);  // COUNTS: [B][NC][ncp] histogram rows of the batch
   uint32_t* s_b = s_row32 + a.row_words;
-  uint32_t* s_cnt = s_b + B * NS1;
+  const int n_bounds = B4 ? max((B >= 8 ? B / 8 : 1) * NSUB + 1, 2 * NS1) : B * NS1;  // as warp_words()
+  uint32_t* s_cnt = s_b + n_bounds;
   int32_t* s_ln = reinterpret_cast<int32_t*>(s_cnt + B * D * NC);
   uint32_t* s_ml = reinterpret_cast<uint32_t*>(s_ln + B);
 
+  PH_STAMP_SET(0);
   unsigned bidx0 = 0;
   if ((threadIdx.x & 31) == 0) bidx0 = atomicAdd(a.counter, 1u);  // first batch of this warp, consumed after the staging
   if (SMEM_LAB)
@@ -206,6 +282,7 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
     }
   }
   __syncthreads();
+  PH_STAMP_SET(1);
   const double* L0 = a.lut_in_smem ? s_L0 : a.L0;
   const double* L1 = a.lut_in_smem ? s_L1 : a.L1;
   const uint8_t* VP = a.lut_in_smem ? s_vp : a.varpos;
@@ -216,11 +293,13 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
   const int lane = threadIdx.x & 31;
   const uint32_t mmask = (a.minor_bits >= 32) ? 0xffffffffu : ((1u << a.minor_bits) - 1u);
   const int n_batches = (a.n_work + B - 1) / B;
+  const unsigned n_items = SPLIT ? (unsigned)a.n_items : (unsigned)n_batches;  // dispenser range
 
   const uint32_t epoch = a.epoch_ptr ? *a.epoch_ptr + 1u : 0u;  // this step (peer modes)
   const int par = (int)(epoch & 1u);
   const uint32_t magic_nch = (65536u + (uint32_t)NCH - 1u) / (uint32_t)NCH;      // exact k / NCH for k < 256 * 32 / NCH
   const uint32_t magic_d = D > 0 ? (65536u + (uint32_t)D - 1u) / (uint32_t)D : 0u;  // exact key / D
+  const uint32_t magic_nsub = NSUB > 0 ? (65536u + (uint32_t)NSUB - 1u) / (uint32_t)NSUB : 0u;  // exact q / NSUB (q < 4 NSUB)
 
   auto label_at = [&](uint32_t addr) -> uint32_t {  // addr = offset into the label image
     return SMEM_LAB ? (uint32_t)lab[addr] : (uint32_t)__ldg(lab + addr);
@@ -240,17 +319,6 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
   // batched-4 stream: ring of RD 16-byte loads per lane in flight (RD * 512 B per warp).  The ring of the NEXT batch is
   // primed before the holders finish the current one (`primed`), so the tail / fp64 / store phase of a batch overlaps the
   // first loads of its successor instead of leaving the warp without a byte in flight.
-#ifndef PH_RING4
-#define PH_RING4 4
-#endif
-#ifndef PH_PIPE
-#define PH_PIPE 0   // 1: prime the next batch's ring before the holders of the current one.  Measured on C3 (same box,
-                    // scripts/probe_r2.py): 168.7 us against 166.7 us for the plain order -- the ring's registers stay live
-                    // across the holders and the compiler gives that back in the streaming loop.  Kept as a switch.
-#endif
-#ifndef PH_TAIL4
-#define PH_TAIL4 0  // 1: rare-code tail four words per round trip.  Measured: 172.7 us against 166.7 us (same reason).
-#endif
   constexpr int RD = PH_RING4;
   uint4 ring[B4 ? RD : 1];
   bool primed = false;
@@ -259,8 +327,18 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
     // the warp that drew the first batch announces how many slots this rank fills in this step
     st_relaxed_sys_u64(a.ll.hdr_dst[lane] + par * PH_MAX_PEERS, ((uint64_t)epoch << 32) | (uint32_t)(n_batches * B));
   }
-  while (bidx < (unsigned)n_batches) {
-    const int first = (int)bidx * B;
+  while (bidx < n_items) {
+    PH_STAMP_T(t_top);
+    unsigned bat = bidx;          // batch of this item
+    uint32_t part = 0;            // split tail: which of the batch's parts
+    bool split = false;
+    if (SPLIT && bidx >= (unsigned)a.split_from) {
+      const unsigned r = bidx - (unsigned)a.split_from;
+      bat = (unsigned)a.split_from + (r >> a.split_sh);
+      part = r & ((1u << a.split_sh) - 1u);
+      split = true;
+    }
+    const int first = (int)bat * B;
     const int nl = min(B, a.n_work - first);
 
     // ---- my line (lane % B): holder duties after the streaming phase
@@ -290,8 +368,9 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
     if (lane < B && have) {
       h_tb = __ldg(a.tail_off + line);
       h_te = __ldg(a.tail_off + line + 1);
-      for (int64_t r = h_tb; r < h_te; r += 32)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.tail_words + r));
+      if (part == 0)
+        for (int64_t r = h_tb; r < h_te; r += 32)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(a.tail_words + r));
     }
     for (int k = lane; k < B * D * NC; k += 32) s_cnt[k] = 0;
     if (MODE == MODE_COUNTS)
@@ -301,8 +380,13 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
     uint32_t* s_e = s_b + (B4 ? ebuf * NS1 : 0);
     uint32_t* s_start = s_b + B * NSUB;
     if (B4 && !primed) {
-      // batched-4 copy: s_e[q] = first warp step of sub-segment q of this batch, s_e[NSUB] = end of the batch
-      for (int k = lane; k <= NSUB; k += 32) s_e[k] = __ldg(a.bstep_off + (size_t)bidx * NSUB + k);
+      // batched-4 copy: s_e[q] = first warp step of sub-segment q of this item (NB8 batches in a row), s_e[NB8 * NSUB] =
+      // its end; past the last batch of the stream every bound is the end of the stream (empty sub-segments)
+      const size_t nbs = (size_t)(a.n_work >> 3) * NSUB;
+      for (int k = lane; k <= NB8 * NSUB; k += 32) {
+        const size_t at = (size_t)bat * (NB8 * NSUB) + k;
+        s_e[k] = __ldg(a.bstep_off + (NB8 > 1 && at > nbs ? nbs : at));
+      }
     }
     for (int k = lane; k < (B4 ? 0 : B * NSUB); k += 32) {
       const int l = k / NSUB, s = k - l * NSUB;
@@ -314,12 +398,14 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
 
     unsigned bnext = 0;
     bool drawn = false;
+    PH_STAMP_T(t_stream);
     // ---- dense part, batched-4 copy: the batch is one contiguous run of warp steps; lane (a, c) = (lane / 4, lane % 4)
     // reads group 4 t + c of line a at step t.  Everything about sub-segments is warp-uniform: q, the chunk base, the
     // flush points.  A lane's packed counters are summed over the 4 lanes of its line and added to the line's
     // (code, cluster) counter by one of them -- no MATCH / REDUX / atomics.
     if (B4 && NSUB > 0) {
-      const int la = lane >> 2;  // my line of the batch
+      const int la = lane >> 2;  // my line of the (current) batch
+      int cur_sb = 0;            // NB8 > 1: which batch of the item the run is in
       // a full pass is ONE run of steps over all sub-segments; a phase walks, per dense code, the run of its chunks
       constexpr bool phased = PHASED;
       const int ch_lo = phased ? a.ch_lo : 0;
@@ -336,19 +422,28 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
           uint32_t v = (acc >> (PH_FIELD_BITS * c)) & FM;
           v += __shfl_xor_sync(FULL, v, 1);
           v += __shfl_xor_sync(FULL, v, 2);
-          if ((lane & 3) == 0 && v) s_cnt[(la * D + cur_d) * NC + c] += v;
+          if ((lane & 3) == 0 && v) s_cnt[((la + 8 * cur_sb) * D + cur_d) * NC + c] += v;
         }
         acc = 0;
       };
       auto slow4 = [&](uint32_t step) {  // warp-uniform: step and all bounds are
         while (step >= s_e[q + 1]) ++q;
-        const int d = (int)(((uint32_t)q * magic_nch) >> 16);  // q / NCH
-        if (d != cur_d || step - st_flush >= kDeadline4) {
+        int qs = q, sb = 0;  // sub-segment within its batch, batch within the item
+        if (NB8 > 1) {
+          sb = (int)(((uint32_t)q * magic_nsub) >> 16);
+          qs = q - sb * NSUB;
+        }
+        const int d = (int)(((uint32_t)qs * magic_nch) >> 16);  // qs / NCH
+        if (d != cur_d || (NB8 > 1 && sb != cur_sb) || step - st_flush >= kDeadline4) {
           flush4();
           cur_d = d;
+          if (NB8 > 1) {
+            cur_sb = sb;
+            if (MODE == MODE_MAPPED) maprow = s_map + s_ml[la + 8 * sb] * K2;
+          }
           st_flush = step;
         }
-        cbase = (((uint32_t)q - (uint32_t)d * (uint32_t)NCH - (uint32_t)ch_lo) << 16) + (AL ? img_base : 0u);
+        cbase = (((uint32_t)qs - (uint32_t)d * (uint32_t)NCH - (uint32_t)ch_lo) << 16) + (AL ? img_base : 0u);
         nb_eff = min(s_e[q + 1], st_flush + kDeadline4);
       };
       auto one4 = [&](uint32_t addr) -> uint32_t {
@@ -368,7 +463,12 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
       for (int run = 0; run < n_runs; ++run) {
         q = phased ? run * NCH + ch_lo : 0;
         st = s_e[q];
-        st_end = phased ? s_e[run * NCH + ch_lo + a.ch_n] : s_e[NSUB];
+        st_end = phased ? s_e[run * NCH + ch_lo + a.ch_n] : s_e[NB8 * NSUB];
+        if (SPLIT && split) {  // this item's share of the batch's steps
+          const uint32_t len = st_end - st, lo = st + ((len * part) >> a.split_sh);
+          st_end = st + ((len * (part + 1u)) >> a.split_sh);
+          st = lo;
+        }
         gp = reinterpret_cast<const uint4*>(a.half4) + ((size_t)st << 5) + lane;
         nb_eff = st;  // the first step of a run enters the slow path
         st_flush = st;
@@ -492,7 +592,29 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
       }
     }
     __syncwarp();
+    PH_STAMP_T(t_hold);
     if (!drawn && lane == 0) bnext = atomicAdd(a.counter, 1u);  // next batch: the round trip overlaps the holders' work
+    bool finisher = true;
+    if (SPLIT && split) {
+      const unsigned sb = bat - (unsigned)a.split_from;
+      uint32_t* gacc = a.part_acc + (size_t)sb * (B * D * NC);
+      for (int k = lane; k < B * D * NC; k += 32) {
+        const uint32_t v = s_cnt[k];
+        if (v) atomicAdd(gacc + k, v);
+      }
+      __threadfence();
+      __syncwarp();
+      unsigned t = 0;
+      if (lane == 0) t = atomicAdd(a.part_tick + sb, 1u);
+      t = __shfl_sync(FULL, t, 0);
+      finisher = t == (1u << a.split_sh) - 1u;
+      if (finisher) {  // every part's counters are in the row: take them (and leave zeros for the next launch)
+        __threadfence();
+        for (int k = lane; k < B * D * NC; k += 32) s_cnt[k] = atomicExch(gacc + k, 0u);
+        if (lane == 0) a.part_tick[sb] = 0u;
+        __syncwarp();
+      }
+    }
     if (PH_PIPE && B4 && NSUB > 0 && !PHASED) {
       // prime the ring of the next batch now: its first loads fly while the holders below finish this one
       const unsigned bn = __shfl_sync(FULL, bnext, 0);
@@ -517,7 +639,7 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
     // code is one run) -- i.e. a function of the integer (code, cluster) histogram only: the result does not depend on
     // how the observations were split over lanes, batches or GPUs.
     uint32_t pay0 = 0xFFFFFF00u, pay1 = 0, pay2 = 0;  // push: this lane's line as LL payloads (empty slot by default)
-    if (lane < B && have) {
+    if (lane < B && have && finisher) {
       double s0[NC], s1[NC];
       unsigned nob[NC], nva[NC];
 #pragma unroll
@@ -643,7 +765,7 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
       }
     }
     __syncwarp();
-    if (PUSHABLE && a.push) {
+    if (PUSHABLE && a.push && finisher) {
       // the batch's LL words -> every rank's window: lane = (peer * words + word, line); the B lanes of a (peer, word)
       // store B consecutive 8-byte words
       constexpr int NW = MODE == MODE_LINEAR ? 2 : 3;
@@ -651,7 +773,7 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
       const int l = lane % B;
       const uint32_t v0 = __shfl_sync(FULL, pay0, l), v1 = __shfl_sync(FULL, pay1, l);
       const uint32_t v2 = NW == 3 ? __shfl_sync(FULL, pay2, l) : 0u;
-      const size_t slot_off = ((size_t)bidx * B + l) * 8 + (size_t)par * a.ll.par_stride;
+      const size_t slot_off = ((size_t)bat * B + l) * 8 + (size_t)par * a.ll.par_stride;
       for (int kk = lane / B; kk < a.world * NW; kk += KPI) {
         const int p = kk / NW, wd = kk - p * NW;
         const uint32_t v = wd == 0 ? v0 : (wd == 1 ? v1 : v2);
@@ -670,8 +792,18 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
       }
       __syncwarp();
     }
+    PH_STAMP_ADD(4, 1);
     bidx = __shfl_sync(FULL, bnext, 0);
+#ifdef PH_STAMPS
+    {  // per-CTA sums over warps and items: prologue, streaming, holders (+ merge, push, next-item round trip)
+      PH_STAMP_T(t_end);
+      PH_STAMP_ADD(5, t_stream - t_top);
+      PH_STAMP_ADD(6, t_hold - t_stream);
+      PH_STAMP_ADD(7, t_end - t_hold);
+    }
+#endif
   }
+  PH_STAMP_MAX(2);
   // The last CTA to finish re-arms the batch dispenser for the next launch (no memset between launches).  Peer modes:
   // all partial rows (or pushed records) of this rank are on their way -- make them visible system-wide first; the last
   // CTA then raises this rank's flag in every peer's window.
@@ -736,6 +868,7 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
       }
     }
   }
+  PH_STAMP_MAX(3);
 }
 
 // label image in global memory, for minor axes whose image does not fit in shared memory
@@ -908,11 +1041,11 @@ __global__ void __launch_bounds__(kBlock, 1) k_node_table(const PassArgs a, cons
 
 // shared memory of one k_pass CTA with `threads` threads; 0 = does not fit
 size_t pass_smem_bytes(const ph_handle* h, const PhOrient* o, int mode, int NC, int K, bool smem_lab, int threads, int B,
-                       int row_words, int* lut_in_smem, long long image_bytes = -1) {
+                       int row_words, int* lut_in_smem, long long image_bytes = -1, bool b4 = false) {
   size_t b = 0;
   if (smem_lab) b += image_bytes >= 0 ? (size_t)image_bytes : (size_t)o->lab_bytes;
   if (mode == MODE_MAPPED) b += (((size_t)(K + 2) * (K + 2)) + 15) & ~(size_t)15;
-  const size_t warps = (size_t)(threads / 32) * (warp_words(B, o->NSUB, o->D, NC) + row_words) * 4 + 16;
+  const size_t warps = (size_t)(threads / 32) * (warp_words(B, o->NSUB, o->D, NC, b4) + row_words) * 4 + 16;
   const size_t lut = ((size_t)h->n_codes * 17 + 15) & ~(size_t)15;
   *lut_in_smem = (b + warps + lut <= (size_t)h->max_smem && h->n_codes <= 4096) ? 1 : 0;
   if (*lut_in_smem) b += lut;
@@ -945,9 +1078,33 @@ int launch_pass(ph_handle* h, const PhOrient* o, PassArgs& a, cudaStream_t st) {
   const bool can4 = MODE != MODE_COUNTS && o->half4 && !a.list && h->batch4 && o->chunk_bits == 16;
   int n_phases = 1, cpp = o->NCH;   // phased pass: chunks per phase (see PassArgs)
   size_t tab4 = 0;
+  // batched-4 items of 2 or 4 consecutive batches (k_pass NB8) where every warp of the grid still gets several items:
+  // the per-item code runs once per 16 / 32 lines instead of once per 8.  Not for pushed results (LL slots are per
+  // 8-line batch), not in phases.
+  int B4items = 8;
+  if (can4 && !a.push && h->item_batches != 1) {
+    // rounds of items per warp x (batches per item + the per-item share, about a quarter of a batch's streaming time):
+    // C3 by SNV, 25 000 batches on 4 736 warps: 6 x 1.25 / 3 x 2.25 / 2 x 4.25 -> pairs (measured 159 / 150 / 169 us)
+    const int64_t warps = (int64_t)h->sm_count * 32;
+    double best = 0.0;
+    for (int nb8 = 1; nb8 <= 4; nb8 *= 2) {
+      const int64_t items = ((int64_t)o->n_batches4 + nb8 - 1) / nb8;
+      const double cost = (double)((items + warps - 1) / warps) * (nb8 + 0.25);
+      if (nb8 == 1 || cost < best) {
+        best = cost;
+        B4items = 8 * nb8;
+      }
+    }
+    if (h->item_batches == 2 || h->item_batches == 4) B4items = 8 * h->item_batches;  // forced (PH_ITEM_BATCHES)
+  }
   if (o->chunk_bits == 16 && (h->aligned_image || can4)) {
-    const int Bt = can4 ? 8 : B;
-    const size_t full = pass_smem_bytes(h, o, MODE, NC, a.K, true, 1024, Bt, a.row_words, &lut);
+    int Bt = can4 ? B4items : B;
+    size_t full = pass_smem_bytes(h, o, MODE, NC, a.K, true, 1024, Bt, a.row_words, &lut, -1, can4);
+    while (can4 && !full && Bt > 8) {  // the tables of the larger item do not fit next to the image: smaller items
+      Bt >>= 1;
+      full = pass_smem_bytes(h, o, MODE, NC, a.K, true, 1024, Bt, a.row_words, &lut, -1, true);
+    }
+    if (can4) B4items = Bt;
     const bool fits_al = h->aligned_image && full && full + 65536 <= (size_t)h->max_smem;
     if (fits_al) {
       smem = full + 65536;
@@ -960,7 +1117,7 @@ int launch_pass(ph_handle* h, const PhOrient* o, PassArgs& a, cudaStream_t st) {
       // the image of the whole minor axis does not fit: walk it in phases of `cpp` chunks.  Aligned image (2 chunks of
       // 64 KB above a 64 KB boundary) when that takes no more phases than the 3 chunks an unaligned image holds.
       int lut0 = 0;
-      tab4 = pass_smem_bytes(h, o, MODE, NC, a.K, true, 1024, 8, a.row_words, &lut0, 0);
+      tab4 = pass_smem_bytes(h, o, MODE, NC, a.K, true, 1024, 8, a.row_words, &lut0, 0, true);
       if (tab4 && tab4 + 65536 <= (size_t)h->max_smem) {
         const int cpp_u = (int)(((size_t)h->max_smem - tab4) >> 16);
         const int cpp_a = h->aligned_image && (size_t)h->max_smem >= tab4 + 65536 + 65536 ? (int)(((size_t)h->max_smem - 65536 - tab4) >> 16) : 0;
@@ -982,11 +1139,22 @@ int launch_pass(ph_handle* h, const PhOrient* o, PassArgs& a, cudaStream_t st) {
       threads = 1024;
       use4 = true;
       aligned = al4;
-      B = 8;
+      B = n_phases > 1 ? 8 : B4items;
       a.list = o->perm4;              // the lines in shape order, 8 per batch, -1 = empty slot
       a.n_work = o->n_batches4 * 8;
       a.half4 = o->half4;
       a.bstep_off = o->bstep_off;
+      // split tail (PassArgs): the last `split_tail` x (warps of the grid) batches go out in 2^split_sh parts
+      a.n_items = a.split_from = o->n_batches4;
+      a.split_sh = 0;
+      if (n_phases == 1 && B == 8 && o->part_acc && h->split_sh > 0 && h->split_tail > 0) {
+        const int64_t n_split = std::min<int64_t>(o->n_batches4, (int64_t)h->sm_count * 32 * h->split_tail / 100);
+        a.split_from = (int)(o->n_batches4 - n_split);
+        a.split_sh = h->split_sh;
+        a.n_items = (int)(a.split_from + (n_split << h->split_sh));
+        a.part_acc = o->part_acc;
+        a.part_tick = o->part_tick;
+      }
       if (n_phases > 1) smem = 1;     // set per phase below
     }
   }
@@ -1070,6 +1238,12 @@ int launch_pass(ph_handle* h, const PhOrient* o, PassArgs& a, cudaStream_t st) {
         if (n_phases > 1) {
           if (al4) PH_LAUNCH(8, true, 5);
           else PH_LAUNCH(8, true, 6);
+        } else if (B == 32) {
+          if (al4) PH_LAUNCH(32, true, 3);
+          else PH_LAUNCH(32, true, 4);
+        } else if (B == 16) {
+          if (al4) PH_LAUNCH(16, true, 3);
+          else PH_LAUNCH(16, true, 4);
         } else if (al4) PH_LAUNCH(8, true, 3);
         else PH_LAUNCH(8, true, 4);
         if (p + 1 < n_phases) ph_count_launch();

@@ -11,6 +11,9 @@ import torch
 import torch.distributed as dist
 
 sys.path.insert(0, ".")
+if os.environ.get("PH_LIB"):   # development aid: an alternative build of the library (e.g. -DPH_STAMPS)
+    from phertilizer_b200 import _lib as _l
+    _l.LIB_PATH = os.path.abspath(os.environ["PH_LIB"])
 from phertilizer_b200.sharded import SnvShardedStore
 from phertilizer_b200.synth import CONFIGS, make_config
 
@@ -87,5 +90,37 @@ for grp in groups:
         out[f"{label}_graph_cold_us"] = round(bench(fn, True, cold=True), 2)
     out["ideal_us_at_4TBps"] = round(info["stream_bytes_by_snv"] / 4.0e12 * 1e6, 2)
     print(json.dumps(out), flush=True)
+
+
+def timeline(fn, label):
+    """-DPH_STAMPS builds: per-CTA timeline of one launch (ns after the first CTA's entry)."""
+    import ctypes
+    import numpy as np
+    from phertilizer_b200 import _lib
+    L = _lib.lib()
+    if not hasattr(L, "ph_debug_stamps"):
+        return
+    buf = np.zeros(256 * 8, np.uint64)
+    rows = []
+    for i in range(6):
+        torch.cuda.synchronize()
+        L.ph_debug_stamps(None, 1)
+        fn(i)
+        torch.cuda.synchronize()
+        L.ph_debug_stamps(buf.ctypes.data_as(ctypes.POINTER(ctypes.c_ulonglong)), 0)
+        t = buf.reshape(256, 8).astype(np.int64)
+        t = t[t[:, 0] > 0]
+        t0 = t[:, 0].min()
+        q = lambda v: [int(np.min(v)), int(np.median(v)), int(np.max(v))]
+        rows.append({"ctas": int(len(t)), "entry_ns": q(t[:, 0] - t0), "staged_ns": q(t[:, 1] - t0),
+                     "stream_end_ns": q(t[:, 2] - t0), "exit_ns": q(t[:, 3] - t0), "batches_per_cta": q(t[:, 4]),
+                     "warp_ns_per_item": {"prologue": round(float(t[:, 5].sum() / t[:, 4].sum()), 1),
+                                          "stream": round(float(t[:, 6].sum() / t[:, 4].sum()), 1),
+                                          "holders": round(float(t[:, 7].sum() / t[:, 4].sum()), 1)}})
+    print(json.dumps({"timeline": label, "launches": rows[2:]}), flush=True)
+
+
+timeline(plain, "plain")
+timeline(push, "push+collect")
 sh.close()
 dist.destroy_process_group()

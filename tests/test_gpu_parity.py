@@ -274,7 +274,7 @@ def test_pairwise_dist(env):
 
 
 # ------------------------------------------------------------------------------------------- seeded random inputs
-@pytest.fixture(scope="module", params=["default", "no_batch4", "unaligned_image", "chunks512", "chunks64_nobank"])
+@pytest.fixture(scope="module", params=["default", "no_batch4", "unaligned_image", "chunks512", "chunks64_nobank", "no_split", "split8_mixed", "items2", "items4"])
 def synth_env(request):
     """T1 (2000 x 3000).  The store is also built with tiny chunks of the minor axis (PH_CHUNK_BITS, a test knob of
     ph_create) so that the multi-chunk sub-segment logic runs on data the dense oracle can hold."""
@@ -284,7 +284,13 @@ def synth_env(request):
     from phertilizer_b200.synth import make_config
 
     knobs = {"default": {}, "no_batch4": {"PH_BATCH4": "0"}, "unaligned_image": {"PH_ALIGNED_IMAGE": "0"}, "chunks512": {"PH_CHUNK_BITS": "9", "PH_DENSE_MIN_AVG": "4", "PH_DENSE_MIN_SHARE": "0"},
-             "chunks64_nobank": {"PH_CHUNK_BITS": "8", "PH_BANK_ORDER": "0", "PH_DENSE_MIN_AVG": "2", "PH_DENSE_MIN_SHARE": "0"}}[request.param]
+             "chunks64_nobank": {"PH_CHUNK_BITS": "8", "PH_BANK_ORDER": "0", "PH_DENSE_MIN_AVG": "2", "PH_DENSE_MIN_SHARE": "0"},
+             # split tail of the batched-4 pass (ph_pass.cu PassArgs): off; 8 parts over the last ~95 batches only, the
+             # rest whole (the default splits every batch of an input this small in 4)
+             "no_split": {"PH_SPLIT_SH": "0", "PH_LPT_ORDER": "0"}, "split8_mixed": {"PH_SPLIT_SH": "3", "PH_SPLIT_TAIL": "2"},
+             # items of 2 / 4 consecutive 8-line batches (k_pass NB8; automatic only from 4 batches per warp of the grid up);
+             # 375 and 250 batches: the last item of either orientation is a partial one
+             "items2": {"PH_ITEM_BATCHES": "2"}, "items4": {"PH_ITEM_BATCHES": "4"}}[request.param]
     saved = {k: os.environ.get(k) for k in knobs}
     os.environ.update(knobs)
 
