@@ -774,7 +774,7 @@ __global__ void __launch_bounds__(1024, 1) k_pass(const PassArgs a) {
       const uint32_t v0 = __shfl_sync(FULL, pay0, l), v1 = __shfl_sync(FULL, pay1, l);
       const uint32_t v2 = NW == 3 ? __shfl_sync(FULL, pay2, l) : 0u;
       const size_t slot_off = ((size_t)bat * B + l) * 8 + (size_t)par * a.ll.par_stride;
-      for (int kk = lane / B; kk < a.world * NW; kk += KPI) {
+      for (int kk = lane < KPI * B ? lane / B : a.world * NW; kk < a.world * NW; kk += KPI) {
         const int p = kk / NW, wd = kk - p * NW;
         const uint32_t v = wd == 0 ? v0 : (wd == 1 ? v1 : v2);
         st_relaxed_sys_u64(a.ll.dst[p] + slot_off + (size_t)wd * a.ll.word_stride, ((uint64_t)epoch << 32) | v);
@@ -1079,29 +1079,35 @@ int launch_pass(ph_handle* h, const PhOrient* o, PassArgs& a, cudaStream_t st) {
   int n_phases = 1, cpp = o->NCH;   // phased pass: chunks per phase (see PassArgs)
   size_t tab4 = 0;
   // batched-4 items of 2 or 4 consecutive batches (k_pass NB8) where every warp of the grid still gets several items:
-  // the per-item code runs once per 16 / 32 lines instead of once per 8.  Not for pushed results (LL slots are per
-  // 8-line batch), not in phases.
+  // the per-item code runs once per 16 / 24 / 32 lines instead of once per 8.  Not in phases.  (Pushed results: the LL
+  // slots of an item are B consecutive ones, ph_peer.cu sizes the windows for the largest item.)
   int B4items = 8;
-  if (can4 && !a.push && h->item_batches != 1) {
+  if (can4 && h->item_batches != 1) {
     // rounds of items per warp x (batches per item + the per-item share, about a quarter of a batch's streaming time):
-    // C3 by SNV, 25 000 batches on 4 736 warps: 6 x 1.25 / 3 x 2.25 / 2 x 4.25 -> pairs (measured 159 / 150 / 169 us)
+    // C3 by SNV, 25 000 batches on 4 736 warps: 6 x 1.25 / 3 x 2.25 / 2 x 3.25 / 2 x 4.25 (measured 159 / 150 / - / 169 us).
+    // Only sizes whose per-warp tables (and the likelihood table) still fit next to the label image.
     const int64_t warps = (int64_t)h->sm_count * 32;
     double best = 0.0;
-    for (int nb8 = 1; nb8 <= 4; nb8 *= 2) {
+    for (int nb8 = 1; nb8 <= 4; ++nb8) {
+      if (h->item_batches >= 2 && h->item_batches <= 4 && nb8 != h->item_batches) continue;  // forced (PH_ITEM_BATCHES)
+      if (nb8 > 1) {
+        int l8 = 0, ln = 0;
+        pass_smem_bytes(h, o, MODE, NC, a.K, true, 1024, 8, a.row_words, &l8, -1, true);
+        if (!pass_smem_bytes(h, o, MODE, NC, a.K, true, 1024, 8 * nb8, a.row_words, &ln, -1, true) || ln < l8) continue;
+      }
       const int64_t items = ((int64_t)o->n_batches4 + nb8 - 1) / nb8;
       const double cost = (double)((items + warps - 1) / warps) * (nb8 + 0.25);
-      if (nb8 == 1 || cost < best) {
+      if (best == 0.0 || cost < best) {
         best = cost;
         B4items = 8 * nb8;
       }
     }
-    if (h->item_batches == 2 || h->item_batches == 4) B4items = 8 * h->item_batches;  // forced (PH_ITEM_BATCHES)
   }
   if (o->chunk_bits == 16 && (h->aligned_image || can4)) {
     int Bt = can4 ? B4items : B;
     size_t full = pass_smem_bytes(h, o, MODE, NC, a.K, true, 1024, Bt, a.row_words, &lut, -1, can4);
     while (can4 && !full && Bt > 8) {  // the tables of the larger item do not fit next to the image: smaller items
-      Bt >>= 1;
+      Bt -= 8;
       full = pass_smem_bytes(h, o, MODE, NC, a.K, true, 1024, Bt, a.row_words, &lut, -1, true);
     }
     if (can4) B4items = Bt;
@@ -1241,6 +1247,9 @@ int launch_pass(ph_handle* h, const PhOrient* o, PassArgs& a, cudaStream_t st) {
         } else if (B == 32) {
           if (al4) PH_LAUNCH(32, true, 3);
           else PH_LAUNCH(32, true, 4);
+        } else if (B == 24) {
+          if (al4) PH_LAUNCH(24, true, 3);
+          else PH_LAUNCH(24, true, 4);
         } else if (B == 16) {
           if (al4) PH_LAUNCH(16, true, 3);
           else PH_LAUNCH(16, true, 4);

@@ -202,7 +202,7 @@ extern "C" int ph_peer_create(ph_handle* h, int rank, int world, int32_t total_s
   p->off_nobs = (p->off_lab + (size_t)p->max_lines + 255) & ~(size_t)255;
   // SNV-sharded steps: every rank pushes the LL words of its block (work order, whole batches of 8) into its own region
   // of each window; blocks are expected to be balanced (at most ceil(total / world) + 8 SNVs per rank)
-  p->cap_slots = (((total_snvs + world - 1) / world + 8 + 7) / 8) * 8 + 8;
+  p->cap_slots = (((total_snvs + world - 1) / world + 8 + 7) / 8) * 8 + 40;  // lines in whole 8-line batches + one 32-line item of slack
   p->off_ll = (p->off_nobs + (size_t)p->max_lines * 3 * sizeof(int32_t) + 255) & ~(size_t)255;
   p->bytes = p->off_ll + (size_t)2 * kLLWords * world * p->cap_slots * 8 + 256;
   cudaError_t e = cudaMalloc(&p->win[rank], p->bytes);
@@ -341,9 +341,9 @@ int peer_assign_snv(ph_peer* p, int mode, const uint8_t* cell_label, double lenA
   cudaStream_t st = (cudaStream_t)stream;
   const int C = mode == 1 ? 1 : 2;
   if (h->n_snvs <= 0) PH_FAIL(PH_ERR_ARG, "this rank holds no SNVs");
-  if (h->n_snvs > p->cap_slots - 8)
+  if (h->n_snvs > p->cap_slots - 40)
     PH_FAIL(PH_ERR_UNSUPPORTED, "%d local SNVs exceed the %d a balanced block may hold (ceil(total / world) + 8)", h->n_snvs,
-            p->cap_slots - 8);
+            p->cap_slots - 40);
   if (p->max_lines >= 0xFFFFFF) PH_FAIL(PH_ERR_UNSUPPORTED, "%d SNVs: the pushed words carry 24-bit SNV ids", p->max_lines);
   // LL words alternate between two parities of the step counter: a fast rank may already push step e+1 into a peer that
   // still polls step e (its own step e+2 cannot start before that peer has pushed step e+1, i.e. finished step e).

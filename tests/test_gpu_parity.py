@@ -274,7 +274,7 @@ def test_pairwise_dist(env):
 
 
 # ------------------------------------------------------------------------------------------- seeded random inputs
-@pytest.fixture(scope="module", params=["default", "no_batch4", "unaligned_image", "chunks512", "chunks64_nobank", "no_split", "split8_mixed", "items2", "items4"])
+@pytest.fixture(scope="module", params=["default", "no_batch4", "unaligned_image", "chunks512", "chunks64_nobank", "no_split", "split8_mixed", "items2", "items3", "items4"])
 def synth_env(request):
     """T1 (2000 x 3000).  The store is also built with tiny chunks of the minor axis (PH_CHUNK_BITS, a test knob of
     ph_create) so that the multi-chunk sub-segment logic runs on data the dense oracle can hold."""
@@ -290,7 +290,7 @@ def synth_env(request):
              "no_split": {"PH_SPLIT_SH": "0", "PH_LPT_ORDER": "0"}, "split8_mixed": {"PH_SPLIT_SH": "3", "PH_SPLIT_TAIL": "2"},
              # items of 2 / 4 consecutive 8-line batches (k_pass NB8; automatic only from 4 batches per warp of the grid up);
              # 375 and 250 batches: the last item of either orientation is a partial one
-             "items2": {"PH_ITEM_BATCHES": "2"}, "items4": {"PH_ITEM_BATCHES": "4"}}[request.param]
+             "items2": {"PH_ITEM_BATCHES": "2"}, "items3": {"PH_ITEM_BATCHES": "3"}, "items4": {"PH_ITEM_BATCHES": "4"}}[request.param]
     saved = {k: os.environ.get(k) for k in knobs}
     os.environ.update(knobs)
 

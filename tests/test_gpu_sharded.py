@@ -14,11 +14,12 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _run(nproc, port, *flags, timeout=900):
+def _run(nproc, port, *flags, timeout=900, knobs=None):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc), "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "scripts", "check_sharded.py"), *flags]
     env = dict(os.environ)
     env.pop("PH_BATCH4", None)
+    env.update(knobs or {})
     out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=timeout, env=env)
     dump = os.path.join(ROOT, "gpurun_out")
     if os.path.isdir(dump):   # keep the ranks' own output next to the other run artefacts
@@ -36,6 +37,13 @@ def test_two_ranks_on_one_gpu():
 
 def test_four_ranks_on_one_gpu():
     _run(4, 29535, "--one-gpu", "--quick")
+
+
+@pytest.mark.parametrize("item_batches", ["2", "3"])
+def test_two_ranks_multi_batch_items(item_batches):
+    """The pushed LL slots of items of 2 / 3 consecutive 8-line batches (k_pass NB8; chosen automatically only on inputs
+    with several batches per warp of the grid, forced here)."""
+    _run(2, 29541 + int(item_batches), "--one-gpu", "--quick", knobs={"PH_ITEM_BATCHES": item_batches})
 
 
 def test_sharded_nccl_equals_single_gpu():
