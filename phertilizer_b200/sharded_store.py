@@ -137,6 +137,55 @@ class CellShardedStore:
             at += w
         return out
 
+    _SIZES = {"S0": (8, np.float64), "S1": (8, np.float64), "Nobs": (4, np.int32), "Nvar": (4, np.int32)}
+
+    def _cell_table_gathered(self, snv_label, Q, want):
+        """K2 tables of ALL cells with the assembly on the device: every rank's pass writes its block straight into its
+        region of one device buffer, ONE all-gather (NCCL, in place) completes it, ONE device-to-host copy brings it home.
+        Same values as `_combine_tables` (rows are computed by their owner either way), a fifth of the host work."""
+        torch, dist = self.torch, self.dist
+        from .sharded import cell_block
+
+        names = [k for k in ("S0", "S1", "Nobs", "Nvar") if k in want]
+        blocks = [cell_block(self.n_cells, r, self.world) for r in range(self.world)]
+        bmax = max(hi - lo for lo, hi in blocks)
+        offs, at = {}, 0
+        for k in names:   # the float64 tables first: every sub-array starts on a multiple of 8 bytes
+            offs[k] = at
+            at += bmax * Q * self._SIZES[k][0]
+        region = (at + 15) & ~15
+        cache = self.__dict__.setdefault("_gather_cache", {})
+        key = (Q, tuple(names))
+        if key not in cache:
+            dev = torch.device("cuda", torch.cuda.current_device())
+            cache[key] = (torch.zeros((self.world, region), dtype=torch.uint8, device=dev),
+                          torch.empty((self.world, region), dtype=torch.uint8).pin_memory())
+        if "_lab_dev" not in self.__dict__:
+            dev = torch.device("cuda", torch.cuda.current_device())
+            self._lab_pin = torch.zeros(self.n_snvs + 16, dtype=torch.uint8).pin_memory()
+            self._lab_dev = torch.zeros(self.n_snvs + 16, dtype=torch.uint8, device=dev)
+        full, host = cache[key]
+        self._lab_pin.numpy()[:self.n_snvs] = np.asarray(snv_label, np.uint8)[:self.n_snvs]
+        self._lab_dev.copy_(self._lab_pin, non_blocking=True)
+        mine = full[self.rank]
+        n_loc = self.hi - self.lo
+        outs = {}
+        for k in names:
+            size, _ = self._SIZES[k]
+            t = mine[offs[k]:offs[k] + n_loc * Q * size]
+            outs[k] = t.view(torch.float64 if size == 8 else torch.int32)
+        self.local.cell_table_dev(self._lab_dev, Q, S0=outs.get("S0"), S1=outs.get("S1"), Nobs=outs.get("Nobs"),
+                                  Nvar=outs.get("Nvar"))   # legacy default stream = torch's current stream: ordered with NCCL
+        dist.all_gather_into_tensor(full.view(-1), mine, group=self.group)
+        host.copy_(full, non_blocking=False)
+        h = host.numpy()
+        res = {}
+        for k in names:
+            size, dt = self._SIZES[k]
+            parts = [h[r, offs[k]:offs[k] + (hi - lo) * Q * size].view(dt).reshape(hi - lo, Q) for r, (lo, hi) in enumerate(blocks)]
+            res[k] = np.concatenate(parts, axis=0)
+        return res
+
     # ------------------------------------------------------------------ K1 family (per SNV, over cell clusters)
     def snv_table(self, cell_label, C_, snv_list=None, want=("S0", "S1", "Nobs", "Nvar")):
         t = self.local.snv_table(self._loc(cell_label), C_, snv_list, want=want)
@@ -154,8 +203,10 @@ class CellShardedStore:
 
     # ------------------------------------------------------------------ K2 family (per cell: owned by one rank)
     def cell_table(self, snv_label, Q, cell_list=None, want=("S0", "S1", "Nobs", "Nvar")):
-        t = self.local.cell_table(snv_label, Q, None, want=want)
-        out = self._combine_tables(t, rows_local=True)
+        if self._device_reduce and self.world > 1:
+            out = self._cell_table_gathered(snv_label, Q, want)
+        else:
+            out = self._combine_tables(self.local.cell_table(snv_label, Q, None, want=want), rows_local=True)
         if cell_list is not None:
             idx = np.asarray(cell_list, np.int64)
             out = {k: v[idx] for k, v in out.items()}
@@ -178,8 +229,7 @@ class CellShardedStore:
         if Q > 3 or self.world == 1:
             s0, s1, no, nv = self.local.block_sums(self._loc(cl), C_, snv_label, Q)
             return self._sum(s0), self._sum(s1), self._sum(no), self._sum(nv)
-        t = self.local.cell_table(snv_label, Q, None)
-        full = self._combine_tables(t, rows_local=True)
+        full = self.cell_table(snv_label, Q)
         return self.local.line_reduce(full["S0"], full["S1"], full["Nobs"], full["Nvar"], _padded(cl, self.n_cells), Q, C_)
 
     def tree_loglik(self, cell_node, snv_node, present, per_cell=False):
