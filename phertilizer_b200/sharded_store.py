@@ -8,7 +8,8 @@ redundantly on all ranks, on identical inputs -- the same RNG streams, the same 
 What makes the results independent of the number of GPUs:
 
 * per-CELL quantities (K2 tables, a cell's tree log-likelihood, reassign_cell scores) are computed wholly by the rank that
-  owns the cell; the blocks are assembled by a sum all-reduce into a zero-initialised array (x + 0 is exact);
+  owns the cell; the blocks are assembled by position -- K2 tables with one NCCL all-gather of a device buffer each rank's
+  pass writes its region of, everything else (and everything over gloo) by a sum all-reduce into a zero array (x + 0 is exact);
 * the scalars that decide which split / tree wins -- block sums (compute_norm_likelihood, check_obs) and per-node tree
   log-likelihoods -- are fixed-order reductions of those assembled per-cell tables, run by the SAME kernels one GPU runs
   (``ph_line_reduce`` / ``ph_node_reduce``): bit-identical for any world size;
