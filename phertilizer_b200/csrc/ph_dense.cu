@@ -28,15 +28,26 @@ __global__ void __launch_bounds__(DX * RL) k_gauss_stat(const double* __restrict
   double acc = 0.0;
   if (d < D && cnt > 0) {
     const double mu = pass ? mean[(size_t)k * D + d] : 0.0;
-    for (int r = beg + threadIdx.y; r < end; r += RL) {
-      const double x = X[(size_t)rows[r] * D + d];
+    auto add = [&](double x) {
       if (pass) {
         const double t = x - mu;
         acc += t * t;
       } else {
         acc += x;
       }
+    };
+    // four rows in flight per thread (a lone dependent load per iteration left the pass latency-bound); the additions
+    // keep their order, so the sums are the same bits as with one row at a time
+    int r = beg + threadIdx.y;
+    for (; r + 3 * RL < end; r += 4 * RL) {
+      const double x0 = X[(size_t)rows[r] * D + d], x1 = X[(size_t)rows[r + RL] * D + d];
+      const double x2 = X[(size_t)rows[r + 2 * RL] * D + d], x3 = X[(size_t)rows[r + 3 * RL] * D + d];
+      add(x0);
+      add(x1);
+      add(x2);
+      add(x3);
     }
+    for (; r < end; r += RL) add(X[(size_t)rows[r] * D + d]);
   }
   __shared__ double sh[RL][DX + 1];
   sh[threadIdx.y][threadIdx.x] = acc;
@@ -118,13 +129,24 @@ __global__ void k_gauss_logpdf(const double* __restrict__ X, int n, int D, const
   const double* mu = mean + (size_t)k * D;
   const double* iv = inv + (size_t)k * D;
   double maha = 0.0, res = 0.0;
-  for (int d = lane; d < D; d += 32) {
-    const double t = x[d] - mu[d];
-    const double w = iv[d];
+  auto add = [&](double xv, double m, double w) {
+    const double t = xv - m;
     const double t2 = t * t;
     maha += t2 * w;
     res += (w == 0.0) ? t2 : 0.0;
+  };
+  // four strides of the row in flight per lane, accumulated in the original order (same bits)
+  int d = lane;
+  for (; d + 96 < D; d += 128) {
+    const double x0 = x[d], x1 = x[d + 32], x2 = x[d + 64], x3 = x[d + 96];
+    const double m0 = mu[d], m1 = mu[d + 32], m2 = mu[d + 64], m3 = mu[d + 96];
+    const double w0 = iv[d], w1 = iv[d + 32], w2 = iv[d + 64], w3 = iv[d + 96];
+    add(x0, m0, w0);
+    add(x1, m1, w1);
+    add(x2, m2, w2);
+    add(x3, m3, w3);
   }
+  for (; d < D; d += 32) add(x[d], mu[d], iv[d]);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     maha += __shfl_xor_sync(0xffffffffu, maha, o);
