@@ -10,6 +10,11 @@
 // sum_code count * L[code]  evaluated once per line in a fixed order -> exact integer tables, deterministic fp64
 // results, no floating-point atomics anywhere.
 //
+// Whole-orientation passes run on the batched-4 copy of the stream instead (LAY >= 3): four lanes per line, eight lines per
+// warp step, sub-segment boundaries uniform across the warp, so the counters are combined with two shuffles and plain
+// shared-memory adds -- no atomics at all -- and the dispenser hands out items of 1 - 4 consecutive 8-line batches, so that
+// the code around the streaming loop runs once per 8 - 32 lines (launch_pass picks the size).
+//
 // HBM traffic: 2 B per observation (+ padding to 16 B per sub-segment, + offsets), the roofline of these kernels.
 #include "ph_common.cuh"
 
