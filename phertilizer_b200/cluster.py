@@ -200,6 +200,21 @@ def device_lobpcg(ctx, X0, maxiter=2000, restart_control=20):
         out[: M.shape[0], : M.shape[1]] = M
         return out
 
+    def sym_blocks(diag, upper):
+        """The symmetric block matrix np.block would build from the diagonal blocks and the blocks above them (row-major:
+        (0,1), (0,2), (1,2)) -- by slice assignment: np.block's nesting checks cost more than the eigenproblem here."""
+        sizes = [d.shape[0] for d in diag]
+        at = np.concatenate([[0], np.cumsum(sizes)])
+        M = np.empty((at[-1], at[-1]))
+        u = 0
+        for a in range(len(diag)):
+            M[at[a]:at[a + 1], at[a]:at[a + 1]] = diag[a]
+            for b in range(a + 1, len(diag)):
+                M[at[a]:at[a + 1], at[b]:at[b + 1]] = upper[u]
+                M[at[b]:at[b + 1], at[a]:at[a + 1]] = upper[u].T
+                u += 1
+        return M
+
     def orthonormalize(slot, ca):
         """In-place (B = I) orthonormalisation of the first ca columns by Cholesky; returns inv(chol) or None."""
         G = ctx.bv_gram([slot], [slot])[:ca, :ca]
@@ -299,15 +314,15 @@ def device_lobpcg(ctx, X0, maxiter=2000, restart_control=20):
                 gPBP = blk(iP, iP, ca, ca)
             else:
                 gPBP = np.eye(ca)
-            gramA = np.block([[gXAX, gXAR, gXAP], [gXAR.T, gRAR, gRAP], [gXAP.T, gRAP.T, gPAP]])
-            gramB = np.block([[gXBX, gXBR, gXBP], [gXBR.T, gRBR, gRBP], [gXBP.T, gRBP.T, gPBP]])
+            gramA = sym_blocks([gXAX, gRAR, gPAP], [gXAR, gXAP, gRAP])
+            gramB = sym_blocks([gXBX, gRBR, gPBP], [gXBR, gXBP, gRBP])
             try:
                 lam_all, Vall = eigh(gramA, gramB, check_finite=False)
             except LinAlgError:
                 restart = True
         if restart:
-            gramA = np.block([[gXAX, gXAR], [gXAR.T, gRAR]])
-            gramB = np.block([[gXBX, gXBR], [gXBR.T, gRBR]])
+            gramA = sym_blocks([gXAX, gRAR], [gXAR])
+            gramB = sym_blocks([gXBX, gRBR], [gXBR])
             try:
                 lam_all, Vall = eigh(gramA, gramB, check_finite=False)
             except LinAlgError:
