@@ -372,6 +372,43 @@ def test_random_labels_all_group_sizes(synth_env, group):
     st.set_group(0, 0)
 
 
+def test_whole_orientation_passes(synth_env):
+    """Calls without a line list run on the batched-4 copy of the stream (k_pass LAY >= 3) -- under every knob of the
+    fixture: items of 1 - 4 batches, split tail, unaligned image, small chunks -- against the dense oracle."""
+    s, st, D = synth_env
+    n, m = s.n, s.m
+    rng = np.random.default_rng(11)
+    lab = np.zeros(n + 16, np.uint8)[:n]
+    lab[:] = rng.integers(0, 3, n)
+    groups = [np.nonzero(lab == c)[0] for c in (1, 2)]
+    t = st.snv_table(lab, 2)
+    S0, S1, No, Nv = O.snv_table(D, groups, np.arange(m))
+    assert np.array_equal(t["Nobs"], No) and np.array_equal(t["Nvar"], Nv)
+    assert rel_close(t["S0"], S0, TOL) and rel_close(t["S1"], S1, TOL)
+    labA, nobs = st.assign_linear(st.cell_labels(groups[0]), len(groups[0]))
+    a, b = O.linear_mut_assignment(D, groups[0], np.arange(m), nobs_per_cluster=-1)
+    assert np.array_equal(np.nonzero(labA == 2)[0], b) and np.array_equal(np.nonzero(labA == 1)[0], a)
+    assert np.array_equal(nobs, No[:, 0])
+    sl = np.zeros(m + 16, np.uint8)[:m]
+    sl[:] = rng.integers(0, 3, m)
+    mg = [np.nonzero(sl == q)[0] for q in (1, 2)]
+    t2 = st.cell_table(sl, 2)
+    A0, A1, No2, Nv2 = O.cell_table(D, np.arange(n), mg)
+    assert np.array_equal(t2["Nobs"], No2) and np.array_equal(t2["Nvar"], Nv2)
+    assert rel_close(t2["S0"], A0, TOL) and rel_close(t2["S1"], A1, TOL)
+    # tree log-likelihood: the cell-major copy through the (node, node) class map
+    cell_node = np.zeros(n + 16, np.uint8)[:n]
+    cell_node[:] = s.cell_clone.numpy()
+    snv_node = np.zeros(m + 16, np.uint8)[:m]
+    snv_node[:] = s.snv_node.numpy()
+    anc = s.ancestor_matrix()
+    got = st.tree_loglik(cell_node, snv_node, anc)
+    for k in range(anc.shape[0]):
+        present = np.nonzero(anc[k][snv_node.astype(np.int64)])[0]
+        ref = O.variant_likelihood_by_node(D, np.nonzero(cell_node == k)[0], present)
+        assert rel_close(got[k], ref, TOL)
+
+
 def test_empty_and_degenerate_inputs(synth_env):
     s, st, D = synth_env
     empty = np.zeros(s.n + 16, np.uint8)[: s.n]
